@@ -1,0 +1,118 @@
+/* include/vit_b200.h -- public C interface of the B200 ViT-B/16 inference engine.
+ *
+ * R/ = /root/reference/MulticoreMainProject/.
+ *
+ * 1. The drop-in entry point.  libvit_b200.so exports the symbol the reference
+ *    declares in R/ViT_opencl.h:6 and calls from R/Main.c:54:
+ *
+ *        void ViT_opencl(ImageData *image, Network *networks, float **prb);
+ *
+ *    so the reference's unmodified Main.c, Network.c and comparator.c link
+ *    against this library instead of ViT_opencl.c + kernelHandler.c + the five
+ *    .cl files (INTEGRATION.md shows the link line).  Semantics kept from the
+ *    reference: n = image->n images of c*h*w floats each, 152 weight blobs,
+ *    caller-allocated prb[i][0..999] receives softmax PROBABILITIES; the call
+ *    is synchronous; all device state is released before returning; any
+ *    failure prints "[file:line] CUDA error N (...)" and exit(EXIT_FAILURE)s,
+ *    the CHECK_ERROR convention of R/kernelHandler.h:6-10.  Differences, all
+ *    deliberate: results are complete on return (the reference relied on an
+ *    implicit drain, R/ViT_opencl.c:978-983); there is no 100-image cap
+ *    (R/ViT_opencl.c:107-111); image side is read from the struct so 384x384
+ *    works; missing blobs are reported instead of dereferenced.
+ *    Environment knobs: VITB200_PRECISION=fp32|bf16 (default fp32, the
+ *    reference's arithmetic), VITB200_GPUS=<n> (default: 1 GPU per 256 images,
+ *    capped by the visible devices), VITB200_BATCH=<images per chunk>.
+ *
+ * 2. The engine API underneath it, for callers that keep the model resident
+ *    (the bench, the tests, a serving loop).  The structs mirror the
+ *    reference's so its own loaders can feed them.
+ */
+#ifndef VIT_B200_H
+#define VIT_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Layout-identical mirrors of R/Network.h:7-14 and :19-23.  When this header is
+ * used together with the reference's Network.h, define VITB200_USE_REFERENCE_TYPES
+ * first and the reference's own typedefs are used instead. */
+#ifndef VITB200_USE_REFERENCE_TYPES
+typedef struct {
+    int n, c, h, w;
+    float *data;
+} vitb200_image; /* == ImageData */
+typedef struct {
+    float *data;
+    size_t size;
+} vitb200_blob; /* == Network */
+#else
+typedef ImageData vitb200_image;
+typedef Network vitb200_blob;
+#endif
+
+#define VITB200_NBLOBS 152
+#define VITB200_CLASSES 1000
+
+enum { VITB200_FP32 = 0, VITB200_BF16 = 1 };
+
+typedef struct vitb200_engine vitb200_engine;
+
+/* the reference's entry point (R/ViT_opencl.h:6) */
+void ViT_opencl(vitb200_image *image, vitb200_blob *networks, float **prb);
+
+/* ---- engine API: every int function returns 0 or an error code whose text is
+ * in vitb200_last_error(). ---- */
+const char *vitb200_last_error(void);
+int vitb200_device_count(void);
+
+/* One engine = one GPU, one image size, one precision.  max_batch = images per
+ * forward chunk (activation buffers are sized for it). */
+int vitb200_create(vitb200_engine **out, int device, int img, int precision, int max_batch);
+void vitb200_destroy(vitb200_engine *e);
+
+/* Upload + pack the 152 blobs (validates presence and sizes). */
+int vitb200_load_weights(vitb200_engine *e, const vitb200_blob *networks);
+
+/* Forward n images from a contiguous host array [n,3,img,img] (pinned memory
+ * from vitb200_host_alloc streams fastest).  probs [n,1000] required; logits
+ * [n,1000] optional (NULL to skip).  Synchronous. */
+int vitb200_forward(vitb200_engine *e, const float *images_host, int n, float *probs_host,
+                    float *logits_host);
+
+/* Same, from the reference's per-image structs into per-image rows (the
+ * ViT_opencl calling convention). */
+int vitb200_forward_structs(vitb200_engine *e, const vitb200_image *images, int n, float **prb);
+
+/* Device-resident variant for kernel-only timing: stage n <= max_batch images
+ * once, then run the forward on them any number of times. */
+int vitb200_stage_images(vitb200_engine *e, const float *images_host, int n);
+int vitb200_forward_resident(vitb200_engine *e, int n);
+int vitb200_read_probs(vitb200_engine *e, int n, float *probs_host, float *logits_host);
+/* elapsed device time of the last vitb200_forward_resident, CUDA events on the
+ * engine's compute stream */
+int vitb200_last_forward_ms(vitb200_engine *e, float *ms);
+/* times `iters` back-to-back resident forwards with one event pair */
+int vitb200_time_resident(vitb200_engine *e, int n, int iters, float *total_ms);
+
+/* debugging / per-stage parity: copy an internal activation of the last
+ * resident forward to the host.  what: 0 = residual stream x [n*T,768] fp32
+ * after the last executed stage; stop_after_layer (set before the forward)
+ * limits execution: -1 = full, 0 = embedding only, L = after encoder layer L. */
+int vitb200_set_stop_after_layer(vitb200_engine *e, int layer);
+int vitb200_read_tokens(vitb200_engine *e, int n, float *x_host);
+
+/* pinned host memory for image batches */
+int vitb200_host_alloc(void **ptr, size_t bytes);
+int vitb200_host_free(void *ptr);
+
+/* kernels launched per forward chunk of the current configuration */
+int vitb200_kernels_per_forward(const vitb200_engine *e);
+int vitb200_tokens(const vitb200_engine *e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,157 @@
+/* include/vit_cuda_layer.h -- the thin C-ABI device layer of the B200 engine.
+ *
+ * This header is what replaces the reference's OpenCL glue
+ * (/root/reference/MulticoreMainProject/kernelHandler.h:6-16, kernelHandler.c and
+ * the clCreate* / clEnqueue* calls all over ViT_opencl.c).  R/ = that directory.
+ * The C host (vit-with-opencl_b200/host/) calls ONLY these functions; they are
+ * implemented in vit-with-opencl_b200/csrc/ as extern "C" wrappers around
+ * hand-written sm_100a kernels.  Plain pointers and sizes only -- no C++,
+ * CUDA-runtime or torch types cross this boundary.
+ *
+ * Conventions
+ *   - every function returns 0 on success and a non-zero code on failure
+ *     (a cudaError_t value, or VITCU_E_* below); vitcu_last_error() then
+ *     describes it with the failing source line.  The reference's convention
+ *     of print + exit (CHECK_ERROR, R/kernelHandler.h:6-10) is applied by the
+ *     C host around these calls (VIT_CHECK in host/vit_engine.c), not in here.
+ *   - `stream` is an opaque handle from vitcu_stream_create (NULL = default).
+ *   - device pointers are `void *` / typed pointers into device memory of the
+ *     current device; "bf16" buffers are uint16_t bit patterns.
+ *   - all matrices are row-major; weights are [out_features, in_features]
+ *     exactly as the reference stores them (R/ViT_seq.c:304), i.e. both GEMM
+ *     operands are K-major, which is what tcgen05 wants.
+ */
+#ifndef VIT_CUDA_LAYER_H
+#define VIT_CUDA_LAYER_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VITCU_E_ARG 90001      /* bad argument / unsupported shape */
+#define VITCU_E_NODEVICE 90002 /* no sm_100 device */
+#define VITCU_E_WATCHDOG 90003 /* a kernel-side pipeline wait timed out */
+
+typedef void *vitcu_stream;
+typedef void *vitcu_event;
+typedef void *vitcu_graph;
+typedef uint16_t vitcu_bf16;
+
+/* ---- runtime (replaces clGetPlatformIDs/clCreateContext/queues, R/ViT_opencl.c:799-861) */
+const char *vitcu_last_error(void);
+int vitcu_device_count(int *count);
+int vitcu_set_device(int device);
+/* one-time per-device set-up (shared-memory opt-ins, watchdog flag); must run
+ * on the current device before any stream capture */
+int vitcu_prepare_device(void);
+/* fills name (<=255 chars), SM count, compute capability major*10+minor, total bytes */
+int vitcu_device_info(int device, char *name, int *sms, int *cc, size_t *mem_bytes);
+int vitcu_stream_create(vitcu_stream *s);
+int vitcu_stream_destroy(vitcu_stream s);
+int vitcu_stream_sync(vitcu_stream s);
+int vitcu_device_sync(void);
+int vitcu_event_create(vitcu_event *e);
+int vitcu_event_destroy(vitcu_event e);
+int vitcu_event_record(vitcu_event e, vitcu_stream s);
+int vitcu_event_sync(vitcu_event e);
+int vitcu_stream_wait_event(vitcu_stream s, vitcu_event e);
+int vitcu_event_elapsed_ms(vitcu_event start, vitcu_event stop, float *ms);
+
+/* ---- memory (replaces clCreateBuffer/clEnqueueWriteBuffer/ReadBuffer, R/ViT_opencl.c:125-330) */
+int vitcu_malloc(void **dptr, size_t bytes);
+int vitcu_free(void *dptr);
+int vitcu_host_alloc(void **hptr, size_t bytes); /* pinned */
+int vitcu_host_free(void *hptr);
+int vitcu_host_register(void *hptr, size_t bytes); /* pin caller memory in place */
+int vitcu_host_unregister(void *hptr);
+int vitcu_memcpy_h2d(void *dst, const void *src, size_t bytes, vitcu_stream s);
+int vitcu_memcpy_d2h(void *dst, const void *src, size_t bytes, vitcu_stream s);
+int vitcu_memcpy_d2d(void *dst, const void *src, size_t bytes, vitcu_stream s);
+int vitcu_memset(void *dst, int value, size_t bytes, vitcu_stream s);
+
+/* ---- CUDA graphs (the 12-layer launch chain is captured once and replayed) */
+int vitcu_graph_begin(vitcu_stream s);
+int vitcu_graph_end(vitcu_stream s, vitcu_graph *g);
+int vitcu_graph_launch(vitcu_graph g, vitcu_stream s);
+int vitcu_graph_destroy(vitcu_graph g);
+
+/* ---- counters: kernels launched by this layer since the last reset */
+void vitcu_launch_count_reset(void);
+unsigned long long vitcu_launch_count(void);
+/* device-side watchdog flag set by a kernel whose mbarrier wait timed out */
+int vitcu_watchdog_check(void);
+
+/* ================= kernels ================================================= */
+
+/* fp32 -> bf16 (round-to-nearest-even), n elements.  One-time weight packing. */
+int vitcu_f32_to_bf16(const float *src, vitcu_bf16 *dst, size_t n, vitcu_stream s);
+
+/* Patch gather (replaces the data movement of conv2d_kernel, R/conv2d.cl:1-36):
+ * images [B,3,img,img] fp32 -> patches [B*P, 768] with column order (c,kh,kw),
+ * the order Conv2d_seq accumulates in (R/ViT_seq.c:37-48).  out_bf16 selects
+ * bf16 or fp32 output. */
+int vitcu_patch_gather(const float *images, void *patches, int batch, int img,
+                       int out_bf16, vitcu_stream s);
+
+/* Row 0 of every image: x[b*T + 0, :] = cls + pos[0, :]  (R/conv2d.cl:39-80 t==0
+ * branch; R/ViT_seq.c:83-118). */
+int vitcu_cls_rows(float *x, const float *cls, const float *pos, int batch, int tokens,
+                   vitcu_stream s);
+
+/* LayerNorm over 768 features (replaces layerNorm, R/layer_norm.cl:3-53; oracle
+ * R/ViT_seq.c:120-142).  rows = number of rows normalised; row r is read at
+ * x + r*x_row_stride (elements) so the final LN can visit only the class-token
+ * rows; output rows are dense [rows,768], fp32 or bf16. */
+int vitcu_layernorm(const float *x, size_t x_row_stride, void *y, int y_bf16,
+                    const float *gamma, const float *beta, int rows, vitcu_stream s);
+
+/* Epilogue selector for both GEMM families */
+enum {
+    VITCU_EPI_BIAS = 0,          /* y = acc + b                               */
+    VITCU_EPI_BIAS_GELU = 1,     /* y = gelu_erf(acc + b)   (R/ll.cl:3-5)      */
+    VITCU_EPI_BIAS_RESIDUAL = 2, /* y = acc + b + residual  (R/layer_norm.cl:55) */
+    VITCU_EPI_PATCH_EMBED = 3    /* row r -> (r/P)*T + 1 + r%P, y = acc + b + pos */
+};
+
+typedef struct {
+    int M, N, K;          /* C[M,N] = A[M,K] * W[N,K]^T                         */
+    size_t lda;           /* A row stride in elements (>= K)                    */
+    int epilogue;         /* VITCU_EPI_*                                        */
+    const float *bias;    /* [N]                                                */
+    const float *residual;/* [M,N] fp32, may alias out (EPI_BIAS_RESIDUAL)      */
+    const float *pos;     /* [T,N] fp32 (EPI_PATCH_EMBED)                       */
+    int patches, tokens;  /* P and T (EPI_PATCH_EMBED)                          */
+    int out_bf16;         /* output element type: 0 fp32, 1 bf16                */
+    size_t ldc;           /* output row stride in elements                      */
+} vitcu_gemm_desc;
+
+/* FP32 SIMT GEMM (replaces linear_layer, R/ll.cl:7-70 and QKV, R/multihead.cl:3-63
+ * on the FP32 path; oracle R/ViT_seq.c:295-309).  A and W fp32. */
+int vitcu_sgemm(const float *A, const float *W, void *C, const vitcu_gemm_desc *d,
+                vitcu_stream s);
+
+/* BF16 tensor-core GEMM: tcgen05.mma with TMEM accumulators, TMA-staged
+ * operands, fused epilogue (same computation, BF16 inputs, FP32 accumulate).
+ * A [M,K] bf16 (lda == K), W [N,K] bf16.  Requires K % 64 == 0, N % 16 == 0. */
+int vitcu_gemm_bf16(const vitcu_bf16 *A, const vitcu_bf16 *W, void *C,
+                    const vitcu_gemm_desc *d, vitcu_stream s);
+
+/* Multi-head attention core over a fused QKV buffer (replaces QKV_TO_SCOREV,
+ * R/multihead.cl:65-137; oracle R/ViT_seq.c:192-262): qkv [B*T, 2304] with
+ * Q|K|V column blocks of 768 (R/ViT_seq.c:150), 12 heads of 64; scores are
+ * scaled by 1/sqrt(64) after the dot product; out [B*T,768].  Element type of
+ * qkv/out: fp32 (is_bf16 = 0) or bf16 (is_bf16 = 1; softmax stays fp32). */
+int vitcu_attention(const void *qkv, void *out, int batch, int tokens, int is_bf16,
+                    vitcu_stream s);
+
+/* Row softmax over `n` logits per row (replaces softMax, R/miniSoftMax.cl:1-50;
+ * oracle R/ViT_seq.c:372-397). */
+int vitcu_softmax_rows(const float *logits, float *probs, int rows, int n, vitcu_stream s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

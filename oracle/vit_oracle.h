@@ -1,0 +1,87 @@
+/* oracle/vit_oracle.h -- CPU oracle for the ViT-B/16 forward path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is linked into, imported by
+ * or executed from the product (libvit_b200.so / the vit-with-opencl_b200
+ * package).  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may use it, and only as the checker.
+ *
+ * What it is: a plain-C restatement of the reference's sequential forward
+ * (/root/reference/MulticoreMainProject/ViT_seq.c, cited per function in
+ * vit_oracle.c) with the image size a run-time argument (the reference fixes
+ * it with `#define img_size 224`, ViT_seq.c:10) so the 384x384 / 577-token
+ * configuration can be checked too.  Every output element is produced by the
+ * same float operations in the same order as the reference, so results are
+ * bit-identical to the reference compiled with the same compiler flags; loops
+ * are only re-nested (vectorised across independent outputs, threaded across
+ * tokens), never re-associated.
+ *
+ * Parity pin: tests/test_oracle.py checks this file bit-for-bit against
+ * oracle/_ref (the reference's own ViT_seq.c compiled unmodified by
+ * oracle/Makefile) and against tests/golden/ vectors generated from it.  The
+ * reference's own golden files (Data/answer_result*.txt) need the 36 weight
+ * blobs that are absent from /root/reference (.MISSING_LARGE_BLOBS), so they
+ * cannot be reproduced here; that limit is stated in DESIGN.md.
+ */
+#ifndef VIT_ORACLE_H
+#define VIT_ORACLE_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VIT_ORACLE_EMBED 768
+#define VIT_ORACLE_HEADS 12
+#define VIT_ORACLE_DEPTH 12
+#define VIT_ORACLE_HIDDEN 3072
+#define VIT_ORACLE_CLASSES 1000
+#define VIT_ORACLE_PATCH 16
+#define VIT_ORACLE_NBLOBS 152
+
+/* tokens for a square image of side img (multiple of 16): (img/16)^2 + 1 */
+int vit_oracle_tokens(int img);
+
+/* conv 16x16/s16 + flatten/transpose + class token + position embedding
+ * (ViT_seq.c:25-118).  image [3,img,img]; tokens out [T,768]. */
+void vit_oracle_patch_embed(const float *image, int img, const float *cls,
+                            const float *conv_w, const float *conv_b,
+                            const float *pos, float *tokens);
+
+/* ViT_seq.c:120-142 */
+void vit_oracle_layer_norm(const float *x, float *y, int tokens,
+                           const float *gamma, const float *beta);
+
+/* ViT_seq.c:295-309 (gelu != 0 additionally applies ViT_seq.c:283-286) */
+void vit_oracle_linear(const float *x, float *y, int tokens, int in_f, int out_f,
+                       const float *w, const float *b, int gelu);
+
+/* scaled-dot-product attention over 12 heads of 64 (ViT_seq.c:192-262).
+ * q,k,v,o are [T,768] token-major. */
+void vit_oracle_attention_core(const float *q, const float *k, const float *v,
+                               float *o, int tokens);
+
+/* ViT_seq.c:144-281: QKV projection + attention + output projection */
+void vit_oracle_mha(const float *x, float *y, int tokens, const float *w_in,
+                    const float *b_in, const float *w_out, const float *b_out);
+
+/* ViT_seq.c:330-370; w points at the 12 blobs of one encoder layer
+ * (ln1 g/b, in_proj w/b, out_proj w/b, ln2 g/b, fc1 w/b, fc2 w/b). */
+void vit_oracle_encoder(const float *x, float *y, int tokens, const float *const *w);
+
+/* ViT_seq.c:372-397 */
+void vit_oracle_softmax(const float *logits, float *probs, int n);
+
+/* ViT_seq.c:402-517.  images: n contiguous [3,img,img] arrays; w: 152 blob
+ * pointers in torchvision state_dict order (pos-embedding blob 3 must be
+ * [T,768] for the chosen img).  probs [n,1000]; logits (nullable) [n,1000];
+ * stage_dump (nullable) receives [13][T*768] for image 0: the embedding output
+ * followed by the 12 encoder outputs.  Returns 0, or -1 on bad arguments. */
+int vit_oracle_forward(const float *images, int n, int img, const float *const *w,
+                       float *probs, float *logits, float *stage_dump);
+
+/* threads used by the OpenMP loops (0 = leave default) */
+void vit_oracle_set_threads(int n);
+int vit_oracle_get_threads(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

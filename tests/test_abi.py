@@ -1,0 +1,94 @@
+"""CPU tests of the boundary: the C-ABI library loads without a GPU, exports
+every symbol the headers declare, mirrors the reference structs, and fails
+loudly (no CPU fallback) when asked to compute without a device."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_functions(header):
+    src = open(os.path.join(ROOT, "include", header)).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = re.findall(r"\b(vitcu_\w+|vitb200_\w+|ViT_opencl)\s*\(", src)
+    # typedef'd struct names etc. never match "name(", so these are functions
+    return sorted(set(names))
+
+
+@pytest.mark.parametrize("header", ["vit_b200.h", "vit_cuda_layer.h"])
+def test_every_declared_symbol_is_exported(pkg, header):
+    L = pkg.lib()
+    names = _declared_functions(header)
+    assert len(names) > 10
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, f"declared in include/{header} but not exported: {missing}"
+
+
+def test_reference_entry_point_is_exported(pkg):
+    assert hasattr(pkg.lib(), "ViT_opencl")
+
+
+def test_struct_layouts_match_reference(pkg):
+    # Network.h:7-14 -> 4 ints + pointer; Network.h:19-23 -> pointer + size_t
+    assert C.sizeof(pkg.ImageData) == 24 and pkg.ImageData.data.offset == 16
+    assert C.sizeof(pkg.Network) == 16 and pkg.Network.size.offset == 8
+
+
+def test_no_cpu_fallback(pkg):
+    if pkg.device_count() > 0:
+        pytest.skip("a GPU is visible; this test is about the GPU-less box")
+    with pytest.raises(pkg.VitError):
+        pkg.Engine(0, 224, pkg.BF16, 2)
+
+
+def test_argument_validation_without_gpu(pkg):
+    L = pkg.lib()
+    h = C.c_void_p()
+    assert L.vitb200_create(C.byref(h), 0, 225, pkg.FP32, 1) != 0  # not a multiple of 16
+    assert b"multiple of 16" in L.vitb200_last_error()
+    assert L.vitb200_create(C.byref(h), 0, 224, 7, 1) != 0
+    assert L.vitb200_create(None, 0, 224, 0, 1) != 0
+
+
+def test_round6_matches_reference_loader(pkg, tmp_path):
+    """synth.round6 == the rounding load_weights applies (Network.c:208-211)"""
+    from oracle import binding
+    if not binding.Reference.available(224):
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(0)
+    raw = (rng.standard_normal(4096, dtype=np.float32) * np.float32(0.3)).astype(np.float32)
+    raw[:4] = [0.4999995, -0.4999995, 1.5e-7, -2.5e-6]
+    d = tmp_path / "Network"
+    d.mkdir()
+    raw.tofile(d / "Weight_5_some_name.bin")
+    ref = binding.Reference(224).lib
+    nets = (binding.Network * 152)()
+    ref.load_weights.argtypes = [C.c_char_p, C.POINTER(binding.Network), C.c_int]
+    ref.load_weights(str(d).encode(), nets, 152)
+    assert nets[5].size == raw.size and not nets[4].data
+    got = np.ctypeslib.as_array(nets[5].data, shape=(raw.size,)).copy()
+    assert np.array_equal(got, pkg.synth.round6(raw))
+    assert np.array_equal(pkg.synth.load_blobs(str(d))[5], got)
+
+
+def test_blob_shapes(pkg):
+    s224, s384 = pkg.synth.blob_shapes(224), pkg.synth.blob_shapes(384)
+    assert len(s224) == 152 and s224[3] == (197, 768) and s384[3] == (577, 768)
+    assert s224[6] == (2304, 768) and s224[12] == (3072, 768) and s224[14] == (768, 3072)
+    assert s224[150] == (1000, 768)
+    total = sum(int(np.prod(s)) for s in s224)
+    assert total == 86567656
+
+
+def test_bf16_helpers_roundtrip(pkg):
+    x = np.array([1.0, -2.5, 3.14159, 1e-8, 65504.0, 0.1], np.float32)
+    b = pkg.f32_to_bf16_bits(x)
+    y = pkg.bf16_bits_to_f32(b)
+    assert np.all(np.abs(y - x) <= np.abs(x) * 2.0 ** -8)
+    # round-to-nearest-even on a tie
+    tie = np.array([np.uint32(0x3F808000)], np.uint32).view(np.float32)
+    assert pkg.f32_to_bf16_bits(tie)[0] == 0x3F80

@@ -1,0 +1,113 @@
+"""CPU tests: the oracle restatement (oracle/vit_oracle.c) is pinned, bit for bit,
+against vectors produced by the reference's own ViT_seq.c (tests/golden/, made by
+tests/golden/make_golden.py from oracle/_ref) and, where oracle/_ref is present,
+against the compiled reference run live."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = np.load(os.path.join(HERE, "golden", "reference_vectors.npz"))
+
+spec = importlib.util.spec_from_file_location("make_golden_inputs", os.path.join(HERE, "golden", "make_golden.py"))
+
+
+def _stage_inputs():
+    # same generator as make_golden.stage_inputs (kept importable without running main)
+    rng = np.random.default_rng(11)
+    d = {}
+    d["lin_x"] = rng.standard_normal((5, 768), dtype=np.float32)
+    d["lin_w"] = rng.standard_normal((40, 768), dtype=np.float32) * np.float32(0.05)
+    d["lin_b"] = rng.standard_normal(40, dtype=np.float32)
+    d["ln_x"] = rng.standard_normal((197, 768), dtype=np.float32) * np.float32(2.0) + np.float32(0.5)
+    d["ln_g"] = rng.standard_normal(768, dtype=np.float32) * np.float32(0.1) + np.float32(1.0)
+    d["ln_b"] = rng.standard_normal(768, dtype=np.float32) * np.float32(0.1)
+    d["mha_x"] = rng.standard_normal((197, 768), dtype=np.float32)
+    d["mha_win"] = rng.standard_normal((2304, 768), dtype=np.float32) * np.float32(0.04)
+    d["mha_bin"] = rng.standard_normal(2304, dtype=np.float32) * np.float32(0.1)
+    d["mha_wout"] = rng.standard_normal((768, 768), dtype=np.float32) * np.float32(0.04)
+    d["mha_bout"] = rng.standard_normal(768, dtype=np.float32) * np.float32(0.1)
+    return d
+
+
+def test_stage_linear_bit_exact(oracle):
+    d = _stage_inputs()
+    assert np.array_equal(oracle.linear(d["lin_x"], d["lin_w"], d["lin_b"]), GOLD["lin_y"])
+
+
+def test_stage_layer_norm_bit_exact(oracle):
+    d = _stage_inputs()
+    y = oracle.layer_norm(d["ln_x"], d["ln_g"], d["ln_b"])
+    assert np.array_equal(y[[0, 1, 196]], GOLD["ln_y_rows"])
+
+
+def test_stage_mha_bit_exact(oracle):
+    d = _stage_inputs()
+    y = oracle.mha(d["mha_x"], d["mha_win"], d["mha_bin"], d["mha_wout"], d["mha_bout"])
+    assert np.array_equal(y[[0, 100, 196]], GOLD["mha_y_rows"])
+    assert y.astype(np.float64).sum() == GOLD["mha_y_sum"][0]
+
+
+def test_forward_synthetic_bit_exact(oracle, pkg, synth_blobs224):
+    imgs = pkg.synth.synthetic_images(2, 224, seed=1234)
+    r = oracle.forward(imgs, synth_blobs224)
+    assert np.array_equal(r["probs"], GOLD["synth_probs"])
+    # probabilities are a softmax of the returned logits
+    assert np.array_equal(oracle.softmax(r["logits"][0]), r["probs"][0])
+    np.testing.assert_allclose(r["probs"].sum(1), 1.0, atol=1e-5)
+
+
+def test_forward_bundled_image_bit_exact(oracle, pkg, ref_dir):
+    net = os.path.join(ref_dir, "Network")
+    img_path = os.path.join(ref_dir, "Data", "input-1.bin")
+    if not (os.path.isdir(net) and os.path.exists(img_path)):
+        pytest.skip("bundled reference data (oracle/_ref) not present on this box")
+    blobs = pkg.synth.model_blobs(net, 224, seed=0)
+    img = pkg.synth.load_image_file(img_path)
+    assert img.shape == (1, 3, 224, 224)
+    r = oracle.forward(img, blobs)
+    assert np.array_equal(r["probs"], GOLD["bundled_input1_probs"])
+    # the value the survey recorded for the reference on these inputs
+    assert int(r["probs"].argmax()) == 606 and abs(float(r["probs"].max()) - 0.007682) < 5e-7
+
+
+def test_forward_384_bit_exact(oracle, pkg):
+    blobs = pkg.synth.model_blobs(None, 384, seed=7)
+    imgs = pkg.synth.synthetic_images(1, 384, seed=4321)
+    r = oracle.forward(imgs, blobs)
+    assert np.array_equal(r["probs"], GOLD["synth384_probs"])
+
+
+def test_live_reference_matches_oracle(oracle, pkg):
+    """the compiled reference itself, on a fresh seed (skipped where oracle/_ref did not travel)"""
+    from oracle import binding
+    if not binding.Reference.available(224):
+        pytest.skip("oracle/_ref not built")
+    blobs = pkg.synth.model_blobs(None, 224, seed=3)
+    imgs = pkg.synth.synthetic_images(1, 224, seed=99)
+    ref = binding.Reference(224).forward(imgs, blobs)
+    assert np.array_equal(ref, oracle.forward(imgs, blobs)["probs"])
+
+
+def test_stage_dump_consistent(oracle, pkg, synth_blobs224):
+    imgs = pkg.synth.synthetic_images(1, 224, seed=5)
+    r = oracle.forward(imgs, synth_blobs224, want_stages=True)
+    st = r["stages"]
+    w = synth_blobs224
+    emb = oracle.patch_embed(imgs[0], w[0], w[1], w[2], w[3])
+    assert np.array_equal(emb, st[0])
+    assert np.array_equal(oracle.encoder(st[0], w[4:16]), st[1])
+
+
+def test_edge_cases(oracle, pkg, synth_blobs224):
+    # empty batch is a no-op; a missing blob is rejected, not dereferenced
+    r = oracle.forward(np.zeros((0, 3, 224, 224), np.float32), synth_blobs224)
+    assert r["probs"].shape == (0, 1000)
+    with pytest.raises(ValueError):
+        oracle.forward(np.zeros((1, 3, 224, 224), np.float32), synth_blobs224[:151])
+    holed = list(synth_blobs224)
+    holed[6] = None
+    with pytest.raises(ValueError):
+        oracle.forward(np.zeros((1, 3, 224, 224), np.float32), holed)

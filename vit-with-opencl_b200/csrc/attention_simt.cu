@@ -1,0 +1,209 @@
+// csrc/attention_simt.cu -- fused multi-head attention core on the CUDA cores
+// (FP32 math; fp32 or bf16 storage).  One CTA owns a 64-query tile of one
+// (image, head): S = Q K^T, the row softmax and O = P V all stay in shared
+// memory / registers, so scores never touch HBM.  Replaces QKV_TO_SCOREV
+// (R/multihead.cl:65-137), which re-read all of K and V from global memory for
+// every (query, head) work-group and was capped at 256 keys; the oracle is
+// R/ViT_seq.c:192-262.  R/ = /root/reference/MulticoreMainProject/.
+//
+// This is the attention of the FP32 path (BASELINE config 2) and the
+// bring-up attention of the BF16 path; any token count that fits shared
+// memory works (197 and 577 both do).
+//
+//   phase 1  Q tile -> smem, transposed [d][q]
+//   phase 2  per 64-key block: K block -> smem transposed [d][key];
+//            4x4 register tiles of S = (Q.K) * 1/8 (the scale is applied after
+//            the dot product, like R/ViT_seq.c:211) -> St[key][q]
+//   phase 3  column softmax of St (max, expf, sum, divide -- R/ViT_seq.c:216-234)
+//   phase 4  per 64-key block: V block -> smem; 4x4 register tiles of O += P V
+//   phase 5  O -> out[(b*T + q), h*64 + d]
+#include "common.cuh"
+
+using namespace vitcu;
+
+namespace {
+
+constexpr int QT = 64;      // queries per CTA
+constexpr int KB = 64;      // keys per staged block
+constexpr int LDT = QT + 4; // padded row of the transposed tiles
+
+template <typename T>
+struct Elem;
+template <>
+struct Elem<float> {
+    static __device__ __forceinline__ float4 load4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+    static __device__ __forceinline__ void store4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
+};
+template <>
+struct Elem<__nv_bfloat16> {
+    static __device__ __forceinline__ float4 load4(const __nv_bfloat16 *p)
+    {
+        const uint2 u = *reinterpret_cast<const uint2 *>(p);
+        const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162 *>(&u.x);
+        const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162 *>(&u.y);
+        const float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+        return make_float4(fa.x, fa.y, fb.x, fb.y);
+    }
+    static __device__ __forceinline__ void store4(__nv_bfloat16 *p, float4 v)
+    {
+        *reinterpret_cast<uint2 *>(p) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) attention_simt_kernel(const T *__restrict__ qkv, T *__restrict__ out, int tokens)
+{
+    extern __shared__ __align__(16) float smem[];
+    const int nkb = (tokens + KB - 1) / KB;
+    float *Qs = smem;                // [64 d][LDT]
+    float *KV = Qs + kHeadDim * LDT; // K block transposed [64 d][LDT], later V block [64 key][LDT]
+    float *St = KV + KB * LDT;       // [nkb*KB keys][LDT]
+    float *red = St + (size_t)nkb * KB * LDT; // [4][QT]
+
+    const int tid = threadIdx.x;
+    const int q0 = blockIdx.x * QT, head = blockIdx.y, img = blockIdx.z;
+    const size_t ld = 3 * kEmbed;
+    const T *base = qkv + (size_t)img * tokens * ld + head * kHeadDim;
+
+    // each thread moves 4 x (4 consecutive d) of a 64x64 tile: rows r, d4
+    auto load_transposed = [&](float *dst, const T *src, int row0) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int f = tid + i * 256, r = f >> 4, d4 = (f & 15) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row0 + r < tokens)
+                v = Elem<T>::load4(src + (size_t)(row0 + r) * ld + d4);
+            dst[(d4 + 0) * LDT + r] = v.x;
+            dst[(d4 + 1) * LDT + r] = v.y;
+            dst[(d4 + 2) * LDT + r] = v.z;
+            dst[(d4 + 3) * LDT + r] = v.w;
+        }
+    };
+
+    load_transposed(Qs, base, q0);
+
+    // ---- phase 2: S = Q K^T / 8 ------------------------------------------------
+    const int tx = tid & 15, ty = tid >> 4; // tx -> 4 queries, ty -> 4 keys
+    for (int kb = 0; kb < nkb; kb++) {
+        __syncthreads(); // previous block's readers are done with KV (and Qs is visible)
+        load_transposed(KV, base + kEmbed, kb * KB);
+        __syncthreads();
+        float acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                acc[i][j] = 0.f;
+#pragma unroll 16
+        for (int d = 0; d < kHeadDim; d++) {
+            const float4 a = *reinterpret_cast<const float4 *>(&Qs[d * LDT + tx * 4]);
+            const float4 b = *reinterpret_cast<const float4 *>(&KV[d * LDT + ty * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    acc[j][i] = fmaf(av[i], bv[j], acc[j][i]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            float *row = St + (size_t)(kb * KB + ty * 4 + j) * LDT + tx * 4;
+            *reinterpret_cast<float4 *>(row) =
+                make_float4(acc[j][0] * 0.125f, acc[j][1] * 0.125f, acc[j][2] * 0.125f, acc[j][3] * 0.125f);
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 3: softmax down each query column -------------------------------
+    {
+        const int q = tid & 63, part = tid >> 6; // 4 key-interleaved parts per query
+        float m = -INFINITY;
+        for (int j = part; j < tokens; j += 4)
+            m = fmaxf(m, St[(size_t)j * LDT + q]);
+        red[part * QT + q] = m;
+        __syncthreads();
+        m = fmaxf(fmaxf(red[q], red[QT + q]), fmaxf(red[2 * QT + q], red[3 * QT + q]));
+        __syncthreads();
+        float s = 0.f;
+        for (int j = part; j < tokens; j += 4) {
+            const float e = expf(St[(size_t)j * LDT + q] - m);
+            St[(size_t)j * LDT + q] = e;
+            s += e;
+        }
+        red[part * QT + q] = s;
+        __syncthreads();
+        s = (red[q] + red[QT + q]) + (red[2 * QT + q] + red[3 * QT + q]);
+        for (int j = part; j < tokens; j += 4)
+            St[(size_t)j * LDT + q] /= s;
+    }
+
+    // ---- phase 4: O = P V -------------------------------------------------------
+    // tx -> 4 head dims, ty -> 4 queries
+    float o[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            o[i][j] = 0.f;
+    for (int kb = 0; kb < nkb; kb++) {
+        __syncthreads(); // softmax writes visible / previous V block consumed
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int f = tid + i * 256, r = f >> 4, d4 = (f & 15) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (kb * KB + r < tokens)
+                v = Elem<T>::load4(base + 2 * kEmbed + (size_t)(kb * KB + r) * ld + d4);
+            *reinterpret_cast<float4 *>(&KV[r * LDT + d4]) = v;
+        }
+        __syncthreads();
+        const int jmax = min(KB, tokens - kb * KB);
+        for (int j = 0; j < jmax; j++) {
+            const float4 a = *reinterpret_cast<const float4 *>(&St[(size_t)(kb * KB + j) * LDT + ty * 4]);
+            const float4 b = *reinterpret_cast<const float4 *>(&KV[j * LDT + tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int d = 0; d < 4; d++)
+                    o[i][d] = fmaf(av[i], bv[d], o[i][d]);
+        }
+    }
+
+    // ---- phase 5 ------------------------------------------------------------------
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int q = q0 + ty * 4 + i;
+        if (q < tokens)
+            Elem<T>::store4(out + ((size_t)img * tokens + q) * kEmbed + head * kHeadDim + tx * 4,
+                            make_float4(o[i][0], o[i][1], o[i][2], o[i][3]));
+    }
+}
+
+size_t attention_simt_smem(int tokens)
+{
+    const int nkb = (tokens + KB - 1) / KB;
+    return sizeof(float) * ((size_t)kHeadDim * LDT + (size_t)KB * LDT + (size_t)nkb * KB * LDT + 4 * QT);
+}
+
+} // namespace
+
+extern "C" int vitcu_attention(const void *qkv, void *out, int batch, int tokens, int is_bf16, vitcu_stream s)
+{
+    VITCU_REQUIRE(qkv && out && batch > 0 && tokens > 0, "bad argument");
+    const size_t smem = attention_simt_smem(tokens);
+    VITCU_REQUIRE(smem <= 227 * 1024, "token count too large for the shared-memory score tile");
+    dim3 grid((tokens + QT - 1) / QT, kHeads, batch);
+    if (is_bf16) {
+        auto k = attention_simt_kernel<__nv_bfloat16>;
+        VITCU_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<grid, 256, smem, as_stream(s)>>>(reinterpret_cast<const __nv_bfloat16 *>(qkv),
+                                             reinterpret_cast<__nv_bfloat16 *>(out), tokens);
+    } else {
+        auto k = attention_simt_kernel<float>;
+        VITCU_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<grid, 256, smem, as_stream(s)>>>(reinterpret_cast<const float *>(qkv), reinterpret_cast<float *>(out),
+                                             tokens);
+    }
+    VITCU_LAUNCHED();
+    return 0;
+}

@@ -1,0 +1,228 @@
+// csrc/elementwise.cu -- the HBM-bound data-movement kernels of the path:
+// weight packing, patch gather, class-token rows, LayerNorm, row softmax.
+// All are vectorised (128-bit) and coalesced; none has data reuse, so none
+// stages through shared memory.  R/ = /root/reference/MulticoreMainProject/.
+#include "common.cuh"
+
+using namespace vitcu;
+
+// ---------------------------------------------------------------------------
+// fp32 -> bf16 (one-time weight packing; also used by tests)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float4 *__restrict__ src,
+                                                          uint2 *__restrict__ dst, size_t n4,
+                                                          const float *__restrict__ src_tail,
+                                                          __nv_bfloat16 *__restrict__ dst_tail, int tail)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n4; i += stride) {
+        float4 v = src[i];
+        dst[i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    }
+    if (blockIdx.x == 0 && (int)threadIdx.x < tail)
+        dst_tail[threadIdx.x] = __float2bfloat16_rn(src_tail[threadIdx.x]);
+}
+
+// ---------------------------------------------------------------------------
+// patch gather: [B,3,img,img] -> [B*P, 768], column = (c*16 + kh)*16 + kw, the
+// accumulation order of Conv2d_seq (R/ViT_seq.c:37-48).  One thread moves one
+// 16-byte chunk (4 kw values): 4 threads cover a contiguous 64-byte image run.
+// ---------------------------------------------------------------------------
+template <bool kBf16>
+__global__ void __launch_bounds__(256) patch_gather_kernel(const float *__restrict__ images,
+                                                           void *__restrict__ patches, int batch,
+                                                           int img, int side)
+{
+    const int P = side * side;
+    const size_t total4 = (size_t)batch * P * (kEmbed / 4);
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < total4; i += stride) {
+        const int col4 = (int)(i % (kEmbed / 4));
+        const size_t row = i / (kEmbed / 4);
+        const int p = (int)(row % P);
+        const int b = (int)(row / P);
+        const int c = col4 >> 6, kh = (col4 >> 2) & 15, kw4 = col4 & 3;
+        const int ph = p / side, pw = p % side;
+        const float4 v = *reinterpret_cast<const float4 *>(
+            images + (((size_t)b * 3 + c) * img + ph * kPatch + kh) * img + pw * kPatch + kw4 * 4);
+        if (kBf16) {
+            reinterpret_cast<uint2 *>(patches)[i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+        } else {
+            reinterpret_cast<float4 *>(patches)[i] = v;
+        }
+    }
+}
+
+// x[b*T, :] = cls + pos[0, :]   (R/ViT_seq.c:83-118; R/conv2d.cl:39-80, t == 0)
+__global__ void __launch_bounds__(192) cls_rows_kernel(float *__restrict__ x, const float *__restrict__ cls,
+                                                       const float *__restrict__ pos, int tokens)
+{
+    const int b = blockIdx.x, i = threadIdx.x; // 192 threads x float4 = 768
+    const float4 c = reinterpret_cast<const float4 *>(cls)[i];
+    const float4 p = reinterpret_cast<const float4 *>(pos)[i];
+    reinterpret_cast<float4 *>(x + (size_t)b * tokens * kEmbed)[i] =
+        make_float4(c.x + p.x, c.y + p.y, c.z + p.z, c.w + p.w);
+}
+
+// ---------------------------------------------------------------------------
+// LayerNorm, one warp per 768-wide row: 6 x float4 per lane held in registers,
+// shuffle reductions, statistics in fp32 (mean first, then centred variance,
+// which is at least as accurate as the reference's E[x^2]-mean^2 single pass,
+// R/ViT_seq.c:126-135), eps 1e-6, output fp32 or bf16.
+// Algorithmic bytes per row: 768*4 read + 768*(4|2) written.
+// ---------------------------------------------------------------------------
+template <bool kBf16>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float *__restrict__ x, size_t x_row_stride,
+                                                        void *__restrict__ y, const float *__restrict__ gamma,
+                                                        const float *__restrict__ beta, int rows)
+{
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows)
+        return;
+    const float4 *xr = reinterpret_cast<const float4 *>(x + (size_t)row * x_row_stride);
+    float4 v[6];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        v[i] = xr[lane + 32 * i];
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = warp_sum(s) * (1.0f / kEmbed);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+        q += (a * a + b * b) + (c * c + d * d);
+    }
+    const float var = warp_sum(q) * (1.0f / kEmbed);
+    const float inv_std = 1.0f / sqrtf(var + 1e-6f);
+    const float4 *g4 = reinterpret_cast<const float4 *>(gamma);
+    const float4 *b4 = reinterpret_cast<const float4 *>(beta);
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        const float4 g = g4[lane + 32 * i], bb = b4[lane + 32 * i];
+        float4 o;
+        o.x = (v[i].x - mean) * inv_std * g.x + bb.x;
+        o.y = (v[i].y - mean) * inv_std * g.y + bb.y;
+        o.z = (v[i].z - mean) * inv_std * g.z + bb.z;
+        o.w = (v[i].w - mean) * inv_std * g.w + bb.w;
+        if (kBf16) {
+            reinterpret_cast<uint2 *>(reinterpret_cast<__nv_bfloat16 *>(y) + (size_t)row * kEmbed)[lane + 32 * i] =
+                make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+        } else {
+            reinterpret_cast<float4 *>(reinterpret_cast<float *>(y) + (size_t)row * kEmbed)[lane + 32 * i] = o;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// row softmax (R/ViT_seq.c:372-397): one 256-thread block per row
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float *__restrict__ logits,
+                                                           float *__restrict__ probs, int n)
+{
+    __shared__ float red[8];
+    const float *l = logits + (size_t)blockIdx.x * n;
+    float *p = probs + (size_t)blockIdx.x * n;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float m = -INFINITY;
+    for (int i = tid; i < n; i += 256)
+        m = fmaxf(m, l[i]);
+    m = warp_max(m);
+    if (lane == 0)
+        red[warp] = m;
+    __syncthreads();
+    m = red[0];
+#pragma unroll
+    for (int i = 1; i < 8; i++)
+        m = fmaxf(m, red[i]);
+    __syncthreads();
+    float s = 0.f;
+    for (int i = tid; i < n; i += 256)
+        s += expf(l[i] - m);
+    s = warp_sum(s);
+    if (lane == 0)
+        red[warp] = s;
+    __syncthreads();
+    s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+        s += red[i];
+    for (int i = tid; i < n; i += 256)
+        p[i] = expf(l[i] - m) / s;
+}
+
+static inline int grid_for(size_t work_items, int block, int max_blocks = 148 * 16)
+{
+    size_t g = (work_items + block - 1) / block;
+    if (g < 1)
+        g = 1;
+    if (g > (size_t)max_blocks)
+        g = max_blocks;
+    return (int)g;
+}
+
+extern "C" {
+
+int vitcu_f32_to_bf16(const float *src, vitcu_bf16 *dst, size_t n, vitcu_stream s)
+{
+    VITCU_REQUIRE(src && dst, "NULL buffer");
+    VITCU_REQUIRE(((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 7) == 0, "unaligned buffer");
+    const size_t n4 = n / 4;
+    const int tail = (int)(n - n4 * 4);
+    f32_to_bf16_kernel<<<grid_for(n4, 256), 256, 0, as_stream(s)>>>(
+        reinterpret_cast<const float4 *>(src), reinterpret_cast<uint2 *>(dst), n4, src + n4 * 4,
+        reinterpret_cast<__nv_bfloat16 *>(dst) + n4 * 4, tail);
+    VITCU_LAUNCHED();
+    return 0;
+}
+
+int vitcu_patch_gather(const float *images, void *patches, int batch, int img, int out_bf16, vitcu_stream s)
+{
+    VITCU_REQUIRE(images && patches, "NULL buffer");
+    VITCU_REQUIRE(batch > 0 && img > 0 && img % kPatch == 0, "image side must be a positive multiple of 16");
+    const int side = img / kPatch;
+    const size_t total4 = (size_t)batch * side * side * (kEmbed / 4);
+    const int grid = grid_for(total4, 256, 148 * 32);
+    if (out_bf16)
+        patch_gather_kernel<true><<<grid, 256, 0, as_stream(s)>>>(images, patches, batch, img, side);
+    else
+        patch_gather_kernel<false><<<grid, 256, 0, as_stream(s)>>>(images, patches, batch, img, side);
+    VITCU_LAUNCHED();
+    return 0;
+}
+
+int vitcu_cls_rows(float *x, const float *cls, const float *pos, int batch, int tokens, vitcu_stream s)
+{
+    VITCU_REQUIRE(x && cls && pos && batch > 0 && tokens > 0, "bad argument");
+    cls_rows_kernel<<<batch, 192, 0, as_stream(s)>>>(x, cls, pos, tokens);
+    VITCU_LAUNCHED();
+    return 0;
+}
+
+int vitcu_layernorm(const float *x, size_t x_row_stride, void *y, int y_bf16, const float *gamma,
+                    const float *beta, int rows, vitcu_stream s)
+{
+    VITCU_REQUIRE(x && y && gamma && beta && rows > 0, "bad argument");
+    VITCU_REQUIRE(x_row_stride % 4 == 0 && x_row_stride >= (size_t)kEmbed, "row stride must be >= 768 and a multiple of 4");
+    const int grid = (rows + 7) / 8;
+    if (y_bf16)
+        layernorm_kernel<true><<<grid, 256, 0, as_stream(s)>>>(x, x_row_stride, y, gamma, beta, rows);
+    else
+        layernorm_kernel<false><<<grid, 256, 0, as_stream(s)>>>(x, x_row_stride, y, gamma, beta, rows);
+    VITCU_LAUNCHED();
+    return 0;
+}
+
+int vitcu_softmax_rows(const float *logits, float *probs, int rows, int n, vitcu_stream s)
+{
+    VITCU_REQUIRE(logits && probs && rows > 0 && n > 0, "bad argument");
+    softmax_rows_kernel<<<rows, 256, 0, as_stream(s)>>>(logits, probs, n);
+    VITCU_LAUNCHED();
+    return 0;
+}
+
+} // extern "C"

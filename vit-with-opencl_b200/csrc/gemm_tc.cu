@@ -1,0 +1,366 @@
+// csrc/gemm_tc.cu -- BF16 tensor-core GEMM for sm_100a:
+//     C[M,N] = A[M,K] * W[N,K]^T  (+ fused epilogue),  FP32 accumulation.
+//
+// This is the B200 replacement for the reference's 8x8-tile OpenCL GEMMs
+// linear_layer (R/ll.cl:7-70) and QKV (R/multihead.cl:3-63), which carry 96 % of
+// the FLOPs of the path; the oracle for the computation is
+// linear_layer_seq (R/ViT_seq.c:295-309).  R/ = /root/reference/MulticoreMainProject/.
+//
+// Structure (one persistent CTA per SM, 320 threads, warp-specialised):
+//   warp 0      TMA producer: cp.async.bulk.tensor 128x64 A tiles and BNx64 W
+//               tiles (both K-major, 128-byte swizzle) into a STAGES-deep ring,
+//               completion on mbarriers
+//   warp 1      MMA issuer: one elected thread issues tcgen05.mma
+//               (cta_group::1, kind::f16, M=128, N=BN, K=16) with the FP32
+//               accumulator in TMEM; tcgen05.commit releases ring slots and
+//               publishes finished accumulators.  Also owns TMEM alloc/dealloc.
+//   warps 2-9   epilogue: tcgen05.ld the accumulator (two warps per 32-lane
+//               TMEM quadrant, half of the columns each), fuse bias / GELU /
+//               residual / patch-embed remap, store bf16 or fp32 rows.
+// The accumulator is double-buffered in TMEM (2 x BN columns), so the epilogue
+// of tile i overlaps the MMAs of tile i+1.  Ragged M (197*B is rarely a
+// multiple of 128) is handled by TMA zero-fill on load and a row predicate on
+// store.  Every mbarrier wait is watchdog-guarded (tc_common.cuh).
+#include "tc_common.cuh"
+
+using namespace vitcu;
+using namespace vitcu::tc;
+
+namespace {
+
+struct EpiParams {
+    int M, N, K;
+    size_t ldc;
+    int epilogue;
+    const float *bias;
+    const float *residual;
+    const float *pos;
+    int patches, tokens;
+    int out_bf16;
+};
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int kThreads = 320;
+constexpr int kEpiWarps = 8;
+
+template <int BN, int STAGES>
+struct SmemLayout {
+    static constexpr uint32_t A_BYTES = BM * BK * 2;
+    static constexpr uint32_t B_BYTES = BN * BK * 2;
+    static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr uint32_t BAR_OFFSET = STAGES * STAGE_BYTES;
+    static constexpr uint32_t NUM_BARS = 2 * STAGES + 4;
+    static constexpr uint32_t TOTAL = BAR_OFFSET + NUM_BARS * 8 + 16 + 1024; // + alignment slack
+};
+
+// one 32-column chunk of one accumulator row -> global memory
+__device__ __forceinline__ void epilogue_chunk(const EpiParams &p, void *C, int row, int col0, const uint32_t (&acc)[32])
+{
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+        const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + col0 + j));
+        v[j + 0] = __uint_as_float(acc[j + 0]) + b.x;
+        v[j + 1] = __uint_as_float(acc[j + 1]) + b.y;
+        v[j + 2] = __uint_as_float(acc[j + 2]) + b.z;
+        v[j + 3] = __uint_as_float(acc[j + 3]) + b.w;
+    }
+    size_t orow = static_cast<size_t>(row);
+    if (p.epilogue == VITCU_EPI_BIAS_GELU) {
+#pragma unroll
+        for (int j = 0; j < 32; j++)
+            v[j] = gelu_erf_fast(v[j]);
+    } else if (p.epilogue == VITCU_EPI_BIAS_RESIDUAL) {
+        const float4 *r = reinterpret_cast<const float4 *>(p.residual + static_cast<size_t>(row) * p.ldc + col0);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const float4 x = r[j];
+            v[4 * j + 0] += x.x;
+            v[4 * j + 1] += x.y;
+            v[4 * j + 2] += x.z;
+            v[4 * j + 3] += x.w;
+        }
+    } else if (p.epilogue == VITCU_EPI_PATCH_EMBED) {
+        const int img = row / p.patches, pi = row - img * p.patches;
+        orow = static_cast<size_t>(img) * p.tokens + 1 + pi;
+        const float4 *e = reinterpret_cast<const float4 *>(p.pos + static_cast<size_t>(1 + pi) * p.N + col0);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const float4 x = __ldg(e + j);
+            v[4 * j + 0] += x.x;
+            v[4 * j + 1] += x.y;
+            v[4 * j + 2] += x.z;
+            v[4 * j + 3] += x.w;
+        }
+    }
+    if (p.out_bf16) {
+        uint4 *dst = reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(C) + orow * p.ldc + col0);
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            dst[j] = make_uint4(pack_bf16x2(v[8 * j + 0], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+    } else {
+        float4 *dst = reinterpret_cast<float4 *>(reinterpret_cast<float *>(C) + orow * p.ldc + col0);
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            dst[j] = make_float4(v[4 * j + 0], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, void *C,
+                    const EpiParams p, uint32_t *watchdog_flag)
+{
+    using L = SmemLayout<BN, STAGES>;
+    static_assert(BN % 64 == 0 && BN <= 256, "BN must be 64..256 in steps of 64");
+    constexpr uint32_t TMEM_COLS = 2 * BN <= 32 ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+    constexpr uint32_t IDESC = umma_idesc_bf16(BM, BN, false, false);
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + L::BAR_OFFSET);
+    uint64_t *empty_bar = full_bar + STAGES;
+    uint64_t *tfull_bar = empty_bar + STAGES;
+    uint64_t *tempty_bar = tfull_bar + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty_bar + 2);
+    volatile uint32_t *cta_abort = tmem_slot + 1;
+
+    const int warp = threadIdx.x >> 5; // warp-uniform
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < STAGES; i++) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; i++) {
+            mbar_init(&tfull_bar[i], 1);
+            mbar_init(&tempty_bar[i], kEpiWarps);
+        }
+        *cta_abort = 0;
+        fence_barrier_init();
+    }
+    if (warp == 1)
+        tmem_alloc(tmem_slot, TMEM_COLS);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const Watchdog wd{cta_abort, watchdog_flag};
+
+    const int num_m = (p.M + BM - 1) / BM, num_n = p.N / BN;
+    const int num_tiles = num_m * num_n, num_kb = p.K / BK;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            prefetch_tensormap(&tmap_a);
+            prefetch_tensormap(&tmap_b);
+            uint32_t stage = 0, phase = 0;
+            bool ok = true;
+            for (int tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x) {
+                const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
+                for (int kb = 0; kb < num_kb; kb++) {
+                    if (!(ok = mbar_wait(&empty_bar[stage], phase ^ 1, wd, 1)))
+                        break;
+                    uint8_t *sa = smem + stage * L::STAGE_BYTES;
+                    mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+                    tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
+                    tma_load_2d(sa + L::A_BYTES, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN);
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0, it = 0;
+            bool ok = true;
+            for (int tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x, it++) {
+                const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+                if (!(ok = mbar_wait(&tempty_bar[acc], acc_phase ^ 1, wd, 2)))
+                    break;
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < num_kb; kb++) {
+                    if (!(ok = mbar_wait(&full_bar[stage], phase, wd, 3)))
+                        break;
+                    tcgen05_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
+                    const uint64_t a_desc = umma_desc_k_sw128(sa);
+                    const uint64_t b_desc = umma_desc_k_sw128(sa + L::A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; k++) // +32 bytes per K=16 step inside the 128B swizzle row
+                        umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, IDESC, (kb | k) != 0);
+                    umma_commit(&empty_bar[stage]); // ring slot reusable once these MMAs retire
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                if (ok)
+                    umma_commit(&tfull_bar[acc]); // accumulator complete
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..9) =====================
+        const int quad = warp & 3;          // TMEM lanes [32*quad, 32*quad+32) are this warp's
+        const int half = (warp - 2) >> 2;   // which half of the BN columns
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
+            const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
+            const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+            bool ok = mbar_wait(&tfull_bar[acc], acc_phase, wd, 4);
+            ok = __all_sync(0xffffffffu, ok);
+            if (!ok)
+                break;
+            tcgen05_fence_after();
+            const int row = m_blk * BM + quad * 32 + lane;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + half * (BN / 2);
+#pragma unroll 1
+            for (int c = 0; c < BN / 64; c++) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(taddr + c * 32, v);
+                tmem_ld_wait();
+                if (row < p.M)
+                    epilogue_chunk(p, C, row, n_blk * BN + half * (BN / 2) + c * 32, v);
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0)
+                mbar_arrive(&tempty_bar[acc]);
+        }
+    }
+
+    // ===================== teardown =====================
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+    return fn;
+}
+
+template <int BN, int STAGES>
+int launch(const CUtensorMap &ta, const CUtensorMap &tb, void *C, const EpiParams &p, int sms, cudaStream_t st)
+{
+    using L = SmemLayout<BN, STAGES>;
+    auto kernel = gemm_bf16_tc_kernel<BN, STAGES>;
+    static bool configured[64] = {false};
+    int dev = 0;
+    VITCU_TRY(cudaGetDevice(&dev));
+    if (dev < 64 && !configured[dev]) {
+        VITCU_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::TOTAL));
+        configured[dev] = true;
+    }
+    const int num_tiles = ((p.M + BM - 1) / BM) * (p.N / BN);
+    const int grid = num_tiles < sms ? num_tiles : sms;
+    kernel<<<grid, kThreads, L::TOTAL, st>>>(ta, tb, C, p, watchdog_flag());
+    VITCU_LAUNCHED();
+    return 0;
+}
+
+} // namespace
+
+namespace vitcu {
+
+int make_tensor_map_2d(CUtensorMap *map, const void *base, int elem_bytes, uint64_t rows, uint64_t cols,
+                       uint64_t ld_bytes, uint32_t box_rows, uint32_t box_cols)
+{
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn)
+        return set_error(VITCU_E_NODEVICE, __FILE__, __LINE__, "cuTensorMapEncodeTiled is unavailable");
+    const CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {ld_bytes};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(map, dt, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return set_error(VITCU_E_ARG, __FILE__, __LINE__, "cuTensorMapEncodeTiled rejected the tensor");
+    return 0;
+}
+
+int device_sm_count()
+{
+    static int sms[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64)
+        return 148;
+    if (!sms[dev]) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
+        sms[dev] = n;
+    }
+    return sms[dev];
+}
+
+} // namespace vitcu
+
+extern "C" int vitcu_gemm_bf16(const vitcu_bf16 *A, const vitcu_bf16 *W, void *C, const vitcu_gemm_desc *d,
+                               vitcu_stream s)
+{
+    VITCU_REQUIRE(A && W && C && d, "NULL argument");
+    VITCU_REQUIRE(d->M > 0 && d->N > 0 && d->K > 0, "empty GEMM");
+    VITCU_REQUIRE(d->K % BK == 0, "bf16 GEMM needs K % 64 == 0");
+    VITCU_REQUIRE(d->N % 128 == 0, "bf16 GEMM needs N % 128 == 0");
+    VITCU_REQUIRE(d->bias, "bias is required");
+    VITCU_REQUIRE(d->epilogue != VITCU_EPI_BIAS_RESIDUAL || d->residual, "residual pointer missing");
+    VITCU_REQUIRE(d->epilogue != VITCU_EPI_PATCH_EMBED || (d->pos && d->patches > 0 && d->tokens > d->patches),
+                  "patch-embed epilogue needs pos, patches, tokens");
+    EpiParams p;
+    p.M = d->M;
+    p.N = d->N;
+    p.K = d->K;
+    p.ldc = d->ldc ? d->ldc : (size_t)d->N;
+    p.epilogue = d->epilogue;
+    p.bias = d->bias;
+    p.residual = d->residual;
+    p.pos = d->pos;
+    p.patches = d->patches;
+    p.tokens = d->tokens;
+    p.out_bf16 = d->out_bf16;
+    VITCU_REQUIRE(p.ldc % 8 == 0, "ldc must be a multiple of 8");
+    const size_t lda = d->lda ? d->lda : (size_t)d->K;
+    VITCU_REQUIRE(lda % 8 == 0 && ((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0, "operands must be 16-byte aligned");
+
+    const int sms = device_sm_count();
+    // 128x256 tiles when they divide N and still give every SM work; else 128x128
+    const bool wide = d->N % 256 == 0 && ((d->M + BM - 1) / BM) * (d->N / 256) >= sms;
+    const int BN = wide ? 256 : 128;
+    CUtensorMap ta, tb;
+    int rc = make_tensor_map_2d(&ta, A, 2, (uint64_t)d->M, (uint64_t)d->K, lda * 2, BM, BK);
+    if (rc)
+        return rc;
+    rc = make_tensor_map_2d(&tb, W, 2, (uint64_t)d->N, (uint64_t)d->K, (uint64_t)d->K * 2, BN, BK);
+    if (rc)
+        return rc;
+    if (wide)
+        return launch<256, 4>(ta, tb, C, p, sms, as_stream(s));
+    return launch<128, 6>(ta, tb, C, p, sms, as_stream(s));
+}

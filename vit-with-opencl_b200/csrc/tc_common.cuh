@@ -1,0 +1,226 @@
+// csrc/tc_common.cuh -- inline-PTX building blocks for the sm_100a tensor-core
+// kernels: mbarrier, TMA (cp.async.bulk.tensor), tcgen05 (alloc / mma / commit /
+// ld / fences) and the UMMA shared-memory + instruction descriptors.
+//
+// Bit layouts follow the PTX ISA for sm_100a; they were cross-checked against
+// the vendored CUTLASS headers (cute/arch/mma_sm100_desc.hpp: SmemDescriptor,
+// InstrDescriptor; cute/arch/tmem_allocator_sm100.hpp; cutlass/arch/barrier.h).
+#pragma once
+#include <cuda.h> // CUtensorMap (types only; the driver entry point is resolved at run time)
+#include "common.cuh"
+
+namespace vitcu {
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ uint64_t globaltimer_ns()
+{
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred = 0;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
+// ---- mbarrier -------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// generic-proxy writes to smem -> visible to the async proxy (TMA / tcgen05.mma reads)
+__device__ __forceinline__ void fence_proxy_async_smem()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\tselp.u32 %0, 1, 0, P;\n\t}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
+
+// Watchdog-guarded wait.  A pipeline bug must never hang the GPU: after
+// kWatchdogNs without progress the waiter raises the CTA-wide abort flag and a
+// device-global diagnostic word, and every role falls through to teardown.
+constexpr uint64_t kWatchdogNs = 2000000000ull;
+struct Watchdog {
+    volatile uint32_t *cta_abort; // shared memory
+    uint32_t *global_flag;        // device memory (vitcu_watchdog_check)
+};
+__device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, const Watchdog &wd, uint32_t tag)
+{
+    if (mbar_try_wait(bar, parity))
+        return true;
+    uint32_t spins = 0;
+    uint64_t t0 = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 1023u) == 0) {
+            if (*wd.cta_abort)
+                return false;
+            const uint64_t now = globaltimer_ns();
+            if (t0 == 0) {
+                t0 = now;
+            } else if (now - t0 > kWatchdogNs) {
+                *wd.cta_abort = 1;
+                if (wd.global_flag)
+                    atomicCAS(wd.global_flag, 0u, 0x80000000u | (tag << 16) | (blockIdx.x & 0xffffu));
+                return false;
+            }
+        }
+    }
+    return true;
+}
+
+// ---- TMA ------------------------------------------------------------------
+__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap *m)
+{
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1, int c2)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
+                 "r"(c2)
+                 : "memory");
+}
+
+// ---- tcgen05 --------------------------------------------------------------
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// whole warp; writes the allocated TMEM base address to *slot (shared memory)
+__device__ __forceinline__ void tmem_alloc(uint32_t *slot, uint32_t cols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+
+// K-major operand tile in shared memory, rows of 128 bytes, 128B swizzle (what
+// TMA writes with CU_TENSOR_MAP_SWIZZLE_128B and a 128-byte inner box):
+// 8-row groups are 1024 B apart (SBO); LBO is unused for swizzled K-major.
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr)
+{
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu);      // start address  [0,14)
+    d |= static_cast<uint64_t>(1) << 16;                         // LBO (ignored)  [16,30)
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;                 // SBO = 1024 B   [32,46)
+    d |= static_cast<uint64_t>(1) << 46;                         // version = 1    [46,48)
+    d |= static_cast<uint64_t>(2) << 61;                         // SWIZZLE_128B   [61,64)
+    return d;
+}
+// MN-major operand tile (rows = K index, 128 bytes = 64 MN elements per row,
+// 128B swizzle): 8-row (K) groups are 1024 B apart (SBO); LBO would step
+// between 64-element MN atoms and is unused when the MN extent is 64.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr)
+{
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu);
+    d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+
+// instruction descriptor, kind::f16, BF16 x BF16 -> FP32
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, bool a_mn_major, bool b_mn_major)
+{
+    return (1u << 4)                          // c_format = F32      [4,6)
+           | (1u << 7)                        // a_format = BF16     [7,10)
+           | (1u << 10)                       // b_format = BF16     [10,13)
+           | ((a_mn_major ? 1u : 0u) << 15)   // a_major             [15]
+           | ((b_mn_major ? 1u : 0u) << 16)   // b_major             [16]
+           | (static_cast<uint32_t>(N >> 3) << 17)  // n_dim          [17,23)
+           | (static_cast<uint32_t>(M >> 4) << 24); // m_dim          [24,29)
+}
+
+// D[tmem] (+)= A[smem] * B[smem]; one thread issues for the CTA
+__device__ __forceinline__ void umma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+                 : "memory");
+}
+// arrives on the mbarrier once all previously issued MMAs of this thread are done
+__device__ __forceinline__ void umma_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+
+// 32 lanes x 32 consecutive 32-bit columns: thread i of the warp gets lane
+// (taddr.lane + i), v[j] = column (taddr.col + j)
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+                   "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
+                   "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
+                   "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// fast exact-form GELU for bf16 outputs: erf by Abramowitz-Stegun 7.1.26
+// (|error| <= 1.5e-7, far below bf16 resolution); 2 MUFU + ~12 FMA per value.
+__device__ __forceinline__ float gelu_erf_fast(float x)
+{
+    const float ax = fabsf(x) * 0.70710678118654752440f;
+    const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+    float poly = fmaf(t, 1.061405429f, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    poly *= t;
+    const float erf_abs = fmaf(-poly, __expf(-ax * ax), 1.0f);
+    return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
+
+} // namespace tc
+
+// host side: build a 2-D tiled tensor map over a row-major [rows, cols] matrix of
+// `elem_bytes`-wide elements (row stride ld_bytes), box {box_cols, box_rows},
+// 128-byte swizzle.  Returns 0 or a cudaError/CUresult-derived code.
+int make_tensor_map_2d(CUtensorMap *map, const void *base, int elem_bytes, uint64_t rows, uint64_t cols,
+                       uint64_t ld_bytes, uint32_t box_rows, uint32_t box_cols);
+
+} // namespace vitcu

@@ -1,0 +1,555 @@
+/* host/vit_engine.c -- C host orchestration of the ViT-B/16 forward on one B200.
+ *
+ * Takes the place of the host side of R/ViT_opencl.c (R/ = /root/reference/
+ * MulticoreMainProject/): weight staging (R/ViT_opencl.c:125-330), the per-image
+ * kernel chain (Conv2d :361, postConv2d :407, Encoder :710, layer_norm :444,
+ * linear_layer :622, Softmax :750) and read-back.  It talks to the GPU only
+ * through include/vit_cuda_layer.h.  Differences in kind, not just in speed:
+ * images are processed in batches (M = batch*tokens rows per GEMM) instead of
+ * one by one; residual adds, bias, GELU, class-token/position adds are fused
+ * into GEMM epilogues so a layer is 7 launches instead of 9 per image; the
+ * whole chunk forward is captured once in a CUDA graph and replayed; image
+ * upload of chunk i+1 overlaps the compute of chunk i.
+ */
+#include "vit_engine_internal.h"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+static _Thread_local char g_msg[640] = "no error";
+
+const char *vitb200_last_error(void) { return g_msg; }
+
+int vit_fail(const char *file, int line, int rc, const char *what)
+{
+    const char *base = strrchr(file, '/');
+    if (what)
+        snprintf(g_msg, sizeof(g_msg), "[%s:%d] CUDA error %d (%s)", base ? base + 1 : file, line, rc, what);
+    else
+        snprintf(g_msg, sizeof(g_msg), "[%s:%d] %s", base ? base + 1 : file, line, vitcu_last_error());
+    return rc;
+}
+
+int vitb200_device_count(void)
+{
+    int n = 0;
+    if (vitcu_device_count(&n) != 0)
+        return 0;
+    return n;
+}
+
+int vitb200_host_alloc(void **ptr, size_t bytes)
+{
+    VIT_TRY(vitcu_host_alloc(ptr, bytes));
+    return 0;
+}
+int vitb200_host_free(void *ptr)
+{
+    VIT_TRY(vitcu_host_free(ptr));
+    return 0;
+}
+
+/* expected element count of blob idx (index map: R/ViT_seq.c:437-513) */
+static size_t blob_elems(int idx, int tokens)
+{
+    if (idx == 0 || idx == 2)
+        return VIT_D;
+    if (idx == 1)
+        return (size_t)VIT_D * 3 * 16 * 16;
+    if (idx == 3)
+        return (size_t)tokens * VIT_D;
+    if (idx >= 4 && idx < 148) {
+        switch ((idx - 4) % 12) {
+        case 2:
+            return (size_t)3 * VIT_D * VIT_D;
+        case 3:
+            return 3 * VIT_D;
+        case 4:
+            return (size_t)VIT_D * VIT_D;
+        case 8:
+            return (size_t)VIT_HID * VIT_D;
+        case 9:
+            return VIT_HID;
+        case 10:
+            return (size_t)VIT_D * VIT_HID;
+        default:
+            return VIT_D;
+        }
+    }
+    if (idx == 148 || idx == 149)
+        return VIT_D;
+    if (idx == 150)
+        return (size_t)VITB200_CLASSES * VIT_D;
+    return VITB200_CLASSES;
+}
+
+/* GEMM weight matrices (everything else stays fp32 in both precisions) */
+static int is_gemm_weight(int idx)
+{
+    if (idx == 1)
+        return 1;
+    if (idx >= 4 && idx < 148) {
+        int k = (idx - 4) % 12;
+        return k == 2 || k == 4 || k == 8 || k == 10;
+    }
+    return 0;
+}
+
+int vitb200_create(vitb200_engine **out, int device, int img, int precision, int max_batch)
+{
+    if (!out)
+        return vit_fail(__FILE__, __LINE__, VITCU_E_ARG, "engine out-pointer is NULL");
+    *out = NULL;
+    if (img <= 0 || img % 16 != 0)
+        return vit_fail(__FILE__, __LINE__, VITCU_E_ARG, "image side must be a positive multiple of 16");
+    if (precision != VITB200_FP32 && precision != VITB200_BF16)
+        return vit_fail(__FILE__, __LINE__, VITCU_E_ARG, "precision must be VITB200_FP32 or VITB200_BF16");
+    if (max_batch <= 0)
+        return vit_fail(__FILE__, __LINE__, VITCU_E_ARG, "max_batch must be positive");
+    int ndev = 0;
+    VIT_TRY(vitcu_device_count(&ndev));
+    if (device < 0 || device >= ndev)
+        return vit_fail(__FILE__, __LINE__, VITCU_E_NODEVICE, "no such CUDA device");
+    int cc = 0;
+    VIT_TRY(vitcu_device_info(device, NULL, NULL, &cc, NULL));
+    if (cc < 100)
+        return vit_fail(__FILE__, __LINE__, VITCU_E_NODEVICE, "device is not sm_100 (B200) class");
+    VIT_TRY(vitcu_set_device(device));
+    VIT_TRY(vitcu_prepare_device());
+
+    vitb200_engine *e = (vitb200_engine *)calloc(1, sizeof(*e));
+    if (!e)
+        return vit_fail(__FILE__, __LINE__, VITCU_E_ARG, "out of host memory");
+    e->device = device;
+    e->img = img;
+    e->side = img / 16;
+    e->P = e->side * e->side;
+    e->T = e->P + 1;
+    e->precision = precision;
+    e->B = max_batch;
+    e->stop_after = -1;
+    e->no_graph = getenv("VITB200_NO_GRAPH") != NULL;
+    const int bf = precision == VITB200_BF16;
+    const size_t act = bf ? 2 : 4;
+    const size_t rows = (size_t)e->B * e->T;
+    const size_t img_elems = (size_t)3 * img * img;
+
+    int rc = 0;
+#define ENG_TRY(x)                                                              \
+    do {                                                                        \
+        rc = (x);                                                               \
+        if (rc) {                                                               \
+            vit_fail(__FILE__, __LINE__, rc, NULL);                             \
+            vitb200_destroy(e);                                                 \
+            return rc;                                                          \
+        }                                                                       \
+    } while (0)
+    ENG_TRY(vitcu_stream_create(&e->stream));
+    ENG_TRY(vitcu_stream_create(&e->copy_stream));
+    for (int i = 0; i < 2; i++) {
+        ENG_TRY(vitcu_event_create(&e->ev_h2d[i]));
+        ENG_TRY(vitcu_event_create(&e->ev_done[i]));
+        ENG_TRY(vitcu_event_create(&e->ev_out[i]));
+        ENG_TRY(vitcu_malloc((void **)&e->d_images[i], (size_t)e->B * img_elems * sizeof(float)));
+        ENG_TRY(vitcu_malloc((void **)&e->d_probs[i], (size_t)e->B * VITB200_CLASSES * sizeof(float)));
+        ENG_TRY(vitcu_malloc((void **)&e->d_logits[i], (size_t)e->B * VITB200_CLASSES * sizeof(float)));
+    }
+    ENG_TRY(vitcu_event_create(&e->ev_t0));
+    ENG_TRY(vitcu_event_create(&e->ev_t1));
+    ENG_TRY(vitcu_malloc(&e->d_patches, (size_t)e->B * e->P * VIT_D * act));
+    ENG_TRY(vitcu_malloc((void **)&e->d_x, rows * VIT_D * sizeof(float)));
+    ENG_TRY(vitcu_malloc(&e->d_ln, rows * VIT_D * act));
+    ENG_TRY(vitcu_malloc(&e->d_qkv, rows * 3 * VIT_D * act));
+    ENG_TRY(vitcu_malloc(&e->d_att, rows * VIT_D * act));
+    ENG_TRY(vitcu_malloc(&e->d_hid, rows * VIT_HID * act));
+    ENG_TRY(vitcu_malloc((void **)&e->d_cls, (size_t)e->B * VIT_D * sizeof(float)));
+    ENG_TRY(vitcu_host_alloc((void **)&e->h_probs, (size_t)e->B * VITB200_CLASSES * sizeof(float) * 2));
+    ENG_TRY(vitcu_host_alloc((void **)&e->h_logits, (size_t)e->B * VITB200_CLASSES * sizeof(float) * 2));
+#undef ENG_TRY
+    *out = e;
+    return 0;
+}
+
+void vitb200_destroy(vitb200_engine *e)
+{
+    if (!e)
+        return;
+    vitcu_set_device(e->device);
+    vitcu_device_sync();
+    for (int i = 0; i < VITB200_NBLOBS; i++) {
+        vitcu_free(e->w32[i]);
+        vitcu_free(e->w16[i]);
+    }
+    for (int i = 0; i < 2; i++) {
+        vitcu_free(e->d_images[i]);
+        vitcu_free(e->d_probs[i]);
+        vitcu_free(e->d_logits[i]);
+        if (e->ev_h2d[i])
+            vitcu_event_destroy(e->ev_h2d[i]);
+        if (e->ev_done[i])
+            vitcu_event_destroy(e->ev_done[i]);
+        if (e->ev_out[i])
+            vitcu_event_destroy(e->ev_out[i]);
+        if (e->graph[i])
+            vitcu_graph_destroy(e->graph[i]);
+    }
+    if (e->ev_t0)
+        vitcu_event_destroy(e->ev_t0);
+    if (e->ev_t1)
+        vitcu_event_destroy(e->ev_t1);
+    vitcu_free(e->d_patches);
+    vitcu_free(e->d_x);
+    vitcu_free(e->d_ln);
+    vitcu_free(e->d_qkv);
+    vitcu_free(e->d_att);
+    vitcu_free(e->d_hid);
+    vitcu_free(e->d_cls);
+    vitcu_host_free(e->h_probs);
+    vitcu_host_free(e->h_logits);
+    if (e->stream)
+        vitcu_stream_destroy(e->stream);
+    if (e->copy_stream)
+        vitcu_stream_destroy(e->copy_stream);
+    free(e);
+}
+
+int vitb200_load_weights(vitb200_engine *e, const vitb200_blob *net)
+{
+    if (!e || !net)
+        return vit_fail(__FILE__, __LINE__, VITCU_E_ARG, "NULL argument");
+    VIT_TRY(vitcu_set_device(e->device));
+    /* validate first: the reference would dereference a NULL blob (R/Network.c:144-148
+     * leaves absent files as {NULL,0}) */
+    for (int i = 0; i < VITB200_NBLOBS; i++) {
+        if (!net[i].data || net[i].size == 0) {
+            char what[96];
+            snprintf(what, sizeof(what), "weight blob %d is missing", i);
+            return vit_fail(__FILE__, __LINE__, VITCU_E_ARG, what);
+        }
+        if (net[i].size != blob_elems(i, e->T)) {
+            char what[128];
+            snprintf(what, sizeof(what), "weight blob %d has %zu elements, expected %zu", i, net[i].size,
+                     blob_elems(i, e->T));
+            return vit_fail(__FILE__, __LINE__, VITCU_E_ARG, what);
+        }
+    }
+    const int bf = e->precision == VITB200_BF16;
+    for (int i = 0; i < VITB200_NBLOBS; i++) {
+        const size_t n = net[i].size;
+        if (!e->w32[i])
+            VIT_TRY(vitcu_malloc((void **)&e->w32[i], n * sizeof(float)));
+        VIT_TRY(vitcu_memcpy_h2d(e->w32[i], net[i].data, n * sizeof(float), e->stream));
+        if (bf && is_gemm_weight(i)) {
+            if (!e->w16[i])
+                VIT_TRY(vitcu_malloc((void **)&e->w16[i], n * sizeof(vitcu_bf16)));
+            VIT_TRY(vitcu_f32_to_bf16(e->w32[i], e->w16[i], n, e->stream));
+        }
+    }
+    VIT_TRY(vitcu_stream_sync(e->stream));
+    if (bf) { /* the fp32 masters of the GEMM weights are not needed on the BF16 path */
+        for (int i = 0; i < VITB200_NBLOBS; i++)
+            if (is_gemm_weight(i)) {
+                VIT_TRY(vitcu_free(e->w32[i]));
+                e->w32[i] = NULL;
+            }
+    }
+    e->weights_loaded = 1;
+    return 0;
+}
+
+/* one GEMM of the chain, dispatched on the engine precision */
+static int gemm(vitb200_engine *e, const void *A, int widx, int bidx, void *C, int M, int N, int K, int epi,
+                int out_bf16)
+{
+    vitcu_gemm_desc d;
+    memset(&d, 0, sizeof(d));
+    d.M = M;
+    d.N = N;
+    d.K = K;
+    d.lda = (size_t)K;
+    d.ldc = (size_t)N;
+    d.epilogue = epi;
+    d.bias = e->w32[bidx];
+    d.out_bf16 = out_bf16;
+    if (epi == VITCU_EPI_BIAS_RESIDUAL)
+        d.residual = (const float *)C;
+    if (epi == VITCU_EPI_PATCH_EMBED) {
+        d.pos = e->w32[3];
+        d.patches = e->P;
+        d.tokens = e->T;
+    }
+    e->launches++;
+    if (e->precision == VITB200_BF16)
+        return vitcu_gemm_bf16((const vitcu_bf16 *)A, e->w16[widx], C, &d, e->stream);
+    return vitcu_sgemm((const float *)A, e->w32[widx], C, &d, e->stream);
+}
+
+/* Enqueue the forward of b images resident in d_images[buf] on e->stream. */
+static int enqueue_forward(vitb200_engine *e, int buf, int b)
+{
+    const int bf = e->precision == VITB200_BF16;
+    const int M = b * e->T;
+    vitcu_stream s = e->stream;
+    e->launches = 0;
+
+    /* patch embedding: gather + GEMM with class/position epilogue
+     * (Conv2d + postConv2d, R/ViT_opencl.c:361-442) */
+    VIT_TRY(vitcu_patch_gather(e->d_images[buf], e->d_patches, b, e->img, bf, s));
+    e->launches++;
+    VIT_TRY(gemm(e, e->d_patches, 1, 2, e->d_x, b * e->P, VIT_D, VIT_D, VITCU_EPI_PATCH_EMBED, 0));
+    VIT_TRY(vitcu_cls_rows(e->d_x, e->w32[0], e->w32[3], b, e->T, s));
+    e->launches++;
+
+    const int layers = e->stop_after < 0 ? VIT_DEPTH : (e->stop_after < VIT_DEPTH ? e->stop_after : VIT_DEPTH);
+    for (int l = 0; l < layers; l++) {
+        const int w = 4 + 12 * l; /* blob base of the layer (R/ViT_seq.c:446-504) */
+        /* x -> LN1 -> QKV -> attention -> out-proj (+x)  (R/ViT_opencl.c:710-730) */
+        VIT_TRY(vitcu_layernorm(e->d_x, VIT_D, e->d_ln, bf, e->w32[w + 0], e->w32[w + 1], M, s));
+        e->launches++;
+        VIT_TRY(gemm(e, e->d_ln, w + 2, w + 3, e->d_qkv, M, 3 * VIT_D, VIT_D, VITCU_EPI_BIAS, bf));
+        VIT_TRY(vitcu_attention(e->d_qkv, e->d_att, b, e->T, bf, s));
+        e->launches++;
+        VIT_TRY(gemm(e, e->d_att, w + 4, w + 5, e->d_x, M, VIT_D, VIT_D, VITCU_EPI_BIAS_RESIDUAL, 0));
+        /* -> LN2 -> fc1+GELU -> fc2 (+r1)  (R/ViT_opencl.c:732-746) */
+        VIT_TRY(vitcu_layernorm(e->d_x, VIT_D, e->d_ln, bf, e->w32[w + 6], e->w32[w + 7], M, s));
+        e->launches++;
+        VIT_TRY(gemm(e, e->d_ln, w + 8, w + 9, e->d_hid, M, VIT_HID, VIT_D, VITCU_EPI_BIAS_GELU, bf));
+        VIT_TRY(gemm(e, e->d_hid, w + 10, w + 11, e->d_x, M, VIT_D, VIT_HID, VITCU_EPI_BIAS_RESIDUAL, 0));
+    }
+    if (e->stop_after >= 0)
+        return 0;
+
+    /* final LN on the class-token rows only, head, softmax
+     * (R/ViT_opencl.c:951-959; R/ViT_seq.c:506-515 normalises all rows but uses row 0) */
+    VIT_TRY(vitcu_layernorm(e->d_x, (size_t)e->T * VIT_D, e->d_cls, 0, e->w32[148], e->w32[149], b, s));
+    e->launches++;
+    vitcu_gemm_desc d;
+    memset(&d, 0, sizeof(d));
+    d.M = b;
+    d.N = VITB200_CLASSES;
+    d.K = VIT_D;
+    d.lda = VIT_D;
+    d.ldc = VITB200_CLASSES;
+    d.epilogue = VITCU_EPI_BIAS;
+    d.bias = e->w32[151];
+    /* the head stays FP32 on both paths: 0.004 % of the FLOPs, all of the logit precision */
+    const float *head_w = e->w32[150];
+    VIT_TRY(vitcu_sgemm(e->d_cls, head_w, e->d_logits[buf], &d, s));
+    e->launches++;
+    VIT_TRY(vitcu_softmax_rows(e->d_logits[buf], e->d_probs[buf], b, VITB200_CLASSES, s));
+    e->launches++;
+    return 0;
+}
+
+/* forward of a chunk, through the captured graph when the chunk is full-size */
+static int run_chunk(vitb200_engine *e, int buf, int b)
+{
+    /* the first full-size chunk runs eagerly (module load, attribute set-up);
+     * later ones are captured once per input buffer and replayed */
+    if (b == e->B && e->stop_after < 0 && !e->no_graph && e->warmed) {
+        if (!e->graph[buf]) {
+            VIT_TRY(vitcu_graph_begin(e->stream));
+            int rc = enqueue_forward(e, buf, b);
+            vitcu_graph g = NULL;
+            int rc2 = vitcu_graph_end(e->stream, &g);
+            if (rc)
+                return rc;
+            if (rc2)
+                return vit_fail(__FILE__, __LINE__, rc2, NULL);
+            e->graph[buf] = g;
+            e->kernels_per_forward = e->launches;
+        }
+        VIT_TRY(vitcu_graph_launch(e->graph[buf], e->stream));
+        return 0;
+    }
+    int rc = enqueue_forward(e, buf, b);
+    if (!rc && e->stop_after < 0) {
+        e->kernels_per_forward = e->launches;
+        if (b == e->B)
+            e->warmed = 1;
+    }
+    return rc;
+}
+
+static int check_ready(vitb200_engine *e)
+{
+    if (!e)
+        return vit_fail(__FILE__, __LINE__, VITCU_E_ARG, "engine is NULL");
+    if (!e->weights_loaded)
+        return vit_fail(__FILE__, __LINE__, VITCU_E_ARG, "weights not loaded");
+    VIT_TRY(vitcu_set_device(e->device));
+    return 0;
+}
+
+/* Shared chunk pipeline.  Source of chunk c is either a contiguous host array
+ * (images_host) or per-image structs.  While chunk c computes, the host copies
+ * chunk c-1's results out of pinned staging and the copy stream uploads chunk
+ * c+1, so the GPU never waits for the host. */
+static int forward_pipeline(vitb200_engine *e, const float *images_host, const vitb200_image *structs, int n,
+                            float *probs_host, float **prob_rows, float *logits_host)
+{
+    const size_t img_elems = (size_t)3 * e->img * e->img;
+    const size_t pbytes = (size_t)VITB200_CLASSES * sizeof(float);
+    const size_t stage = (size_t)e->B * VITB200_CLASSES;
+    int done = 0, chunk = 0;
+    int pend_n = 0, pend_off = 0, pend_buf = 0;
+    while (done < n || pend_n) {
+        const int buf = chunk & 1;
+        int b = 0;
+        if (done < n) {
+            b = n - done < e->B ? n - done : e->B;
+            /* d_images[buf] is free once the forward that read it (chunk-2) finished */
+            VIT_TRY(vitcu_stream_wait_event(e->copy_stream, e->ev_done[buf]));
+            if (images_host) {
+                VIT_TRY(vitcu_memcpy_h2d(e->d_images[buf], images_host + (size_t)done * img_elems,
+                                         (size_t)b * img_elems * sizeof(float), e->copy_stream));
+            } else {
+                /* per-image malloc'd buffers (R/Network.c:84-105): one copy per image */
+                for (int i = 0; i < b; i++)
+                    VIT_TRY(vitcu_memcpy_h2d(e->d_images[buf] + (size_t)i * img_elems, structs[done + i].data,
+                                             img_elems * sizeof(float), e->copy_stream));
+            }
+            VIT_TRY(vitcu_event_record(e->ev_h2d[buf], e->copy_stream));
+            VIT_TRY(vitcu_stream_wait_event(e->stream, e->ev_h2d[buf]));
+            VIT_TRY_RC(run_chunk(e, buf, b));
+            VIT_TRY(vitcu_event_record(e->ev_done[buf], e->stream));
+            VIT_TRY(vitcu_memcpy_d2h(e->h_probs + buf * stage, e->d_probs[buf], (size_t)b * pbytes, e->stream));
+            if (logits_host)
+                VIT_TRY(vitcu_memcpy_d2h(e->h_logits + buf * stage, e->d_logits[buf], (size_t)b * pbytes,
+                                         e->stream));
+            VIT_TRY(vitcu_event_record(e->ev_out[buf], e->stream));
+        }
+        if (pend_n) {
+            VIT_TRY(vitcu_event_sync(e->ev_out[pend_buf]));
+            const float *src = e->h_probs + pend_buf * stage;
+            if (probs_host)
+                memcpy(probs_host + (size_t)pend_off * VITB200_CLASSES, src, (size_t)pend_n * pbytes);
+            if (prob_rows)
+                for (int i = 0; i < pend_n; i++)
+                    memcpy(prob_rows[pend_off + i], src + (size_t)i * VITB200_CLASSES, pbytes);
+            if (logits_host)
+                memcpy(logits_host + (size_t)pend_off * VITB200_CLASSES, e->h_logits + pend_buf * stage,
+                       (size_t)pend_n * pbytes);
+            pend_n = 0;
+        }
+        if (b) {
+            pend_n = b;
+            pend_off = done;
+            pend_buf = buf;
+            done += b;
+            chunk++;
+        }
+    }
+    VIT_TRY(vitcu_stream_sync(e->stream));
+    VIT_TRY(vitcu_watchdog_check());
+    return 0;
+}
+
+int vitb200_forward(vitb200_engine *e, const float *images_host, int n, float *probs_host, float *logits_host)
+{
+    VIT_TRY_RC(check_ready(e));
+    if (n < 0 || (n > 0 && (!images_host || !probs_host)))
+        return vit_fail(__FILE__, __LINE__, VITCU_E_ARG, "bad images/probs argument");
+    if (n == 0)
+        return 0;
+    return forward_pipeline(e, images_host, NULL, n, probs_host, NULL, logits_host);
+}
+
+int vitb200_forward_structs(vitb200_engine *e, const vitb200_image *images, int n, float **prb)
+{
+    VIT_TRY_RC(check_ready(e));
+    if (n < 0 || (n > 0 && (!images || !prb)))
+        return vit_fail(__FILE__, __LINE__, VITCU_E_ARG, "bad images/prb argument");
+    for (int i = 0; i < n; i++) {
+        if (!images[i].data || !prb[i])
+            return vit_fail(__FILE__, __LINE__, VITCU_E_ARG, "NULL image data or probability row");
+        if (images[i].c != 3 || images[i].h != e->img || images[i].w != e->img)
+            return vit_fail(__FILE__, __LINE__, VITCU_E_ARG, "image shape does not match the engine");
+    }
+    if (n == 0)
+        return 0;
+    return forward_pipeline(e, NULL, images, n, NULL, prb, NULL);
+}
+
+int vitb200_stage_images(vitb200_engine *e, const float *images_host, int n)
+{
+    VIT_TRY_RC(check_ready(e));
+    if (n <= 0 || n > e->B || !images_host)
+        return vit_fail(__FILE__, __LINE__, VITCU_E_ARG, "stage_images: need 0 < n <= max_batch");
+    VIT_TRY(vitcu_memcpy_h2d(e->d_images[0], images_host, (size_t)n * 3 * e->img * e->img * sizeof(float),
+                             e->stream));
+    VIT_TRY(vitcu_stream_sync(e->stream));
+    return 0;
+}
+
+int vitb200_forward_resident(vitb200_engine *e, int n)
+{
+    VIT_TRY_RC(check_ready(e));
+    if (n <= 0 || n > e->B)
+        return vit_fail(__FILE__, __LINE__, VITCU_E_ARG, "forward_resident: need 0 < n <= max_batch");
+    VIT_TRY(vitcu_event_record(e->ev_t0, e->stream));
+    VIT_TRY_RC(run_chunk(e, 0, n));
+    VIT_TRY(vitcu_event_record(e->ev_t1, e->stream));
+    VIT_TRY(vitcu_stream_sync(e->stream));
+    VIT_TRY(vitcu_watchdog_check());
+    return 0;
+}
+
+int vitb200_time_resident(vitb200_engine *e, int n, int iters, float *total_ms)
+{
+    VIT_TRY_RC(check_ready(e));
+    if (n <= 0 || n > e->B || iters <= 0 || !total_ms)
+        return vit_fail(__FILE__, __LINE__, VITCU_E_ARG, "time_resident: bad argument");
+    VIT_TRY(vitcu_event_record(e->ev_t0, e->stream));
+    for (int i = 0; i < iters; i++)
+        VIT_TRY_RC(run_chunk(e, 0, n));
+    VIT_TRY(vitcu_event_record(e->ev_t1, e->stream));
+    VIT_TRY(vitcu_stream_sync(e->stream));
+    VIT_TRY(vitcu_event_elapsed_ms(e->ev_t0, e->ev_t1, total_ms));
+    VIT_TRY(vitcu_watchdog_check());
+    return 0;
+}
+
+int vitb200_last_forward_ms(vitb200_engine *e, float *ms)
+{
+    if (!e || !ms)
+        return vit_fail(__FILE__, __LINE__, VITCU_E_ARG, "NULL argument");
+    VIT_TRY(vitcu_event_elapsed_ms(e->ev_t0, e->ev_t1, ms));
+    return 0;
+}
+
+int vitb200_read_probs(vitb200_engine *e, int n, float *probs_host, float *logits_host)
+{
+    VIT_TRY_RC(check_ready(e));
+    if (n <= 0 || n > e->B)
+        return vit_fail(__FILE__, __LINE__, VITCU_E_ARG, "read_probs: need 0 < n <= max_batch");
+    const size_t bytes = (size_t)n * VITB200_CLASSES * sizeof(float);
+    if (probs_host)
+        VIT_TRY(vitcu_memcpy_d2h(probs_host, e->d_probs[0], bytes, e->stream));
+    if (logits_host)
+        VIT_TRY(vitcu_memcpy_d2h(logits_host, e->d_logits[0], bytes, e->stream));
+    VIT_TRY(vitcu_stream_sync(e->stream));
+    return 0;
+}
+
+int vitb200_set_stop_after_layer(vitb200_engine *e, int layer)
+{
+    if (!e || layer < -1 || layer > VIT_DEPTH)
+        return vit_fail(__FILE__, __LINE__, VITCU_E_ARG, "stop_after_layer must be in [-1,12]");
+    e->stop_after = layer;
+    return 0;
+}
+
+int vitb200_read_tokens(vitb200_engine *e, int n, float *x_host)
+{
+    VIT_TRY_RC(check_ready(e));
+    if (n <= 0 || n > e->B || !x_host)
+        return vit_fail(__FILE__, __LINE__, VITCU_E_ARG, "read_tokens: bad argument");
+    VIT_TRY(vitcu_memcpy_d2h(x_host, e->d_x, (size_t)n * e->T * VIT_D * sizeof(float), e->stream));
+    VIT_TRY(vitcu_stream_sync(e->stream));
+    return 0;
+}
+
+int vitb200_kernels_per_forward(const vitb200_engine *e) { return e ? e->kernels_per_forward : 0; }
+int vitb200_tokens(const vitb200_engine *e) { return e ? e->T : 0; }

@@ -1,0 +1,49 @@
+/* host/vit_engine_internal.h -- engine state shared by the C host files. */
+#ifndef VIT_ENGINE_INTERNAL_H
+#define VIT_ENGINE_INTERNAL_H
+
+#include "../../include/vit_b200.h"
+#include "../../include/vit_cuda_layer.h"
+
+#define VIT_D 768
+#define VIT_HID 3072
+#define VIT_DEPTH 12
+
+struct vitb200_engine {
+    int device, img, side, P, T, precision, B;
+    int weights_loaded, stop_after, no_graph, warmed;
+    int launches, kernels_per_forward;
+    vitcu_stream stream, copy_stream;
+    vitcu_event ev_h2d[2], ev_done[2], ev_out[2], ev_t0, ev_t1;
+    vitcu_graph graph[2];
+    float *w32[VITB200_NBLOBS];      /* fp32 blobs on the device */
+    vitcu_bf16 *w16[VITB200_NBLOBS]; /* bf16 copies of the GEMM weights (BF16 path) */
+    float *d_images[2];              /* double-buffered input chunk [B,3,img,img] */
+    void *d_patches;                 /* [B*P,768] gathered patches */
+    float *d_x;                      /* [B*T,768] fp32 residual stream */
+    void *d_ln, *d_qkv, *d_att, *d_hid;
+    float *d_cls;                    /* [B,768] final-LN class tokens */
+    float *d_logits[2], *d_probs[2]; /* [B,1000] */
+    float *h_probs, *h_logits;       /* pinned staging [2][B,1000] */
+};
+
+/* records "[file:line] ..." for vitb200_last_error(); what == NULL takes the
+ * device layer's message */
+int vit_fail(const char *file, int line, int rc, const char *what);
+
+/* device-layer call: on failure record its message and return the code */
+#define VIT_TRY(call)                                                          \
+    do {                                                                       \
+        int _rc = (call);                                                      \
+        if (_rc)                                                               \
+            return vit_fail(__FILE__, __LINE__, _rc, NULL);                    \
+    } while (0)
+/* host-level call whose message is already recorded */
+#define VIT_TRY_RC(call)                                                       \
+    do {                                                                       \
+        int _rc = (call);                                                      \
+        if (_rc)                                                               \
+            return _rc;                                                        \
+    } while (0)
+
+#endif

@@ -1,0 +1,138 @@
+/* host/vit_opencl.c -- the reference's entry point, re-implemented on the engine.
+ *
+ *     void ViT_opencl(ImageData *image, Network *networks, float **prb);
+ *
+ * declared in R/ViT_opencl.h:6, called once from R/Main.c:54 between clock()
+ * calls (R/ = /root/reference/MulticoreMainProject/).  Like the reference
+ * (R/ViT_opencl.c:794-986) this call owns everything: it brings the device(s)
+ * up, uploads the weights, runs all image->n images, writes probabilities into
+ * the caller's rows and releases the device state before returning.  Unlike
+ * the reference it batches images, may shard them over several GPUs (one host
+ * thread per GPU, contiguous shards, replicated weights, no collective -- the
+ * images are independent, R/ViT_opencl.c:926), and it returns only after every
+ * result is on the host.
+ *
+ * Failure convention: print "[file:line] CUDA error N (...)" and
+ * exit(EXIT_FAILURE), as CHECK_ERROR does (R/kernelHandler.h:6-10).
+ */
+#include "vit_engine_internal.h"
+
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+typedef struct {
+    int device, precision, batch, img;
+    const vitb200_image *images;
+    const vitb200_blob *networks;
+    float **prb;
+    int first, count;
+    int rc;
+    char msg[640];
+} shard_job;
+
+static void *shard_main(void *arg)
+{
+    shard_job *j = (shard_job *)arg;
+    vitb200_engine *e = NULL;
+    j->rc = vitb200_create(&e, j->device, j->img, j->precision, j->batch);
+    if (!j->rc)
+        j->rc = vitb200_load_weights(e, j->networks);
+    if (!j->rc)
+        j->rc = vitb200_forward_structs(e, j->images + j->first, j->count, j->prb + j->first);
+    if (j->rc)
+        snprintf(j->msg, sizeof(j->msg), "%s", vitb200_last_error());
+    vitb200_destroy(e);
+    return NULL;
+}
+
+static int env_int(const char *name, int dflt)
+{
+    const char *v = getenv(name);
+    if (!v || !*v)
+        return dflt;
+    int x = atoi(v);
+    return x > 0 ? x : dflt;
+}
+
+static void die(const char *msg)
+{
+    /* the reference's CHECK_ERROR prints to stdout and exits (R/kernelHandler.h:6-10) */
+    printf("%s\n", msg);
+    fflush(stdout);
+    exit(EXIT_FAILURE);
+}
+
+void ViT_opencl(vitb200_image *image, vitb200_blob *networks, float **prb)
+{
+    if (!image || !networks || !prb)
+        die("[vit_opencl.c] CUDA error 90001 (ViT_opencl: NULL argument)");
+    const int n = image->n; /* every struct carries the total count (R/Network.c:86) */
+    if (n <= 0)
+        return;
+    if (image->c != 3 || image->h != image->w || image->h % 16 != 0)
+        die("[vit_opencl.c] CUDA error 90001 (ViT_opencl: images must be 3 x S x S with S a multiple of 16)");
+
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+
+    const char *prec = getenv("VITB200_PRECISION");
+    const int precision = (prec && (!strcmp(prec, "bf16") || !strcmp(prec, "BF16"))) ? VITB200_BF16 : VITB200_FP32;
+    const int ndev = vitb200_device_count();
+    if (ndev <= 0)
+        die("[vit_opencl.c] CUDA error 90002 (ViT_opencl: no CUDA device; there is no CPU fallback)");
+    int gpus = env_int("VITB200_GPUS", (n + 255) / 256);
+    if (gpus > ndev)
+        gpus = ndev;
+    if (gpus > n)
+        gpus = n;
+    if (gpus < 1)
+        gpus = 1;
+    const int per = (n + gpus - 1) / gpus;
+    int batch = env_int("VITB200_BATCH", precision == VITB200_BF16 ? 256 : 64);
+    if (batch > per)
+        batch = per;
+
+    shard_job *jobs = (shard_job *)calloc((size_t)gpus, sizeof(shard_job));
+    pthread_t *threads = (pthread_t *)calloc((size_t)gpus, sizeof(pthread_t));
+    if (!jobs || !threads)
+        die("[vit_opencl.c] CUDA error 90001 (ViT_opencl: out of host memory)");
+    int used = 0;
+    for (int g = 0; g < gpus; g++) {
+        const int first = g * per;
+        if (first >= n)
+            break;
+        shard_job *j = &jobs[used];
+        j->device = g;
+        j->precision = precision;
+        j->batch = batch;
+        j->img = image->h;
+        j->images = image;
+        j->networks = networks;
+        j->prb = prb;
+        j->first = first;
+        j->count = first + per <= n ? per : n - first;
+        used++;
+    }
+    if (used == 1) {
+        shard_main(&jobs[0]);
+    } else {
+        for (int g = 0; g < used; g++)
+            if (pthread_create(&threads[g], NULL, shard_main, &jobs[g]) != 0)
+                die("[vit_opencl.c] CUDA error 90001 (ViT_opencl: pthread_create failed)");
+        for (int g = 0; g < used; g++)
+            pthread_join(threads[g], NULL);
+    }
+    for (int g = 0; g < used; g++)
+        if (jobs[g].rc)
+            die(jobs[g].msg);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    /* the reference prints its own timings (R/ViT_opencl.c:910,964); keep one line */
+    printf("ViT_b200: %d images, %d GPU(s), %s, %.3f s wall (device bring-up + weight upload + forward)\n", n,
+           used, precision == VITB200_BF16 ? "bf16" : "fp32",
+           (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec));
+    free(jobs);
+    free(threads);
+}
