@@ -1,0 +1,494 @@
+#!/usr/bin/env python
+"""bench.py -- ViT-B/16 images/sec on 1..8 B200 (BASELINE.json metric), one JSON line.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # our engine
+    python bench.py --impl reference [--gpus N] [--steps K] ...    # reference CPU path
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload): BASELINE config 3 -- ViT-B/16, 224x224, BF16 tensor-core
+path, 256 synthetic images per step per GPU, random-init weights of the reference's
+blob shapes (bundled blobs where oracle/_ref/Network travelled).  A step is one
+forward of the whole hot path (patch embedding .. softmax) over one batch.
+
+  value    images/s with the batch already resident in HBM; K steps timed with one
+           CUDA-event pair on the engine's compute stream, max over ranks
+  e2e      images/s through the public C-ABI call vitb200_forward(): pinned host
+           images in, probabilities out, H2D/D2H inside the timed region
+  roofline the dominant kernel (tcgen05 BF16 GEMM): algorithmic FLOPs of its four
+           per-layer launches / their CUDA-event time, against MEASURED_PEAKS.json
+  cpu_baseline  the reference's own ViT_seq.c (oracle/_ref) timed on the host cores
+           on a bounded sample (rank 0, N=1 only)
+
+Only the cpu_baseline / --impl reference legs touch oracle/; the engine never does.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GFLOP_PER_IMAGE_224 = 35.1277  # SURVEY.md section 8d, unpadded T=197, 2*M*N*K convention
+IMG, BATCH = 224, 256
+METRIC, UNIT = "ViT-B/16 images/sec (224x224, batch 256 per GPU)", "images/s"
+
+
+# --------------------------------------------------------------------------- helpers
+def env_rank():
+    return (int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)),
+            int(os.environ.get("WORLD_SIZE", 1)))
+
+
+def shard_range(total: int, rank: int, world: int):
+    """contiguous shard [lo, hi) of `total` units for `rank`"""
+    per = (total + world - 1) // world
+    lo = min(total, rank * per)
+    return lo, min(total, lo + per)
+
+
+class Dist:
+    """barrier + max/sum over ranks; a no-op for a single process"""
+
+    def __init__(self, backend=None):
+        self.rank, self.local_rank, self.world = env_rank()
+        self.on = self.world > 1
+        self.torch = None
+        if self.on:
+            import torch
+            import torch.distributed as dist
+            self.torch, self.dist = torch, dist
+            if backend is None:
+                backend = "nccl" if torch.cuda.is_available() else "gloo"
+            self.backend = backend
+            if backend == "nccl":
+                torch.cuda.set_device(self.local_rank)
+            dist.init_process_group(backend=backend)
+            self.device = torch.device("cuda", self.local_rank) if backend == "nccl" else torch.device("cpu")
+
+    def barrier(self):
+        if self.on:
+            self.dist.barrier()
+            if self.backend == "nccl":
+                self.torch.cuda.synchronize()
+
+    def reduce(self, value: float, op: str) -> float:
+        if not self.on:
+            return value
+        t = self.torch.tensor([value], dtype=self.torch.float64, device=self.device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX if op == "max" else self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def close(self):
+        if self.on:
+            self.dist.destroy_process_group()
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms during the timed region"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "200", "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        time.sleep(0.25)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                smax.append(float(c[2]))
+                power.append(float(c[3]))
+            except ValueError:
+                continue
+            for name, v in zip(names, c[5:9]):
+                if v.lower() == "active":
+                    reasons.add(name)
+        self.f.close()
+        os.unlink(self.f.name)
+        if sm:
+            busy = [s for s, p in zip(sm, power) if p > 300.0] or sm
+            out.update(sm_mhz=statistics.median(busy), sm_max_mhz=max(smax), reasons=sorted(reasons),
+                       samples=len(sm), power_w_max=max(power))
+        return out
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"bf16_burst": d["bf16_tflops"], "bf16_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "hbm_gbs": d["hbm_gbs"], "source": "MEASURED_PEAKS.json (of measured)"}
+    return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm_gbs": 6650.0,
+            "source": "B200_PROFILING.md fallback (of fallback)"}
+
+
+def model_blobs(pkg, img=224):
+    return pkg.synth.model_blobs(os.path.join(ROOT, "oracle", "_ref", "Network"), img, seed=0)
+
+
+# --------------------------------------------------------------------------- CPU reference
+def _ref_worker(args):
+    """one process = one single-threaded ViT_seq run on `n` images (the reference has no threads)"""
+    seed, n, img, blob_file, sizes = args
+    from oracle import binding
+    import __graft_entry__ as g
+    pkg = g.load_package()
+    # weights are shared read-only between the workers through one memory-mapped file
+    flat = np.memmap(blob_file, dtype=np.float32, mode="r")
+    blobs, off = [], 0
+    for sz in sizes:
+        blobs.append(np.asarray(flat[off:off + sz]))
+        off += sz
+    images = pkg.synth.synthetic_images(n, img, seed=seed)
+    ref = binding.Reference(img)
+    # silence the reference's per-call printf noise (ViT_seq.c:173-181,516)
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    saved = os.dup(1)
+    os.dup2(devnull, 1)
+    try:
+        t0 = time.perf_counter()
+        probs = ref.forward(images, blobs)
+        dt = time.perf_counter() - t0
+    finally:
+        os.dup2(saved, 1)
+        os.close(devnull)
+        os.close(saved)
+    return dt, int(probs.argmax(1)[0])
+
+
+_BLOB_FILE = {}
+
+
+def _shared_blob_file(img):
+    if img not in _BLOB_FILE:
+        import __graft_entry__ as g
+        pkg = g.load_package()
+        blobs = model_blobs(pkg, img)
+        d = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else tempfile.gettempdir()
+        path = os.path.join(d, f"vitb200_blobs_{os.getpid()}_{img}.f32")
+        with open(path, "wb") as f:
+            for b in blobs:
+                np.ascontiguousarray(b, np.float32).tofile(f)
+        import atexit
+        atexit.register(lambda: os.path.exists(path) and os.unlink(path))
+        _BLOB_FILE[img] = (path, [int(b.size) for b in blobs])
+    return _BLOB_FILE[img]
+
+
+def cpu_reference_step(procs: int, images_per_proc: int = 1, img: int = IMG):
+    """P independent processes, each the reference's ViT_seq on its own image slice
+    (BASELINE.md section 4.4).  Returns (seconds of the slowest worker, images)."""
+    import multiprocessing as mp
+    path, sizes = _shared_blob_file(img)
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(procs) as pool:
+        res = pool.map(_ref_worker, [(1000 + i, images_per_proc, img, path, sizes) for i in range(procs)])
+    return max(r[0] for r in res), procs * images_per_proc
+
+
+def cpu_port_step(images: int, img: int = IMG):
+    """fallback when oracle/_ref is absent: the OpenMP oracle port on all host threads"""
+    from oracle import binding
+    import __graft_entry__ as g
+    pkg = g.load_package()
+    o = binding.Oracle()
+    blobs = model_blobs(pkg, img)
+    x = pkg.synth.synthetic_images(images, img, seed=1000)
+    t0 = time.perf_counter()
+    o.forward(x, blobs, want_logits=False)
+    return time.perf_counter() - t0, images, o.threads()
+
+
+def host_cores() -> int:
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def run_reference_arm(args, dist: Dist):
+    """--impl reference: the reference's own CPU implementation of the path, all host cores."""
+    if dist.rank != 0:
+        return
+    from oracle import binding
+    cores = host_cores()
+    have_ref = binding.Reference.available(IMG)
+    total_steps = args.steps + args.warmup
+    # ViT_seq needs ~12-15 s per image per core; keep the whole run within a few minutes
+    use_ref = have_ref and total_steps * 15.0 <= 300.0
+    times, images = [], 0
+    if use_ref:
+        procs = cores
+        for s in range(total_steps):
+            dt, n = cpu_reference_step(procs)
+            if s >= args.warmup:
+                times.append(dt)
+                images += n
+        kind, sample = "reference", f"{procs} processes x 1 image of ViT_seq (oracle/_ref, gcc -O2) per step"
+    else:
+        per_step = 2
+        threads = 0
+        for s in range(total_steps):
+            dt, n, threads = cpu_port_step(per_step)
+            if s >= args.warmup:
+                times.append(dt)
+                images += n
+        kind, sample = "port", f"{per_step} images per step through oracle/vit_oracle.c with {threads} OpenMP threads"
+        cores = threads
+    total = sum(times)
+    value = images / total if total > 0 else 0.0
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / max(1, len(times)),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "ViT-B/16 224x224 forward (patch-embed..softmax), CPU reference ViT_seq.c",
+                   "images_per_step": images // max(1, len(times))},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- GEMM roofline
+def time_gemms(pkg, L, M: int, reps: int = 10):
+    """CUDA-event time of the four per-layer launches of the dominant kernel
+    (vitcu_gemm_bf16) at the bench's M = BATCH*197, on the default stream."""
+    shapes = [("qkv", 2304, 768, pkg.EPI_BIAS, 1), ("out_proj", 768, 768, pkg.EPI_BIAS_RESIDUAL, 0),
+              ("fc1", 3072, 768, pkg.EPI_BIAS_GELU, 1), ("fc2", 768, 3072, pkg.EPI_BIAS_RESIDUAL, 0)]
+    rng = np.random.default_rng(0)
+    out = {}
+    ev0, ev1 = C.c_void_p(), C.c_void_p()
+    pkg.layer_check(L.vitcu_event_create(C.byref(ev0)))
+    pkg.layer_check(L.vitcu_event_create(C.byref(ev1)))
+    tot_flops = tot_ms = 0.0
+    for name, N, K, epi, out_bf16 in shapes:
+        a = pkg.DeviceBuffer.from_numpy(pkg.f32_to_bf16_bits(rng.standard_normal((M, K), dtype=np.float32)))
+        w = pkg.DeviceBuffer.from_numpy(pkg.f32_to_bf16_bits(
+            (rng.standard_normal((N, K), dtype=np.float32) * 0.02).astype(np.float32)))
+        bias = pkg.DeviceBuffer.from_numpy(np.zeros(N, np.float32))
+        c = pkg.DeviceBuffer(M * N * (2 if out_bf16 else 4))
+        pkg.layer_check(L.vitcu_memset(c.ptr, 0, c.nbytes, None))
+        d = pkg.GemmDesc()
+        d.M, d.N, d.K, d.lda, d.ldc, d.epilogue, d.out_bf16 = M, N, K, K, N, epi, out_bf16
+        d.bias = bias.ptr.value
+        d.residual = c.ptr.value if epi == pkg.EPI_BIAS_RESIDUAL else None
+        for _ in range(3):
+            pkg.layer_check(L.vitcu_gemm_bf16(a.ptr, w.ptr, c.ptr, C.byref(d), None))
+        pkg.layer_check(L.vitcu_device_sync())
+        pkg.layer_check(L.vitcu_event_record(ev0, None))
+        for _ in range(reps):
+            pkg.layer_check(L.vitcu_gemm_bf16(a.ptr, w.ptr, c.ptr, C.byref(d), None))
+        pkg.layer_check(L.vitcu_event_record(ev1, None))
+        pkg.layer_check(L.vitcu_event_sync(ev1))
+        ms = C.c_float()
+        pkg.layer_check(L.vitcu_event_elapsed_ms(ev0, ev1, C.byref(ms)))
+        per = ms.value / reps
+        flops = 2.0 * M * N * K
+        out[name] = {"ms": per, "tflops": flops / per / 1e9}
+        tot_flops += flops
+        tot_ms += per
+        for b in (a, w, bias, c):
+            b.free()
+    L.vitcu_event_destroy(ev0)
+    L.vitcu_event_destroy(ev1)
+    return out, tot_flops, tot_ms
+
+
+# --------------------------------------------------------------------------- main arm
+def run_engine_arm(args, dist: Dist):
+    import __graft_entry__ as g
+    pkg = g.load_package()
+    L = pkg.lib()
+    ndev = pkg.device_count()
+    if ndev < 1:
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    dev = dist.local_rank % ndev
+    peaks = measured_peaks()
+    blobs = model_blobs(pkg)
+
+    eng = pkg.Engine(dev, IMG, pkg.BF16, max_batch=BATCH)
+    eng.load_weights(blobs)
+    # per-rank synthetic images in pinned host memory
+    pinned = pkg.PinnedArray((BATCH, 3, IMG, IMG))
+    pinned.array[...] = pkg.synth.synthetic_images(BATCH, IMG, seed=1234 + dist.rank)
+    probs = np.empty((BATCH, 1000), np.float32)
+
+    # ---- device-resident throughput ("value") ----
+    eng.stage(pinned.array)
+    for _ in range(max(args.warmup, 3)):
+        eng.forward_resident(BATCH)
+    sampler = ClockSampler(dev)
+    dist.barrier()
+    sampler.start()
+    total_ms = eng.time_resident(BATCH, args.steps)  # K steps, one CUDA-event pair on the compute stream
+    dist.barrier()
+    clocks = sampler.stop()
+    total_ms = dist.reduce(total_ms, "max")
+    value = dist.world * BATCH * args.steps / (total_ms / 1e3)
+    kernels = eng.kernels_per_forward
+
+    # ---- end to end through the public C-ABI call, host buffers ----
+    for _ in range(max(args.warmup, 3)):
+        eng.forward_into(pinned.array, probs)
+    dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        eng.forward_into(pinned.array, probs)
+    e2e_s = time.perf_counter() - t0
+    dist.barrier()
+    e2e_s = dist.reduce(e2e_s, "max")
+    e2e = dist.world * BATCH * args.steps / e2e_s
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": dist.world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "ViT-B/16 224x224 forward (patch-embed..softmax), BF16 tcgen05 path, "
+                               "256 images per step per GPU, weights resident",
+                   "images_per_step_per_gpu": BATCH, "tokens": 197, "parallelism": f"image-sharded dp{dist.world}, "
+                   "replicated weights, no collective on the data path",
+                   "l2": "no explicit flush: per-step working set (~1 GB of activations + 154 MB of images) "
+                         "is far larger than the 126 MB L2"},
+        "clocks": clocks,
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": BATCH * 3 * IMG * IMG * 4,
+                "d2h_bytes_per_step": BATCH * 1000 * 4, "api": "vitb200_forward (pinned host images in, probabilities out)"},
+        "gpu_launches": kernels * args.steps,
+        "path_tflops": value / dist.world * GFLOP_PER_IMAGE_224 / 1e3,
+        "path_frac_of_sustained_peak": value / dist.world * GFLOP_PER_IMAGE_224 / 1e3 / peaks["bf16_sustained"],
+    }
+
+    if dist.rank == 0:
+        # ---- roofline of the dominant kernel ----
+        try:
+            per, flops, ms = time_gemms(pkg, L, BATCH * 197)
+            achieved = flops / ms / 1e9
+            line["roofline"] = {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
+                                "frac": achieved / peaks["bf16_burst"], "traffic": None,
+                                "kernel": "gemm_bf16_tc_kernel (qkv + out_proj + fc1 + fc2 launches of one layer, M=50432)",
+                                "per_launch": per, "peak_source": peaks["source"] + ", burst figure (kernel timed alone)"}
+        except Exception as ex:  # keep the headline even if the side measurement fails
+            line["roofline"] = {"error": str(ex)}
+    eng.close()
+
+    if dist.rank == 0 and dist.world == 1:
+        # ---- batch-1 latency (BASELINE config 2: FP32; BF16 beside it) ----
+        lat = {}
+        one = pkg.PinnedArray((1, 3, IMG, IMG))
+        one.array[...] = pinned.array[:1]
+        p1 = np.empty((1, 1000), np.float32)
+        for prec, name in ((pkg.FP32, "fp32"), (pkg.BF16, "bf16")):
+            with pkg.Engine(dev, IMG, prec, max_batch=1) as e1:
+                e1.load_weights(blobs)
+                e1.stage(one.array)
+                for _ in range(5):
+                    e1.forward_resident(1)
+                res = sorted(e1.forward_resident(1) for _ in range(50))
+                for _ in range(3):
+                    e1.forward_into(one.array, p1)
+                ee = []
+                for _ in range(50):
+                    t0 = time.perf_counter()
+                    e1.forward_into(one.array, p1)
+                    ee.append(1e3 * (time.perf_counter() - t0))
+                lat[name] = {"p50_ms_resident": res[len(res) // 2], "p50_ms_e2e": sorted(ee)[len(ee) // 2]}
+        line["latency_batch1"] = lat
+        one.free()
+
+        # ---- CPU baseline: the reference's own ViT_seq.c on the host cores, bounded sample ----
+        try:
+            from oracle import binding
+            cores = host_cores()
+            if binding.Reference.available(IMG):
+                dt, n = cpu_reference_step(cores)
+                line["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "reference",
+                                        "sample": f"{cores} processes x 1 image of ViT_seq (oracle/_ref, gcc -O2), "
+                                                  f"{dt:.1f} s wall"}
+            else:
+                dt, n, threads = cpu_port_step(4)
+                line["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": threads, "kind": "port",
+                                        "sample": f"4 images through oracle/vit_oracle.c, {dt:.1f} s wall"}
+        except Exception as ex:
+            line["cpu_baseline"] = {"error": str(ex)}
+    pinned.free()
+    if dist.rank == 0:
+        print(json.dumps(line), flush=True)
+
+
+def run_dist_selftest(args, dist: Dist):
+    """CPU-only check of the multi-rank plumbing (tests/test_bench_dist.py, gloo, world_size 2)"""
+    lo, hi = shard_range(4096, dist.rank, dist.world)
+    fake_ms = 10.0 * (dist.rank + 1)
+    dist.barrier()
+    mx = dist.reduce(fake_ms, "max")
+    units = dist.reduce(float(hi - lo), "sum")
+    if dist.rank == 0:
+        print(json.dumps({"selftest": True, "n_gpus": dist.world, "max_ms": mx, "units": units,
+                          "value": units / (mx / 1e3)}), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--selftest-dist", action="store_true", help=argparse.SUPPRESS)
+    args = ap.parse_args()
+    if args.selftest_dist:
+        dist = Dist(backend="gloo")
+        run_dist_selftest(args, dist)
+        dist.close()
+        return
+    if args.impl == "reference":
+        rank, _, _ = env_rank()
+        if rank != 0:
+            return  # other ranks exit 0 without work
+        dist = Dist.__new__(Dist)
+        dist.rank, dist.local_rank, dist.world, dist.on = 0, 0, 1, False
+        run_reference_arm(args, dist)
+        return
+    dist = Dist()
+    try:
+        run_engine_arm(args, dist)
+    finally:
+        dist.close()
+
+
+if __name__ == "__main__":
+    main()

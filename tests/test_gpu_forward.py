@@ -1,0 +1,221 @@
+"""GPU parity tests of the whole path, through the reference-facing C-ABI
+(ViT_opencl and the engine API of include/vit_b200.h), against the CPU oracle
+and the reference-generated golden vectors.
+
+Stated tolerances (BASELINE.json north_star):
+  FP32 path : max|logit - ref| <= 1e-4 * max|ref logit|
+  BF16 path : max|logit - ref| <= 2e-2 (absolute) and identical top-1 on every image
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+GOLD = np.load(os.path.join(HERE, "golden", "reference_vectors.npz"))
+
+FP32_REL = 1e-4
+BF16_ABS = 2e-2
+
+
+@pytest.fixture(scope="module")
+def case224(pkg, oracle, blobs224):
+    """5 images (a ragged batch for max_batch=2/4) and their oracle outputs incl. stage dump"""
+    imgs = pkg.synth.synthetic_images(5, 224, seed=1234)
+    ref = oracle.forward(imgs, blobs224, want_stages=True)
+    return imgs, ref
+
+
+def test_fp32_engine_matches_oracle(pkg, lib, blobs224, case224):
+    imgs, ref = case224
+    with pkg.Engine(0, 224, pkg.FP32, max_batch=2) as eng:
+        eng.load_weights(blobs224)
+        probs, logits = eng.forward(imgs, want_logits=True)  # chunks of 2,2,1
+    scale = np.abs(ref["logits"]).max()
+    assert np.abs(logits - ref["logits"]).max() <= FP32_REL * scale
+    assert np.abs(probs - ref["probs"]).max() <= 1e-6
+    assert np.array_equal(probs.argmax(1), ref["probs"].argmax(1))
+
+
+def test_fp32_stage_by_stage(pkg, lib, blobs224, case224):
+    """embedding and encoder outputs of image 0 against the oracle's stage dump"""
+    imgs, ref = case224
+    with pkg.Engine(0, 224, pkg.FP32, max_batch=1) as eng:
+        eng.load_weights(blobs224)
+        eng.stage(imgs[:1])
+        for layer in (0, 1, 2, 6, 12):
+            eng.stop_after_layer(layer)
+            eng.forward_resident(1)
+            x = eng.read_tokens(1)[0]
+            want = ref["stages"][layer]
+            err = np.abs(x - want).max() / np.abs(want).max()
+            assert err <= 5e-5, f"stage {layer}: rel err {err}"
+
+
+def test_bf16_engine_matches_oracle(pkg, lib, blobs224, case224):
+    imgs, ref = case224
+    with pkg.Engine(0, 224, pkg.BF16, max_batch=4) as eng:
+        eng.load_weights(blobs224)
+        probs, logits = eng.forward(imgs, want_logits=True)
+        assert eng.kernels_per_forward == 90
+    err = np.abs(logits - ref["logits"]).max()
+    assert err <= BF16_ABS, f"bf16 max|dlogit| = {err}"
+    assert np.array_equal(logits.argmax(1), ref["logits"].argmax(1))
+    np.testing.assert_allclose(probs.sum(1), 1.0, atol=1e-5)
+
+
+def test_bf16_stage_by_stage(pkg, lib, blobs224, case224):
+    imgs, ref = case224
+    with pkg.Engine(0, 224, pkg.BF16, max_batch=1) as eng:
+        eng.load_weights(blobs224)
+        eng.stage(imgs[:1])
+        for layer in (0, 1, 12):
+            eng.stop_after_layer(layer)
+            eng.forward_resident(1)
+            x = eng.read_tokens(1)[0]
+            want = ref["stages"][layer]
+            err = np.abs(x - want).max() / np.abs(want).max()
+            assert err <= 2e-2, f"stage {layer}: rel err {err}"
+
+
+def test_vit_opencl_drop_in(pkg, lib, blobs224, case224, monkeypatch):
+    """the reference's calling convention (Main.c:54): ImageData[], Network[152], float** rows"""
+    imgs, ref = case224
+    monkeypatch.setenv("VITB200_PRECISION", "fp32")
+    probs = pkg.vit_opencl(imgs[:3], blobs224)
+    # comparator.c:74-86 semantics: same label, |dprob| <= 0.01 -- and far tighter here
+    assert np.array_equal(probs.argmax(1), ref["probs"][:3].argmax(1))
+    assert np.abs(probs - ref["probs"][:3]).max() <= 1e-6
+    monkeypatch.setenv("VITB200_PRECISION", "bf16")
+    monkeypatch.setenv("VITB200_BATCH", "2")
+    probs16 = pkg.vit_opencl(imgs[:3], blobs224)
+    assert np.array_equal(probs16.argmax(1), ref["probs"][:3].argmax(1))
+    assert np.abs(probs16 - ref["probs"][:3]).max() <= 0.01
+
+
+def test_forward_structs_equals_contiguous(pkg, lib, blobs224, case224):
+    imgs, _ = case224
+    with pkg.Engine(0, 224, pkg.FP32, max_batch=4) as eng:
+        eng.load_weights(blobs224)
+        a = eng.forward(imgs)
+        b = eng.forward_structs(imgs)
+    assert np.array_equal(a, b)
+
+
+def test_golden_reference_vectors(pkg, lib, synth_blobs224):
+    """probabilities the reference's own ViT_seq.c produced (tests/golden/make_golden.py)"""
+    imgs = pkg.synth.synthetic_images(2, 224, seed=1234)
+    with pkg.Engine(0, 224, pkg.FP32, max_batch=2) as eng:
+        eng.load_weights(synth_blobs224)
+        probs = eng.forward(imgs)
+    want = GOLD["synth_probs"]
+    assert np.abs(probs - want).max() <= 1e-4 * want.max()
+    assert np.array_equal(probs.argmax(1), want.argmax(1))
+
+
+def test_golden_bundled_image(pkg, lib, ref_dir):
+    net, img_path = os.path.join(ref_dir, "Network"), os.path.join(ref_dir, "Data", "input-1.bin")
+    if not (os.path.isdir(net) and os.path.exists(img_path)):
+        pytest.skip("bundled reference data (oracle/_ref) not present on this box")
+    blobs = pkg.synth.model_blobs(net, 224, seed=0)
+    img = pkg.synth.load_image_file(img_path)
+    want = GOLD["bundled_input1_probs"]
+    for precision, tol in ((pkg.FP32, 1e-4 * want.max()), (pkg.BF16, 0.01)):
+        with pkg.Engine(0, 224, precision, max_batch=1) as eng:
+            eng.load_weights(blobs)
+            probs = eng.forward(img)
+        assert int(probs.argmax()) == 606
+        assert np.abs(probs - want).max() <= tol
+
+
+def test_384_matches_reference(pkg, lib):
+    """577 tokens: beyond what the reference's OpenCL attention could run (256-key cap)"""
+    blobs = pkg.synth.model_blobs(None, 384, seed=7)
+    imgs = pkg.synth.synthetic_images(1, 384, seed=4321)
+    want = GOLD["synth384_probs"]
+    with pkg.Engine(0, 384, pkg.FP32, max_batch=1) as eng:
+        eng.load_weights(blobs)
+        probs = eng.forward(imgs)
+    assert np.abs(probs - want).max() <= 1e-4 * want.max()
+    assert np.array_equal(probs.argmax(1), want.argmax(1))
+    with pkg.Engine(0, 384, pkg.BF16, max_batch=1) as eng:
+        eng.load_weights(blobs)
+        probs16 = eng.forward(imgs)
+    assert np.abs(probs16 - want).max() <= 0.01
+
+
+def test_edge_cases(pkg, lib, blobs224):
+    with pkg.Engine(0, 224, pkg.FP32, max_batch=2) as eng:
+        with pytest.raises(pkg.VitError):  # weights not loaded
+            eng.forward(np.zeros((1, 3, 224, 224), np.float32))
+        holed = list(blobs224)
+        holed[6] = None
+        with pytest.raises(pkg.VitError, match="blob 6 is missing"):
+            eng.load_weights(holed)
+        bad = list(blobs224)
+        bad[3] = bad[3][:-768]
+        with pytest.raises(pkg.VitError, match="blob 3"):
+            eng.load_weights(bad)
+        eng.load_weights(blobs224)
+        assert eng.forward(np.zeros((0, 3, 224, 224), np.float32)).shape == (0, 1000)
+
+
+def test_full_batch_properties_bf16(pkg, lib, blobs224):
+    """BASELINE config 3 size (batch 256): size-independent properties instead of the 50-minute oracle run"""
+    n = 256
+    imgs = pkg.synth.synthetic_images(n, 224, seed=77)
+    with pkg.Engine(0, 224, pkg.BF16, max_batch=n) as eng:
+        eng.load_weights(blobs224)
+        p1 = eng.forward(imgs)
+        p2 = eng.forward(imgs)          # second call replays the captured CUDA graph
+        perm = np.random.default_rng(0).permutation(n)
+        p3 = eng.forward(np.ascontiguousarray(imgs[perm]))
+        assert lib.vitcu_watchdog_check() == 0
+    assert np.isfinite(p1).all()
+    np.testing.assert_allclose(p1.sum(1), 1.0, atol=1e-5)
+    assert np.array_equal(p1, p2)                       # deterministic, graph == eager
+    assert np.array_equal(p3, p1[perm])                 # images are independent of their batch position
+    # the same images through a small-batch engine: same math, other tiling
+    with pkg.Engine(0, 224, pkg.BF16, max_batch=8) as eng:
+        eng.load_weights(blobs224)
+        p4 = eng.forward(imgs[:16])
+    assert np.abs(p4 - p1[:16]).max() <= 1e-4
+    assert np.array_equal(p4.argmax(1), p1[:16].argmax(1))
+
+
+def test_main_c_drop_in(pkg, lib, oracle, blobs224, ref_dir, tmp_path):
+    """The reference's UNMODIFIED Main.c + Network.c + comparator.c (objects built by
+    oracle/Makefile) linked against libvit_b200.so instead of ViT_opencl.c: the
+    reference's own end-to-end check must print "good"."""
+    objs = [os.path.join(ref_dir, f) for f in ("Main.o", "comparator.o", "Network.o")]
+    if not all(os.path.exists(o) for o in objs):
+        pytest.skip("oracle/_ref objects not present on this box")
+    exe = tmp_path / "main_b200"
+    subprocess.run(["gcc", "-o", str(exe), *objs, "-L" + os.path.dirname(pkg.LIB_PATH), "-lvit_b200",
+                    "-Wl,-rpath," + os.path.dirname(pkg.LIB_PATH), "-lm"], check=True)
+    (tmp_path / "Data").mkdir()
+    (tmp_path / "Network").mkdir()
+    for i, b in enumerate(blobs224):
+        b.tofile(tmp_path / "Network" / f"Weight_{i}_blob.bin")
+    # comparator.c insists on 100 lines (IMAGE_COUNT): 4 distinct images, repeated
+    base = pkg.synth.synthetic_images(4, 224, seed=31)
+    imgs = np.ascontiguousarray(base[np.arange(100) % 4])
+    pkg.synth.write_image_file(str(tmp_path / "Data" / "input-100.bin"), imgs)
+    ref = oracle.forward(base, blobs224)["probs"]
+    # answer file in Main.c's format; Main.c:59-69 carries pred_idx over between images
+    pred = 0
+    with open(tmp_path / "Data" / "answer_result.txt", "w") as f:
+        for i in range(100):
+            row = ref[i % 4]
+            for j in range(1, 1000):
+                if row[j] > row[pred]:
+                    pred = j
+            f.write("[%d] label: %d / prob: %.6f\n" % (i, pred, row[pred]))
+    env = dict(os.environ, VITB200_PRECISION="fp32")
+    out = subprocess.run([str(exe)], cwd=tmp_path, env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "good" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]

@@ -1,0 +1,267 @@
+"""GPU parity tests, kernel by kernel, through the C-ABI device layer
+(include/vit_cuda_layer.h) against the CPU oracle's stage functions.
+
+Tolerances: FP32 kernels must agree with the oracle to ~1e-5 relative (only the
+summation order differs); BF16 tensor-core kernels are compared (a) tightly
+against an exact float64 product of the SAME bf16-rounded operands, which
+isolates kernel bugs from rounding, and (b) loosely against the fp32 oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(pkg, a):
+    return pkg.DeviceBuffer.from_numpy(np.ascontiguousarray(a))
+
+
+def _gemm_desc(pkg, M, N, K, epi, bias, residual=None, pos=None, patches=0, tokens=0, out_bf16=0, lda=None, ldc=None):
+    d = pkg.GemmDesc()
+    d.M, d.N, d.K = M, N, K
+    d.lda = lda or K
+    d.ldc = ldc or N
+    d.epilogue = epi
+    d.bias = bias.ptr.value
+    d.residual = residual.ptr.value if residual is not None else None
+    d.pos = pos.ptr.value if pos is not None else None
+    d.patches, d.tokens, d.out_bf16 = patches, tokens, out_bf16
+    return d
+
+
+def _rel_err(a, b):
+    return float(np.abs(a.astype(np.float64) - b.astype(np.float64)).max() / max(1e-30, np.abs(b).max()))
+
+
+# ---------------------------------------------------------------- LayerNorm
+@pytest.mark.parametrize("rows", [1, 197, 1000])
+def test_layernorm_fp32(pkg, lib, oracle, rows):
+    rng = np.random.default_rng(rows)
+    x = (rng.standard_normal((rows, 768), dtype=np.float32) * 3 + 1).astype(np.float32)
+    g = (1 + 0.1 * rng.standard_normal(768, dtype=np.float32)).astype(np.float32)
+    b = (0.1 * rng.standard_normal(768, dtype=np.float32)).astype(np.float32)
+    dx, dg, db = _dev(pkg, x), _dev(pkg, g), _dev(pkg, b)
+    dy = pkg.DeviceBuffer(x.nbytes)
+    pkg.layer_check(lib.vitcu_layernorm(dx.ptr, 768, dy.ptr, 0, dg.ptr, db.ptr, rows, None))
+    y = dy.to_numpy(np.float32, x.shape)
+    ref = oracle.layer_norm(x, g, b)
+    assert np.abs(y - ref).max() <= 2e-5
+
+
+def test_layernorm_bf16_and_strided(pkg, lib, oracle):
+    rng = np.random.default_rng(5)
+    T = 197
+    x = rng.standard_normal((3 * T, 768), dtype=np.float32)
+    g = np.ones(768, np.float32)
+    b = np.zeros(768, np.float32)
+    dx, dg, db = _dev(pkg, x), _dev(pkg, g), _dev(pkg, b)
+    # bf16 output, every row
+    dy = pkg.DeviceBuffer(x.size * 2)
+    pkg.layer_check(lib.vitcu_layernorm(dx.ptr, 768, dy.ptr, 1, dg.ptr, db.ptr, 3 * T, None))
+    y = pkg.bf16_bits_to_f32(dy.to_numpy(np.uint16, x.shape))
+    ref = oracle.layer_norm(x, g, b)
+    assert np.abs(y - ref).max() <= 2.0 ** -8 * np.abs(ref).max() + 1e-5
+    # class-token rows only (row stride T*768), fp32 output
+    dc = pkg.DeviceBuffer(3 * 768 * 4)
+    pkg.layer_check(lib.vitcu_layernorm(dx.ptr, T * 768, dc.ptr, 0, dg.ptr, db.ptr, 3, None))
+    yc = dc.to_numpy(np.float32, (3, 768))
+    assert np.abs(yc - ref[::T]).max() <= 2e-5
+
+
+# ---------------------------------------------------------------- FP32 GEMM
+@pytest.mark.parametrize("M,N,K,gelu", [(197, 2304, 768, False), (394, 3072, 768, True), (5, 1000, 768, False),
+                                        (130, 768, 3072, False), (19000, 768, 768, False)])
+def test_sgemm_bias_gelu(pkg, lib, oracle, M, N, K, gelu):
+    rng = np.random.default_rng(M + N)
+    x = rng.standard_normal((M, K), dtype=np.float32)
+    w = (rng.standard_normal((N, K), dtype=np.float32) * 0.03).astype(np.float32)
+    b = rng.standard_normal(N, dtype=np.float32)
+    dx, dw, db = _dev(pkg, x), _dev(pkg, w), _dev(pkg, b)
+    dy = pkg.DeviceBuffer(M * N * 4)
+    d = _gemm_desc(pkg, M, N, K, pkg.EPI_BIAS_GELU if gelu else pkg.EPI_BIAS, db)
+    pkg.layer_check(lib.vitcu_sgemm(dx.ptr, dw.ptr, dy.ptr, C.byref(d), None))
+    y = dy.to_numpy(np.float32, (M, N))
+    if M <= 400:
+        ref = oracle.linear(x, w, b, gelu=gelu)
+    else:  # too slow for the sequential oracle: float64 product (same math, exact order-free)
+        ref = (x.astype(np.float64) @ w.astype(np.float64).T + b).astype(np.float32)
+    assert _rel_err(y, ref) <= 2e-5
+
+
+def test_sgemm_residual_in_place(pkg, lib, oracle):
+    rng = np.random.default_rng(17)
+    M, N, K = 197, 768, 768
+    x = rng.standard_normal((M, K), dtype=np.float32)
+    w = (rng.standard_normal((N, K), dtype=np.float32) * 0.03).astype(np.float32)
+    b = rng.standard_normal(N, dtype=np.float32)
+    r = rng.standard_normal((M, N), dtype=np.float32)
+    dx, dw, db, dr = _dev(pkg, x), _dev(pkg, w), _dev(pkg, b), _dev(pkg, r)
+    d = _gemm_desc(pkg, M, N, K, pkg.EPI_BIAS_RESIDUAL, db, residual=dr)
+    pkg.layer_check(lib.vitcu_sgemm(dx.ptr, dw.ptr, dr.ptr, C.byref(d), None))  # out aliases residual
+    y = dr.to_numpy(np.float32, (M, N))
+    ref = r + oracle.linear(x, w, b)  # R/ViT_seq.c:348-351
+    assert _rel_err(y, ref) <= 2e-5
+
+
+# ---------------------------------------------------------------- patch embedding
+@pytest.mark.parametrize("img,batch", [(224, 3), (384, 1)])
+def test_patch_embed_fp32(pkg, lib, oracle, img, batch):
+    rng = np.random.default_rng(img)
+    side = img // 16
+    P, T = side * side, side * side + 1
+    images = rng.standard_normal((batch, 3, img, img), dtype=np.float32)
+    cls = rng.standard_normal(768, dtype=np.float32)
+    cw = (rng.standard_normal((768, 768), dtype=np.float32) * 0.03).astype(np.float32)
+    cb = rng.standard_normal(768, dtype=np.float32)
+    pos = rng.standard_normal((T, 768), dtype=np.float32)
+    di, dcls, dcw, dcb, dpos = (_dev(pkg, a) for a in (images, cls, cw, cb, pos))
+    dpat = pkg.DeviceBuffer(batch * P * 768 * 4)
+    dx = pkg.DeviceBuffer(batch * T * 768 * 4)
+    pkg.layer_check(lib.vitcu_patch_gather(di.ptr, dpat.ptr, batch, img, 0, None))
+    d = _gemm_desc(pkg, batch * P, 768, 768, pkg.EPI_PATCH_EMBED, dcb, pos=dpos, patches=P, tokens=T)
+    pkg.layer_check(lib.vitcu_sgemm(dpat.ptr, dcw.ptr, dx.ptr, C.byref(d), None))
+    pkg.layer_check(lib.vitcu_cls_rows(dx.ptr, dcls.ptr, dpos.ptr, batch, T, None))
+    x = dx.to_numpy(np.float32, (batch, T, 768))
+    for i in range(batch):
+        ref = oracle.patch_embed(images[i], cls, cw.reshape(768, 3, 16, 16), cb, pos)
+        assert _rel_err(x[i], ref) <= 2e-5
+    # the gather itself is pure data movement: bit-exact against a numpy im2col
+    pat = dpat.to_numpy(np.float32, (batch, P, 768))
+    im2col = images.reshape(batch, 3, side, 16, side, 16).transpose(0, 2, 4, 1, 3, 5).reshape(batch, P, 768)
+    assert np.array_equal(pat, im2col)
+
+
+# ---------------------------------------------------------------- attention
+@pytest.mark.parametrize("T,batch,bf16", [(197, 2, False), (577, 1, False), (197, 2, True), (577, 1, True), (50, 1, False)])
+def test_attention_simt(pkg, lib, oracle, T, batch, bf16):
+    rng = np.random.default_rng(T + batch)
+    qkv = (rng.standard_normal((batch, T, 2304), dtype=np.float32) * 1.5).astype(np.float32)
+    if bf16:
+        bits = pkg.f32_to_bf16_bits(qkv)
+        qkv = pkg.bf16_bits_to_f32(bits).reshape(batch, T, 2304)
+        dq = _dev(pkg, bits.reshape(batch, T, 2304))
+        do = pkg.DeviceBuffer(batch * T * 768 * 2)
+    else:
+        dq = _dev(pkg, qkv)
+        do = pkg.DeviceBuffer(batch * T * 768 * 4)
+    pkg.layer_check(lib.vitcu_attention(dq.ptr, do.ptr, batch, T, int(bf16), None))
+    if bf16:
+        out = pkg.bf16_bits_to_f32(do.to_numpy(np.uint16, (batch, T, 768)))
+    else:
+        out = do.to_numpy(np.float32, (batch, T, 768))
+    for i in range(batch):
+        ref = oracle.attention_core(qkv[i, :, :768], qkv[i, :, 768:1536], qkv[i, :, 1536:])
+        tol = 2.0 ** -8 * np.abs(ref).max() + 1e-4 if bf16 else 2e-5 * max(1.0, np.abs(ref).max())
+        assert np.abs(out[i] - ref).max() <= tol
+
+
+# ---------------------------------------------------------------- softmax
+def test_softmax_rows(pkg, lib, oracle):
+    rng = np.random.default_rng(3)
+    l = (rng.standard_normal((7, 1000), dtype=np.float32) * 4).astype(np.float32)
+    dl = _dev(pkg, l)
+    dp = pkg.DeviceBuffer(l.nbytes)
+    pkg.layer_check(lib.vitcu_softmax_rows(dl.ptr, dp.ptr, 7, 1000, None))
+    p = dp.to_numpy(np.float32, l.shape)
+    for i in range(7):
+        assert np.abs(p[i] - oracle.softmax(l[i])).max() <= 1e-6
+    np.testing.assert_allclose(p.sum(1), 1.0, atol=1e-5)
+
+
+# ---------------------------------------------------------------- weight packing
+def test_f32_to_bf16_bit_exact(pkg, lib):
+    rng = np.random.default_rng(9)
+    x = rng.standard_normal(100003, dtype=np.float32)
+    dx = _dev(pkg, x)
+    dy = pkg.DeviceBuffer(x.size * 2)
+    pkg.layer_check(lib.vitcu_f32_to_bf16(dx.ptr, dy.ptr, x.size, None))
+    assert np.array_equal(dy.to_numpy(np.uint16, x.shape), pkg.f32_to_bf16_bits(x))
+
+
+# ---------------------------------------------------------------- tcgen05 GEMM
+def _bf16_gemm_case(pkg, lib, M, N, K, epi, seed, P=0, T=0):
+    rng = np.random.default_rng(seed)
+    a_bits = pkg.f32_to_bf16_bits(rng.standard_normal((M, K), dtype=np.float32))
+    w_bits = pkg.f32_to_bf16_bits((rng.standard_normal((N, K), dtype=np.float32) * 0.03).astype(np.float32))
+    a, w = pkg.bf16_bits_to_f32(a_bits), pkg.bf16_bits_to_f32(w_bits)
+    b = rng.standard_normal(N, dtype=np.float32)
+    da, dw, db = _dev(pkg, a_bits), _dev(pkg, w_bits), _dev(pkg, b)
+    exact = a.astype(np.float64) @ w.astype(np.float64).T + b
+    if epi == pkg.EPI_BIAS_RESIDUAL:
+        r = rng.standard_normal((M, N), dtype=np.float32)
+        dr = _dev(pkg, r)
+        d = _gemm_desc(pkg, M, N, K, epi, db, residual=dr)
+        pkg.layer_check(lib.vitcu_gemm_bf16(da.ptr, dw.ptr, dr.ptr, C.byref(d), None))
+        y = dr.to_numpy(np.float32, (M, N))
+        ref = exact + r
+        tol = 1e-4 * np.abs(ref).max()
+    elif epi == pkg.EPI_PATCH_EMBED:
+        nimg = M // P
+        pos = rng.standard_normal((T, N), dtype=np.float32)
+        dpos = _dev(pkg, pos)
+        dout = pkg.DeviceBuffer(nimg * T * N * 4)
+        pkg.layer_check(lib.vitcu_memset(dout.ptr, 0, nimg * T * N * 4, None))
+        d = _gemm_desc(pkg, M, N, K, epi, db, pos=dpos, patches=P, tokens=T)
+        pkg.layer_check(lib.vitcu_gemm_bf16(da.ptr, dw.ptr, dout.ptr, C.byref(d), None))
+        y = dout.to_numpy(np.float32, (nimg, T, N))
+        assert np.all(y[:, 0] == 0)  # class-token rows are left to vitcu_cls_rows
+        y = y[:, 1:].reshape(M, N)
+        ref = exact + np.tile(pos[1:], (nimg, 1))
+        tol = 1e-4 * np.abs(ref).max()
+    else:
+        dy = pkg.DeviceBuffer(M * N * 2)
+        d = _gemm_desc(pkg, M, N, K, epi, db, out_bf16=1)
+        pkg.layer_check(lib.vitcu_gemm_bf16(da.ptr, dw.ptr, dy.ptr, C.byref(d), None))
+        y = pkg.bf16_bits_to_f32(dy.to_numpy(np.uint16, (M, N)))
+        ref = exact
+        if epi == pkg.EPI_BIAS_GELU:
+            from scipy.special import erf
+            ref = 0.5 * exact * (1.0 + erf(exact / np.sqrt(2.0)))
+        tol = 2.0 ** -8 * np.abs(ref).max() + 1e-4  # output rounding to bf16
+    assert lib.vitcu_watchdog_check() == 0
+    err = np.abs(y - ref)
+    assert err.max() <= tol, f"max err {err.max()} at {np.unravel_index(err.argmax(), err.shape)} (tol {tol})"
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 256, 128), (197, 768, 768), (300, 2304, 768),
+                                   (1000, 768, 3072)])
+def test_gemm_bf16_narrow_tiles(pkg, lib, M, N, K):
+    """BN=128 configuration (small M), incl. ragged M and a single k-block"""
+    _bf16_gemm_case(pkg, lib, M, N, K, pkg.EPI_BIAS, seed=M + K)
+
+
+@pytest.mark.parametrize("M,N,K,epi", [(6304, 2304, 768, 0), (6304, 3072, 768, 1), (6400, 768, 3072, 2),
+                                       (12608, 768, 768, 2), (19001, 2304, 768, 0)])
+def test_gemm_bf16_wide_tiles(pkg, lib, M, N, K, epi):
+    """BN=256 persistent configuration: >1 tile per CTA, all fused epilogues, ragged M"""
+    _bf16_gemm_case(pkg, lib, M, N, K, epi, seed=M + N + epi)
+
+
+def test_gemm_bf16_patch_embed_epilogue(pkg, lib):
+    _bf16_gemm_case(pkg, lib, 32 * 196, 768, 768, pkg.EPI_PATCH_EMBED, seed=1, P=196, T=197)
+
+
+def test_gemm_bf16_matches_oracle_linear(pkg, lib, oracle):
+    """against the fp32 oracle (R/ViT_seq.c:295-309): error is the bf16 rounding of the operands"""
+    rng = np.random.default_rng(21)
+    M, N, K = 197, 768, 768
+    x = rng.standard_normal((M, K), dtype=np.float32)
+    w = (rng.standard_normal((N, K), dtype=np.float32) * 0.03).astype(np.float32)
+    b = rng.standard_normal(N, dtype=np.float32)
+    r = rng.standard_normal((M, N), dtype=np.float32)
+    da, dw, db, dr = _dev(pkg, pkg.f32_to_bf16_bits(x)), _dev(pkg, pkg.f32_to_bf16_bits(w)), _dev(pkg, b), _dev(pkg, r)
+    d = _gemm_desc(pkg, M, N, K, pkg.EPI_BIAS_RESIDUAL, db, residual=dr)
+    pkg.layer_check(lib.vitcu_gemm_bf16(da.ptr, dw.ptr, dr.ptr, C.byref(d), None))
+    y = dr.to_numpy(np.float32, (M, N))
+    ref = r + oracle.linear(x, w, b)
+    assert np.abs(y - ref).max() <= 2e-2
+
+
+def test_gemm_rejects_bad_shapes(pkg, lib):
+    b = pkg.DeviceBuffer(4096)
+    d = _gemm_desc(pkg, 128, 128, 100, 0, b)  # K not a multiple of 64
+    assert lib.vitcu_gemm_bf16(b.ptr, b.ptr, b.ptr, C.byref(d), None) != 0
+    assert b"K % 64" in lib.vitcu_last_error()
+    d = _gemm_desc(pkg, 0, 128, 64, 0, b)  # empty
+    assert lib.vitcu_sgemm(b.ptr, b.ptr, b.ptr, C.byref(d), None) != 0
