@@ -165,7 +165,8 @@ def test_softmax_rows(pkg, lib, oracle):
     pkg.layer_check(lib.vitcu_softmax_rows(dl.ptr, dp.ptr, 7, 1000, None))
     p = dp.to_numpy(np.float32, l.shape)
     for i in range(7):
-        assert np.abs(p[i] - oracle.softmax(l[i])).max() <= 1e-6
+        ref = oracle.softmax(l[i])
+        assert np.abs(p[i] - ref).max() <= 1e-5 * ref.max() + 1e-9
     np.testing.assert_allclose(p.sum(1), 1.0, atol=1e-5)
 
 
