@@ -156,6 +156,27 @@ def test_attention_simt(pkg, lib, oracle, T, batch, bf16):
         assert np.abs(out[i] - ref).max() <= tol
 
 
+@pytest.mark.parametrize("T,batch", [(197, 3), (50, 2), (128, 1), (129, 1), (256, 2), (16, 1), (197, 40)])
+def test_attention_tensor_core(pkg, lib, oracle, T, batch):
+    """tcgen05 attention (bf16 storage, tokens <= 256): one and two query tiles, ragged key counts,
+    more work items than SMs (persistent loop, barrier phases flip)"""
+    rng = np.random.default_rng(1000 + T + batch)
+    bits = pkg.f32_to_bf16_bits((rng.standard_normal((batch, T, 2304), dtype=np.float32) * 1.5).astype(np.float32))
+    qkv = pkg.bf16_bits_to_f32(bits).reshape(batch, T, 2304)
+    dq = _dev(pkg, bits)
+    do = pkg.DeviceBuffer(batch * T * 768 * 2)
+    pkg.layer_check(lib.vitcu_memset(do.ptr, 0xFF, batch * T * 768 * 2, None))  # NaN pattern: every element must be written
+    pkg.layer_check(lib.vitcu_attention(dq.ptr, do.ptr, batch, T, 1, None))
+    assert lib.vitcu_watchdog_check() == 0
+    out = pkg.bf16_bits_to_f32(do.to_numpy(np.uint16, (batch, T, 768)))
+    assert np.isfinite(out).all()
+    for i in list(range(min(batch, 3))) + ([batch - 1] if batch > 3 else []):
+        ref = oracle.attention_core(qkv[i, :, :768], qkv[i, :, 768:1536], qkv[i, :, 1536:])
+        tol = 3 * 2.0 ** -8 * np.abs(ref).max() + 1e-3  # P and O are rounded to bf16
+        err = np.abs(out[i] - ref)
+        assert err.max() <= tol, f"image {i}: max err {err.max()} at {np.unravel_index(err.argmax(), err.shape)} tol {tol}"
+
+
 # ---------------------------------------------------------------- softmax
 def test_softmax_rows(pkg, lib, oracle):
     rng = np.random.default_rng(3)

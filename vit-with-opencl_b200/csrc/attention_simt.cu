@@ -18,6 +18,7 @@
 //   phase 4  per 64-key block: V block -> smem; 4x4 register tiles of O += P V
 //   phase 5  O -> out[(b*T + q), h*64 + d]
 #include "common.cuh"
+#include <stdlib.h>
 
 using namespace vitcu;
 
@@ -187,9 +188,18 @@ size_t attention_simt_smem(int tokens)
 
 } // namespace
 
+namespace vitcu {
+int attention_bf16_tc(const void *qkv, void *out, int batch, int tokens, cudaStream_t st); // attention_tc.cu
+}
+
 extern "C" int vitcu_attention(const void *qkv, void *out, int batch, int tokens, int is_bf16, vitcu_stream s)
 {
     VITCU_REQUIRE(qkv && out && batch > 0 && tokens > 0, "bad argument");
+    // BF16 storage and a key count that fits one TMEM accumulator: tensor-core kernel.
+    // (VITCU_ATTN_SIMT=1 forces the CUDA-core kernel, for A/B measurements.)
+    static const bool force_simt = getenv("VITCU_ATTN_SIMT") != nullptr;
+    if (is_bf16 && tokens <= 256 && !force_simt)
+        return attention_bf16_tc(qkv, out, batch, tokens, as_stream(s));
     const size_t smem = attention_simt_smem(tokens);
     VITCU_REQUIRE(smem <= 227 * 1024, "token count too large for the shared-memory score tile");
     dim3 grid((tokens + QT - 1) / QT, kHeads, batch);
