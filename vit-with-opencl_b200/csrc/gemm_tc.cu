@@ -22,6 +22,8 @@
 // multiple of 128) is handled by TMA zero-fill on load and a row predicate on
 // store.  Every mbarrier wait is watchdog-guarded (tc_common.cuh).
 #include "tc_common.cuh"
+#include <stdlib.h>
+#include <string.h>
 
 using namespace vitcu;
 using namespace vitcu::tc;
@@ -43,20 +45,34 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int kThreads = 320;
 constexpr int kEpiWarps = 8;
+constexpr int kStageLd = 36;                // floats per staged epilogue row (32 + 4 pad)
+constexpr int kStageFloats = 32 * kStageLd; // per epilogue warp
 
 template <int BN, int STAGES>
 struct SmemLayout {
     static constexpr uint32_t A_BYTES = BM * BK * 2;
     static constexpr uint32_t B_BYTES = BN * BK * 2;
     static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr uint32_t BAR_OFFSET = STAGES * STAGE_BYTES;
+    static constexpr uint32_t EPI_OFFSET = STAGES * STAGE_BYTES;              // per-warp transpose tiles
+    static constexpr uint32_t BAR_OFFSET = EPI_OFFSET + kEpiWarps * kStageFloats * 4;
     static constexpr uint32_t NUM_BARS = 2 * STAGES + 4;
     static constexpr uint32_t TOTAL = BAR_OFFSET + NUM_BARS * 8 + 16 + 1024; // + alignment slack
+    static_assert(TOTAL <= 227 * 1024, "shared memory budget");
 };
 
-// one 32-column chunk of one accumulator row -> global memory
-__device__ __forceinline__ void epilogue_chunk(const EpiParams &p, void *C, int row, int col0, const uint32_t (&acc)[32])
+// Epilogue of one 32x32 accumulator chunk (the 32 rows of this warp's TMEM
+// quadrant x 32 columns).  tcgen05.ld hands every thread one ROW (32 consecutive
+// columns); storing that straight to global memory makes each warp instruction
+// touch 32 different 128-byte lines (32 L1 wavefronts), and that LSU traffic
+// competes with the tensor core's operand reads for the L1/shared-memory data
+// pipe (profiles/r01_v4_epilogue.md: lsu wavefronts 59 % + tensor 33 % of the
+// pipe).  So the chunk is transposed through a per-warp shared-memory tile
+// ([32][36] floats, conflict-free for 128-bit accesses both ways) and leaves the
+// SM as fully coalesced 128-bit accesses: 8 lanes per row, 4 rows per instruction.
+__device__ __forceinline__ void epilogue_chunk(const EpiParams &p, void *C, float *stage, int lane, int row0, int col0,
+                                               const uint32_t (&acc)[32])
 {
+    // ---- row-per-thread part: bias (+ GELU), then into the staging tile ----
     float v[32];
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
@@ -66,46 +82,60 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams &p, void *C, int 
         v[j + 2] = __uint_as_float(acc[j + 2]) + b.z;
         v[j + 3] = __uint_as_float(acc[j + 3]) + b.w;
     }
-    size_t orow = static_cast<size_t>(row);
     if (p.epilogue == VITCU_EPI_BIAS_GELU) {
 #pragma unroll
         for (int j = 0; j < 32; j++)
             v[j] = gelu_erf_fast(v[j]);
-    } else if (p.epilogue == VITCU_EPI_BIAS_RESIDUAL) {
-        const float4 *r = reinterpret_cast<const float4 *>(p.residual + static_cast<size_t>(row) * p.ldc + col0);
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const float4 x = r[j];
-            v[4 * j + 0] += x.x;
-            v[4 * j + 1] += x.y;
-            v[4 * j + 2] += x.z;
-            v[4 * j + 3] += x.w;
-        }
-    } else if (p.epilogue == VITCU_EPI_PATCH_EMBED) {
-        const int img = row / p.patches, pi = row - img * p.patches;
-        orow = static_cast<size_t>(img) * p.tokens + 1 + pi;
-        const float4 *e = reinterpret_cast<const float4 *>(p.pos + static_cast<size_t>(1 + pi) * p.N + col0);
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const float4 x = __ldg(e + j);
-            v[4 * j + 0] += x.x;
-            v[4 * j + 1] += x.y;
-            v[4 * j + 2] += x.z;
-            v[4 * j + 3] += x.w;
-        }
     }
+    float4 *srow = reinterpret_cast<float4 *>(stage + lane * kStageLd);
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+        srow[j] = make_float4(v[4 * j + 0], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    __syncwarp();
+
+    // ---- coalesced part ----
     if (p.out_bf16) {
-        uint4 *dst = reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(C) + orow * p.ldc + col0);
+        // 4 lanes x 16 B cover the 64-byte bf16 row segment; 8 rows per instruction
+        const int rsub = lane >> 2, c8 = (lane & 3) * 8;
 #pragma unroll
-        for (int j = 0; j < 4; j++)
-            dst[j] = make_uint4(pack_bf16x2(v[8 * j + 0], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                                pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+        for (int i = 0; i < 4; i++) {
+            const int r = i * 8 + rsub, row = row0 + r;
+            const float4 x = *reinterpret_cast<const float4 *>(stage + r * kStageLd + c8);
+            const float4 y = *reinterpret_cast<const float4 *>(stage + r * kStageLd + c8 + 4);
+            if (row < p.M)
+                *reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(C) + static_cast<size_t>(row) * p.ldc + col0 + c8) =
+                    make_uint4(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w), pack_bf16x2(y.x, y.y), pack_bf16x2(y.z, y.w));
+        }
     } else {
-        float4 *dst = reinterpret_cast<float4 *>(reinterpret_cast<float *>(C) + orow * p.ldc + col0);
+        // 8 lanes x 16 B cover the 128-byte fp32 row segment; 4 rows per instruction
+        const int rsub = lane >> 3, c4 = (lane & 7) * 4;
+        float4 add[8];
+        size_t off[8];
 #pragma unroll
-        for (int j = 0; j < 8; j++)
-            dst[j] = make_float4(v[4 * j + 0], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        for (int i = 0; i < 8; i++) {
+            const int row = row0 + i * 4 + rsub;
+            add[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            off[i] = static_cast<size_t>(row) * p.ldc + col0 + c4;
+            if (row < p.M) {
+                if (p.epilogue == VITCU_EPI_BIAS_RESIDUAL) {
+                    add[i] = *reinterpret_cast<const float4 *>(p.residual + off[i]);
+                } else if (p.epilogue == VITCU_EPI_PATCH_EMBED) {
+                    const int img = row / p.patches, pi = row - img * p.patches;
+                    off[i] = (static_cast<size_t>(img) * p.tokens + 1 + pi) * p.ldc + col0 + c4;
+                    add[i] = __ldg(reinterpret_cast<const float4 *>(p.pos + static_cast<size_t>(1 + pi) * p.N + col0 + c4));
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int r = i * 4 + rsub;
+            const float4 x = *reinterpret_cast<const float4 *>(stage + r * kStageLd + c4);
+            if (row0 + r < p.M)
+                *reinterpret_cast<float4 *>(reinterpret_cast<float *>(C) + off[i]) =
+                    make_float4(x.x + add[i].x, x.y + add[i].y, x.z + add[i].z, x.w + add[i].w);
+        }
     }
+    __syncwarp(); // the staging tile is reused by the next chunk
 }
 
 template <int BN, int STAGES>
@@ -155,42 +185,49 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        // The whole warp runs the loop and one elected lane issues: with warp-uniform
+        // control flow the descriptors/addresses stay in uniform registers (a lane-0-only
+        // branch made ptxas emit ELECT + R2UR.BROADCAST chains per instruction, which made
+        // the single issuing thread the bottleneck -- profiles/r01_v4_issue_loop.md).
+        if (elect_one()) {
             prefetch_tensormap(&tmap_a);
             prefetch_tensormap(&tmap_b);
-            uint32_t stage = 0, phase = 0;
-            bool ok = true;
-            for (int tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x) {
-                const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
-                for (int kb = 0; kb < num_kb; kb++) {
-                    if (!(ok = mbar_wait(&empty_bar[stage], phase ^ 1, wd, 1)))
-                        break;
+        }
+        uint32_t stage = 0, phase = 0;
+        bool ok = true;
+        for (int tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x) {
+            const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
+            for (int kb = 0; kb < num_kb; kb++) {
+                if (!(ok = mbar_wait_warp(&empty_bar[stage], phase ^ 1, wd, 1)))
+                    break;
+                if (elect_one()) {
                     uint8_t *sa = smem + stage * L::STAGE_BYTES;
                     mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
                     tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
                     tma_load_2d(sa + L::A_BYTES, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN);
-                    if (++stage == STAGES) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
+                }
+                __syncwarp();
+                if (++stage == STAGES) {
+                    stage = 0;
+                    phase ^= 1;
                 }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            uint32_t stage = 0, phase = 0, it = 0;
-            bool ok = true;
-            for (int tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x, it++) {
-                const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-                if (!(ok = mbar_wait(&tempty_bar[acc], acc_phase ^ 1, wd, 2)))
+        uint32_t stage = 0, phase = 0, it = 0;
+        bool ok = true;
+        for (int tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x, it++) {
+            const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+            if (!(ok = mbar_wait_warp(&tempty_bar[acc], acc_phase ^ 1, wd, 2)))
+                break;
+            tcgen05_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BN;
+            for (int kb = 0; kb < num_kb; kb++) {
+                if (!(ok = mbar_wait_warp(&full_bar[stage], phase, wd, 3)))
                     break;
                 tcgen05_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int kb = 0; kb < num_kb; kb++) {
-                    if (!(ok = mbar_wait(&full_bar[stage], phase, wd, 3)))
-                        break;
-                    tcgen05_fence_after();
+                if (elect_one()) {
                     const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
                     const uint64_t a_desc = umma_desc_k_sw128(sa);
                     const uint64_t b_desc = umma_desc_k_sw128(sa + L::A_BYTES);
@@ -198,13 +235,14 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     for (int k = 0; k < BK / 16; k++) // +32 bytes per K=16 step inside the 128B swizzle row
                         umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, IDESC, (kb | k) != 0);
                     umma_commit(&empty_bar[stage]); // ring slot reusable once these MMAs retire
-                    if (++stage == STAGES) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
+                    if (kb == num_kb - 1)
+                        umma_commit(&tfull_bar[acc]); // accumulator complete
                 }
-                if (ok)
-                    umma_commit(&tfull_bar[acc]); // accumulator complete
+                __syncwarp();
+                if (++stage == STAGES) {
+                    stage = 0;
+                    phase ^= 1;
+                }
             }
         }
     } else {
@@ -220,15 +258,16 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             if (!ok)
                 break;
             tcgen05_fence_after();
-            const int row = m_blk * BM + quad * 32 + lane;
+            const int row0 = m_blk * BM + quad * 32;
+            float *stage_tile = reinterpret_cast<float *>(smem + L::EPI_OFFSET) + (warp - 2) * kStageFloats;
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + half * (BN / 2);
 #pragma unroll 1
             for (int c = 0; c < BN / 64; c++) {
                 uint32_t v[32];
                 tmem_ld_32x32b_x32(taddr + c * 32, v);
                 tmem_ld_wait();
-                if (row < p.M)
-                    epilogue_chunk(p, C, row, n_blk * BN + half * (BN / 2) + c * 32, v);
+                if (row0 < p.M) // warp-uniform
+                    epilogue_chunk(p, C, stage_tile, lane, row0, n_blk * BN + half * (BN / 2) + c * 32, v);
             }
             tcgen05_fence_before();
             __syncwarp();
@@ -243,6 +282,181 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (warp == 1) {
         tcgen05_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): two CTAs on the two SMs of a TPC own one
+// 256x256 output tile.  Each CTA stages its own 128 A rows and HALF of the W
+// tile (128 rows), so a k-block costs 32 KB of shared-memory writes + 32 KB of
+// reads per SM instead of 48 + 48 -- the 1-CTA kernel is shared-memory-port
+// bound at ~62 % tensor-pipe utilisation (profiles/r01_v1_summary.md).  The
+// leader CTA (cluster rank 0) issues tcgen05.mma.cta_group::2 with M = 256; the
+// accumulator rows of each CTA live in that CTA's TMEM, and each CTA runs its
+// own epilogue.  Barrier topology:
+//   full[s]    leader's barrier, 2 arrivals (each CTA's producer: expect_tx of its
+//              own bytes) + the TMA bytes of both CTAs
+//   empty[s]   one per CTA, released by the leader's multicast tcgen05.commit
+//   tfull[a]   one per CTA, multicast commit when the accumulator is complete
+//   tempty[a]  leader's barrier, 16 arrivals (8 epilogue warps of each CTA)
+// ---------------------------------------------------------------------------
+template <int STAGES>
+struct SmemLayout2 {
+    static constexpr uint32_t A_BYTES = BM * BK * 2;       // this CTA's 128 A rows
+    static constexpr uint32_t B_BYTES = 128 * BK * 2;      // this CTA's half of the 256-row W tile
+    static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr uint32_t EPI_OFFSET = STAGES * STAGE_BYTES;
+    static constexpr uint32_t BAR_OFFSET = EPI_OFFSET + kEpiWarps * kStageFloats * 4;
+    static constexpr uint32_t NUM_BARS = 2 * STAGES + 4;
+    static constexpr uint32_t TOTAL = BAR_OFFSET + NUM_BARS * 8 + 16 + 1024;
+    static_assert(TOTAL <= 227 * 1024, "shared memory budget");
+};
+
+template <int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, void *C,
+                     const EpiParams p, uint32_t *watchdog_flag)
+{
+    using L = SmemLayout2<STAGES>;
+    constexpr int BN = 256, BM2 = 256;
+    constexpr uint32_t TMEM_COLS = 512;
+    constexpr uint32_t IDESC = umma_idesc_bf16(BM2, BN, false, false);
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + L::BAR_OFFSET);
+    uint64_t *empty_bar = full_bar + STAGES;
+    uint64_t *tfull_bar = empty_bar + STAGES;
+    uint64_t *tempty_bar = tfull_bar + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty_bar + 2);
+    volatile uint32_t *cta_abort = tmem_slot + 1;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < STAGES; i++) {
+            mbar_init(&full_bar[i], 2);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; i++) {
+            mbar_init(&tfull_bar[i], 1);
+            mbar_init(&tempty_bar[i], 2 * kEpiWarps);
+        }
+        *cta_abort = 0;
+        fence_barrier_init();
+    }
+    if (warp == 1)
+        tmem_alloc_2sm(tmem_slot, TMEM_COLS);
+    tcgen05_fence_before();
+    cluster_sync_all(); // both CTAs' barriers are initialised before any remote arrive / TMA signal
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const Watchdog wd{cta_abort, watchdog_flag};
+
+    const int num_m = (p.M + BM2 - 1) / BM2, num_n = p.N / BN;
+    const int num_tiles = num_m * num_n, num_kb = p.K / BK;
+    const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs) =====================
+        if (elect_one()) {
+            prefetch_tensormap(&tmap_a);
+            prefetch_tensormap(&tmap_b);
+        }
+        uint32_t stage = 0, phase = 0;
+        bool ok = true;
+        for (int tile = pair; tile < num_tiles && ok; tile += num_pairs) {
+            const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
+            for (int kb = 0; kb < num_kb; kb++) {
+                if (!(ok = mbar_wait_warp(&empty_bar[stage], phase ^ 1, wd, 1)))
+                    break;
+                if (elect_one()) {
+                    uint8_t *sa = smem + stage * L::STAGE_BYTES;
+                    const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
+                    mbar_arrive_expect_tx_cluster(full_leader, L::STAGE_BYTES);
+                    tma_load_2d_2sm(sa, &tmap_a, full_leader, kb * BK, m_blk * BM2 + (int)rank * BM);
+                    tma_load_2d_2sm(sa + L::A_BYTES, &tmap_b, full_leader, kb * BK, n_blk * BN + (int)rank * 128);
+                }
+                __syncwarp();
+                if (++stage == STAGES) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (leader) {
+            uint32_t stage = 0, phase = 0, it = 0;
+            bool ok = true;
+            for (int tile = pair; tile < num_tiles && ok; tile += num_pairs, it++) {
+                const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+                if (!(ok = mbar_wait_warp(&tempty_bar[acc], acc_phase ^ 1, wd, 2)))
+                    break;
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < num_kb; kb++) {
+                    if (!(ok = mbar_wait_warp(&full_bar[stage], phase, wd, 3)))
+                        break;
+                    tcgen05_fence_after();
+                    if (elect_one()) {
+                        const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
+                        const uint64_t a_desc = umma_desc_k_sw128(sa);
+                        const uint64_t b_desc = umma_desc_k_sw128(sa + L::A_BYTES);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; k++)
+                            umma_bf16_ss_2sm(d_tmem, a_desc + 2 * k, b_desc + 2 * k, IDESC, (kb | k) != 0);
+                        umma_commit_2sm(&empty_bar[stage], 0x3); // frees the slot in both CTAs
+                        if (kb == num_kb - 1)
+                            umma_commit_2sm(&tfull_bar[acc], 0x3); // accumulator complete in both CTAs
+                    }
+                    __syncwarp();
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..9, both CTAs) =====================
+        const int quad = warp & 3;
+        const int half = (warp - 2) >> 2;
+        uint32_t it = 0;
+        for (int tile = pair; tile < num_tiles; tile += num_pairs, it++) {
+            const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
+            const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+            bool ok = mbar_wait(&tfull_bar[acc], acc_phase, wd, 4);
+            ok = __all_sync(0xffffffffu, ok);
+            if (!ok)
+                break;
+            tcgen05_fence_after();
+            const int row0 = m_blk * BM2 + (int)rank * BM + quad * 32;
+            float *stage_tile = reinterpret_cast<float *>(smem + L::EPI_OFFSET) + (warp - 2) * kStageFloats;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + half * (BN / 2);
+#pragma unroll 1
+            for (int c = 0; c < BN / 64; c++) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(taddr + c * 32, v);
+                tmem_ld_wait();
+                if (row0 < p.M) // warp-uniform
+                    epilogue_chunk(p, C, stage_tile, lane, row0, n_blk * BN + half * (BN / 2) + c * 32, v);
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0)
+                mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0)); // the leader's barrier
+        }
+    }
+
+    // ===================== teardown =====================
+    tcgen05_fence_before();
+    cluster_sync_all(); // neither CTA may exit (or free TMEM) while its peer can still touch it
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc_2sm(tmem_base, TMEM_COLS);
     }
 }
 
@@ -278,6 +492,25 @@ int launch(const CUtensorMap &ta, const CUtensorMap &tb, void *C, const EpiParam
     const int num_tiles = ((p.M + BM - 1) / BM) * (p.N / BN);
     const int grid = num_tiles < sms ? num_tiles : sms;
     kernel<<<grid, kThreads, L::TOTAL, st>>>(ta, tb, C, p, watchdog_flag());
+    VITCU_LAUNCHED();
+    return 0;
+}
+
+template <int STAGES>
+int launch_pair(const CUtensorMap &ta, const CUtensorMap &tb, void *C, const EpiParams &p, int sms, cudaStream_t st)
+{
+    using L = SmemLayout2<STAGES>;
+    auto kernel = gemm_bf16_tc2_kernel<STAGES>;
+    static bool configured[64] = {false};
+    int dev = 0;
+    VITCU_TRY(cudaGetDevice(&dev));
+    if (dev < 64 && !configured[dev]) {
+        VITCU_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::TOTAL));
+        configured[dev] = true;
+    }
+    const int num_tiles = ((p.M + 255) / 256) * (p.N / 256);
+    const int pairs = num_tiles < sms / 2 ? num_tiles : sms / 2;
+    kernel<<<2 * pairs, kThreads, L::TOTAL, st>>>(ta, tb, C, p, watchdog_flag());
     VITCU_LAUNCHED();
     return 0;
 }
@@ -350,6 +583,20 @@ extern "C" int vitcu_gemm_bf16(const vitcu_bf16 *A, const vitcu_bf16 *W, void *C
     VITCU_REQUIRE(lda % 8 == 0 && ((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0, "operands must be 16-byte aligned");
 
     const int sms = device_sm_count();
+    // VITCU_GEMM_MODE=1cta forces the single-CTA kernels (A/B measurements)
+    static const bool force_1cta = getenv("VITCU_GEMM_MODE") && !strcmp(getenv("VITCU_GEMM_MODE"), "1cta");
+    // CTA pairs on 256x256 tiles when N allows and every pair gets work
+    const bool pair = !force_1cta && d->N % 256 == 0 && ((d->M + 255) / 256) * (d->N / 256) >= sms / 2;
+    if (pair) {
+        CUtensorMap ta, tb;
+        int rc = make_tensor_map_2d(&ta, A, 2, (uint64_t)d->M, (uint64_t)d->K, lda * 2, BM, BK);
+        if (rc)
+            return rc;
+        rc = make_tensor_map_2d(&tb, W, 2, (uint64_t)d->N, (uint64_t)d->K, (uint64_t)d->K * 2, 128, BK);
+        if (rc)
+            return rc;
+        return launch_pair<5>(ta, tb, C, p, sms, as_stream(s));
+    }
     // 128x256 tiles when they divide N and still give every SM work; else 128x128
     const bool wide = d->N % 256 == 0 && ((d->M + BM - 1) / BM) * (d->N / 256) >= sms;
     const int BN = wide ? 256 : 128;
@@ -361,6 +608,6 @@ extern "C" int vitcu_gemm_bf16(const vitcu_bf16 *A, const vitcu_bf16 *W, void *C
     if (rc)
         return rc;
     if (wide)
-        return launch<256, 4>(ta, tb, C, p, sms, as_stream(s));
-    return launch<128, 6>(ta, tb, C, p, sms, as_stream(s));
+        return launch<256, 3>(ta, tb, C, p, sms, as_stream(s));
+    return launch<128, 5>(ta, tb, C, p, sms, as_stream(s));
 }

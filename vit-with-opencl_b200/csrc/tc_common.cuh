@@ -93,6 +93,16 @@ __device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, const 
     return true;
 }
 
+// warp-collective flavour: every lane polls the same barrier (converged warp => same
+// answer); the slow path votes so the whole warp leaves together on an abort
+__device__ __forceinline__ bool mbar_wait_warp(uint64_t *bar, uint32_t parity, const Watchdog &wd, uint32_t tag)
+{
+    if (mbar_try_wait(bar, parity))
+        return true;
+    const bool ok = mbar_wait(bar, parity, wd, tag);
+    return __all_sync(0xffffffffu, ok);
+}
+
 // ---- TMA ------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap *m)
 {
@@ -109,6 +119,70 @@ __device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *m
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                  ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
                  "r"(c2)
+                 : "memory");
+}
+
+// ---- clusters / CTA pairs ---------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same smem offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr)
+{
+    // default semantics (.release.cta): an explicit .release.cluster compiles to MEMBAR.ALL.GPU,
+    // which throttled the producer to one k-block per fence (profiles/r01_v3_pair_membar.md)
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_cluster(uint32_t cluster_addr, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes)
+                 : "memory");
+}
+// TMA load for a CTA pair: data lands in the executing CTA's smem, the
+// completion bytes are signalled on the barrier at cluster address `bar_cluster`
+__device__ __forceinline__ void tma_load_2d_2sm(void *smem_dst, const CUtensorMap *m, uint32_t bar_cluster, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t *slot, uint32_t cols)
+{
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t cols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A * B over the CTA pair (M = 256); leader CTA issues
+__device__ __forceinline__ void umma_bf16_ss_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                 uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+                 : "memory");
+}
+// arrive (once the pair's MMAs retire) on the barrier at this smem offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_2sm(uint64_t *bar, uint16_t mask)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask)
                  : "memory");
 }
 
