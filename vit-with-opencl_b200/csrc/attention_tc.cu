@@ -3,22 +3,24 @@
 //
 // Replaces QKV_TO_SCOREV (R/multihead.cl:65-137); oracle R/ViT_seq.c:192-262.
 // R/ = /root/reference/MulticoreMainProject/.  S = Q K^T, the row softmax and
-// O = P V never leave the SM: S and O live in TMEM, P goes through shared
-// memory as the A operand of the second MMA.
+// O = P V never leave the SM: S, P and O all live in tensor memory.
 //
 // One persistent CTA per SM walks over (image, head) work items.  Per item the
 // whole K and V of the head (KP = tokens rounded up to 16 rows) and up to two
-// 128-query tiles are resident in shared memory:
+// 128-query tiles sit in shared memory; shared memory is double-buffered so the
+// TMA loads of item i+1 run under the math of item i.
 //   warp 0       TMA producer: 3-D tensor map over qkv [B][T][2304]; rows past T
 //                are zero-filled by TMA, so no neighbour image leaks in
-//   warp 1       MMA issuer:  S_i = Q_i K^T   (M=128, N=KP, K=64, both K-major)
-//                             O_i = P_i V     (M=128, N=64, K=KP, A K-major from
-//                                              smem, B = V used MN-major as loaded)
-//   warp 2       TMEM allocation (512 columns: S_0|O_0 at 0, S_1|O_1 at 256;
-//                O_i reuses the columns of S_i once the softmax has consumed it)
-//   warps 4-7    softmax + epilogue of query tile 0 (thread = one query row)
+//   warp 1       MMA issuer:  S_t = Q_t K^T  (M=128, N=KP, K=64, operands in smem)
+//                             O_t = P_t V    (M=128, N=64, K=KP, A = P read from
+//                                             TMEM, B = V used MN-major as loaded)
+//   warp 2       TMEM allocation: one 256-column slot per query tile,
+//                S in columns [0,KP), P (bf16 pairs) overwrites columns [0,KP/2)
+//                of S as the softmax consumes it, O in columns [128,192)
+//   warps 4-7    softmax + epilogue of query tile 0 (thread = one query row =
+//                one TMEM lane, so S -> P in place needs no cross-thread sync)
 //   warps 8-11   softmax + epilogue of query tile 1
-// so the two query tiles ping-pong: while one tile's softmax runs on the CUDA
+// The two query tiles ping-pong: while one tile's softmax runs on the CUDA
 // cores the other tile's MMAs run on the tensor cores.
 //
 // Softmax (R/ViT_seq.c:204-234): scores are scaled by 1/sqrt(64) after the dot
@@ -35,10 +37,11 @@ namespace {
 constexpr int kThreadsAttn = 384;
 constexpr int QT = 128;                   // queries per tile
 constexpr uint32_t Q_BYTES = QT * 128;    // [128 x 64] bf16
-constexpr uint32_t P_SLAB = QT * 128;     // one 64-key slab of P: [128 x 64] bf16
 constexpr int MAX_KP = 256;
+constexpr uint32_t O_COL = 128;           // O accumulator columns inside a tile's TMEM slot
 
-enum Bar { QK_FULL = 0, V_FULL, S_FULL0, S_FULL1, P_FULL0, P_FULL1, O_FULL0, O_FULL1, O_READ0, O_READ1, MMA_DONE, NUM_BARS };
+// barriers: per smem stage {QK_FULL, V_FULL, SMEM_FREE}; per query tile {S_FULL, P_FULL, O_FULL, O_READ}
+enum Bar { QK_FULL = 0, V_FULL = 2, SMEM_FREE = 4, S_FULL = 6, P_FULL = 8, O_FULL = 10, O_READ = 12, NUM_BARS = 14 };
 
 struct AttnParams {
     int batch, tokens, kp;     // kp = tokens rounded up to a multiple of 16
@@ -53,12 +56,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     const uint32_t kv_bytes = static_cast<uint32_t>(p.kp) * 128u;
-    const uint32_t slabs = (static_cast<uint32_t>(p.kp) + 63u) / 64u;
-    uint8_t *sQ = smem;                          // 2 x [128 x 64]
-    uint8_t *sK = sQ + 2 * Q_BYTES;              // [kp x 64]
-    uint8_t *sV = sK + kv_bytes;                 // [kp x 64]
-    uint8_t *sP = sV + kv_bytes;                 // 2 x slabs x [128 x 64]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sP + 2 * slabs * P_SLAB);
+    const uint32_t stage_bytes = 2 * Q_BYTES + 2 * kv_bytes; // Q0 | Q1 | K | V
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 2 * stage_bytes);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + NUM_BARS);
     volatile uint32_t *cta_abort = tmem_slot + 1;
 
@@ -66,17 +65,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     const int ntiles = (p.tokens + QT - 1) / QT; // 1 or 2
 
     if (threadIdx.x == 0) {
-        mbar_init(&bars[QK_FULL], 1);
-        mbar_init(&bars[V_FULL], 1);
-        mbar_init(&bars[S_FULL0], 1);
-        mbar_init(&bars[S_FULL1], 1);
-        mbar_init(&bars[P_FULL0], 4);
-        mbar_init(&bars[P_FULL1], 4);
-        mbar_init(&bars[O_FULL0], 1);
-        mbar_init(&bars[O_FULL1], 1);
-        mbar_init(&bars[O_READ0], 4);
-        mbar_init(&bars[O_READ1], 4);
-        mbar_init(&bars[MMA_DONE], 1);
+        for (int s = 0; s < 2; s++) {
+            mbar_init(&bars[QK_FULL + s], 1);
+            mbar_init(&bars[V_FULL + s], 1);
+            mbar_init(&bars[SMEM_FREE + s], 1);
+            mbar_init(&bars[S_FULL + s], 1);
+            mbar_init(&bars[P_FULL + s], 4);
+            mbar_init(&bars[O_FULL + s], 1);
+            mbar_init(&bars[O_READ + s], 4);
+        }
         *cta_abort = 0;
         fence_barrier_init();
     }
@@ -90,65 +87,75 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        if (elect_one()) {
             prefetch_tensormap(&tmap_q);
             prefetch_tensormap(&tmap_kv);
-            uint32_t it = 0;
-            for (int item = blockIdx.x; item < p.items; item += gridDim.x, it++) {
-                const int img = item / kHeads, head = item - img * kHeads;
-                if (it > 0 && !mbar_wait(&bars[MMA_DONE], (it - 1) & 1, wd, 1))
-                    break;
-                mbar_arrive_expect_tx(&bars[QK_FULL], ntiles * Q_BYTES + kv_bytes);
+        }
+        uint32_t it = 0;
+        for (int item = blockIdx.x; item < p.items; item += gridDim.x, it++) {
+            const int img = item / kHeads, head = item - img * kHeads;
+            const uint32_t s = it & 1;
+            // stage s was last used by item it-2: wait until its MMAs have retired
+            if (it >= 2 && !mbar_wait_warp(&bars[SMEM_FREE + s], ((it >> 1) - 1) & 1, wd, 1))
+                break;
+            if (elect_one()) {
+                uint8_t *sq = smem + s * stage_bytes;
+                uint8_t *sk = sq + 2 * Q_BYTES;
+                mbar_arrive_expect_tx(&bars[QK_FULL + s], ntiles * Q_BYTES + kv_bytes);
                 for (int t = 0; t < ntiles; t++)
-                    tma_load_3d(sQ + t * Q_BYTES, &tmap_q, &bars[QK_FULL], head * kHeadDim, t * QT, img);
-                tma_load_3d(sK, &tmap_kv, &bars[QK_FULL], kEmbed + head * kHeadDim, 0, img);
-                mbar_arrive_expect_tx(&bars[V_FULL], kv_bytes);
-                tma_load_3d(sV, &tmap_kv, &bars[V_FULL], 2 * kEmbed + head * kHeadDim, 0, img);
+                    tma_load_3d(sq + t * Q_BYTES, &tmap_q, &bars[QK_FULL + s], head * kHeadDim, t * QT, img);
+                tma_load_3d(sk, &tmap_kv, &bars[QK_FULL + s], kEmbed + head * kHeadDim, 0, img);
+                mbar_arrive_expect_tx(&bars[V_FULL + s], kv_bytes);
+                tma_load_3d(sk + kv_bytes, &tmap_kv, &bars[V_FULL + s], 2 * kEmbed + head * kHeadDim, 0, img);
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            const uint32_t idesc_s = umma_idesc_bf16(QT, p.kp, false, false);
-            const uint32_t idesc_o = umma_idesc_bf16(QT, kHeadDim, false, true);
-            const uint32_t ksteps = static_cast<uint32_t>(p.kp) / 16u;
-            uint32_t it = 0;
-            bool ok = true;
-            for (int item = blockIdx.x; item < p.items && ok; item += gridDim.x, it++) {
-                const uint32_t ph = it & 1;
-                if (!(ok = mbar_wait(&bars[QK_FULL], ph, wd, 2)))
+        const uint32_t idesc_s = umma_idesc_bf16(QT, p.kp, false, false);
+        const uint32_t idesc_o = umma_idesc_bf16(QT, kHeadDim, false, true);
+        const uint32_t ksteps = static_cast<uint32_t>(p.kp) / 16u;
+        uint32_t it = 0;
+        bool ok = true;
+        for (int item = blockIdx.x; item < p.items && ok; item += gridDim.x, it++) {
+            const uint32_t s = it & 1, sph = (it >> 1) & 1, ph = it & 1;
+            const uint32_t sq = smem_u32(smem + s * stage_bytes);
+            const uint32_t sk = sq + 2 * Q_BYTES, sv = sk + kv_bytes;
+            if (!(ok = mbar_wait_warp(&bars[QK_FULL + s], sph, wd, 2)))
+                break;
+            for (int t = 0; t < ntiles && ok; t++) {
+                // S_t overwrites the TMEM slot whose O_t the previous item's epilogue is still reading
+                if (it > 0 && !(ok = mbar_wait_warp(&bars[O_READ + t], (it - 1) & 1, wd, 3)))
                     break;
-                const uint64_t k_desc = umma_desc_k_sw128(smem_u32(sK));
-                for (int t = 0; t < ntiles && ok; t++) {
-                    // S_t overwrites the TMEM columns O_t of the previous item occupied
-                    if (it > 0 && !(ok = mbar_wait(&bars[O_READ0 + t], (it - 1) & 1, wd, 3)))
-                        break;
-                    tcgen05_fence_after();
-                    const uint64_t q_desc = umma_desc_k_sw128(smem_u32(sQ + t * Q_BYTES));
+                tcgen05_fence_after();
+                if (elect_one()) {
+                    const uint64_t q_desc = umma_desc_k_sw128(sq + t * Q_BYTES);
+                    const uint64_t k_desc = umma_desc_k_sw128(sk);
 #pragma unroll
                     for (int k = 0; k < kHeadDim / 16; k++)
                         umma_bf16_ss(tmem_base + t * 256, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0);
-                    umma_commit(&bars[S_FULL0 + t]);
+                    umma_commit(&bars[S_FULL + t]);
                 }
-                if (!ok || !(ok = mbar_wait(&bars[V_FULL], ph, wd, 4)))
+                __syncwarp();
+            }
+            if (!ok || !(ok = mbar_wait_warp(&bars[V_FULL + s], sph, wd, 4)))
+                break;
+            for (int t = 0; t < ntiles && ok; t++) {
+                if (!(ok = mbar_wait_warp(&bars[P_FULL + t], ph, wd, 5)))
                     break;
-                for (int t = 0; t < ntiles && ok; t++) {
-                    if (!(ok = mbar_wait(&bars[P_FULL0 + t], ph, wd, 5)))
-                        break;
-                    tcgen05_fence_after();
-                    const uint32_t p_base = smem_u32(sP + t * slabs * P_SLAB);
-                    const uint32_t v_base = smem_u32(sV);
+                tcgen05_fence_after();
+                if (elect_one()) {
+                    const uint32_t slot = tmem_base + t * 256;
                     for (uint32_t k = 0; k < ksteps; k++) {
-                        // A: slab k/4 of P, +32 B per 16-key step inside the slab's 128-byte rows
-                        const uint64_t a_desc = umma_desc_k_sw128(p_base + (k >> 2) * P_SLAB + (k & 3) * 32);
-                        // B: 16 key rows of V (= two 8-row swizzle atoms, 2048 B)
-                        const uint64_t b_desc = umma_desc_mn_sw128(v_base + k * 2048);
-                        umma_bf16_ss(tmem_base + t * 256, a_desc, b_desc, idesc_o, k != 0);
+                        // A: 16 keys = 8 packed columns of P in TMEM; B: 16 key rows of V (two 8-row swizzle atoms)
+                        const uint64_t b_desc = umma_desc_mn_sw128(sv + k * 2048);
+                        umma_bf16_ts(slot + O_COL, slot + k * 8, b_desc, idesc_o, k != 0);
                     }
-                    umma_commit(&bars[O_FULL0 + t]);
+                    umma_commit(&bars[O_FULL + t]);
+                    if (t == ntiles - 1)
+                        umma_commit(&bars[SMEM_FREE + s]); // Q/K/V of this stage may be overwritten
                 }
-                if (ok)
-                    umma_commit(&bars[MMA_DONE]); // smem of this item may be overwritten
+                __syncwarp();
             }
         }
     } else if (warp >= 4) {
@@ -159,80 +166,88 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + tile * 256;
         const float sl2 = 0.125f * 1.4426950408889634f; // log2(e) / sqrt(64)
         const int nchunks = (p.kp + 31) / 32;
-        uint8_t *prow = sP + tile * slabs * P_SLAB + row * 128;
         uint32_t it = 0;
         if (tile < ntiles) {
             for (int item = blockIdx.x; item < p.items; item += gridDim.x, it++) {
                 const int img = item / kHeads, head = item - img * kHeads;
                 const uint32_t ph = it & 1;
-                bool ok = mbar_wait(&bars[S_FULL0 + tile], ph, wd, 6);
-                if (!__all_sync(0xffffffffu, ok))
+                if (!mbar_wait_warp(&bars[S_FULL + tile], ph, wd, 6))
                     break;
                 tcgen05_fence_after();
-                // pass 1: row maximum over the valid keys
+                uint32_t va[32], vb[32];
+                // pass 1: row maximum over the valid keys (loads double-buffered in registers)
                 float mx = -INFINITY;
+                tmem_ld_32x32b_x32(taddr, va);
                 for (int c = 0; c < nchunks; c++) {
-                    uint32_t v[32];
-                    tmem_ld_32x32b_x32(taddr + c * 32, v);
                     tmem_ld_wait();
+                    uint32_t(&cur)[32] = (c & 1) ? vb : va;
+                    if (c + 1 < nchunks)
+                        tmem_ld_32x32b_x32(taddr + (c + 1) * 32, (c & 1) ? va : vb);
+                    else
+                        tmem_ld_32x32b_x32(taddr, (c & 1) ? va : vb); // chunk 0 again, for pass 2
+                    if (c * 32 + 32 <= p.tokens) {
 #pragma unroll
-                    for (int j = 0; j < 32; j++)
-                        if (c * 32 + j < p.tokens)
-                            mx = fmaxf(mx, __uint_as_float(v[j]));
+                        for (int j = 0; j < 32; j++)
+                            mx = fmaxf(mx, __uint_as_float(cur[j]));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; j++)
+                            if (c * 32 + j < p.tokens)
+                                mx = fmaxf(mx, __uint_as_float(cur[j]));
+                    }
                 }
-                // pass 2: p = exp2((s - max) * log2e/8), row sum, P -> smem (bf16, 128B-swizzled K-major)
+                // pass 2: p = exp2((s - max) * log2e/8), row sum, P (bf16 pairs) back into TMEM over S
                 const float mxs = mx * sl2;
                 float sum = 0.f;
                 for (int c = 0; c < nchunks; c++) {
-                    uint32_t v[32];
-                    tmem_ld_32x32b_x32(taddr + c * 32, v);
                     tmem_ld_wait();
-                    float e[32];
-#pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        const float x = exp2f(fmaf(__uint_as_float(v[j]), sl2, -mxs));
-                        e[j] = (c * 32 + j < p.tokens) ? x : 0.f;
-                    }
-                    // the bf16-rounded values are what the MMA sums, so sum those
+                    // pass 1 left chunk 0 in the buffer selected by nchunks' parity
+                    uint32_t(&cur)[32] = ((c + nchunks) & 1) ? vb : va;
+                    if (c + 1 < nchunks)
+                        tmem_ld_32x32b_x32(taddr + (c + 1) * 32, ((c + nchunks) & 1) ? va : vb);
                     uint32_t packed[16];
 #pragma unroll
                     for (int j = 0; j < 16; j++) {
-                        const __nv_bfloat162 h = __floats2bfloat162_rn(e[2 * j], e[2 * j + 1]);
+                        float e0 = ex2_approx(fmaf(__uint_as_float(cur[2 * j]), sl2, -mxs));
+                        float e1 = ex2_approx(fmaf(__uint_as_float(cur[2 * j + 1]), sl2, -mxs));
+                        if (c * 32 + 2 * j >= p.tokens)
+                            e0 = 0.f;
+                        if (c * 32 + 2 * j + 1 >= p.tokens)
+                            e1 = 0.f;
+                        // the bf16-rounded values are what the MMA sums, so sum those
+                        const __nv_bfloat162 h = __floats2bfloat162_rn(e0, e1);
                         packed[j] = *reinterpret_cast<const uint32_t *>(&h);
                         const float2 f = __bfloat1622float2(h);
                         sum += f.x + f.y;
                     }
-                    // 32 keys = 4 chunks of 16 B; slab = c/2, chunk index inside the 128-B row = (c&1)*4 + q
-                    uint8_t *slab_row = prow + (c >> 1) * P_SLAB;
-#pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        if (c * 32 + q * 8 < p.kp) {
-                            const int chunk = ((c & 1) * 4 + q) ^ (row & 7);
-                            *reinterpret_cast<uint4 *>(slab_row + chunk * 16) =
-                                make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
-                        }
-                    }
+                    // P columns [16c, 16c+16) overwrite S columns that are already consumed
+                    // (chunk c/2 <= c) or not yet prefetched (chunk c+1 starts at column 32c+32)
+                    tmem_st_32x32b_x16(taddr + c * 16, packed);
                 }
+                tmem_st_wait();
                 tcgen05_fence_before();
-                fence_proxy_async_smem(); // generic-proxy smem writes -> visible to the MMA (async proxy)
                 __syncwarp();
                 if (lane == 0)
-                    mbar_arrive(&bars[P_FULL0 + tile]);
+                    mbar_arrive(&bars[P_FULL + tile]);
 
                 // epilogue: O / sum -> bf16 -> out[(img*T + q), head*64 ..]
-                ok = mbar_wait(&bars[O_FULL0 + tile], ph, wd, 7);
-                if (!__all_sync(0xffffffffu, ok))
+                if (!mbar_wait_warp(&bars[O_FULL + tile], ph, wd, 7))
                     break;
                 tcgen05_fence_after();
                 const float inv = 1.0f / sum;
                 const int q = tile * QT + row;
                 __nv_bfloat16 *dst = p.out + (static_cast<size_t>(img) * p.tokens + q) * kEmbed + head * kHeadDim;
+                tmem_ld_32x32b_x32(taddr + O_COL, va);
+                tmem_ld_32x32b_x32(taddr + O_COL + 32, vb);
+                tmem_ld_wait();
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0)
+                    mbar_arrive(&bars[O_READ + tile]); // the TMEM slot is free for the next item's S
+                if (q < p.tokens) {
 #pragma unroll
-                for (int c = 0; c < 2; c++) {
-                    uint32_t v[32];
-                    tmem_ld_32x32b_x32(taddr + c * 32, v);
-                    tmem_ld_wait();
-                    if (q < p.tokens) {
+                    for (int c = 0; c < 2; c++) {
+                        const uint32_t(&v)[32] = c ? vb : va;
 #pragma unroll
                         for (int j = 0; j < 4; j++)
                             reinterpret_cast<uint4 *>(dst + c * 32)[j] = make_uint4(
@@ -242,10 +257,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                                 pack_bf16x2(__uint_as_float(v[8 * j + 6]) * inv, __uint_as_float(v[8 * j + 7]) * inv));
                     }
                 }
-                tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0)
-                    mbar_arrive(&bars[O_READ0 + tile]);
             }
         }
     }
@@ -305,8 +316,7 @@ int attention_bf16_tc(const void *qkv, void *out, int batch, int tokens, cudaStr
     rc = make_qkv_map(&tkv, qkv, batch, tokens, (uint32_t)kp);
     if (rc)
         return rc;
-    const uint32_t slabs = ((uint32_t)kp + 63u) / 64u;
-    const size_t smem = 2 * Q_BYTES + 2 * (size_t)kp * 128 + 2 * slabs * P_SLAB + NUM_BARS * 8 + 16 + 1024;
+    const size_t smem = 2 * (2 * (size_t)Q_BYTES + 2 * (size_t)kp * 128) + NUM_BARS * 8 + 16 + 1024;
     VITCU_REQUIRE(smem <= 227 * 1024, "attention tile does not fit shared memory");
     static int configured[64] = {0};
     int dev = 0;

@@ -261,13 +261,16 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const int row0 = m_blk * BM + quad * 32;
             float *stage_tile = reinterpret_cast<float *>(smem + L::EPI_OFFSET) + (warp - 2) * kStageFloats;
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + half * (BN / 2);
-#pragma unroll 1
+            // two register buffers: the tcgen05.ld of chunk c+1 is in flight while chunk c is processed
+            uint32_t va[32], vb[32];
+            tmem_ld_32x32b_x32(taddr, va);
+#pragma unroll
             for (int c = 0; c < BN / 64; c++) {
-                uint32_t v[32];
-                tmem_ld_32x32b_x32(taddr + c * 32, v);
                 tmem_ld_wait();
+                if (c + 1 < BN / 64)
+                    tmem_ld_32x32b_x32(taddr + (c + 1) * 32, (c & 1) ? va : vb);
                 if (row0 < p.M) // warp-uniform
-                    epilogue_chunk(p, C, stage_tile, lane, row0, n_blk * BN + half * (BN / 2) + c * 32, v);
+                    epilogue_chunk(p, C, stage_tile, lane, row0, n_blk * BN + half * (BN / 2) + c * 32, (c & 1) ? vb : va);
             }
             tcgen05_fence_before();
             __syncwarp();
@@ -436,13 +439,16 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             const int row0 = m_blk * BM2 + (int)rank * BM + quad * 32;
             float *stage_tile = reinterpret_cast<float *>(smem + L::EPI_OFFSET) + (warp - 2) * kStageFloats;
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + half * (BN / 2);
-#pragma unroll 1
+            // two register buffers: the tcgen05.ld of chunk c+1 is in flight while chunk c is processed
+            uint32_t va[32], vb[32];
+            tmem_ld_32x32b_x32(taddr, va);
+#pragma unroll
             for (int c = 0; c < BN / 64; c++) {
-                uint32_t v[32];
-                tmem_ld_32x32b_x32(taddr + c * 32, v);
                 tmem_ld_wait();
+                if (c + 1 < BN / 64)
+                    tmem_ld_32x32b_x32(taddr + (c + 1) * 32, (c & 1) ? va : vb);
                 if (row0 < p.M) // warp-uniform
-                    epilogue_chunk(p, C, stage_tile, lane, row0, n_blk * BN + half * (BN / 2) + c * 32, v);
+                    epilogue_chunk(p, C, stage_tile, lane, row0, n_blk * BN + half * (BN / 2) + c * 32, (c & 1) ? vb : va);
             }
             tcgen05_fence_before();
             __syncwarp();
