@@ -60,82 +60,116 @@ struct SmemLayout {
     static_assert(TOTAL <= 227 * 1024, "shared memory budget");
 };
 
-// Epilogue of one 32x32 accumulator chunk (the 32 rows of this warp's TMEM
-// quadrant x 32 columns).  tcgen05.ld hands every thread one ROW (32 consecutive
-// columns); storing that straight to global memory makes each warp instruction
-// touch 32 different 128-byte lines (32 L1 wavefronts), and that LSU traffic
-// competes with the tensor core's operand reads for the L1/shared-memory data
-// pipe (profiles/r01_v4_epilogue.md: lsu wavefronts 59 % + tensor 33 % of the
-// pipe).  So the chunk is transposed through a per-warp shared-memory tile
-// ([32][36] floats, conflict-free for 128-bit accesses both ways) and leaves the
-// SM as fully coalesced 128-bit accesses: 8 lanes per row, 4 rows per instruction.
-__device__ __forceinline__ void epilogue_chunk(const EpiParams &p, void *C, float *stage, int lane, int row0, int col0,
-                                               const uint32_t (&acc)[32])
+// Epilogue of one warp's share of an accumulator tile: 32 rows (its TMEM lane quadrant) x BN/2
+// columns, in 32-column chunks.
+//
+// tcgen05.ld hands every thread one ROW (32 consecutive columns); storing that straight to global
+// memory makes each warp instruction touch 32 different 128-byte lines (32 L1 wavefronts), and that
+// LSU traffic competes with the tensor core's operand reads for the L1/shared-memory data pipe
+// (profiles/r01_v4_epilogue.md: lsu wavefronts 59 % + tensor 33 % of the pipe).  So every chunk is
+// transposed through a per-warp shared-memory tile ([32][36] floats, conflict-free for 128-bit
+// accesses both ways) and leaves the SM as fully coalesced 128-bit accesses: 8 lanes per fp32 row
+// (4 per bf16 row).  Latency hiding: the tcgen05.ld of chunk c+1 and the residual / position rows
+// of chunk c+1 are in flight while chunk c is processed, and the first residual rows are requested
+// before the wait for the accumulator.
+template <int BN>
+__device__ __forceinline__ bool epilogue_tile(const EpiParams &p, void *C, float *stage, int lane, int row0, int col_base,
+                                              uint32_t taddr, uint64_t *tfull, uint32_t parity, const Watchdog &wd)
 {
-    // ---- row-per-thread part: bias (+ GELU), then into the staging tile ----
-    float v[32];
-#pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-        const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + col0 + j));
-        v[j + 0] = __uint_as_float(acc[j + 0]) + b.x;
-        v[j + 1] = __uint_as_float(acc[j + 1]) + b.y;
-        v[j + 2] = __uint_as_float(acc[j + 2]) + b.z;
-        v[j + 3] = __uint_as_float(acc[j + 3]) + b.w;
-    }
-    if (p.epilogue == VITCU_EPI_BIAS_GELU) {
-#pragma unroll
-        for (int j = 0; j < 32; j++)
-            v[j] = gelu_erf_fast(v[j]);
-    }
-    float4 *srow = reinterpret_cast<float4 *>(stage + lane * kStageLd);
-#pragma unroll
-    for (int j = 0; j < 8; j++)
-        srow[j] = make_float4(v[4 * j + 0], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-    __syncwarp();
-
-    // ---- coalesced part ----
-    if (p.out_bf16) {
-        // 4 lanes x 16 B cover the 64-byte bf16 row segment; 8 rows per instruction
-        const int rsub = lane >> 2, c8 = (lane & 3) * 8;
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const int r = i * 8 + rsub, row = row0 + r;
-            const float4 x = *reinterpret_cast<const float4 *>(stage + r * kStageLd + c8);
-            const float4 y = *reinterpret_cast<const float4 *>(stage + r * kStageLd + c8 + 4);
-            if (row < p.M)
-                *reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(C) + static_cast<size_t>(row) * p.ldc + col0 + c8) =
-                    make_uint4(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w), pack_bf16x2(y.x, y.y), pack_bf16x2(y.z, y.w));
+    constexpr int NCHUNK = BN / 64;
+    const bool fp32_add = !p.out_bf16 && p.epilogue != VITCU_EPI_BIAS; // residual or position rows to fetch
+    const int rsub = lane >> 3, c4 = (lane & 7) * 4;
+    const float *addsrc = p.epilogue == VITCU_EPI_PATCH_EMBED ? p.pos : p.residual;
+    // element offset of (row, first column of this lane) in the output / in the rows to add
+    auto out_off = [&](int row) -> size_t {
+        if (p.epilogue == VITCU_EPI_PATCH_EMBED) {
+            const int img = row / p.patches, pi = row - img * p.patches;
+            return (static_cast<size_t>(img) * p.tokens + 1 + pi) * p.ldc + col_base + c4;
         }
-    } else {
-        // 8 lanes x 16 B cover the 128-byte fp32 row segment; 4 rows per instruction
-        const int rsub = lane >> 3, c4 = (lane & 7) * 4;
-        float4 add[8];
-        size_t off[8];
+        return static_cast<size_t>(row) * p.ldc + col_base + c4;
+    };
+    auto add_off = [&](int row) -> size_t {
+        if (p.epilogue == VITCU_EPI_PATCH_EMBED)
+            return static_cast<size_t>(1 + row % p.patches) * p.N + col_base + c4;
+        return static_cast<size_t>(row) * p.ldc + col_base + c4;
+    };
+    float4 add[8];
+    auto fetch_add = [&](int chunk) {
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             const int row = row0 + i * 4 + rsub;
             add[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            off[i] = static_cast<size_t>(row) * p.ldc + col0 + c4;
-            if (row < p.M) {
-                if (p.epilogue == VITCU_EPI_BIAS_RESIDUAL) {
-                    add[i] = *reinterpret_cast<const float4 *>(p.residual + off[i]);
-                } else if (p.epilogue == VITCU_EPI_PATCH_EMBED) {
-                    const int img = row / p.patches, pi = row - img * p.patches;
-                    off[i] = (static_cast<size_t>(img) * p.tokens + 1 + pi) * p.ldc + col0 + c4;
-                    add[i] = __ldg(reinterpret_cast<const float4 *>(p.pos + static_cast<size_t>(1 + pi) * p.N + col0 + c4));
-                }
-            }
+            if (fp32_add && row < p.M)
+                add[i] = *reinterpret_cast<const float4 *>(addsrc + add_off(row) + chunk * 32);
         }
+    };
+    fetch_add(0); // does not depend on the accumulator: in flight during the wait below
+
+    bool ok = mbar_wait(tfull, parity, wd, 4);
+    ok = __all_sync(0xffffffffu, ok);
+    if (!ok)
+        return false;
+    tcgen05_fence_after();
+
+    uint32_t acc[2][32];
+    tmem_ld_32x32b_x32(taddr, acc[0]);
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const int r = i * 4 + rsub;
-            const float4 x = *reinterpret_cast<const float4 *>(stage + r * kStageLd + c4);
-            if (row0 + r < p.M)
-                *reinterpret_cast<float4 *>(reinterpret_cast<float *>(C) + off[i]) =
-                    make_float4(x.x + add[i].x, x.y + add[i].y, x.z + add[i].z, x.w + add[i].w);
+    for (int c = 0; c < NCHUNK; c++) {
+        tmem_ld_wait();
+        if (c + 1 < NCHUNK)
+            tmem_ld_32x32b_x32(taddr + (c + 1) * 32, acc[(c + 1) & 1]);
+        if (row0 >= p.M) // warp-uniform: nothing of this warp's rows exists
+            continue;
+        const int col0 = col_base + c * 32;
+        // ---- row-per-thread part: bias (+ GELU), then into the staging tile ----
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + col0 + j));
+            v[j + 0] = __uint_as_float(acc[c & 1][j + 0]) + b.x;
+            v[j + 1] = __uint_as_float(acc[c & 1][j + 1]) + b.y;
+            v[j + 2] = __uint_as_float(acc[c & 1][j + 2]) + b.z;
+            v[j + 3] = __uint_as_float(acc[c & 1][j + 3]) + b.w;
         }
+        if (p.epilogue == VITCU_EPI_BIAS_GELU) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 2)
+                unpack2(gelu_erf_fast2(pack2(v[j], v[j + 1])), v[j], v[j + 1]);
+        }
+        float4 *srow = reinterpret_cast<float4 *>(stage + lane * kStageLd);
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            srow[j] = make_float4(v[4 * j + 0], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        __syncwarp();
+        // ---- coalesced part ----
+        if (p.out_bf16) {
+            // 4 lanes x 16 B cover the 64-byte bf16 row segment; 8 rows per instruction
+            const int rs = lane >> 2, c8 = (lane & 3) * 8;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int r = i * 8 + rs, row = row0 + r;
+                const float4 x = *reinterpret_cast<const float4 *>(stage + r * kStageLd + c8);
+                const float4 y = *reinterpret_cast<const float4 *>(stage + r * kStageLd + c8 + 4);
+                if (row < p.M)
+                    *reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(C) + static_cast<size_t>(row) * p.ldc + col0 + c8) =
+                        make_uint4(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w), pack_bf16x2(y.x, y.y), pack_bf16x2(y.z, y.w));
+            }
+        } else {
+            // 8 lanes x 16 B cover the 128-byte fp32 row segment; 4 rows per instruction
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int r = i * 4 + rsub, row = row0 + r;
+                const float4 x = *reinterpret_cast<const float4 *>(stage + r * kStageLd + c4);
+                if (row < p.M)
+                    *reinterpret_cast<float4 *>(reinterpret_cast<float *>(C) + out_off(row) + c * 32) =
+                        make_float4(x.x + add[i].x, x.y + add[i].y, x.z + add[i].z, x.w + add[i].w);
+            }
+            if (c + 1 < NCHUNK)
+                fetch_add(c + 1); // in flight during the next chunk's tcgen05.ld wait, bias and staging
+        }
+        __syncwarp(); // the staging tile is reused by the next chunk
     }
-    __syncwarp(); // the staging tile is reused by the next chunk
+    return true;
 }
 
 template <int BN, int STAGES>
@@ -253,25 +287,11 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
             const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
             const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-            bool ok = mbar_wait(&tfull_bar[acc], acc_phase, wd, 4);
-            ok = __all_sync(0xffffffffu, ok);
-            if (!ok)
-                break;
-            tcgen05_fence_after();
-            const int row0 = m_blk * BM + quad * 32;
             float *stage_tile = reinterpret_cast<float *>(smem + L::EPI_OFFSET) + (warp - 2) * kStageFloats;
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + half * (BN / 2);
-            // two register buffers: the tcgen05.ld of chunk c+1 is in flight while chunk c is processed
-            uint32_t va[32], vb[32];
-            tmem_ld_32x32b_x32(taddr, va);
-#pragma unroll
-            for (int c = 0; c < BN / 64; c++) {
-                tmem_ld_wait();
-                if (c + 1 < BN / 64)
-                    tmem_ld_32x32b_x32(taddr + (c + 1) * 32, (c & 1) ? va : vb);
-                if (row0 < p.M) // warp-uniform
-                    epilogue_chunk(p, C, stage_tile, lane, row0, n_blk * BN + half * (BN / 2) + c * 32, (c & 1) ? vb : va);
-            }
+            if (!epilogue_tile<BN>(p, C, stage_tile, lane, m_blk * BM + quad * 32, n_blk * BN + half * (BN / 2), taddr,
+                                   &tfull_bar[acc], acc_phase, wd))
+                break;
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0)
@@ -431,25 +451,11 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         for (int tile = pair; tile < num_tiles; tile += num_pairs, it++) {
             const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
             const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-            bool ok = mbar_wait(&tfull_bar[acc], acc_phase, wd, 4);
-            ok = __all_sync(0xffffffffu, ok);
-            if (!ok)
-                break;
-            tcgen05_fence_after();
-            const int row0 = m_blk * BM2 + (int)rank * BM + quad * 32;
             float *stage_tile = reinterpret_cast<float *>(smem + L::EPI_OFFSET) + (warp - 2) * kStageFloats;
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + half * (BN / 2);
-            // two register buffers: the tcgen05.ld of chunk c+1 is in flight while chunk c is processed
-            uint32_t va[32], vb[32];
-            tmem_ld_32x32b_x32(taddr, va);
-#pragma unroll
-            for (int c = 0; c < BN / 64; c++) {
-                tmem_ld_wait();
-                if (c + 1 < BN / 64)
-                    tmem_ld_32x32b_x32(taddr + (c + 1) * 32, (c & 1) ? va : vb);
-                if (row0 < p.M) // warp-uniform
-                    epilogue_chunk(p, C, stage_tile, lane, row0, n_blk * BN + half * (BN / 2) + c * 32, (c & 1) ? vb : va);
-            }
+            if (!epilogue_tile<BN>(p, C, stage_tile, lane, m_blk * BM2 + (int)rank * BM + quad * 32,
+                                   n_blk * BN + half * (BN / 2), taddr, &tfull_bar[acc], acc_phase, wd))
+                break;
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0)

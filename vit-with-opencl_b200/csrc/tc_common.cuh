@@ -302,30 +302,66 @@ __device__ __forceinline__ float ex2_approx(float x)
     return y;
 }
 
-// Exact-form (erf) GELU for bf16 outputs without special-function-unit calls:
+// ---- packed fp32x2 arithmetic (sm_100: FFMA2 / FMUL2 / FADD2, two lanes per issue slot) ----
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi)
+{
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
+{
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b)
+{
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b)
+{
+    f32x2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+// Exact-form (erf) GELU for bf16 outputs without special-function-unit calls, two values at a time:
 // erf(z) = z * q(u), q a degree-10 minimax polynomial in u = 2 z^2/a^2 - 1 on |z| <= a = 3.2,
-// z clamped to [-a, a] (1 - erf(3.2) = 6e-6).  Max |erf error| 4.8e-6, max |GELU error| 1.5e-5 in
+// z clamped to [-a, a] (1 - erf(3.2) = 6e-6).  Max |erf error| 4.8e-6, max |GELU error| 2e-5 in
 // fp32 arithmetic (fit + check: tools/fit_gelu.py) -- two orders below bf16 output rounding.
-// 19 FMA-pipe instructions per value, no MUFU: the GELU epilogue of fc1 is issue-bound
-// (profiles/r01_v4_epilogue.md), and the Abramowitz-Stegun form it replaces cost ~25 incl. 2 MUFU.
-__device__ __forceinline__ float gelu_erf_fast(float x)
+// The GELU epilogue of fc1 is issue-bound (profiles/r01_v4_epilogue.md): the Abramowitz-Stegun
+// form cost ~25 instructions per value incl. 2 MUFU, the scalar polynomial 19, and with the
+// packed FFMA2 pipe of sm_100 the pair costs 20 (10 per value).
+__device__ __forceinline__ f32x2 gelu_erf_fast2(f32x2 x)
 {
     const float a = 3.2f;
-    const float z = fminf(fmaxf(x * 0.70710678118654752440f, -a), a);
-    const float u = fmaf(z * z, 2.0f / (a * a), -1.0f);
-    float q = 0.002396130235865712f;
-    q = fmaf(q, u, -0.00675334595143795f);
-    q = fmaf(q, u, 0.009276138618588448f);
-    q = fmaf(q, u, -0.015805140137672424f);
-    q = fmaf(q, u, 0.03215679153800011f);
-    q = fmaf(q, u, -0.0543348491191864f);
-    q = fmaf(q, u, 0.08094772696495056f);
-    q = fmaf(q, u, -0.1137382909655571f);
-    q = fmaf(q, u, 0.1543205976486206f);
-    q = fmaf(q, u, -0.21730200946331024f);
-    q = fmaf(q, u, 0.4413347542285919f);
-    const float hx = 0.5f * x;
-    return fmaf(hx, z * q, hx);
+    float z0, z1;
+    unpack2(mul2(x, pack2(0.70710678118654752440f, 0.70710678118654752440f)), z0, z1);
+    const f32x2 z = pack2(fminf(fmaxf(z0, -a), a), fminf(fmaxf(z1, -a), a));
+    const f32x2 u = fma2(mul2(z, z), pack2(2.0f / (a * a), 2.0f / (a * a)), pack2(-1.0f, -1.0f));
+#define VITCU_C2(c) pack2(c, c)
+    f32x2 q = VITCU_C2(0.002396130235865712f);
+    q = fma2(q, u, VITCU_C2(-0.00675334595143795f));
+    q = fma2(q, u, VITCU_C2(0.009276138618588448f));
+    q = fma2(q, u, VITCU_C2(-0.015805140137672424f));
+    q = fma2(q, u, VITCU_C2(0.03215679153800011f));
+    q = fma2(q, u, VITCU_C2(-0.0543348491191864f));
+    q = fma2(q, u, VITCU_C2(0.08094772696495056f));
+    q = fma2(q, u, VITCU_C2(-0.1137382909655571f));
+    q = fma2(q, u, VITCU_C2(0.1543205976486206f));
+    q = fma2(q, u, VITCU_C2(-0.21730200946331024f));
+    q = fma2(q, u, VITCU_C2(0.4413347542285919f));
+#undef VITCU_C2
+    const f32x2 hx = mul2(x, pack2(0.5f, 0.5f));
+    return fma2(hx, mul2(z, q), hx);
 }
 
 } // namespace tc
