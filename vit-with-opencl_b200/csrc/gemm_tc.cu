@@ -39,14 +39,15 @@ struct EpiParams {
     const float *pos;
     int patches, tokens;
     int out_bf16;
+    int tma_out; // 0: epilogue writes with LSU stores; 1: bf16 tiles by TMA store; 2: fp32 tiles by TMA reduce-add (C += tile)
 };
 
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int kThreads = 320;
 constexpr int kEpiWarps = 8;
-constexpr int kStageLd = 36;                // floats per staged epilogue row (32 + 4 pad)
-constexpr int kStageFloats = 32 * kStageLd; // per epilogue warp
+constexpr int kStageLd = 36;                // floats per staged epilogue row (32 + 4 pad), LSU path
+constexpr int kStageFloats = 2048;          // per epilogue warp: 2 x 4 KB TMA-store buffers (>= 32 * kStageLd floats)
 
 template <int BN, int STAGES>
 struct SmemLayout {
@@ -73,11 +74,12 @@ struct SmemLayout {
 // of chunk c+1 are in flight while chunk c is processed, and the first residual rows are requested
 // before the wait for the accumulator.
 template <int BN>
-__device__ __forceinline__ bool epilogue_tile(const EpiParams &p, void *C, float *stage, int lane, int row0, int col_base,
-                                              uint32_t taddr, uint64_t *tfull, uint32_t parity, const Watchdog &wd)
+__device__ __forceinline__ bool epilogue_tile(const EpiParams &p, void *C, const CUtensorMap *tmap_c, uint32_t &chunk_ctr,
+                                              float *stage, int lane, int row0, int col_base, uint32_t taddr,
+                                              uint64_t *tfull, uint32_t parity, const Watchdog &wd)
 {
     constexpr int NCHUNK = BN / 64;
-    const bool fp32_add = !p.out_bf16 && p.epilogue != VITCU_EPI_BIAS; // residual or position rows to fetch
+    const bool fp32_add = !p.tma_out && !p.out_bf16 && p.epilogue != VITCU_EPI_BIAS; // residual or position rows to fetch
     const int rsub = lane >> 3, c4 = (lane & 7) * 4;
     const float *addsrc = p.epilogue == VITCU_EPI_PATCH_EMBED ? p.pos : p.residual;
     // element offset of (row, first column of this lane) in the output / in the rows to add
@@ -136,6 +138,38 @@ __device__ __forceinline__ bool epilogue_tile(const EpiParams &p, void *C, float
             for (int j = 0; j < 32; j += 2)
                 unpack2(gelu_erf_fast2(pack2(v[j], v[j + 1])), v[j], v[j + 1]);
         }
+        if (p.tma_out) {
+            // ---- TMA path: the row-per-thread registers go straight into a swizzled shared-memory
+            // tile and the TMA engine writes (bf16) or reduce-adds (fp32 residual stream) it to global
+            // memory, clipped at M.  No global-memory latency is left on this warp's critical path.
+            uint8_t *buf = reinterpret_cast<uint8_t *>(stage) + (chunk_ctr & 1) * 4096;
+            if (lane == 0)
+                tma_wait_group_read<1>(); // the store that used this buffer two chunks ago has read it
+            __syncwarp();
+            if (p.tma_out == 1) { // 32 x 64 B rows, 64-byte swizzle: 16-byte chunk ^= (row / 2) % 4
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    *reinterpret_cast<uint4 *>(buf + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) =
+                        make_uint4(pack_bf16x2(v[8 * q + 0], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
+                                   pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
+            } else { // 32 x 128 B rows, 128-byte swizzle: 16-byte chunk ^= row % 8
+#pragma unroll
+                for (int q = 0; q < 8; q++)
+                    *reinterpret_cast<float4 *>(buf + lane * 128 + ((q ^ (lane & 7)) << 4)) =
+                        make_float4(v[4 * q + 0], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                if (p.tma_out == 1)
+                    tma_store_2d(tmap_c, buf, col0, row0);
+                else
+                    tma_reduce_add_2d(tmap_c, buf, col0, row0);
+                tma_commit_group();
+            }
+            chunk_ctr++;
+            continue;
+        }
         float4 *srow = reinterpret_cast<float4 *>(stage + lane * kStageLd);
 #pragma unroll
         for (int j = 0; j < 8; j++)
@@ -174,8 +208,8 @@ __device__ __forceinline__ bool epilogue_tile(const EpiParams &p, void *C, float
 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, void *C,
-                    const EpiParams p, uint32_t *watchdog_flag)
+gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const __grid_constant__ CUtensorMap tmap_c, void *C, const EpiParams p, uint32_t *watchdog_flag)
 {
     using L = SmemLayout<BN, STAGES>;
     static_assert(BN % 64 == 0 && BN <= 256, "BN must be 64..256 in steps of 64");
@@ -283,20 +317,24 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         // ===================== epilogue (warps 2..9) =====================
         const int quad = warp & 3;          // TMEM lanes [32*quad, 32*quad+32) are this warp's
         const int half = (warp - 2) >> 2;   // which half of the BN columns
-        uint32_t it = 0;
+        uint32_t it = 0, chunk_ctr = 0;
+        if (warp == 2 && lane == 0)
+            prefetch_tensormap(&tmap_c);
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
             const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
             const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
             float *stage_tile = reinterpret_cast<float *>(smem + L::EPI_OFFSET) + (warp - 2) * kStageFloats;
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + half * (BN / 2);
-            if (!epilogue_tile<BN>(p, C, stage_tile, lane, m_blk * BM + quad * 32, n_blk * BN + half * (BN / 2), taddr,
-                                   &tfull_bar[acc], acc_phase, wd))
+            if (!epilogue_tile<BN>(p, C, &tmap_c, chunk_ctr, stage_tile, lane, m_blk * BM + quad * 32,
+                                   n_blk * BN + half * (BN / 2), taddr, &tfull_bar[acc], acc_phase, wd))
                 break;
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0)
                 mbar_arrive(&tempty_bar[acc]);
         }
+        if (lane == 0)
+            tma_wait_group<0>(); // this warp's TMA stores have landed before the CTA retires
     }
 
     // ===================== teardown =====================
@@ -337,8 +375,8 @@ struct SmemLayout2 {
 
 template <int STAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, void *C,
-                     const EpiParams p, uint32_t *watchdog_flag)
+gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                     const __grid_constant__ CUtensorMap tmap_c, void *C, const EpiParams p, uint32_t *watchdog_flag)
 {
     using L = SmemLayout2<STAGES>;
     constexpr int BN = 256, BM2 = 256;
@@ -447,13 +485,15 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         // ===================== epilogue (warps 2..9, both CTAs) =====================
         const int quad = warp & 3;
         const int half = (warp - 2) >> 2;
-        uint32_t it = 0;
+        uint32_t it = 0, chunk_ctr = 0;
+        if (warp == 2 && lane == 0)
+            prefetch_tensormap(&tmap_c);
         for (int tile = pair; tile < num_tiles; tile += num_pairs, it++) {
             const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
             const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
             float *stage_tile = reinterpret_cast<float *>(smem + L::EPI_OFFSET) + (warp - 2) * kStageFloats;
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + half * (BN / 2);
-            if (!epilogue_tile<BN>(p, C, stage_tile, lane, m_blk * BM2 + (int)rank * BM + quad * 32,
+            if (!epilogue_tile<BN>(p, C, &tmap_c, chunk_ctr, stage_tile, lane, m_blk * BM2 + (int)rank * BM + quad * 32,
                                    n_blk * BN + half * (BN / 2), taddr, &tfull_bar[acc], acc_phase, wd))
                 break;
             tcgen05_fence_before();
@@ -461,6 +501,8 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             if (lane == 0)
                 mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0)); // the leader's barrier
         }
+        if (lane == 0)
+            tma_wait_group<0>();
     }
 
     // ===================== teardown =====================
@@ -490,7 +532,8 @@ EncodeTiledFn encode_tiled_fn()
 }
 
 template <int BN, int STAGES>
-int launch(const CUtensorMap &ta, const CUtensorMap &tb, void *C, const EpiParams &p, int sms, cudaStream_t st)
+int launch(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &tc, void *C, const EpiParams &p, int sms,
+           cudaStream_t st)
 {
     using L = SmemLayout<BN, STAGES>;
     auto kernel = gemm_bf16_tc_kernel<BN, STAGES>;
@@ -503,13 +546,14 @@ int launch(const CUtensorMap &ta, const CUtensorMap &tb, void *C, const EpiParam
     }
     const int num_tiles = ((p.M + BM - 1) / BM) * (p.N / BN);
     const int grid = num_tiles < sms ? num_tiles : sms;
-    kernel<<<grid, kThreads, L::TOTAL, st>>>(ta, tb, C, p, watchdog_flag());
+    kernel<<<grid, kThreads, L::TOTAL, st>>>(ta, tb, tc, C, p, watchdog_flag());
     VITCU_LAUNCHED();
     return 0;
 }
 
 template <int STAGES>
-int launch_pair(const CUtensorMap &ta, const CUtensorMap &tb, void *C, const EpiParams &p, int sms, cudaStream_t st)
+int launch_pair(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &tc, void *C, const EpiParams &p, int sms,
+                cudaStream_t st)
 {
     using L = SmemLayout2<STAGES>;
     auto kernel = gemm_bf16_tc2_kernel<STAGES>;
@@ -522,7 +566,7 @@ int launch_pair(const CUtensorMap &ta, const CUtensorMap &tb, void *C, const Epi
     }
     const int num_tiles = ((p.M + 255) / 256) * (p.N / 256);
     const int pairs = num_tiles < sms / 2 ? num_tiles : sms / 2;
-    kernel<<<2 * pairs, kThreads, L::TOTAL, st>>>(ta, tb, C, p, watchdog_flag());
+    kernel<<<2 * pairs, kThreads, L::TOTAL, st>>>(ta, tb, tc, C, p, watchdog_flag());
     VITCU_LAUNCHED();
     return 0;
 }
@@ -532,7 +576,7 @@ int launch_pair(const CUtensorMap &ta, const CUtensorMap &tb, void *C, const Epi
 namespace vitcu {
 
 int make_tensor_map_2d(CUtensorMap *map, const void *base, int elem_bytes, uint64_t rows, uint64_t cols,
-                       uint64_t ld_bytes, uint32_t box_rows, uint32_t box_cols)
+                       uint64_t ld_bytes, uint32_t box_rows, uint32_t box_cols, int swizzle_bytes)
 {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn)
@@ -542,9 +586,11 @@ int make_tensor_map_2d(CUtensorMap *map, const void *base, int elem_bytes, uint6
     cuuint64_t strides[1] = {ld_bytes};
     cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                  : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                  : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
     const CUresult r = fn(map, dt, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                          sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
         return set_error(VITCU_E_ARG, __FILE__, __LINE__, "cuTensorMapEncodeTiled rejected the tensor");
     return 0;
@@ -595,31 +641,45 @@ extern "C" int vitcu_gemm_bf16(const vitcu_bf16 *A, const vitcu_bf16 *W, void *C
     VITCU_REQUIRE(lda % 8 == 0 && ((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0, "operands must be 16-byte aligned");
 
     const int sms = device_sm_count();
-    // VITCU_GEMM_MODE=1cta forces the single-CTA kernels (A/B measurements)
+    // VITCU_GEMM_MODE=1cta forces the single-CTA kernels, VITCU_GEMM_EPI=lsu the LSU-store epilogue (A/B measurements)
     static const bool force_1cta = getenv("VITCU_GEMM_MODE") && !strcmp(getenv("VITCU_GEMM_MODE"), "1cta");
+    static const bool force_lsu = getenv("VITCU_GEMM_EPI") && !strcmp(getenv("VITCU_GEMM_EPI"), "lsu");
+    // Output through the TMA engine: bf16 tiles are stored; the in-place residual update
+    // C = C + (acc + bias) becomes a TMA reduce-add, so the fp32 residual stream is never read by the SMs.
+    p.tma_out = 0;
+    if (!force_lsu && ((uintptr_t)C & 15) == 0) {
+        if (p.out_bf16 && (p.epilogue == VITCU_EPI_BIAS || p.epilogue == VITCU_EPI_BIAS_GELU))
+            p.tma_out = 1;
+        else if (!p.out_bf16 && p.epilogue == VITCU_EPI_BIAS_RESIDUAL && p.residual == (const float *)C)
+            p.tma_out = 2;
+    }
+    CUtensorMap ta, tb, tc;
+    int rc = 0;
+    if (p.tma_out == 1)
+        rc = make_tensor_map_2d(&tc, C, 2, (uint64_t)d->M, (uint64_t)d->N, p.ldc * 2, 32, 32, 64);
+    else if (p.tma_out == 2)
+        rc = make_tensor_map_2d(&tc, C, 4, (uint64_t)d->M, (uint64_t)d->N, p.ldc * 4, 32, 32, 128);
+    else
+        memset(&tc, 0, sizeof(tc));
+    if (rc)
+        return rc;
     // CTA pairs on 256x256 tiles when N allows and every pair gets work
     const bool pair = !force_1cta && d->N % 256 == 0 && ((d->M + 255) / 256) * (d->N / 256) >= sms / 2;
+    rc = make_tensor_map_2d(&ta, A, 2, (uint64_t)d->M, (uint64_t)d->K, lda * 2, BM, BK);
+    if (rc)
+        return rc;
     if (pair) {
-        CUtensorMap ta, tb;
-        int rc = make_tensor_map_2d(&ta, A, 2, (uint64_t)d->M, (uint64_t)d->K, lda * 2, BM, BK);
-        if (rc)
-            return rc;
         rc = make_tensor_map_2d(&tb, W, 2, (uint64_t)d->N, (uint64_t)d->K, (uint64_t)d->K * 2, 128, BK);
         if (rc)
             return rc;
-        return launch_pair<5>(ta, tb, C, p, sms, as_stream(s));
+        return launch_pair<5>(ta, tb, tc, C, p, sms, as_stream(s));
     }
     // 128x256 tiles when they divide N and still give every SM work; else 128x128
     const bool wide = d->N % 256 == 0 && ((d->M + BM - 1) / BM) * (d->N / 256) >= sms;
-    const int BN = wide ? 256 : 128;
-    CUtensorMap ta, tb;
-    int rc = make_tensor_map_2d(&ta, A, 2, (uint64_t)d->M, (uint64_t)d->K, lda * 2, BM, BK);
-    if (rc)
-        return rc;
-    rc = make_tensor_map_2d(&tb, W, 2, (uint64_t)d->N, (uint64_t)d->K, (uint64_t)d->K * 2, BN, BK);
+    rc = make_tensor_map_2d(&tb, W, 2, (uint64_t)d->N, (uint64_t)d->K, (uint64_t)d->K * 2, wide ? 256 : 128, BK);
     if (rc)
         return rc;
     if (wide)
-        return launch<256, 3>(ta, tb, C, p, sms, as_stream(s));
-    return launch<128, 5>(ta, tb, C, p, sms, as_stream(s));
+        return launch<256, 3>(ta, tb, tc, C, p, sms, as_stream(s));
+    return launch<128, 5>(ta, tb, tc, C, p, sms, as_stream(s));
 }

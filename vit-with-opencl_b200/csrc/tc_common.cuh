@@ -122,6 +122,33 @@ __device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *m
                  : "memory");
 }
 
+// TMA stores (shared -> global), bulk-group completion
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *m, const void *smem_src, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+// global[tile] += shared[tile] (fp32), performed by the memory system: the residual add of the path
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap *m, const void *smem_src, int c0, int c1)
+{
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until at most N of this thread's bulk groups still READ their shared-memory source
+template <int N>
+__device__ __forceinline__ void tma_wait_group_read()
+{
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_wait_group()
+{
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // ---- clusters / CTA pairs ---------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank()
 {
@@ -370,6 +397,6 @@ __device__ __forceinline__ f32x2 gelu_erf_fast2(f32x2 x)
 // `elem_bytes`-wide elements (row stride ld_bytes), box {box_cols, box_rows},
 // 128-byte swizzle.  Returns 0 or a cudaError/CUresult-derived code.
 int make_tensor_map_2d(CUtensorMap *map, const void *base, int elem_bytes, uint64_t rows, uint64_t cols,
-                       uint64_t ld_bytes, uint32_t box_rows, uint32_t box_cols);
+                       uint64_t ld_bytes, uint32_t box_rows, uint32_t box_cols, int swizzle_bytes = 128);
 
 } // namespace vitcu
