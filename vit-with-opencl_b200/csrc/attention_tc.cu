@@ -49,6 +49,18 @@ struct AttnParams {
     __nv_bfloat16 *out;        // [B*T, 768]
 };
 
+__device__ __forceinline__ float max3(float a, float b, float c)
+{
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
+// NCH = number of 32-column chunks of S (ceil(KP/32)); a template parameter so the register
+// double-buffering below indexes statically (a run-time chunk loop made ptxas select between the two
+// buffers with 32 SELs per chunk and pass, and the ALU pipe, not the MUFU, became the limiter:
+// profiles/r01_v6_attention.md)
+template <int NCH>
 __global__ void __launch_bounds__(kThreadsAttn, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
                     const AttnParams p, uint32_t *watchdog_flag)
@@ -165,7 +177,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         const int row = quad * 32 + lane;   // query row inside the tile
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + tile * 256;
         const float sl2 = 0.125f * 1.4426950408889634f; // log2(e) / sqrt(64)
-        const int nchunks = (p.kp + 31) / 32;
         uint32_t it = 0;
         if (tile < ntiles) {
             for (int item = blockIdx.x; item < p.items; item += gridDim.x, it++) {
@@ -174,21 +185,21 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                 if (!mbar_wait_warp(&bars[S_FULL + tile], ph, wd, 6))
                     break;
                 tcgen05_fence_after();
-                uint32_t va[32], vb[32];
-                // pass 1: row maximum over the valid keys (loads double-buffered in registers)
+                uint32_t buf[2][32];
+                // pass 1: row maximum over the valid keys; tcgen05.ld double-buffered in registers.
+                // Only the last chunk can hold padded keys (tokens > 32 * (NCH - 1) by construction).
                 float mx = -INFINITY;
-                tmem_ld_32x32b_x32(taddr, va);
-                for (int c = 0; c < nchunks; c++) {
-                    tmem_ld_wait();
-                    uint32_t(&cur)[32] = (c & 1) ? vb : va;
-                    if (c + 1 < nchunks)
-                        tmem_ld_32x32b_x32(taddr + (c + 1) * 32, (c & 1) ? va : vb);
-                    else
-                        tmem_ld_32x32b_x32(taddr, (c & 1) ? va : vb); // chunk 0 again, for pass 2
-                    if (c * 32 + 32 <= p.tokens) {
+                tmem_ld_32x32b_x32(taddr, buf[0]);
 #pragma unroll
-                        for (int j = 0; j < 32; j++)
-                            mx = fmaxf(mx, __uint_as_float(cur[j]));
+                for (int c = 0; c < NCH; c++) {
+                    tmem_ld_wait();
+                    // next chunk, or chunk 0 again for pass 2
+                    tmem_ld_32x32b_x32(taddr + (c + 1 < NCH ? (c + 1) * 32 : 0), buf[(c + 1) & 1]);
+                    const uint32_t(&cur)[32] = buf[c & 1];
+                    if (c + 1 < NCH) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2)
+                            mx = max3(mx, __uint_as_float(cur[j]), __uint_as_float(cur[j + 1]));
                     } else {
 #pragma unroll
                         for (int j = 0; j < 32; j++)
@@ -196,34 +207,39 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                                 mx = fmaxf(mx, __uint_as_float(cur[j]));
                     }
                 }
-                // pass 2: p = exp2((s - max) * log2e/8), row sum, P (bf16 pairs) back into TMEM over S
-                const float mxs = mx * sl2;
-                float sum = 0.f;
-                for (int c = 0; c < nchunks; c++) {
+                // pass 2: p = exp2((s - max) * log2e/8), row sum, P (bf16 pairs) back into TMEM over S.
+                // The row sum is taken over the fp32 values (3 instructions per element in total:
+                // 1/2 FFMA2, 1 MUFU.EX2, 1/2 F2FP pack, 1/2 FADD2, + the max above).
+                const f32x2 sl2v = pack2(sl2, sl2), nmx = pack2(-mx * sl2, -mx * sl2);
+                f32x2 sum2 = pack2(0.f, 0.f);
+#pragma unroll
+                for (int c = 0; c < NCH; c++) {
                     tmem_ld_wait();
-                    // pass 1 left chunk 0 in the buffer selected by nchunks' parity
-                    uint32_t(&cur)[32] = ((c + nchunks) & 1) ? vb : va;
-                    if (c + 1 < nchunks)
-                        tmem_ld_32x32b_x32(taddr + (c + 1) * 32, ((c + nchunks) & 1) ? va : vb);
+                    if (c + 1 < NCH)
+                        tmem_ld_32x32b_x32(taddr + (c + 1) * 32, buf[(NCH + c + 1) & 1]);
+                    const uint32_t(&cur)[32] = buf[(NCH + c) & 1];
                     uint32_t packed[16];
 #pragma unroll
                     for (int j = 0; j < 16; j++) {
-                        float e0 = ex2_approx(fmaf(__uint_as_float(cur[2 * j]), sl2, -mxs));
-                        float e1 = ex2_approx(fmaf(__uint_as_float(cur[2 * j + 1]), sl2, -mxs));
-                        if (c * 32 + 2 * j >= p.tokens)
-                            e0 = 0.f;
-                        if (c * 32 + 2 * j + 1 >= p.tokens)
-                            e1 = 0.f;
-                        // the bf16-rounded values are what the MMA sums, so sum those
-                        const __nv_bfloat162 h = __floats2bfloat162_rn(e0, e1);
-                        packed[j] = *reinterpret_cast<const uint32_t *>(&h);
-                        const float2 f = __bfloat1622float2(h);
-                        sum += f.x + f.y;
+                        float a0, a1;
+                        unpack2(fma2(pack2(__uint_as_float(cur[2 * j]), __uint_as_float(cur[2 * j + 1])), sl2v, nmx), a0, a1);
+                        float e0 = ex2_approx(a0), e1 = ex2_approx(a1);
+                        if (c + 1 == NCH) { // padded keys contribute nothing
+                            if (c * 32 + 2 * j >= p.tokens)
+                                e0 = 0.f;
+                            if (c * 32 + 2 * j + 1 >= p.tokens)
+                                e1 = 0.f;
+                        }
+                        sum2 = add2(sum2, pack2(e0, e1));
+                        packed[j] = pack_bf16x2(e0, e1);
                     }
                     // P columns [16c, 16c+16) overwrite S columns that are already consumed
                     // (chunk c/2 <= c) or not yet prefetched (chunk c+1 starts at column 32c+32)
                     tmem_st_32x32b_x16(taddr + c * 16, packed);
                 }
+                float sum, sum_hi;
+                unpack2(sum2, sum, sum_hi);
+                sum += sum_hi;
                 tmem_st_wait();
                 tcgen05_fence_before();
                 __syncwarp();
@@ -237,8 +253,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                 const float inv = 1.0f / sum;
                 const int q = tile * QT + row;
                 __nv_bfloat16 *dst = p.out + (static_cast<size_t>(img) * p.tokens + q) * kEmbed + head * kHeadDim;
-                tmem_ld_32x32b_x32(taddr + O_COL, va);
-                tmem_ld_32x32b_x32(taddr + O_COL + 32, vb);
+                tmem_ld_32x32b_x32(taddr + O_COL, buf[0]);
+                tmem_ld_32x32b_x32(taddr + O_COL + 32, buf[1]);
                 tmem_ld_wait();
                 tcgen05_fence_before();
                 __syncwarp();
@@ -247,7 +263,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                 if (q < p.tokens) {
 #pragma unroll
                     for (int c = 0; c < 2; c++) {
-                        const uint32_t(&v)[32] = c ? vb : va;
+                        const uint32_t(&v)[32] = buf[c];
 #pragma unroll
                         for (int j = 0; j < 4; j++)
                             reinterpret_cast<uint4 *>(dst + c * 32)[j] = make_uint4(
@@ -318,13 +334,6 @@ int attention_bf16_tc(const void *qkv, void *out, int batch, int tokens, cudaStr
         return rc;
     const size_t smem = 2 * (2 * (size_t)Q_BYTES + 2 * (size_t)kp * 128) + NUM_BARS * 8 + 16 + 1024;
     VITCU_REQUIRE(smem <= 227 * 1024, "attention tile does not fit shared memory");
-    static int configured[64] = {0};
-    int dev = 0;
-    VITCU_TRY(cudaGetDevice(&dev));
-    if (dev < 64 && configured[dev] < (int)smem) {
-        VITCU_TRY(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[dev] = (int)smem;
-    }
     AttnParams p;
     p.batch = batch;
     p.tokens = tokens;
@@ -333,7 +342,33 @@ int attention_bf16_tc(const void *qkv, void *out, int batch, int tokens, cudaStr
     p.out = reinterpret_cast<__nv_bfloat16 *>(out);
     const int sms = device_sm_count();
     const int grid = p.items < sms ? p.items : sms;
-    attention_tc_kernel<<<grid, kThreadsAttn, smem, st>>>(tq, tkv, p, watchdog_flag());
+    int dev = 0;
+    VITCU_TRY(cudaGetDevice(&dev));
+    const int nch = (kp + 31) / 32;
+#define VITCU_ATTN_CASE(N)                                                                                          \
+    case N: {                                                                                                       \
+        static int configured[64] = {0};                                                                            \
+        if (dev < 64 && configured[dev] < (int)smem) {                                                              \
+            VITCU_TRY(cudaFuncSetAttribute(attention_tc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                           (int)smem));                                                             \
+            configured[dev] = (int)smem;                                                                            \
+        }                                                                                                           \
+        attention_tc_kernel<N><<<grid, kThreadsAttn, smem, st>>>(tq, tkv, p, watchdog_flag());                     \
+        break;                                                                                                      \
+    }
+    switch (nch) {
+        VITCU_ATTN_CASE(1)
+        VITCU_ATTN_CASE(2)
+        VITCU_ATTN_CASE(3)
+        VITCU_ATTN_CASE(4)
+        VITCU_ATTN_CASE(5)
+        VITCU_ATTN_CASE(6)
+        VITCU_ATTN_CASE(7)
+        VITCU_ATTN_CASE(8)
+    default:
+        return set_error(VITCU_E_ARG, __FILE__, __LINE__, "unsupported key count");
+    }
+#undef VITCU_ATTN_CASE
     VITCU_LAUNCHED();
     return 0;
 }
