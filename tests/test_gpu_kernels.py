@@ -177,6 +177,26 @@ def test_attention_tensor_core(pkg, lib, oracle, T, batch):
         assert err.max() <= tol, f"image {i}: max err {err.max()} at {np.unravel_index(err.argmax(), err.shape)} tol {tol}"
 
 
+@pytest.mark.parametrize("T,batch", [(577, 2), (300, 1), (257, 1), (640, 1), (1025, 1), (577, 20)])
+def test_attention_flash_tensor_core(pkg, lib, oracle, T, batch):
+    """key-blocked tcgen05 attention (tokens > 256): odd tile counts, ragged last key block, 577 tokens"""
+    rng = np.random.default_rng(2000 + T + batch)
+    bits = pkg.f32_to_bf16_bits((rng.standard_normal((batch, T, 2304), dtype=np.float32) * 1.5).astype(np.float32))
+    qkv = pkg.bf16_bits_to_f32(bits).reshape(batch, T, 2304)
+    dq = _dev(pkg, bits)
+    do = pkg.DeviceBuffer(batch * T * 768 * 2)
+    pkg.layer_check(lib.vitcu_memset(do.ptr, 0xFF, batch * T * 768 * 2, None))
+    pkg.layer_check(lib.vitcu_attention(dq.ptr, do.ptr, batch, T, 1, None))
+    assert lib.vitcu_watchdog_check() == 0
+    out = pkg.bf16_bits_to_f32(do.to_numpy(np.uint16, (batch, T, 768)))
+    assert np.isfinite(out).all()
+    for i in sorted({0, batch - 1}):
+        ref = oracle.attention_core(qkv[i, :, :768], qkv[i, :, 768:1536], qkv[i, :, 1536:])
+        tol = 3 * 2.0 ** -8 * np.abs(ref).max() + 1e-3
+        err = np.abs(out[i] - ref)
+        assert err.max() <= tol, f"image {i}: max err {err.max()} at {np.unravel_index(err.argmax(), err.shape)} tol {tol}"
+
+
 # ---------------------------------------------------------------- softmax
 def test_softmax_rows(pkg, lib, oracle):
     rng = np.random.default_rng(3)

@@ -189,17 +189,23 @@ size_t attention_simt_smem(int tokens)
 } // namespace
 
 namespace vitcu {
-int attention_bf16_tc(const void *qkv, void *out, int batch, int tokens, cudaStream_t st); // attention_tc.cu
+int attention_bf16_tc(const void *qkv, void *out, int batch, int tokens, cudaStream_t st);       // attention_tc.cu
+int attention_bf16_flash_tc(const void *qkv, void *out, int batch, int tokens, cudaStream_t st); // attention_flash_tc.cu
 }
 
 extern "C" int vitcu_attention(const void *qkv, void *out, int batch, int tokens, int is_bf16, vitcu_stream s)
 {
     VITCU_REQUIRE(qkv && out && batch > 0 && tokens > 0, "bad argument");
-    // BF16 storage and a key count that fits one TMEM accumulator: tensor-core kernel.
-    // (VITCU_ATTN_SIMT=1 forces the CUDA-core kernel, for A/B measurements.)
+    // BF16 storage: tensor-core kernels -- all keys in one TMEM accumulator when they fit (<= 256),
+    // key-blocked online softmax otherwise.  (VITCU_ATTN_SIMT=1 forces the CUDA-core kernel and
+    // VITCU_ATTN_FLASH=1 the key-blocked kernel, for A/B measurements.)
     static const bool force_simt = getenv("VITCU_ATTN_SIMT") != nullptr;
-    if (is_bf16 && tokens <= 256 && !force_simt)
-        return attention_bf16_tc(qkv, out, batch, tokens, as_stream(s));
+    static const bool force_flash = getenv("VITCU_ATTN_FLASH") != nullptr;
+    if (is_bf16 && !force_simt) {
+        if (tokens <= 256 && !force_flash)
+            return attention_bf16_tc(qkv, out, batch, tokens, as_stream(s));
+        return attention_bf16_flash_tc(qkv, out, batch, tokens, as_stream(s));
+    }
     const size_t smem = attention_simt_smem(tokens);
     VITCU_REQUIRE(smem <= 227 * 1024, "token count too large for the shared-memory score tile");
     dim3 grid((tokens + QT - 1) / QT, kHeads, batch);
