@@ -364,16 +364,31 @@ def run_engine_arm(args, dist: Dist):
     kernels = eng.kernels_per_forward
 
     # ---- end to end through the public C-ABI call, host buffers ----
-    for _ in range(max(args.warmup, 3)):
+    # The reference-facing call takes n images and returns n probability rows (ViT_opencl's
+    # contract), so the K steps go through ONE vitb200_forward over K*256 pinned host images:
+    # every step's 154 MB of pixels crosses PCIe inside the timed region and every step's
+    # probabilities come back, with the engine overlapping the upload of step i+1 with the
+    # compute of step i, as it does for any caller.
+    n_e2e = BATCH * args.steps
+    big = pkg.PinnedArray((n_e2e, 3, IMG, IMG))
+    for s_ in range(args.steps):
+        big.array[s_ * BATCH:(s_ + 1) * BATCH] = pinned.array
+    probs_big = np.empty((n_e2e, 1000), np.float32)
+    for _ in range(2):
         eng.forward_into(pinned.array, probs)
     dist.barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        eng.forward_into(pinned.array, probs)
+    eng.forward_into(big.array, probs_big)
     e2e_s = time.perf_counter() - t0
     dist.barrier()
     e2e_s = dist.reduce(e2e_s, "max")
-    e2e = dist.world * BATCH * args.steps / e2e_s
+    e2e = dist.world * n_e2e / e2e_s
+    # the same call for a single 256-image batch (no cross-step overlap possible)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        eng.forward_into(pinned.array, probs)
+    e2e_single = 3 * BATCH / (time.perf_counter() - t0)
+    big.free()
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": dist.world, "steps": args.steps,
@@ -387,7 +402,10 @@ def run_engine_arm(args, dist: Dist):
                          "is far larger than the 126 MB L2"},
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": BATCH * 3 * IMG * IMG * 4,
-                "d2h_bytes_per_step": BATCH * 1000 * 4, "api": "vitb200_forward (pinned host images in, probabilities out)"},
+                "d2h_bytes_per_step": BATCH * 1000 * 4,
+                "api": "one vitb200_forward call over steps*256 pinned host images (probabilities out); "
+                       "upload of step i+1 overlaps compute of step i",
+                "single_batch_call_images_per_s": e2e_single * dist.world},
         "gpu_launches": kernels * args.steps,
         "path_tflops": value / dist.world * GFLOP_PER_IMAGE_224 / 1e3,
         "path_frac_of_sustained_peak": value / dist.world * GFLOP_PER_IMAGE_224 / 1e3 / peaks["bf16_sustained"],
