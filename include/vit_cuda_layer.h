@@ -89,6 +89,10 @@ int vitcu_watchdog_check(void);
 /* fp32 -> bf16 (round-to-nearest-even), n elements.  One-time weight packing. */
 int vitcu_f32_to_bf16(const float *src, vitcu_bf16 *dst, size_t n, vitcu_stream s);
 
+/* fp32 [rows,K] (row stride ld) -> bf16 [rows, 3K] = [x1 | x2 | x3] with x = x1 + x2 + x3 to 24
+ * mantissa bits: the operand format of vitcu_gemm_bf16x3 (FP32 path on the tensor cores). */
+int vitcu_split3(const float *x, size_t ld, vitcu_bf16 *out, size_t rows, int K, vitcu_stream s);
+
 /* Patch gather (replaces the data movement of conv2d_kernel, R/conv2d.cl:1-36):
  * images [B,3,img,img] fp32 -> patches [B*P, 768] with column order (c,kh,kw),
  * the order Conv2d_seq accumulates in (R/ViT_seq.c:37-48).  out_bf16 selects
@@ -104,7 +108,8 @@ int vitcu_cls_rows(float *x, const float *cls, const float *pos, int batch, int 
 /* LayerNorm over 768 features (replaces layerNorm, R/layer_norm.cl:3-53; oracle
  * R/ViT_seq.c:120-142).  rows = number of rows normalised; row r is read at
  * x + r*x_row_stride (elements) so the final LN can visit only the class-token
- * rows; output rows are dense [rows,768], fp32 or bf16. */
+ * rows; output rows are dense: y_bf16 = 0 fp32 [rows,768], 1 bf16 [rows,768], 2 three bf16
+ * pieces [rows,3*768] (see vitcu_split3). */
 int vitcu_layernorm(const float *x, size_t x_row_stride, void *y, int y_bf16,
                     const float *gamma, const float *beta, int rows, vitcu_stream s);
 
@@ -138,6 +143,13 @@ int vitcu_sgemm(const float *A, const float *W, void *C, const vitcu_gemm_desc *
  * A [M,K] bf16 (lda == K), W [N,K] bf16.  Requires K % 64 == 0, N % 16 == 0. */
 int vitcu_gemm_bf16(const vitcu_bf16 *A, const vitcu_bf16 *W, void *C,
                     const vitcu_gemm_desc *d, vitcu_stream s);
+
+/* FP32-accurate GEMM on the BF16 tensor cores: A3 [M,3K] and W3 [N,3K] hold the three bf16 pieces
+ * of the fp32 operands (vitcu_split3); C = sum of the six significant piece products, FP32
+ * accumulation in TMEM, relative error ~1e-7.  d->K is the logical K (K % 64 == 0); epilogues as
+ * above, GELU evaluated with erff when the output is fp32. */
+int vitcu_gemm_bf16x3(const vitcu_bf16 *A3, const vitcu_bf16 *W3, void *C, const vitcu_gemm_desc *d,
+                      vitcu_stream s);
 
 /* Multi-head attention core over a fused QKV buffer (replaces QKV_TO_SCOREV,
  * R/multihead.cl:65-137; oracle R/ViT_seq.c:192-262): qkv [B*T, 2304] with

@@ -307,3 +307,49 @@ def test_gemm_rejects_bad_shapes(pkg, lib):
     assert b"K % 64" in lib.vitcu_last_error()
     d = _gemm_desc(pkg, 0, 128, 64, 0, b)  # empty
     assert lib.vitcu_sgemm(b.ptr, b.ptr, b.ptr, C.byref(d), None) != 0
+
+
+# ---------------------------------------------------------------- FP32 on the tensor cores (split-bf16)
+def test_split3_reconstructs_fp32(pkg, lib):
+    rng = np.random.default_rng(4)
+    x = (rng.standard_normal((37, 768), dtype=np.float32) * np.float32(3.0)).astype(np.float32)
+    dx = _dev(pkg, x)
+    do = pkg.DeviceBuffer(37 * 3 * 768 * 2)
+    pkg.layer_check(lib.vitcu_split3(dx.ptr, 768, do.ptr, 37, 768, None))
+    parts = pkg.bf16_bits_to_f32(do.to_numpy(np.uint16, (37, 3, 768)))
+    assert np.array_equal(parts[:, 0], pkg.bf16_bits_to_f32(pkg.f32_to_bf16_bits(x)))
+    recon = parts[:, 0].astype(np.float64) + parts[:, 1] + parts[:, 2]
+    assert np.abs(recon - x).max() <= 2.0 ** -23 * np.abs(x).max()
+
+
+@pytest.mark.parametrize("M,N,K,epi", [(197, 2304, 768, 0), (197, 3072, 768, 1), (197, 768, 3072, 2), (6304, 768, 768, 2),
+                                       (12608, 3072, 768, 1)])
+def test_gemm_bf16x3_is_fp32_accurate(pkg, lib, oracle, M, N, K, epi):
+    """six split-bf16 products on tcgen05 == fp32 GEMM to ~1e-6 relative (oracle: R/ViT_seq.c:295-309)"""
+    rng = np.random.default_rng(M + N + K)
+    x = rng.standard_normal((M, K), dtype=np.float32)
+    w = (rng.standard_normal((N, K), dtype=np.float32) * 0.03).astype(np.float32)
+    b = rng.standard_normal(N, dtype=np.float32)
+    dx, dw, db = _dev(pkg, x), _dev(pkg, w), _dev(pkg, b)
+    dx3, dw3 = pkg.DeviceBuffer(M * 3 * K * 2), pkg.DeviceBuffer(N * 3 * K * 2)
+    pkg.layer_check(lib.vitcu_split3(dx.ptr, K, dx3.ptr, M, K, None))
+    pkg.layer_check(lib.vitcu_split3(dw.ptr, K, dw3.ptr, N, K, None))
+    exact = x.astype(np.float64) @ w.astype(np.float64).T + b
+    if epi == 2:
+        r = rng.standard_normal((M, N), dtype=np.float32)
+        dc = _dev(pkg, r)
+        d = _gemm_desc(pkg, M, N, K, pkg.EPI_BIAS_RESIDUAL, db, residual=dc)
+        ref = exact + r
+    else:
+        dc = pkg.DeviceBuffer(M * N * 4)
+        d = _gemm_desc(pkg, M, N, K, pkg.EPI_BIAS_GELU if epi == 1 else pkg.EPI_BIAS, db)
+        ref = exact
+        if epi == 1:
+            from scipy.special import erf
+            ref = 0.5 * exact * (1.0 + erf(exact / np.sqrt(2.0)))
+    pkg.layer_check(lib.vitcu_gemm_bf16x3(dx3.ptr, dw3.ptr, dc.ptr, C.byref(d), None))
+    assert lib.vitcu_watchdog_check() == 0
+    y = dc.to_numpy(np.float32, (M, N))
+    assert np.abs(y - ref).max() <= 5e-6 * np.abs(ref).max()  # fp32 accumulation over up to 6*3072 products
+    if M <= 400 and epi == 0:  # and against the sequential fp32 oracle itself
+        assert _rel_err(y, oracle.linear(x, w, b)) <= 2e-5

@@ -116,6 +116,8 @@ def lib() -> C.CDLL:
                                       C.c_void_p]
         L.vitcu_sgemm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(GemmDesc), C.c_void_p]
         L.vitcu_gemm_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(GemmDesc), C.c_void_p]
+        L.vitcu_gemm_bf16x3.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(GemmDesc), C.c_void_p]
+        L.vitcu_split3.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
         L.vitcu_attention.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.vitcu_softmax_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         _lib = L

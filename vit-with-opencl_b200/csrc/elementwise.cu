@@ -25,6 +25,43 @@ __global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float4 *__restri
 }
 
 // ---------------------------------------------------------------------------
+// fp32 -> three bf16 pieces (x = x1 + x2 + x3 to 24 mantissa bits).  The FP32 path of the engine
+// runs its GEMMs on the BF16 tensor cores as six piece products with FP32 accumulation
+// (a3 w1 + a2 w2 + a1 w3 + a2 w1 + a1 w2 + a1 w1: relative error ~1e-7, below a plain fp32 GEMM's
+// summation error), see vitcu_gemm_bf16x3.  Output row r = [x1 | x2 | x3], each K wide.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void split3(float x, __nv_bfloat16 &p1, __nv_bfloat16 &p2, __nv_bfloat16 &p3)
+{
+    p1 = __float2bfloat16_rn(x);
+    const float r1 = x - __bfloat162float(p1);
+    p2 = __float2bfloat16_rn(r1);
+    p3 = __float2bfloat16_rn(r1 - __bfloat162float(p2));
+}
+__device__ __forceinline__ void split3_store4(__nv_bfloat16 *row, int K, int col, float4 v)
+{
+    __nv_bfloat16 a[4], b[4], c[4];
+    split3(v.x, a[0], b[0], c[0]);
+    split3(v.y, a[1], b[1], c[1]);
+    split3(v.z, a[2], b[2], c[2]);
+    split3(v.w, a[3], b[3], c[3]);
+    *reinterpret_cast<uint2 *>(row + col) = *reinterpret_cast<const uint2 *>(a);
+    *reinterpret_cast<uint2 *>(row + K + col) = *reinterpret_cast<const uint2 *>(b);
+    *reinterpret_cast<uint2 *>(row + 2 * K + col) = *reinterpret_cast<const uint2 *>(c);
+}
+__global__ void __launch_bounds__(256) split3_kernel(const float *__restrict__ x, size_t ld, __nv_bfloat16 *__restrict__ out,
+                                                     size_t rows, int K)
+{
+    const size_t k4 = K / 4, total = rows * k4;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) {
+        const size_t r = i / k4;
+        const int c = (int)(i - r * k4) * 4;
+        split3_store4(out + r * 3 * (size_t)K, K, c, *reinterpret_cast<const float4 *>(x + r * ld + c));
+    }
+}
+
+// ---------------------------------------------------------------------------
 // patch gather: [B,3,img,img] -> [B*P, 768], column = (c*16 + kh)*16 + kw, the
 // accumulation order of Conv2d_seq (R/ViT_seq.c:37-48).  One thread moves one
 // 16-byte chunk (4 kw values): 4 threads cover a contiguous 64-byte image run.
@@ -73,7 +110,7 @@ __global__ void __launch_bounds__(192) cls_rows_kernel(float *__restrict__ x, co
 // R/ViT_seq.c:126-135), eps 1e-6, output fp32 or bf16.
 // Algorithmic bytes per row: 768*4 read + 768*(4|2) written.
 // ---------------------------------------------------------------------------
-template <bool kBf16>
+template <int kOut> // 0: fp32, 1: bf16, 2: three bf16 pieces [rows, 3*768]
 __global__ void __launch_bounds__(256) layernorm_kernel(const float *__restrict__ x, size_t x_row_stride,
                                                         void *__restrict__ y, const float *__restrict__ gamma,
                                                         const float *__restrict__ beta, int rows)
@@ -109,9 +146,11 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float *__restrict_
         o.y = (v[i].y - mean) * inv_std * g.y + bb.y;
         o.z = (v[i].z - mean) * inv_std * g.z + bb.z;
         o.w = (v[i].w - mean) * inv_std * g.w + bb.w;
-        if (kBf16) {
+        if (kOut == 1) {
             reinterpret_cast<uint2 *>(reinterpret_cast<__nv_bfloat16 *>(y) + (size_t)row * kEmbed)[lane + 32 * i] =
                 make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+        } else if (kOut == 2) {
+            split3_store4(reinterpret_cast<__nv_bfloat16 *>(y) + (size_t)row * 3 * kEmbed, kEmbed, (lane + 32 * i) * 4, o);
         } else {
             reinterpret_cast<float4 *>(reinterpret_cast<float *>(y) + (size_t)row * kEmbed)[lane + 32 * i] = o;
         }
@@ -180,6 +219,15 @@ int vitcu_f32_to_bf16(const float *src, vitcu_bf16 *dst, size_t n, vitcu_stream 
     return 0;
 }
 
+int vitcu_split3(const float *x, size_t ld, vitcu_bf16 *out, size_t rows, int K, vitcu_stream s)
+{
+    VITCU_REQUIRE(x && out && rows > 0 && K > 0 && K % 4 == 0 && ld % 4 == 0 && ld >= (size_t)K, "bad argument");
+    split3_kernel<<<grid_for(rows * (size_t)(K / 4), 256, 148 * 32), 256, 0, as_stream(s)>>>(
+        x, ld, reinterpret_cast<__nv_bfloat16 *>(out), rows, K);
+    VITCU_LAUNCHED();
+    return 0;
+}
+
 int vitcu_patch_gather(const float *images, void *patches, int batch, int img, int out_bf16, vitcu_stream s)
 {
     VITCU_REQUIRE(images && patches, "NULL buffer");
@@ -209,10 +257,12 @@ int vitcu_layernorm(const float *x, size_t x_row_stride, void *y, int y_bf16, co
     VITCU_REQUIRE(x && y && gamma && beta && rows > 0, "bad argument");
     VITCU_REQUIRE(x_row_stride % 4 == 0 && x_row_stride >= (size_t)kEmbed, "row stride must be >= 768 and a multiple of 4");
     const int grid = (rows + 7) / 8;
-    if (y_bf16)
-        layernorm_kernel<true><<<grid, 256, 0, as_stream(s)>>>(x, x_row_stride, y, gamma, beta, rows);
+    if (y_bf16 == 1)
+        layernorm_kernel<1><<<grid, 256, 0, as_stream(s)>>>(x, x_row_stride, y, gamma, beta, rows);
+    else if (y_bf16 == 2)
+        layernorm_kernel<2><<<grid, 256, 0, as_stream(s)>>>(x, x_row_stride, y, gamma, beta, rows);
     else
-        layernorm_kernel<false><<<grid, 256, 0, as_stream(s)>>>(x, x_row_stride, y, gamma, beta, rows);
+        layernorm_kernel<0><<<grid, 256, 0, as_stream(s)>>>(x, x_row_stride, y, gamma, beta, rows);
     VITCU_LAUNCHED();
     return 0;
 }

@@ -39,7 +39,11 @@ struct EpiParams {
     const float *pos;
     int patches, tokens;
     int out_bf16;
-    int tma_out; // 0: epilogue writes with LSU stores; 1: bf16 tiles by TMA store; 2: fp32 tiles by TMA reduce-add (C += tile)
+    int tma_out; // 0: epilogue writes with LSU stores; 1: bf16 tiles by TMA store; 2: fp32 tiles by TMA reduce-add (C += tile); 3: fp32 tiles by TMA store
+    int exact_gelu; // erff instead of the polynomial (fp32 outputs of the split-bf16 FP32 path)
+    // K loop as a list of segments (split-bf16 FP32 path: six piece products over one K range)
+    int nseg, seg_kb;        // segments, k-blocks per segment
+    int a_seg[6], b_seg[6];  // column offset (elements) of each segment in A and in W
 };
 
 constexpr int BM = 128;
@@ -134,9 +138,15 @@ __device__ __forceinline__ bool epilogue_tile(const EpiParams &p, void *C, const
             v[j + 3] = __uint_as_float(acc[c & 1][j + 3]) + b.w;
         }
         if (p.epilogue == VITCU_EPI_BIAS_GELU) {
+            if (p.exact_gelu) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 2)
-                unpack2(gelu_erf_fast2(pack2(v[j], v[j + 1])), v[j], v[j + 1]);
+                for (int j = 0; j < 32; j++)
+                    v[j] = gelu_erf(v[j]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; j += 2)
+                    unpack2(gelu_erf_fast2(pack2(v[j], v[j + 1])), v[j], v[j + 1]);
+            }
         }
         if (p.tma_out) {
             // ---- TMA path: the row-per-thread registers go straight into a swizzled shared-memory
@@ -161,10 +171,10 @@ __device__ __forceinline__ bool epilogue_tile(const EpiParams &p, void *C, const
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-                if (p.tma_out == 1)
-                    tma_store_2d(tmap_c, buf, col0, row0);
-                else
+                if (p.tma_out == 2)
                     tma_reduce_add_2d(tmap_c, buf, col0, row0);
+                else
+                    tma_store_2d(tmap_c, buf, col0, row0);
                 tma_commit_group();
             }
             chunk_ctr++;
@@ -249,7 +259,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const Watchdog wd{cta_abort, watchdog_flag};
 
     const int num_m = (p.M + BM - 1) / BM, num_n = p.N / BN;
-    const int num_tiles = num_m * num_n, num_kb = p.K / BK;
+    const int num_tiles = num_m * num_n, num_kb = p.nseg * p.seg_kb;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -271,8 +281,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 if (elect_one()) {
                     uint8_t *sa = smem + stage * L::STAGE_BYTES;
                     mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-                    tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
-                    tma_load_2d(sa + L::A_BYTES, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN);
+                    const int seg = kb / p.seg_kb, kk = (kb - seg * p.seg_kb) * BK;
+                    tma_load_2d(sa, &tmap_a, &full_bar[stage], p.a_seg[seg] + kk, m_blk * BM);
+                    tma_load_2d(sa + L::A_BYTES, &tmap_b, &full_bar[stage], p.b_seg[seg] + kk, n_blk * BN);
                 }
                 __syncwarp();
                 if (++stage == STAGES) {
@@ -417,7 +428,7 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     const Watchdog wd{cta_abort, watchdog_flag};
 
     const int num_m = (p.M + BM2 - 1) / BM2, num_n = p.N / BN;
-    const int num_tiles = num_m * num_n, num_kb = p.K / BK;
+    const int num_tiles = num_m * num_n, num_kb = p.nseg * p.seg_kb;
     const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
 
     if (warp == 0) {
@@ -437,8 +448,9 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                     uint8_t *sa = smem + stage * L::STAGE_BYTES;
                     const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
                     mbar_arrive_expect_tx_cluster(full_leader, L::STAGE_BYTES);
-                    tma_load_2d_2sm(sa, &tmap_a, full_leader, kb * BK, m_blk * BM2 + (int)rank * BM);
-                    tma_load_2d_2sm(sa + L::A_BYTES, &tmap_b, full_leader, kb * BK, n_blk * BN + (int)rank * 128);
+                    const int seg = kb / p.seg_kb, kk = (kb - seg * p.seg_kb) * BK;
+                    tma_load_2d_2sm(sa, &tmap_a, full_leader, p.a_seg[seg] + kk, m_blk * BM2 + (int)rank * BM);
+                    tma_load_2d_2sm(sa + L::A_BYTES, &tmap_b, full_leader, p.b_seg[seg] + kk, n_blk * BN + (int)rank * 128);
                 }
                 __syncwarp();
                 if (++stage == STAGES) {
@@ -613,8 +625,8 @@ int device_sm_count()
 
 } // namespace vitcu
 
-extern "C" int vitcu_gemm_bf16(const vitcu_bf16 *A, const vitcu_bf16 *W, void *C, const vitcu_gemm_desc *d,
-                               vitcu_stream s)
+static int gemm_dispatch(const vitcu_bf16 *A, const vitcu_bf16 *W, void *C, const vitcu_gemm_desc *d, bool split3,
+                         vitcu_stream s)
 {
     VITCU_REQUIRE(A && W && C && d, "NULL argument");
     VITCU_REQUIRE(d->M > 0 && d->N > 0 && d->K > 0, "empty GEMM");
@@ -625,6 +637,7 @@ extern "C" int vitcu_gemm_bf16(const vitcu_bf16 *A, const vitcu_bf16 *W, void *C
     VITCU_REQUIRE(d->epilogue != VITCU_EPI_PATCH_EMBED || (d->pos && d->patches > 0 && d->tokens > d->patches),
                   "patch-embed epilogue needs pos, patches, tokens");
     EpiParams p;
+    memset(&p, 0, sizeof(p));
     p.M = d->M;
     p.N = d->N;
     p.K = d->K;
@@ -636,28 +649,46 @@ extern "C" int vitcu_gemm_bf16(const vitcu_bf16 *A, const vitcu_bf16 *W, void *C
     p.patches = d->patches;
     p.tokens = d->tokens;
     p.out_bf16 = d->out_bf16;
+    p.exact_gelu = split3 && !d->out_bf16;
     VITCU_REQUIRE(p.ldc % 8 == 0, "ldc must be a multiple of 8");
-    const size_t lda = d->lda ? d->lda : (size_t)d->K;
+    const uint64_t kphys = split3 ? 3 * (uint64_t)d->K : (uint64_t)d->K; // physical operand width
+    const size_t lda = split3 ? (size_t)kphys : (d->lda ? d->lda : (size_t)d->K);
     VITCU_REQUIRE(lda % 8 == 0 && ((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0, "operands must be 16-byte aligned");
+    p.seg_kb = d->K / BK;
+    if (split3) {
+        // small products first: a3 w1, a2 w2, a1 w3, a2 w1, a1 w2, a1 w1
+        const int K = d->K;
+        const int as[6] = {2 * K, K, 0, K, 0, 0}, bs[6] = {0, K, 2 * K, 0, K, 0};
+        p.nseg = 6;
+        for (int i = 0; i < 6; i++) {
+            p.a_seg[i] = as[i];
+            p.b_seg[i] = bs[i];
+        }
+    } else {
+        p.nseg = 1;
+    }
 
     const int sms = device_sm_count();
     // VITCU_GEMM_MODE=1cta forces the single-CTA kernels, VITCU_GEMM_EPI=lsu the LSU-store epilogue (A/B measurements)
     static const bool force_1cta = getenv("VITCU_GEMM_MODE") && !strcmp(getenv("VITCU_GEMM_MODE"), "1cta");
     static const bool force_lsu = getenv("VITCU_GEMM_EPI") && !strcmp(getenv("VITCU_GEMM_EPI"), "lsu");
-    // Output through the TMA engine: bf16 tiles are stored; the in-place residual update
+    // Output through the TMA engine: bf16 / fp32 tiles are stored; the in-place residual update
     // C = C + (acc + bias) becomes a TMA reduce-add, so the fp32 residual stream is never read by the SMs.
     p.tma_out = 0;
     if (!force_lsu && ((uintptr_t)C & 15) == 0) {
-        if (p.out_bf16 && (p.epilogue == VITCU_EPI_BIAS || p.epilogue == VITCU_EPI_BIAS_GELU))
+        const bool plain = p.epilogue == VITCU_EPI_BIAS || p.epilogue == VITCU_EPI_BIAS_GELU;
+        if (p.out_bf16 && plain)
             p.tma_out = 1;
         else if (!p.out_bf16 && p.epilogue == VITCU_EPI_BIAS_RESIDUAL && p.residual == (const float *)C)
             p.tma_out = 2;
+        else if (!p.out_bf16 && plain)
+            p.tma_out = 3;
     }
     CUtensorMap ta, tb, tc;
     int rc = 0;
     if (p.tma_out == 1)
         rc = make_tensor_map_2d(&tc, C, 2, (uint64_t)d->M, (uint64_t)d->N, p.ldc * 2, 32, 32, 64);
-    else if (p.tma_out == 2)
+    else if (p.tma_out >= 2)
         rc = make_tensor_map_2d(&tc, C, 4, (uint64_t)d->M, (uint64_t)d->N, p.ldc * 4, 32, 32, 128);
     else
         memset(&tc, 0, sizeof(tc));
@@ -665,21 +696,33 @@ extern "C" int vitcu_gemm_bf16(const vitcu_bf16 *A, const vitcu_bf16 *W, void *C
         return rc;
     // CTA pairs on 256x256 tiles when N allows and every pair gets work
     const bool pair = !force_1cta && d->N % 256 == 0 && ((d->M + 255) / 256) * (d->N / 256) >= sms / 2;
-    rc = make_tensor_map_2d(&ta, A, 2, (uint64_t)d->M, (uint64_t)d->K, lda * 2, BM, BK);
+    rc = make_tensor_map_2d(&ta, A, 2, (uint64_t)d->M, kphys, lda * 2, BM, BK);
     if (rc)
         return rc;
     if (pair) {
-        rc = make_tensor_map_2d(&tb, W, 2, (uint64_t)d->N, (uint64_t)d->K, (uint64_t)d->K * 2, 128, BK);
+        rc = make_tensor_map_2d(&tb, W, 2, (uint64_t)d->N, kphys, kphys * 2, 128, BK);
         if (rc)
             return rc;
         return launch_pair<5>(ta, tb, tc, C, p, sms, as_stream(s));
     }
     // 128x256 tiles when they divide N and still give every SM work; else 128x128
     const bool wide = d->N % 256 == 0 && ((d->M + BM - 1) / BM) * (d->N / 256) >= sms;
-    rc = make_tensor_map_2d(&tb, W, 2, (uint64_t)d->N, (uint64_t)d->K, (uint64_t)d->K * 2, wide ? 256 : 128, BK);
+    rc = make_tensor_map_2d(&tb, W, 2, (uint64_t)d->N, kphys, kphys * 2, wide ? 256 : 128, BK);
     if (rc)
         return rc;
     if (wide)
         return launch<256, 3>(ta, tb, tc, C, p, sms, as_stream(s));
     return launch<128, 5>(ta, tb, tc, C, p, sms, as_stream(s));
+}
+
+extern "C" int vitcu_gemm_bf16(const vitcu_bf16 *A, const vitcu_bf16 *W, void *C, const vitcu_gemm_desc *d,
+                               vitcu_stream s)
+{
+    return gemm_dispatch(A, W, C, d, false, s);
+}
+
+extern "C" int vitcu_gemm_bf16x3(const vitcu_bf16 *A3, const vitcu_bf16 *W3, void *C, const vitcu_gemm_desc *d,
+                                 vitcu_stream s)
+{
+    return gemm_dispatch(A3, W3, C, d, true, s);
 }

@@ -130,6 +130,9 @@ int vitb200_create(vitb200_engine **out, int device, int img, int precision, int
     e->B = max_batch;
     e->stop_after = -1;
     e->no_graph = getenv("VITB200_NO_GRAPH") != NULL;
+    /* FP32 precision runs its GEMMs on the tensor cores as split-bf16 (error ~1e-7 relative);
+     * VITB200_FP32_SIMT=1 selects the CUDA-core FFMA GEMM instead */
+    e->fp32_tc = precision == VITB200_FP32 && getenv("VITB200_FP32_SIMT") == NULL;
     const int bf = precision == VITB200_BF16;
     const size_t act = bf ? 2 : 4;
     const size_t rows = (size_t)e->B * e->T;
@@ -159,7 +162,9 @@ int vitb200_create(vitb200_engine **out, int device, int img, int precision, int
     ENG_TRY(vitcu_event_create(&e->ev_t1));
     ENG_TRY(vitcu_malloc(&e->d_patches, (size_t)e->B * e->P * VIT_D * act));
     ENG_TRY(vitcu_malloc((void **)&e->d_x, rows * VIT_D * sizeof(float)));
-    ENG_TRY(vitcu_malloc(&e->d_ln, rows * VIT_D * act));
+    ENG_TRY(vitcu_malloc(&e->d_ln, rows * VIT_D * (e->fp32_tc ? 6 : act)));
+    if (e->fp32_tc)
+        ENG_TRY(vitcu_malloc((void **)&e->d_a3, rows * VIT_HID * 3 * sizeof(vitcu_bf16)));
     ENG_TRY(vitcu_malloc(&e->d_qkv, rows * 3 * VIT_D * act));
     ENG_TRY(vitcu_malloc(&e->d_att, rows * VIT_D * act));
     ENG_TRY(vitcu_malloc(&e->d_hid, rows * VIT_HID * act));
@@ -199,6 +204,7 @@ void vitb200_destroy(vitb200_engine *e)
     if (e->ev_t1)
         vitcu_event_destroy(e->ev_t1);
     vitcu_free(e->d_patches);
+    vitcu_free(e->d_a3);
     vitcu_free(e->d_x);
     vitcu_free(e->d_ln);
     vitcu_free(e->d_qkv);
@@ -245,9 +251,15 @@ int vitb200_load_weights(vitb200_engine *e, const vitb200_blob *net)
                 VIT_TRY(vitcu_malloc((void **)&e->w16[i], n * sizeof(vitcu_bf16)));
             VIT_TRY(vitcu_f32_to_bf16(e->w32[i], e->w16[i], n, e->stream));
         }
+        if (e->fp32_tc && is_gemm_weight(i)) { /* [N,K] fp32 -> [N,3K] bf16 pieces */
+            const int K = (i == 1 || (i - 4) % 12 != 10) ? VIT_D : VIT_HID;
+            if (!e->w16[i])
+                VIT_TRY(vitcu_malloc((void **)&e->w16[i], 3 * n * sizeof(vitcu_bf16)));
+            VIT_TRY(vitcu_split3(e->w32[i], (size_t)K, e->w16[i], n / (size_t)K, K, e->stream));
+        }
     }
     VIT_TRY(vitcu_stream_sync(e->stream));
-    if (bf) { /* the fp32 masters of the GEMM weights are not needed on the BF16 path */
+    if (bf || e->fp32_tc) { /* the fp32 masters of the GEMM weights are not needed on the tensor-core paths */
         for (int i = 0; i < VITB200_NBLOBS; i++)
             if (is_gemm_weight(i)) {
                 VIT_TRY(vitcu_free(e->w32[i]));
@@ -258,8 +270,9 @@ int vitb200_load_weights(vitb200_engine *e, const vitb200_blob *net)
     return 0;
 }
 
-/* one GEMM of the chain, dispatched on the engine precision */
-static int gemm(vitb200_engine *e, const void *A, int widx, int bidx, void *C, int M, int N, int K, int epi,
+/* one GEMM of the chain, dispatched on the engine precision.  a_split: A already holds the three
+ * bf16 pieces (FP32 tensor-core path; the LayerNorm kernel emits them directly). */
+static int gemm(vitb200_engine *e, const void *A, int a_split, int widx, int bidx, void *C, int M, int N, int K, int epi,
                 int out_bf16)
 {
     vitcu_gemm_desc d;
@@ -282,6 +295,16 @@ static int gemm(vitb200_engine *e, const void *A, int widx, int bidx, void *C, i
     e->launches++;
     if (e->precision == VITB200_BF16)
         return vitcu_gemm_bf16((const vitcu_bf16 *)A, e->w16[widx], C, &d, e->stream);
+    if (e->fp32_tc) {
+        if (!a_split) {
+            int rc = vitcu_split3((const float *)A, (size_t)K, e->d_a3, (size_t)M, K, e->stream);
+            if (rc)
+                return rc;
+            e->launches++;
+            A = e->d_a3;
+        }
+        return vitcu_gemm_bf16x3((const vitcu_bf16 *)A, e->w16[widx], C, &d, e->stream);
+    }
     return vitcu_sgemm((const float *)A, e->w32[widx], C, &d, e->stream);
 }
 
@@ -290,6 +313,7 @@ static int enqueue_forward(vitb200_engine *e, int buf, int b)
 {
     const int bf = e->precision == VITB200_BF16;
     const int M = b * e->T;
+    const int ln_mode = bf ? 1 : (e->fp32_tc ? 2 : 0); /* LayerNorm output: bf16 / three bf16 pieces / fp32 */
     vitcu_stream s = e->stream;
     e->launches = 0;
 
@@ -297,7 +321,7 @@ static int enqueue_forward(vitb200_engine *e, int buf, int b)
      * (Conv2d + postConv2d, R/ViT_opencl.c:361-442) */
     VIT_TRY(vitcu_patch_gather(e->d_images[buf], e->d_patches, b, e->img, bf, s));
     e->launches++;
-    VIT_TRY(gemm(e, e->d_patches, 1, 2, e->d_x, b * e->P, VIT_D, VIT_D, VITCU_EPI_PATCH_EMBED, 0));
+    VIT_TRY(gemm(e, e->d_patches, 0, 1, 2, e->d_x, b * e->P, VIT_D, VIT_D, VITCU_EPI_PATCH_EMBED, 0));
     VIT_TRY(vitcu_cls_rows(e->d_x, e->w32[0], e->w32[3], b, e->T, s));
     e->launches++;
 
@@ -305,17 +329,17 @@ static int enqueue_forward(vitb200_engine *e, int buf, int b)
     for (int l = 0; l < layers; l++) {
         const int w = 4 + 12 * l; /* blob base of the layer (R/ViT_seq.c:446-504) */
         /* x -> LN1 -> QKV -> attention -> out-proj (+x)  (R/ViT_opencl.c:710-730) */
-        VIT_TRY(vitcu_layernorm(e->d_x, VIT_D, e->d_ln, bf, e->w32[w + 0], e->w32[w + 1], M, s));
+        VIT_TRY(vitcu_layernorm(e->d_x, VIT_D, e->d_ln, ln_mode, e->w32[w + 0], e->w32[w + 1], M, s));
         e->launches++;
-        VIT_TRY(gemm(e, e->d_ln, w + 2, w + 3, e->d_qkv, M, 3 * VIT_D, VIT_D, VITCU_EPI_BIAS, bf));
+        VIT_TRY(gemm(e, e->d_ln, 1, w + 2, w + 3, e->d_qkv, M, 3 * VIT_D, VIT_D, VITCU_EPI_BIAS, bf));
         VIT_TRY(vitcu_attention(e->d_qkv, e->d_att, b, e->T, bf, s));
         e->launches++;
-        VIT_TRY(gemm(e, e->d_att, w + 4, w + 5, e->d_x, M, VIT_D, VIT_D, VITCU_EPI_BIAS_RESIDUAL, 0));
+        VIT_TRY(gemm(e, e->d_att, 0, w + 4, w + 5, e->d_x, M, VIT_D, VIT_D, VITCU_EPI_BIAS_RESIDUAL, 0));
         /* -> LN2 -> fc1+GELU -> fc2 (+r1)  (R/ViT_opencl.c:732-746) */
-        VIT_TRY(vitcu_layernorm(e->d_x, VIT_D, e->d_ln, bf, e->w32[w + 6], e->w32[w + 7], M, s));
+        VIT_TRY(vitcu_layernorm(e->d_x, VIT_D, e->d_ln, ln_mode, e->w32[w + 6], e->w32[w + 7], M, s));
         e->launches++;
-        VIT_TRY(gemm(e, e->d_ln, w + 8, w + 9, e->d_hid, M, VIT_HID, VIT_D, VITCU_EPI_BIAS_GELU, bf));
-        VIT_TRY(gemm(e, e->d_hid, w + 10, w + 11, e->d_x, M, VIT_D, VIT_HID, VITCU_EPI_BIAS_RESIDUAL, 0));
+        VIT_TRY(gemm(e, e->d_ln, 1, w + 8, w + 9, e->d_hid, M, VIT_HID, VIT_D, VITCU_EPI_BIAS_GELU, bf));
+        VIT_TRY(gemm(e, e->d_hid, 0, w + 10, w + 11, e->d_x, M, VIT_D, VIT_HID, VITCU_EPI_BIAS_RESIDUAL, 0));
     }
     if (e->stop_after >= 0)
         return 0;

@@ -12,12 +12,14 @@
 struct vitb200_engine {
     int device, img, side, P, T, precision, B;
     int weights_loaded, stop_after, no_graph, warmed;
+    int fp32_tc;                     /* FP32 precision computed as split-bf16 (x3 pieces, 6 products) on the tensor cores */
     int launches, kernels_per_forward;
     vitcu_stream stream, copy_stream;
     vitcu_event ev_h2d[2], ev_done[2], ev_out[2], ev_t0, ev_t1;
     vitcu_graph graph[2];
     float *w32[VITB200_NBLOBS];      /* fp32 blobs on the device */
-    vitcu_bf16 *w16[VITB200_NBLOBS]; /* bf16 copies of the GEMM weights (BF16 path) */
+    vitcu_bf16 *w16[VITB200_NBLOBS]; /* BF16 path: bf16 GEMM weights [N,K]; FP32 tensor-core path: three bf16 pieces [N,3K] */
+    vitcu_bf16 *d_a3;                /* FP32 tensor-core path: split form [rows,3K] of the current GEMM A operand */
     float *d_images[2];              /* double-buffered input chunk [B,3,img,img] */
     void *d_patches;                 /* [B*P,768] gathered patches */
     float *d_x;                      /* [B*T,768] fp32 residual stream */
