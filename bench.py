@@ -39,6 +39,14 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 GFLOP_PER_IMAGE_224 = 35.1277  # SURVEY.md section 8d, unpadded T=197, 2*M*N*K convention
+
+
+def gflop_per_image(img: int) -> float:
+    """algorithmic FLOPs of one forward (2*M*N*K, unpadded tokens)"""
+    p = (img // 16) ** 2
+    t = p + 1
+    layer = 2 * t * 768 * (2304 + 768 + 3072 + 3072) + 4 * 12 * t * t * 64
+    return (2 * p * 768 * 768 + 12 * layer + 2 * 1000 * 768) / 1e9
 IMG, BATCH = 224, 256
 METRIC, UNIT = "ViT-B/16 images/sec (224x224, batch 256 per GPU)", "images/s"
 
@@ -210,10 +218,11 @@ def _shared_blob_file(img):
     return _BLOB_FILE[img]
 
 
-def cpu_reference_step(procs: int, images_per_proc: int = 1, img: int = IMG):
+def cpu_reference_step(procs: int, images_per_proc: int = 1, img: int = 0):
     """P independent processes, each the reference's ViT_seq on its own image slice
     (BASELINE.md section 4.4).  Returns (seconds of the slowest worker, images)."""
     import multiprocessing as mp
+    img = img or IMG
     path, sizes = _shared_blob_file(img)
     ctx = mp.get_context("spawn")
     with ctx.Pool(procs) as pool:
@@ -221,11 +230,12 @@ def cpu_reference_step(procs: int, images_per_proc: int = 1, img: int = IMG):
     return max(r[0] for r in res), procs * images_per_proc
 
 
-def cpu_port_step(images: int, img: int = IMG):
+def cpu_port_step(images: int, img: int = 0):
     """fallback when oracle/_ref is absent: the OpenMP oracle port on all host threads"""
     from oracle import binding
     import __graft_entry__ as g
     pkg = g.load_package()
+    img = img or IMG
     o = binding.Oracle()
     blobs = model_blobs(pkg, img)
     x = pkg.synth.synthetic_images(images, img, seed=1000)
@@ -340,7 +350,7 @@ def run_engine_arm(args, dist: Dist):
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
     dev = dist.local_rank % ndev
     peaks = measured_peaks()
-    blobs = model_blobs(pkg)
+    blobs = model_blobs(pkg, IMG)
 
     eng = pkg.Engine(dev, IMG, pkg.BF16, max_batch=BATCH)
     eng.load_weights(blobs)
@@ -394,9 +404,9 @@ def run_engine_arm(args, dist: Dist):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": dist.world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "ViT-B/16 224x224 forward (patch-embed..softmax), BF16 tcgen05 path, "
-                               "256 images per step per GPU, weights resident",
-                   "images_per_step_per_gpu": BATCH, "tokens": 197, "parallelism": f"image-sharded dp{dist.world}, "
+        "config": {"workload": f"ViT-B/16 {IMG}x{IMG} forward (patch-embed..softmax), BF16 tcgen05 path, "
+                               f"{BATCH} images per step per GPU, weights resident",
+                   "images_per_step_per_gpu": BATCH, "tokens": (IMG // 16) ** 2 + 1, "parallelism": f"image-sharded dp{dist.world}, "
                    "replicated weights, no collective on the data path",
                    "l2": "no explicit flush: per-step working set (~1 GB of activations + 154 MB of images) "
                          "is far larger than the 126 MB L2"},
@@ -407,18 +417,18 @@ def run_engine_arm(args, dist: Dist):
                        "upload of step i+1 overlaps compute of step i",
                 "single_batch_call_images_per_s": e2e_single * dist.world},
         "gpu_launches": kernels * args.steps,
-        "path_tflops": value / dist.world * GFLOP_PER_IMAGE_224 / 1e3,
-        "path_frac_of_sustained_peak": value / dist.world * GFLOP_PER_IMAGE_224 / 1e3 / peaks["bf16_sustained"],
+        "path_tflops": value / dist.world * gflop_per_image(IMG) / 1e3,
+        "path_frac_of_sustained_peak": value / dist.world * gflop_per_image(IMG) / 1e3 / peaks["bf16_sustained"],
     }
 
     if dist.rank == 0:
         # ---- roofline of the dominant kernel ----
         try:
-            per, flops, ms = time_gemms(pkg, L, BATCH * 197)
+            per, flops, ms = time_gemms(pkg, L, BATCH * ((IMG // 16) ** 2 + 1))
             achieved = flops / ms / 1e9
             line["roofline"] = {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
                                 "frac": achieved / peaks["bf16_burst"], "traffic": None,
-                                "kernel": "gemm_bf16_tc_kernel (qkv + out_proj + fc1 + fc2 launches of one layer, M=50432)",
+                                "kernel": f"gemm_bf16_tc2_kernel (qkv + out_proj + fc1 + fc2 launches of one layer, M={BATCH * ((IMG // 16) ** 2 + 1)})",
                                 "per_launch": per, "peak_source": peaks["source"] + ", burst figure (kernel timed alone)"}
         except Exception as ex:  # keep the headline even if the side measurement fails
             line["roofline"] = {"error": str(ex)}
@@ -486,8 +496,14 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--img", type=int, default=224, help="image side (384 = BASELINE config 5 shape, 577 tokens)")
+    ap.add_argument("--batch", type=int, default=256, help="images per step per GPU")
     ap.add_argument("--selftest-dist", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
+    global IMG, BATCH, METRIC
+    IMG, BATCH = args.img, args.batch
+    if (IMG, BATCH) != (224, 256):
+        METRIC = f"ViT-B/16 images/sec ({IMG}x{IMG}, batch {BATCH} per GPU)"
     if args.selftest_dist:
         dist = Dist(backend="gloo")
         run_dist_selftest(args, dist)
