@@ -100,6 +100,13 @@ int vitcu_split3(const float *x, size_t ld, vitcu_bf16 *out, size_t rows, int K,
 int vitcu_patch_gather(const float *images, void *patches, int batch, int img,
                        int out_bf16, vitcu_stream s);
 
+/* Patch embedding as one TF32 tensor-core GEMM whose patch gather is staged by TMA (5-D tensor map
+ * over the NCHW image; replaces conv2d_kernel + postprocess, R/conv2d.cl:1-80): for every image b
+ * and patch p, x[b*T + 1 + p, :] = conv(patch) + conv_b + pos[1 + p, :].  images [B,3,S,S] fp32,
+ * conv_w [768, 3*16*16] fp32.  Class-token rows are left to vitcu_cls_rows. */
+int vitcu_patch_embed_tc(const float *images, const float *conv_w, const float *conv_b, const float *pos,
+                         float *x, int batch, int img, vitcu_stream s);
+
 /* Row 0 of every image: x[b*T + 0, :] = cls + pos[0, :]  (R/conv2d.cl:39-80 t==0
  * branch; R/ViT_seq.c:83-118). */
 int vitcu_cls_rows(float *x, const float *cls, const float *pos, int batch, int tokens,

@@ -132,6 +132,30 @@ def test_patch_embed_fp32(pkg, lib, oracle, img, batch):
     assert np.array_equal(pat, im2col)
 
 
+@pytest.mark.parametrize("img,batch", [(224, 3), (384, 2), (224, 200), (32, 1)])
+def test_patch_embed_tma_gather_tf32(pkg, lib, oracle, img, batch):
+    """TF32 tcgen05 GEMM with the patch gather done by a 5-D TMA tensor map (no im2col buffer)"""
+    rng = np.random.default_rng(img + batch)
+    side = img // 16
+    P, T = side * side, side * side + 1
+    images = rng.standard_normal((batch, 3, img, img), dtype=np.float32)
+    cw = (rng.standard_normal((768, 768), dtype=np.float32) * 0.03).astype(np.float32)
+    cb = rng.standard_normal(768, dtype=np.float32)
+    pos = rng.standard_normal((T, 768), dtype=np.float32)
+    cls = rng.standard_normal(768, dtype=np.float32)
+    di, dcw, dcb, dpos = (_dev(pkg, a) for a in (images, cw, cb, pos))
+    dx = pkg.DeviceBuffer(batch * T * 768 * 4)
+    pkg.layer_check(lib.vitcu_memset(dx.ptr, 0, batch * T * 768 * 4, None))
+    pkg.layer_check(lib.vitcu_patch_embed_tc(di.ptr, dcw.ptr, dcb.ptr, dpos.ptr, dx.ptr, batch, img, None))
+    assert lib.vitcu_watchdog_check() == 0
+    x = dx.to_numpy(np.float32, (batch, T, 768))
+    assert np.all(x[:, 0] == 0)  # class-token rows are not this kernel's
+    for i in sorted({0, batch - 1}):
+        ref = oracle.patch_embed(images[i], cls, cw.reshape(768, 3, 16, 16), cb, pos)[1:]
+        # TF32 keeps 10 mantissa bits of both operands: 768-term dot products of N(0,1) x N(0,0.03^2) values
+        assert np.abs(x[i, 1:] - ref).max() <= 4e-3, np.abs(x[i, 1:] - ref).max()
+
+
 # ---------------------------------------------------------------- attention
 @pytest.mark.parametrize("T,batch,bf16", [(197, 2, False), (577, 1, False), (197, 2, True), (577, 1, True), (50, 1, False)])
 def test_attention_simt(pkg, lib, oracle, T, batch, bf16):

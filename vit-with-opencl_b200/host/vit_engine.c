@@ -133,6 +133,8 @@ int vitb200_create(vitb200_engine **out, int device, int img, int precision, int
     /* FP32 precision runs its GEMMs on the tensor cores as split-bf16 (error ~1e-7 relative);
      * VITB200_FP32_SIMT=1 selects the CUDA-core FFMA GEMM instead */
     e->fp32_tc = precision == VITB200_FP32 && getenv("VITB200_FP32_SIMT") == NULL;
+    /* VITB200_PE_GATHER=1: separate gather kernel + BF16 GEMM instead of the TMA-gather TF32 GEMM */
+    e->pe_gather = getenv("VITB200_PE_GATHER") != NULL;
     const int bf = precision == VITB200_BF16;
     const size_t act = bf ? 2 : 4;
     const size_t rows = (size_t)e->B * e->T;
@@ -261,7 +263,7 @@ int vitb200_load_weights(vitb200_engine *e, const vitb200_blob *net)
     VIT_TRY(vitcu_stream_sync(e->stream));
     if (bf || e->fp32_tc) { /* the fp32 masters of the GEMM weights are not needed on the tensor-core paths */
         for (int i = 0; i < VITB200_NBLOBS; i++)
-            if (is_gemm_weight(i)) {
+            if (is_gemm_weight(i) && !(bf && i == 1)) { /* the TF32 patch embedding reads the fp32 conv filters */
                 VIT_TRY(vitcu_free(e->w32[i]));
                 e->w32[i] = NULL;
             }
@@ -317,11 +319,17 @@ static int enqueue_forward(vitb200_engine *e, int buf, int b)
     vitcu_stream s = e->stream;
     e->launches = 0;
 
-    /* patch embedding: gather + GEMM with class/position epilogue
-     * (Conv2d + postConv2d, R/ViT_opencl.c:361-442) */
-    VIT_TRY(vitcu_patch_gather(e->d_images[buf], e->d_patches, b, e->img, bf, s));
-    e->launches++;
-    VIT_TRY(gemm(e, e->d_patches, 0, 1, 2, e->d_x, b * e->P, VIT_D, VIT_D, VITCU_EPI_PATCH_EMBED, 0));
+    /* patch embedding (Conv2d + postConv2d, R/ViT_opencl.c:361-442).  BF16 path: one TF32
+     * tensor-core GEMM that gathers the patches by TMA straight from the NCHW image; FP32 path:
+     * gather kernel + FP32-accurate GEMM with the class/position epilogue */
+    if (bf && !e->pe_gather) {
+        VIT_TRY(vitcu_patch_embed_tc(e->d_images[buf], e->w32[1], e->w32[2], e->w32[3], e->d_x, b, e->img, s));
+        e->launches++;
+    } else {
+        VIT_TRY(vitcu_patch_gather(e->d_images[buf], e->d_patches, b, e->img, bf, s));
+        e->launches++;
+        VIT_TRY(gemm(e, e->d_patches, 0, 1, 2, e->d_x, b * e->P, VIT_D, VIT_D, VITCU_EPI_PATCH_EMBED, 0));
+    }
     VIT_TRY(vitcu_cls_rows(e->d_x, e->w32[0], e->w32[3], b, e->T, s));
     e->launches++;
 

@@ -12,6 +12,7 @@
 struct vitb200_engine {
     int device, img, side, P, T, precision, B;
     int weights_loaded, stop_after, no_graph, warmed;
+    int pe_gather;                   /* BF16 path: use the gather kernel + BF16 GEMM for the patch embedding */
     int fp32_tc;                     /* FP32 precision computed as split-bf16 (x3 pieces, 6 products) on the tensor cores */
     int launches, kernels_per_forward;
     vitcu_stream stream, copy_stream;
