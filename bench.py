@@ -426,8 +426,14 @@ def run_engine_arm(args, dist: Dist):
         try:
             per, flops, ms = time_gemms(pkg, L, BATCH * ((IMG // 16) ** 2 + 1))
             achieved = flops / ms / 1e9
+            traffic = None
+            tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+            if (IMG, BATCH) == (224, 256) and os.path.exists(tpath):
+                # dram__bytes_read.sum + dram__bytes_write.sum of the same four launches, from the committed
+                # `ncu --set full` capture (profiles/r01_v6_summary.md); bytes per launch set, like `achieved`
+                traffic = json.load(open(tpath))["traffic_bytes"]
             line["roofline"] = {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
-                                "frac": achieved / peaks["bf16_burst"], "traffic": None,
+                                "frac": achieved / peaks["bf16_burst"], "traffic": traffic,
                                 "kernel": f"gemm_bf16_tc2_kernel (qkv + out_proj + fc1 + fc2 launches of one layer, M={BATCH * ((IMG // 16) ** 2 + 1)})",
                                 "per_launch": per, "peak_source": peaks["source"] + ", burst figure (kernel timed alone)"}
         except Exception as ex:  # keep the headline even if the side measurement fails
