@@ -103,7 +103,9 @@ def test_forward_structs_equals_contiguous(pkg, lib, blobs224, case224):
         eng.load_weights(blobs224)
         a = eng.forward(imgs)
         b = eng.forward_structs(imgs)
-    assert np.array_equal(a, b)
+    # same images, same kernels; at this small batch the residual GEMMs are split along K and meet
+    # through TMA reduce-add, whose fp32 summation order is not fixed -> equal to rounding, not bitwise
+    np.testing.assert_allclose(a, b, rtol=1e-5, atol=1e-9)
 
 
 def test_golden_reference_vectors(pkg, lib, synth_blobs224):

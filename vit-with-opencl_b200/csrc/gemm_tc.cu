@@ -40,6 +40,7 @@ struct EpiParams {
     int patches, tokens;
     int out_bf16;
     int tma_out; // 0: epilogue writes with LSU stores; 1: bf16 tiles by TMA store; 2: fp32 tiles by TMA reduce-add (C += tile); 3: fp32 tiles by TMA store
+    int splits;     // split-K factor (1-CTA kernel, TMA reduce-add epilogue only): work item = (tile, K slice)
     int exact_gelu; // erff instead of the polynomial (fp32 outputs of the split-bf16 FP32 path)
     // K loop as a list of segments (split-bf16 FP32 path: six piece products over one K range)
     int nseg, seg_kb;        // segments, k-blocks per segment
@@ -80,7 +81,7 @@ struct SmemLayout {
 template <int BN>
 __device__ __forceinline__ bool epilogue_tile(const EpiParams &p, void *C, const CUtensorMap *tmap_c, uint32_t &chunk_ctr,
                                               float *stage, int lane, int row0, int col_base, uint32_t taddr,
-                                              uint64_t *tfull, uint32_t parity, const Watchdog &wd)
+                                              uint64_t *tfull, uint32_t parity, const Watchdog &wd, float bias_on = 1.0f)
 {
     constexpr int NCHUNK = BN / 64;
     const bool fp32_add = !p.tma_out && !p.out_bf16 && p.epilogue != VITCU_EPI_BIAS; // residual or position rows to fetch
@@ -132,10 +133,10 @@ __device__ __forceinline__ bool epilogue_tile(const EpiParams &p, void *C, const
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
             const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + col0 + j));
-            v[j + 0] = __uint_as_float(acc[c & 1][j + 0]) + b.x;
-            v[j + 1] = __uint_as_float(acc[c & 1][j + 1]) + b.y;
-            v[j + 2] = __uint_as_float(acc[c & 1][j + 2]) + b.z;
-            v[j + 3] = __uint_as_float(acc[c & 1][j + 3]) + b.w;
+            v[j + 0] = fmaf(b.x, bias_on, __uint_as_float(acc[c & 1][j + 0]));
+            v[j + 1] = fmaf(b.y, bias_on, __uint_as_float(acc[c & 1][j + 1]));
+            v[j + 2] = fmaf(b.z, bias_on, __uint_as_float(acc[c & 1][j + 2]));
+            v[j + 3] = fmaf(b.w, bias_on, __uint_as_float(acc[c & 1][j + 3]));
         }
         if (p.epilogue == VITCU_EPI_BIAS_GELU) {
             if (p.exact_gelu) {
@@ -259,7 +260,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const Watchdog wd{cta_abort, watchdog_flag};
 
     const int num_m = (p.M + BM - 1) / BM, num_n = p.N / BN;
-    const int num_tiles = num_m * num_n, num_kb = p.nseg * p.seg_kb;
+    // work item = (output tile, K slice): with splits > 1 every slice reduce-adds its partial tile
+    // into C through the TMA engine (only slice 0 carries the bias), so small-M GEMMs fill the SMs
+    const int total_kb = p.nseg * p.seg_kb, kb_per = (total_kb + p.splits - 1) / p.splits;
+    const int num_tiles = num_m * num_n * p.splits;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -274,8 +278,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         uint32_t stage = 0, phase = 0;
         bool ok = true;
         for (int tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x) {
-            const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
-            for (int kb = 0; kb < num_kb; kb++) {
+            const int split = tile % p.splits, t2 = tile / p.splits;
+            const int m_blk = t2 / num_n, n_blk = t2 - m_blk * num_n;
+            const int kb_end = min(total_kb, (split + 1) * kb_per);
+            for (int kb = split * kb_per; kb < kb_end; kb++) {
                 if (!(ok = mbar_wait_warp(&empty_bar[stage], phase ^ 1, wd, 1)))
                     break;
                 if (elect_one()) {
@@ -302,7 +308,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 break;
             tcgen05_fence_after();
             const uint32_t d_tmem = tmem_base + acc * BN;
-            for (int kb = 0; kb < num_kb; kb++) {
+            const int split = tile % p.splits;
+            const int kb_begin = split * kb_per, kb_end = min(total_kb, (split + 1) * kb_per);
+            for (int kb = kb_begin; kb < kb_end; kb++) {
                 if (!(ok = mbar_wait_warp(&full_bar[stage], phase, wd, 3)))
                     break;
                 tcgen05_fence_after();
@@ -312,9 +320,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     const uint64_t b_desc = umma_desc_k_sw128(sa + L::A_BYTES);
 #pragma unroll
                     for (int k = 0; k < BK / 16; k++) // +32 bytes per K=16 step inside the 128B swizzle row
-                        umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, IDESC, (kb | k) != 0);
+                        umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, IDESC, (kb != kb_begin) | (k != 0));
                     umma_commit(&empty_bar[stage]); // ring slot reusable once these MMAs retire
-                    if (kb == num_kb - 1)
+                    if (kb == kb_end - 1)
                         umma_commit(&tfull_bar[acc]); // accumulator complete
                 }
                 __syncwarp();
@@ -332,12 +340,14 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (warp == 2 && lane == 0)
             prefetch_tensormap(&tmap_c);
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
-            const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
+            const int split = tile % p.splits, t2 = tile / p.splits;
+            const int m_blk = t2 / num_n, n_blk = t2 - m_blk * num_n;
             const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
             float *stage_tile = reinterpret_cast<float *>(smem + L::EPI_OFFSET) + (warp - 2) * kStageFloats;
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + half * (BN / 2);
             if (!epilogue_tile<BN>(p, C, &tmap_c, chunk_ctr, stage_tile, lane, m_blk * BM + quad * 32,
-                                   n_blk * BN + half * (BN / 2), taddr, &tfull_bar[acc], acc_phase, wd))
+                                   n_blk * BN + half * (BN / 2), taddr, &tfull_bar[acc], acc_phase, wd,
+                                   split == 0 ? 1.0f : 0.0f))
                 break;
             tcgen05_fence_before();
             __syncwarp();
@@ -556,7 +566,7 @@ int launch(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &tc, 
         VITCU_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::TOTAL));
         configured[dev] = true;
     }
-    const int num_tiles = ((p.M + BM - 1) / BM) * (p.N / BN);
+    const int num_tiles = ((p.M + BM - 1) / BM) * (p.N / BN) * p.splits;
     const int grid = num_tiles < sms ? num_tiles : sms;
     kernel<<<grid, kThreads, L::TOTAL, st>>>(ta, tb, tc, C, p, watchdog_flag());
     VITCU_LAUNCHED();
@@ -655,6 +665,7 @@ static int gemm_dispatch(const vitcu_bf16 *A, const vitcu_bf16 *W, void *C, cons
     const size_t lda = split3 ? (size_t)kphys : (d->lda ? d->lda : (size_t)d->K);
     VITCU_REQUIRE(lda % 8 == 0 && ((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0, "operands must be 16-byte aligned");
     p.seg_kb = d->K / BK;
+    p.splits = 1;
     if (split3) {
         // small products first: a3 w1, a2 w2, a1 w3, a2 w1, a1 w2, a1 w1
         const int K = d->K;
@@ -707,6 +718,15 @@ static int gemm_dispatch(const vitcu_bf16 *A, const vitcu_bf16 *W, void *C, cons
     }
     // 128x256 tiles when they divide N and still give every SM work; else 128x128
     const bool wide = d->N % 256 == 0 && ((d->M + BM - 1) / BM) * (d->N / 256) >= sms;
+    if (!wide && p.tma_out == 2) {
+        // small M (batch-1 latency): split K so that the work items roughly fill the SMs, at least
+        // two k-blocks per slice; the slices meet in C through TMA reduce-add
+        const int tiles = ((d->M + BM - 1) / BM) * (d->N / 128), total_kb = p.nseg * p.seg_kb;
+        int splits = sms / tiles;
+        if (splits > total_kb / 2)
+            splits = total_kb / 2;
+        p.splits = splits < 1 ? 1 : splits;
+    }
     rc = make_tensor_map_2d(&tb, W, 2, (uint64_t)d->N, kphys, kphys * 2, wide ? 256 : 128, BK);
     if (rc)
         return rc;

@@ -175,6 +175,33 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float *__restrict__ A,
     }
 }
 
+// Small-M case (the classification head at batch <= 8): one warp per output feature, the weight
+// row is read once (coalesced, 128-bit) and dotted with every input row; the 64x64 tile kernel
+// would run M = 1 on 16 CTAs for 55 us.
+__global__ void __launch_bounds__(256) gemv_rows_kernel(const float *__restrict__ A, const float *__restrict__ W,
+                                                        float *__restrict__ C, const EpiParams p)
+{
+    const int lane = threadIdx.x & 31;
+    const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (n >= p.N)
+        return;
+    const float4 *w4 = reinterpret_cast<const float4 *>(W + (size_t)n * p.K);
+    for (int m = 0; m < p.M; m++) {
+        const float4 *a4 = reinterpret_cast<const float4 *>(A + (size_t)m * p.lda);
+        float acc = 0.f;
+        for (int k = lane; k < p.K / 4; k += 32) {
+            const float4 a = a4[k], w = __ldg(w4 + k);
+            acc = fmaf(a.x, w.x, acc);
+            acc = fmaf(a.y, w.y, acc);
+            acc = fmaf(a.z, w.z, acc);
+            acc = fmaf(a.w, w.w, acc);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0)
+            C[(size_t)m * p.ldc + n] = acc + p.bias[n];
+    }
+}
+
 } // namespace
 
 extern "C" int vitcu_sgemm(const float *A, const float *W, void *C, const vitcu_gemm_desc *d, vitcu_stream s)
@@ -200,6 +227,11 @@ extern "C" int vitcu_sgemm(const float *A, const float *W, void *C, const vitcu_
     p.patches = d->patches;
     p.tokens = d->tokens;
     p.out_bf16 = d->out_bf16;
+    if (p.M <= 8 && p.epilogue == VITCU_EPI_BIAS && !p.out_bf16) {
+        gemv_rows_kernel<<<(p.N + 7) / 8, 256, 0, as_stream(s)>>>(A, W, reinterpret_cast<float *>(C), p);
+        VITCU_LAUNCHED();
+        return 0;
+    }
     // Big tile when it still fills the 148 SMs, small tile for the batch-1 /
     // head shapes where parallelism matters more than reuse.
     const long big_ctas = (long)((p.M + 127) / 128) * ((p.N + 127) / 128);
