@@ -78,12 +78,11 @@ struct SmemLayout {
 // (4 per bf16 row).  Latency hiding: the tcgen05.ld of chunk c+1 and the residual / position rows
 // of chunk c+1 are in flight while chunk c is processed, and the first residual rows are requested
 // before the wait for the accumulator.
-template <int BN>
+template <int NCHUNK, int STAGE_BYTES_PER_WARP, bool PREFETCH>
 __device__ __forceinline__ bool epilogue_tile(const EpiParams &p, void *C, const CUtensorMap *tmap_c, uint32_t &chunk_ctr,
                                               float *stage, int lane, int row0, int col_base, uint32_t taddr,
                                               uint64_t *tfull, uint32_t parity, const Watchdog &wd, float bias_on = 1.0f)
 {
-    constexpr int NCHUNK = BN / 64;
     const bool fp32_add = !p.tma_out && !p.out_bf16 && p.epilogue != VITCU_EPI_BIAS; // residual or position rows to fetch
     const int rsub = lane >> 3, c4 = (lane & 7) * 4;
     const float *addsrc = p.epilogue == VITCU_EPI_PATCH_EMBED ? p.pos : p.residual;
@@ -118,13 +117,19 @@ __device__ __forceinline__ bool epilogue_tile(const EpiParams &p, void *C, const
         return false;
     tcgen05_fence_after();
 
-    uint32_t acc[2][32];
-    tmem_ld_32x32b_x32(taddr, acc[0]);
+    // with 8 epilogue warps the accumulator chunks are double-buffered in registers; with 16 warps
+    // (96 registers per thread) the other warps hide the tcgen05.ld latency instead
+    constexpr int NACC = PREFETCH ? 2 : 1;
+    uint32_t acc[NACC][32];
+    if (PREFETCH)
+        tmem_ld_32x32b_x32(taddr, acc[0]);
 #pragma unroll
     for (int c = 0; c < NCHUNK; c++) {
+        if (!PREFETCH)
+            tmem_ld_32x32b_x32(taddr + c * 32, acc[0]);
         tmem_ld_wait();
-        if (c + 1 < NCHUNK)
-            tmem_ld_32x32b_x32(taddr + (c + 1) * 32, acc[(c + 1) & 1]);
+        if (PREFETCH && c + 1 < NCHUNK)
+            tmem_ld_32x32b_x32(taddr + (c + 1) * 32, acc[(c + 1) % NACC]);
         if (row0 >= p.M) // warp-uniform: nothing of this warp's rows exists
             continue;
         const int col0 = col_base + c * 32;
@@ -133,10 +138,10 @@ __device__ __forceinline__ bool epilogue_tile(const EpiParams &p, void *C, const
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
             const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + col0 + j));
-            v[j + 0] = fmaf(b.x, bias_on, __uint_as_float(acc[c & 1][j + 0]));
-            v[j + 1] = fmaf(b.y, bias_on, __uint_as_float(acc[c & 1][j + 1]));
-            v[j + 2] = fmaf(b.z, bias_on, __uint_as_float(acc[c & 1][j + 2]));
-            v[j + 3] = fmaf(b.w, bias_on, __uint_as_float(acc[c & 1][j + 3]));
+            v[j + 0] = fmaf(b.x, bias_on, __uint_as_float(acc[c % NACC][j + 0]));
+            v[j + 1] = fmaf(b.y, bias_on, __uint_as_float(acc[c % NACC][j + 1]));
+            v[j + 2] = fmaf(b.z, bias_on, __uint_as_float(acc[c % NACC][j + 2]));
+            v[j + 3] = fmaf(b.w, bias_on, __uint_as_float(acc[c % NACC][j + 3]));
         }
         if (p.epilogue == VITCU_EPI_BIAS_GELU) {
             if (p.exact_gelu) {
@@ -153,9 +158,16 @@ __device__ __forceinline__ bool epilogue_tile(const EpiParams &p, void *C, const
             // ---- TMA path: the row-per-thread registers go straight into a swizzled shared-memory
             // tile and the TMA engine writes (bf16) or reduce-adds (fp32 residual stream) it to global
             // memory, clipped at M.  No global-memory latency is left on this warp's critical path.
-            uint8_t *buf = reinterpret_cast<uint8_t *>(stage) + (chunk_ctr & 1) * 4096;
-            if (lane == 0)
-                tma_wait_group_read<1>(); // the store that used this buffer two chunks ago has read it
+            // staging tiles: 2 KB (bf16) or 4 KB (fp32) each, double-buffered when the warp's share allows
+            const uint32_t tile_bytes = p.tma_out == 1 ? 2048u : 4096u;
+            const bool two = STAGE_BYTES_PER_WARP >= 8192 || (STAGE_BYTES_PER_WARP >= 4096 && p.tma_out == 1);
+            uint8_t *buf = reinterpret_cast<uint8_t *>(stage) + (two ? (chunk_ctr & 1) * tile_bytes : 0u);
+            if (lane == 0) { // the store that used this buffer before has finished reading it
+                if (two)
+                    tma_wait_group_read<1>();
+                else
+                    tma_wait_group_read<0>();
+            }
             __syncwarp();
             if (p.tma_out == 1) { // 32 x 64 B rows, 64-byte swizzle: 16-byte chunk ^= (row / 2) % 4
 #pragma unroll
@@ -345,7 +357,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
             float *stage_tile = reinterpret_cast<float *>(smem + L::EPI_OFFSET) + (warp - 2) * kStageFloats;
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + half * (BN / 2);
-            if (!epilogue_tile<BN>(p, C, &tmap_c, chunk_ctr, stage_tile, lane, m_blk * BM + quad * 32,
+            if (!epilogue_tile<BN / 64, kStageFloats * 4, true>(p, C, &tmap_c, chunk_ctr, stage_tile, lane, m_blk * BM + quad * 32,
                                    n_blk * BN + half * (BN / 2), taddr, &tfull_bar[acc], acc_phase, wd,
                                    split == 0 ? 1.0f : 0.0f))
                 break;
@@ -394,8 +406,11 @@ struct SmemLayout2 {
     static_assert(TOTAL <= 227 * 1024, "shared memory budget");
 };
 
-template <int STAGES>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+// EW = epilogue warps per CTA: 8 (two per TMEM lane quadrant, 128 columns each, 168 registers) or
+// 16 (four per quadrant, 64 columns each, 96 registers): the heavier epilogues (GELU) are bound by
+// the latency of one warp's chunk chain, which more warps overlap
+template <int STAGES, int EW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EW, 1)
 gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                      const __grid_constant__ CUtensorMap tmap_c, void *C, const EpiParams p, uint32_t *watchdog_flag)
 {
@@ -424,7 +439,7 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         }
         for (int i = 0; i < 2; i++) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], 2 * kEpiWarps);
+            mbar_init(&tempty_bar[i], 2 * EW);
         }
         *cta_abort = 0;
         fence_barrier_init();
@@ -504,19 +519,22 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             }
         }
     } else {
-        // ===================== epilogue (warps 2..9, both CTAs) =====================
+        // ===================== epilogue (warps 2.., both CTAs) =====================
+        constexpr int CW = BN / (EW / 4);          // columns per warp
+        constexpr int SBW = 65536 / EW;            // staging bytes per warp
         const int quad = warp & 3;
-        const int half = (warp - 2) >> 2;
+        const int cgrp = (warp - 2) >> 2;
         uint32_t it = 0, chunk_ctr = 0;
         if (warp == 2 && lane == 0)
             prefetch_tensormap(&tmap_c);
         for (int tile = pair; tile < num_tiles; tile += num_pairs, it++) {
             const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
             const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-            float *stage_tile = reinterpret_cast<float *>(smem + L::EPI_OFFSET) + (warp - 2) * kStageFloats;
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + half * (BN / 2);
-            if (!epilogue_tile<BN>(p, C, &tmap_c, chunk_ctr, stage_tile, lane, m_blk * BM2 + (int)rank * BM + quad * 32,
-                                   n_blk * BN + half * (BN / 2), taddr, &tfull_bar[acc], acc_phase, wd))
+            float *stage_tile = reinterpret_cast<float *>(smem + L::EPI_OFFSET + (warp - 2) * SBW);
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + cgrp * CW;
+            if (!epilogue_tile<CW / 32, SBW, EW == 8>(p, C, &tmap_c, chunk_ctr, stage_tile, lane,
+                                                     m_blk * BM2 + (int)rank * BM + quad * 32, n_blk * BN + cgrp * CW, taddr,
+                                                     &tfull_bar[acc], acc_phase, wd))
                 break;
             tcgen05_fence_before();
             __syncwarp();
@@ -573,12 +591,12 @@ int launch(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &tc, 
     return 0;
 }
 
-template <int STAGES>
+template <int STAGES, int EW>
 int launch_pair(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &tc, void *C, const EpiParams &p, int sms,
                 cudaStream_t st)
 {
     using L = SmemLayout2<STAGES>;
-    auto kernel = gemm_bf16_tc2_kernel<STAGES>;
+    auto kernel = gemm_bf16_tc2_kernel<STAGES, EW>;
     static bool configured[64] = {false};
     int dev = 0;
     VITCU_TRY(cudaGetDevice(&dev));
@@ -588,7 +606,7 @@ int launch_pair(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap 
     }
     const int num_tiles = ((p.M + 255) / 256) * (p.N / 256);
     const int pairs = num_tiles < sms / 2 ? num_tiles : sms / 2;
-    kernel<<<2 * pairs, kThreads, L::TOTAL, st>>>(ta, tb, tc, C, p, watchdog_flag());
+    kernel<<<2 * pairs, 64 + 32 * EW, L::TOTAL, st>>>(ta, tb, tc, C, p, watchdog_flag());
     VITCU_LAUNCHED();
     return 0;
 }
@@ -714,7 +732,12 @@ static int gemm_dispatch(const vitcu_bf16 *A, const vitcu_bf16 *W, void *C, cons
         rc = make_tensor_map_2d(&tb, W, 2, (uint64_t)d->N, kphys, kphys * 2, 128, BK);
         if (rc)
             return rc;
-        return launch_pair<5>(ta, tb, tc, C, p, sms, as_stream(s));
+        // 16 epilogue warps need the TMA output path (their staging share is 4 KB); VITCU_GEMM_EW=8|16 overrides
+        static const int force_ew = getenv("VITCU_GEMM_EW") ? atoi(getenv("VITCU_GEMM_EW")) : 0;
+        const bool ew16 = p.tma_out != 0 && (force_ew ? force_ew == 16 : p.epilogue == VITCU_EPI_BIAS_GELU);
+        if (ew16)
+            return launch_pair<5, 16>(ta, tb, tc, C, p, sms, as_stream(s));
+        return launch_pair<5, 8>(ta, tb, tc, C, p, sms, as_stream(s));
     }
     // 128x256 tiles when they divide N and still give every SM work; else 128x128
     const bool wide = d->N % 256 == 0 && ((d->M + BM - 1) / BM) * (d->N / 256) >= sms;
