@@ -360,35 +360,39 @@ __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b)
     return d;
 }
 
-// Exact-form (erf) GELU for bf16 outputs without special-function-unit calls, two values at a time:
-// erf(z) = z * q(u), q a degree-10 minimax polynomial in u = 2 z^2/a^2 - 1 on |z| <= a = 3.2,
-// z clamped to [-a, a] (1 - erf(3.2) = 6e-6).  Max |erf error| 4.8e-6, max |GELU error| 2e-5 in
-// fp32 arithmetic (fit + check: tools/fit_gelu.py) -- two orders below bf16 output rounding.
-// The GELU epilogue of fc1 is issue-bound (profiles/r01_v4_epilogue.md): the Abramowitz-Stegun
-// form cost ~25 instructions per value incl. 2 MUFU, the scalar polynomial 19, and with the
-// packed FFMA2 pipe of sm_100 the pair costs 20 (10 per value).
+// Exact-form (erf) GELU for bf16 outputs, two values at a time:
+//     erf(x / sqrt 2) = xc * P3(u) / Q3(u),   xc = clamp(x, +-A), A = 3.2 sqrt 2, u = 2 xc^2 / A^2 - 1,
+// a (3,3) rational minimax fit (tools/fit_gelu.py): max |erf error| 4.8e-6 (the clamp: 1 - erf(3.2) =
+// 6e-6), max |GELU error| 2e-5 in fp32 arithmetic -- two orders below bf16 output rounding.
+// The GELU epilogue of fc1 is bound by FMA-pipe throughput (profiles/r01_v4_epilogue.md), so the
+// form is chosen for few FMA-pipe instructions: per PAIR 11 packed FFMA2/FMUL2 + 4 FMNMX + 2 MUFU.RCP
+// (the Abramowitz-Stegun form cost ~25 per value incl. 2 MUFU, a degree-10 polynomial 16 per pair).
+__device__ __forceinline__ float rcp_approx(float x)
+{
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ f32x2 gelu_erf_fast2(f32x2 x)
 {
-    const float a = 3.2f;
-    float z0, z1;
-    unpack2(mul2(x, pack2(0.70710678118654752440f, 0.70710678118654752440f)), z0, z1);
-    const f32x2 z = pack2(fminf(fmaxf(z0, -a), a), fminf(fmaxf(z1, -a), a));
-    const f32x2 u = fma2(mul2(z, z), pack2(2.0f / (a * a), 2.0f / (a * a)), pack2(-1.0f, -1.0f));
+    const float A = 4.525483399593905f;
 #define VITCU_C2(c) pack2(c, c)
-    f32x2 q = VITCU_C2(0.002396130235865712f);
-    q = fma2(q, u, VITCU_C2(-0.00675334595143795f));
-    q = fma2(q, u, VITCU_C2(0.009276138618588448f));
-    q = fma2(q, u, VITCU_C2(-0.015805140137672424f));
-    q = fma2(q, u, VITCU_C2(0.03215679153800011f));
-    q = fma2(q, u, VITCU_C2(-0.0543348491191864f));
-    q = fma2(q, u, VITCU_C2(0.08094772696495056f));
-    q = fma2(q, u, VITCU_C2(-0.1137382909655571f));
-    q = fma2(q, u, VITCU_C2(0.1543205976486206f));
-    q = fma2(q, u, VITCU_C2(-0.21730200946331024f));
-    q = fma2(q, u, VITCU_C2(0.4413347542285919f));
+    float x0, x1;
+    unpack2(x, x0, x1);
+    const f32x2 xc = pack2(fminf(fmaxf(x0, -A), A), fminf(fmaxf(x1, -A), A));
+    const f32x2 u = fma2(mul2(xc, xc), VITCU_C2(0.09765625f), VITCU_C2(-1.0f));
+    f32x2 pn = fma2(VITCU_C2(0.010084574110805988f), u, VITCU_C2(0.142758309841156f));
+    pn = fma2(pn, u, VITCU_C2(0.3330913782119751f));
+    pn = fma2(pn, u, VITCU_C2(0.31207016110420227f));
+    f32x2 qd = fma2(VITCU_C2(0.1759948879480362f), u, VITCU_C2(0.8756541609764099f));
+    qd = fma2(qd, u, VITCU_C2(1.5597238540649414f));
+    qd = fma2(qd, u, VITCU_C2(1.0f));
 #undef VITCU_C2
+    float q0, q1;
+    unpack2(qd, q0, q1);
+    const f32x2 e = mul2(xc, mul2(pn, pack2(rcp_approx(q0), rcp_approx(q1))));
     const f32x2 hx = mul2(x, pack2(0.5f, 0.5f));
-    return fma2(hx, mul2(z, q), hx);
+    return fma2(hx, e, hx);
 }
 
 } // namespace tc
