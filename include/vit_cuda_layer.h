@@ -166,6 +166,10 @@ int vitcu_gemm_bf16x3(const vitcu_bf16 *A3, const vitcu_bf16 *W3, void *C, const
 int vitcu_attention(const void *qkv, void *out, int batch, int tokens, int is_bf16,
                     vitcu_stream s);
 
+/* Debug aid for the single-block attention kernel: record clock64 stamps of CTA 0's first 16 units
+ * into `buffer` (device memory, 3*16*8 uint64); NULL switches it off.  See tools/attn_timeline.py. */
+int vitcu_attention_debug_timeline(unsigned long long *buffer);
+
 /* Row softmax over `n` logits per row (replaces softMax, R/miniSoftMax.cl:1-50;
  * oracle R/ViT_seq.c:372-397). */
 int vitcu_softmax_rows(const float *logits, float *probs, int rows, int n, vitcu_stream s);

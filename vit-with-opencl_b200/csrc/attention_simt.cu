@@ -196,13 +196,13 @@ int attention_bf16_flash_tc(const void *qkv, void *out, int batch, int tokens, c
 extern "C" int vitcu_attention(const void *qkv, void *out, int batch, int tokens, int is_bf16, vitcu_stream s)
 {
     VITCU_REQUIRE(qkv && out && batch > 0 && tokens > 0, "bad argument");
-    // BF16 storage: tensor-core kernels -- all keys in one TMEM accumulator when they fit (<= 256),
+    // BF16 storage: tensor-core kernels -- all keys in one TMEM score buffer when they fit (<= 224),
     // key-blocked online softmax otherwise.  (VITCU_ATTN_SIMT=1 forces the CUDA-core kernel and
     // VITCU_ATTN_FLASH=1 the key-blocked kernel, for A/B measurements.)
     static const bool force_simt = getenv("VITCU_ATTN_SIMT") != nullptr;
     static const bool force_flash = getenv("VITCU_ATTN_FLASH") != nullptr;
     if (is_bf16 && !force_simt) {
-        if (tokens <= 256 && !force_flash)
+        if (tokens <= 224 && !force_flash)
             return attention_bf16_tc(qkv, out, batch, tokens, as_stream(s));
         return attention_bf16_flash_tc(qkv, out, batch, tokens, as_stream(s));
     }
