@@ -40,6 +40,17 @@ constexpr int QT = 128;                   // queries per tile
 constexpr uint32_t Q_BYTES = QT * 128;    // [128 x 64] bf16
 constexpr uint32_t S_STRIDE = 224;         // score buffers at columns 0 and 224 (<= 224 columns each)
 constexpr uint32_t O_COL = 448;           // output accumulator, 64 columns
+#ifndef VITCU_ATTN_POLY_MASK
+// Bit j set = pair j of every 8 evaluates 2^x with an FMA-pipe polynomial instead of MUFU.EX2.
+// Measured (profiles/r01_v6_attention.md): pass 2 takes ~1 950 cycles per unit for any mix from
+// 0/8 to 3/8 -- the two pipes do not overlap well with two softmax warps per sub-partition -- so
+// the default keeps everything on the MUFU.
+#define VITCU_ATTN_POLY_MASK 0x00
+#endif
+constexpr uint32_t kPolyMask = VITCU_ATTN_POLY_MASK;
+#ifndef VITCU_ATTN_SCALAR
+#define VITCU_ATTN_SCALAR 0
+#endif
 
 // barriers: per smem stage {QK_FULL, V_FULL, SMEM_FREE}; per score buffer {S_FULL}; P_FULL, O_FULL, O_FREE, XCHG
 enum Bar { QK_FULL = 0, V_FULL = 2, SMEM_FREE = 4, S_FULL = 6, P_FULL = 8, O_FULL = 9, O_FREE = 10, XCHG = 11, NUM_BARS = 12 };
@@ -99,6 +110,37 @@ __device__ __forceinline__ float softmax_half(uint32_t taddr_s, int valid_cols, 
         }
     }
     mx = exchange(mx); // row maximum over BOTH halves
+#if VITCU_ATTN_SCALAR
+    const float nm = -mx * sl2;
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+        uint32_t packed[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const float a0 = fmaf(__uint_as_float(sc[c][2 * j]), sl2, nm), a1 = fmaf(__uint_as_float(sc[c][2 * j + 1]), sl2, nm);
+            float e0, e1;
+            if (kPolyMask & (1 << j)) {
+                e0 = exp2_poly(a0);
+                e1 = exp2_poly(a1);
+            } else {
+                e0 = ex2_approx(a0);
+                e1 = ex2_approx(a1);
+            }
+            if (c + 1 == NC) {
+                if (c * 16 + 2 * j >= valid_cols)
+                    e0 = 0.f;
+                if (c * 16 + 2 * j + 1 >= valid_cols)
+                    e1 = 0.f;
+            }
+            s0 += e0;
+            s1 += e1;
+            packed[j] = pack_bf16x2(e0, e1);
+        }
+        tmem_st_32x32b_x8(taddr_s + c * 8, packed);
+    }
+    return s0 + s1;
+#else
     const f32x2 sl2v = pack2(sl2, sl2), nmx = pack2(-mx * sl2, -mx * sl2);
     f32x2 sum2 = pack2(0.f, 0.f);
 #pragma unroll
@@ -106,9 +148,16 @@ __device__ __forceinline__ float softmax_half(uint32_t taddr_s, int valid_cols, 
         uint32_t packed[8];
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            float a0, a1;
-            unpack2(fma2(pack2(__uint_as_float(sc[c][2 * j]), __uint_as_float(sc[c][2 * j + 1])), sl2v, nmx), a0, a1);
-            float e0 = ex2_approx(a0), e1 = ex2_approx(a1);
+            const f32x2 arg = fma2(pack2(__uint_as_float(sc[c][2 * j]), __uint_as_float(sc[c][2 * j + 1])), sl2v, nmx);
+            float e0, e1;
+            if (kPolyMask & (1 << j)) { // this pair on the FMA pipe, the others on the MUFU
+                exp2_poly2(arg, e0, e1);
+            } else {
+                float a0, a1;
+                unpack2(arg, a0, a1);
+                e0 = ex2_approx(a0);
+                e1 = ex2_approx(a1);
+            }
             if (c + 1 == NC) {
                 if (c * 16 + 2 * j >= valid_cols)
                     e0 = 0.f;
@@ -124,6 +173,7 @@ __device__ __forceinline__ float softmax_half(uint32_t taddr_s, int valid_cols, 
     float s0, s1;
     unpack2(sum2, s0, s1);
     return s0 + s1;
+#endif
 }
 
 // NCH = number of 16-column chunks of S (KP / 16); the left warp group takes ceil(NCH/2) chunks

@@ -350,6 +350,15 @@ __device__ __forceinline__ float ex2_approx(float x)
     return y;
 }
 
+// 2^x for x <= 0 on the FMA pipe (no MUFU): round-to-nearest split x = n + f with the 1.5*2^23 magic
+// constant, degree-3 minimax polynomial for 2^f on [-0.5, 0.5] (relative error 1e-4, far below the
+// bf16 rounding of the probabilities it feeds), exponent patched in with an integer add.  Used for
+// a fraction of the attention scores so the MUFU.EX2 pipe is not the only thing pass 2 waits for.
+__device__ __forceinline__ float exp2_poly_finish(float p, float t)
+{
+    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
 // ---- packed fp32x2 arithmetic (sm_100: FFMA2 / FMUL2 / FADD2, two lanes per issue slot) ----
 typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 pack2(float lo, float hi)
@@ -379,6 +388,34 @@ __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b)
     f32x2 d;
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
+}
+
+__device__ __forceinline__ float exp2_poly(float x)
+{
+    const float xc = fmaxf(x, -126.0f);
+    const float t = xc + 12582912.0f; // integer part in the low mantissa bits
+    const float f = xc - (t - 12582912.0f);
+    float q = fmaf(0.05592203512787819f, f, 0.24264007806777954f);
+    q = fmaf(q, f, 0.6931210160255432f);
+    q = fmaf(q, f, 0.9999244809150696f);
+    return exp2_poly_finish(q, t);
+}
+__device__ __forceinline__ void exp2_poly2(f32x2 x, float &e0, float &e1)
+{
+    float x0, x1;
+    unpack2(x, x0, x1);
+    const f32x2 xc = pack2(fmaxf(x0, -126.0f), fmaxf(x1, -126.0f));
+    const f32x2 t = add2(xc, pack2(12582912.0f, 12582912.0f));      // integer part in the low mantissa bits
+    const f32x2 n = add2(t, pack2(-12582912.0f, -12582912.0f));
+    const f32x2 f = fma2(n, pack2(-1.0f, -1.0f), xc);               // in [-0.5, 0.5]
+    f32x2 q = fma2(pack2(0.05592203512787819f, 0.05592203512787819f), f, pack2(0.24264007806777954f, 0.24264007806777954f));
+    q = fma2(q, f, pack2(0.6931210160255432f, 0.6931210160255432f));
+    q = fma2(q, f, pack2(0.9999244809150696f, 0.9999244809150696f));
+    float q0, q1, t0, t1;
+    unpack2(q, q0, q1);
+    unpack2(t, t0, t1);
+    e0 = exp2_poly_finish(q0, t0);
+    e1 = exp2_poly_finish(q1, t1);
 }
 
 // Exact-form (erf) GELU for bf16 outputs, two values at a time:
