@@ -22,6 +22,9 @@
 // multiple of 128) is handled by TMA zero-fill on load and a row predicate on
 // store.  Every mbarrier wait is watchdog-guarded (tc_common.cuh).
 #include "tc_common.cuh"
+#ifndef VITCU_GELU_SCALAR
+#define VITCU_GELU_SCALAR 0
+#endif
 #include <stdlib.h>
 #include <string.h>
 
@@ -149,9 +152,15 @@ __device__ __forceinline__ bool epilogue_tile(const EpiParams &p, void *C, const
                 for (int j = 0; j < 32; j++)
                     v[j] = gelu_erf(v[j]);
             } else {
+#if VITCU_GELU_SCALAR
+#pragma unroll
+                for (int j = 0; j < 32; j++)
+                    v[j] = gelu_erf_fast1(v[j]);
+#else
 #pragma unroll
                 for (int j = 0; j < 32; j += 2)
                     unpack2(gelu_erf_fast2(pack2(v[j], v[j + 1])), v[j], v[j + 1]);
+#endif
             }
         }
         if (p.tma_out) {

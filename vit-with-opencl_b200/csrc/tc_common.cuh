@@ -431,6 +431,22 @@ __device__ __forceinline__ float rcp_approx(float x)
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// scalar form of the same rational approximation (A/B: -DVITCU_GELU_SCALAR=1)
+__device__ __forceinline__ float gelu_erf_fast1(float x)
+{
+    const float A = 4.525483399593905f;
+    const float xc = fminf(fmaxf(x, -A), A);
+    const float u = fmaf(xc * xc, 0.09765625f, -1.0f);
+    float pn = fmaf(0.010084574110805988f, u, 0.142758309841156f);
+    pn = fmaf(pn, u, 0.3330913782119751f);
+    pn = fmaf(pn, u, 0.31207016110420227f);
+    float qd = fmaf(0.1759948879480362f, u, 0.8756541609764099f);
+    qd = fmaf(qd, u, 1.5597238540649414f);
+    qd = fmaf(qd, u, 1.0f);
+    const float e = xc * (pn * rcp_approx(qd));
+    const float hx = 0.5f * x;
+    return fmaf(hx, e, hx);
+}
 __device__ __forceinline__ f32x2 gelu_erf_fast2(f32x2 x)
 {
     const float A = 4.525483399593905f;
