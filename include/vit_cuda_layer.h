@@ -67,6 +67,8 @@ int vitcu_host_alloc(void **hptr, size_t bytes); /* pinned */
 int vitcu_host_free(void *hptr);
 int vitcu_host_register(void *hptr, size_t bytes); /* pin caller memory in place */
 int vitcu_host_unregister(void *hptr);
+/* *pinned = 1 when hptr is page-locked (cudaHostAlloc / cudaHostRegister) memory a DMA can read in place */
+int vitcu_host_is_pinned(const void *hptr, int *pinned);
 int vitcu_memcpy_h2d(void *dst, const void *src, size_t bytes, vitcu_stream s);
 int vitcu_memcpy_d2h(void *dst, const void *src, size_t bytes, vitcu_stream s);
 int vitcu_memcpy_d2d(void *dst, const void *src, size_t bytes, vitcu_stream s);

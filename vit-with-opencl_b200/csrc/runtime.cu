@@ -175,6 +175,14 @@ int vitcu_host_unregister(void *hptr)
     VITCU_TRY(cudaHostUnregister(hptr));
     return 0;
 }
+int vitcu_host_is_pinned(const void *hptr, int *pinned)
+{
+    VITCU_REQUIRE(hptr && pinned, "NULL argument");
+    cudaPointerAttributes a;
+    VITCU_TRY(cudaPointerGetAttributes(&a, hptr));
+    *pinned = a.type == cudaMemoryTypeHost;
+    return 0;
+}
 int vitcu_memcpy_h2d(void *dst, const void *src, size_t bytes, vitcu_stream s)
 {
     VITCU_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, as_stream(s)));

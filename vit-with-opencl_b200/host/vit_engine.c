@@ -184,10 +184,7 @@ void vitb200_destroy(vitb200_engine *e)
         return;
     vitcu_set_device(e->device);
     vitcu_device_sync();
-    for (int i = 0; i < VITB200_NBLOBS; i++) {
-        vitcu_free(e->w32[i]);
-        vitcu_free(e->w16[i]);
-    }
+    vitcu_free(e->w_arena); /* every w32[] / w16[] pointer lives in it */
     for (int i = 0; i < 2; i++) {
         vitcu_free(e->d_images[i]);
         vitcu_free(e->d_probs[i]);
@@ -215,6 +212,11 @@ void vitb200_destroy(vitb200_engine *e)
     vitcu_free(e->d_cls);
     vitcu_host_free(e->h_probs);
     vitcu_host_free(e->h_logits);
+    vit_stager_destroy(e->stager);
+    vitcu_host_free(e->h_stage);
+    for (int i = 0; i < VIT_STAGE_SLOTS; i++)
+        if (e->ev_slot[i])
+            vitcu_event_destroy(e->ev_slot[i]);
     if (e->stream)
         vitcu_stream_destroy(e->stream);
     if (e->copy_stream)
@@ -243,31 +245,67 @@ int vitb200_load_weights(vitb200_engine *e, const vitb200_blob *net)
         }
     }
     const int bf = e->precision == VITB200_BF16;
+    /* One device allocation for all weights (152 cudaMalloc + 49 cudaFree calls cost more than the
+     * upload itself) and two fp32 scratch buffers through which the GEMM weights pass on their way
+     * to the packed form: bf16 [N,K] on the BF16 path, three bf16 pieces [N,3K] on the FP32
+     * tensor-core path.  Everything else (biases, LayerNorm, class token, position embedding, head,
+     * and the conv filters of the TF32 patch embedding) stays fp32. */
+    size_t off32[VITB200_NBLOBS], off16[VITB200_NBLOBS], total = 0, scratch_elems = 0;
     for (int i = 0; i < VITB200_NBLOBS; i++) {
         const size_t n = net[i].size;
-        if (!e->w32[i])
-            VIT_TRY(vitcu_malloc((void **)&e->w32[i], n * sizeof(float)));
-        VIT_TRY(vitcu_memcpy_h2d(e->w32[i], net[i].data, n * sizeof(float), e->stream));
-        if (bf && is_gemm_weight(i)) {
-            if (!e->w16[i])
-                VIT_TRY(vitcu_malloc((void **)&e->w16[i], n * sizeof(vitcu_bf16)));
-            VIT_TRY(vitcu_f32_to_bf16(e->w32[i], e->w16[i], n, e->stream));
+        const int packed = is_gemm_weight(i) && (bf || e->fp32_tc);
+        const int keep32 = !packed || (bf && i == 1 && !e->pe_gather);
+        const int need16 = packed && !(bf && i == 1 && !e->pe_gather);
+        off32[i] = off16[i] = (size_t)-1;
+        if (keep32) {
+            off32[i] = total;
+            total += (n * sizeof(float) + 255) & ~(size_t)255;
         }
-        if (e->fp32_tc && is_gemm_weight(i)) { /* [N,K] fp32 -> [N,3K] bf16 pieces */
-            const int K = (i == 1 || (i - 4) % 12 != 10) ? VIT_D : VIT_HID;
-            if (!e->w16[i])
-                VIT_TRY(vitcu_malloc((void **)&e->w16[i], 3 * n * sizeof(vitcu_bf16)));
-            VIT_TRY(vitcu_split3(e->w32[i], (size_t)K, e->w16[i], n / (size_t)K, K, e->stream));
+        if (need16) {
+            off16[i] = total;
+            total += (n * (e->fp32_tc ? 3 : 1) * sizeof(vitcu_bf16) + 255) & ~(size_t)255;
+            if (n > scratch_elems)
+                scratch_elems = n;
         }
     }
-    VIT_TRY(vitcu_stream_sync(e->stream));
-    if (bf || e->fp32_tc) { /* the fp32 masters of the GEMM weights are not needed on the tensor-core paths */
-        for (int i = 0; i < VITB200_NBLOBS; i++)
-            if (is_gemm_weight(i) && !(bf && i == 1)) { /* the TF32 patch embedding reads the fp32 conv filters */
-                VIT_TRY(vitcu_free(e->w32[i]));
-                e->w32[i] = NULL;
+    if (e->w_arena) {
+        VIT_TRY(vitcu_free(e->w_arena));
+        e->w_arena = NULL;
+    }
+    VIT_TRY(vitcu_malloc(&e->w_arena, total));
+    float *scratch[2] = {NULL, NULL};
+    if (scratch_elems)
+        for (int k = 0; k < 2; k++)
+            VIT_TRY(vitcu_malloc((void **)&scratch[k], scratch_elems * sizeof(float)));
+    int k = 0, rc = 0;
+    for (int i = 0; i < VITB200_NBLOBS && !rc; i++) {
+        const size_t n = net[i].size;
+        e->w32[i] = off32[i] == (size_t)-1 ? NULL : (float *)((char *)e->w_arena + off32[i]);
+        e->w16[i] = off16[i] == (size_t)-1 ? NULL : (vitcu_bf16 *)((char *)e->w_arena + off16[i]);
+        if (e->w32[i])
+            rc = vitcu_memcpy_h2d(e->w32[i], net[i].data, n * sizeof(float), e->stream);
+        if (!rc && e->w16[i]) {
+            /* stream order makes the scratch reuse safe: the conversion that read it two blobs ago
+             * precedes this copy on the same stream */
+            float *src = e->w32[i] ? e->w32[i] : scratch[k++ & 1];
+            if (src != e->w32[i])
+                rc = vitcu_memcpy_h2d(src, net[i].data, n * sizeof(float), e->stream);
+            if (!rc && bf)
+                rc = vitcu_f32_to_bf16(src, e->w16[i], n, e->stream);
+            if (!rc && e->fp32_tc) { /* [N,K] fp32 -> [N,3K] bf16 pieces */
+                const int K = (i == 1 || (i - 4) % 12 != 10) ? VIT_D : VIT_HID;
+                rc = vitcu_split3(src, (size_t)K, e->w16[i], n / (size_t)K, K, e->stream);
             }
+        }
     }
+    if (!rc)
+        rc = vitcu_stream_sync(e->stream);
+    if (rc)
+        vit_fail(__FILE__, __LINE__, rc, NULL);
+    vitcu_free(scratch[0]);
+    vitcu_free(scratch[1]);
+    if (rc)
+        return rc;
     e->weights_loaded = 1;
     return 0;
 }
@@ -414,6 +452,44 @@ static int check_ready(vitb200_engine *e)
     return 0;
 }
 
+/* Upload of b images from pageable host memory into d_images[buf]: the pool gathers a group of
+ * images into a pinned slot, the copy stream DMAs the slot, and a slot is refilled once the DMA
+ * that read it (VIT_STAGE_SLOTS groups ago) has finished -- so gathering group g+1 overlaps the
+ * DMA of group g.  The ring and the threads are created on first use. */
+static int upload_pageable(vitb200_engine *e, int buf, const float *contig, const vitb200_image *structs, int b)
+{
+    const size_t img_elems = (size_t)3 * e->img * e->img, img_bytes = img_elems * sizeof(float);
+    if (!e->stager) {
+        /* small slots: page-locking costs ~0.4 ms per MB and is paid inside the first call */
+        const char *mb = getenv("VITB200_STAGE_SLOT_MB");
+        e->stage_group = (int)(((size_t)(mb && atoi(mb) > 0 ? atoi(mb) : 4) << 20) / img_bytes);
+        if (e->stage_group < 1)
+            e->stage_group = 1;
+        if (e->stage_group > e->B)
+            e->stage_group = e->B;
+        VIT_TRY(vitcu_host_alloc((void **)&e->h_stage, (size_t)VIT_STAGE_SLOTS * e->stage_group * img_bytes));
+        for (int i = 0; i < VIT_STAGE_SLOTS; i++)
+            VIT_TRY(vitcu_event_create(&e->ev_slot[i]));
+        e->stager = vit_stager_create(vit_stager_threads_default());
+        if (!e->stager)
+            return vit_fail(__FILE__, __LINE__, VITCU_E_ARG, "out of host memory");
+    }
+    for (int g0 = 0; g0 < b; g0 += e->stage_group) {
+        const int g = b - g0 < e->stage_group ? b - g0 : e->stage_group;
+        const int slot = e->stage_next++ % VIT_STAGE_SLOTS;
+        char *h = e->h_stage + (size_t)slot * e->stage_group * img_bytes;
+        if (e->stage_used[slot])
+            VIT_TRY(vitcu_event_sync(e->ev_slot[slot]));
+        vit_stager_copy(e->stager, h, structs ? structs + g0 : NULL, contig ? contig + (size_t)g0 * img_elems : NULL,
+                        img_bytes, g);
+        VIT_TRY(vitcu_memcpy_h2d(e->d_images[buf] + (size_t)g0 * img_elems, h, (size_t)g * img_bytes,
+                                 e->copy_stream));
+        VIT_TRY(vitcu_event_record(e->ev_slot[slot], e->copy_stream));
+        e->stage_used[slot] = 1;
+    }
+    return 0;
+}
+
 /* Shared chunk pipeline.  Source of chunk c is either a contiguous host array
  * (images_host) or per-image structs.  While chunk c computes, the host copies
  * chunk c-1's results out of pinned staging and the copy stream uploads chunk
@@ -426,6 +502,11 @@ static int forward_pipeline(vitb200_engine *e, const float *images_host, const v
     const size_t stage = (size_t)e->B * VITB200_CLASSES;
     int done = 0, chunk = 0;
     int pend_n = 0, pend_off = 0, pend_buf = 0;
+    /* a pinned (or registered) source is DMA'd in place; pageable memory goes through the stager */
+    int pinned = 0;
+    VIT_TRY(vitcu_host_is_pinned(images_host ? (const void *)images_host : (const void *)structs[0].data, &pinned));
+    if (getenv("VITB200_NO_STAGER"))
+        pinned = 1; /* let the driver stage pageable copies itself */
     while (done < n || pend_n) {
         const int buf = chunk & 1;
         int b = 0;
@@ -433,7 +514,10 @@ static int forward_pipeline(vitb200_engine *e, const float *images_host, const v
             b = n - done < e->B ? n - done : e->B;
             /* d_images[buf] is free once the forward that read it (chunk-2) finished */
             VIT_TRY(vitcu_stream_wait_event(e->copy_stream, e->ev_done[buf]));
-            if (images_host) {
+            if (!pinned) {
+                VIT_TRY_RC(upload_pageable(e, buf, images_host ? images_host + (size_t)done * img_elems : NULL,
+                                           structs ? structs + done : NULL, b));
+            } else if (images_host) {
                 VIT_TRY(vitcu_memcpy_h2d(e->d_images[buf], images_host + (size_t)done * img_elems,
                                          (size_t)b * img_elems * sizeof(float), e->copy_stream));
             } else {

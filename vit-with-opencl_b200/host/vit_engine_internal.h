@@ -18,7 +18,8 @@ struct vitb200_engine {
     vitcu_stream stream, copy_stream;
     vitcu_event ev_h2d[2], ev_done[2], ev_out[2], ev_t0, ev_t1;
     vitcu_graph graph[2];
-    float *w32[VITB200_NBLOBS];      /* fp32 blobs on the device */
+    void *w_arena;                   /* one device allocation holding every weight below */
+    float *w32[VITB200_NBLOBS];      /* fp32 blobs on the device (pointers into w_arena) */
     vitcu_bf16 *w16[VITB200_NBLOBS]; /* BF16 path: bf16 GEMM weights [N,K]; FP32 tensor-core path: three bf16 pieces [N,3K] */
     vitcu_bf16 *d_a3;                /* FP32 tensor-core path: split form [rows,3K] of the current GEMM A operand */
     float *d_images[2];              /* double-buffered input chunk [B,3,img,img] */
@@ -28,7 +29,22 @@ struct vitb200_engine {
     float *d_cls;                    /* [B,768] final-LN class tokens */
     float *d_logits[2], *d_probs[2]; /* [B,1000] */
     float *h_probs, *h_logits;       /* pinned staging [2][B,1000] */
+    /* pageable sources: worker threads gather images into a ring of pinned slots (vit_stage.c) */
+    struct vit_stager *stager;
+    char *h_stage;                   /* [VIT_STAGE_SLOTS][stage_group images] pinned */
+    int stage_group, stage_next, stage_used[4];
+    vitcu_event ev_slot[4];
 };
+
+#define VIT_STAGE_SLOTS 3
+typedef struct vit_stager vit_stager;
+int vit_stager_threads_default(void);
+vit_stager *vit_stager_create(int threads);
+void vit_stager_destroy(vit_stager *s);
+/* copies `count` blocks of `bytes` into dst (block i from structs[i].data, or contig + i*bytes when
+ * structs is NULL) on all threads of the pool plus the caller; returns when every block is copied */
+void vit_stager_copy(vit_stager *s, void *dst, const vitb200_image *structs, const void *contig, size_t bytes,
+                     int count);
 
 /* records "[file:line] ..." for vitb200_last_error(); what == NULL takes the
  * device layer's message */

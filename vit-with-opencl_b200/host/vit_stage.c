@@ -1,0 +1,144 @@
+/* host/vit_stage.c -- worker threads that gather pageable host images into pinned staging.
+ *
+ * The reference hands ViT_opencl one malloc'd buffer per image (R/Network.c:84-105, R/ =
+ * /root/reference/MulticoreMainProject/).  A DMA engine cannot read pageable memory, so something
+ * has to copy every image into pinned memory first; the CUDA driver does that on the calling
+ * thread at ~10 GB/s, which is slower than the GPU consumes images.  This pool spreads the copy
+ * over several cores so the upload of a chunk costs less than its forward.
+ */
+#include "vit_engine_internal.h"
+
+#include <pthread.h>
+#include <stdatomic.h>
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+
+#define VIT_STAGE_MAX_THREADS 32
+#define VIT_STAGE_PIECE ((size_t)128 << 10)
+
+struct vit_stager {
+    pthread_t th[VIT_STAGE_MAX_THREADS];
+    int nth; /* workers besides the calling thread */
+    pthread_mutex_t mu;
+    pthread_cond_t cv_job, cv_done;
+    unsigned gen;
+    int stop, running;
+    /* the current job: `count` blocks of `bytes`, block i from structs[i].data or contig + i*bytes,
+     * handed out in pieces of VIT_STAGE_PIECE bytes so a small group still occupies every thread */
+    char *dst;
+    const vitb200_image *structs;
+    const char *contig;
+    size_t bytes;
+    int count, pieces; /* pieces per block */
+    atomic_int next;
+};
+
+static void run_job(vit_stager *s)
+{
+    for (;;) {
+        const int u = atomic_fetch_add(&s->next, 1);
+        if (u >= s->count * s->pieces)
+            break;
+        const int i = u / s->pieces;
+        const size_t off = (size_t)(u % s->pieces) * VIT_STAGE_PIECE;
+        const size_t len = s->bytes - off < VIT_STAGE_PIECE ? s->bytes - off : VIT_STAGE_PIECE;
+        const char *src = s->structs ? (const char *)s->structs[i].data : s->contig + (size_t)i * s->bytes;
+        memcpy(s->dst + (size_t)i * s->bytes + off, src + off, len);
+    }
+}
+
+static void *worker(void *arg)
+{
+    vit_stager *s = (vit_stager *)arg;
+    unsigned seen = 0;
+    pthread_mutex_lock(&s->mu);
+    for (;;) {
+        while (!s->stop && s->gen == seen)
+            pthread_cond_wait(&s->cv_job, &s->mu);
+        if (s->stop)
+            break;
+        seen = s->gen;
+        pthread_mutex_unlock(&s->mu);
+        run_job(s);
+        pthread_mutex_lock(&s->mu);
+        if (--s->running == 0)
+            pthread_cond_signal(&s->cv_done);
+    }
+    pthread_mutex_unlock(&s->mu);
+    return NULL;
+}
+
+int vit_stager_threads_default(void)
+{
+    const char *env = getenv("VITB200_STAGE_THREADS");
+    long n = env ? atol(env) : 0;
+    if (n <= 0) {
+        n = sysconf(_SC_NPROCESSORS_ONLN) / 2;
+        if (n > 8)
+            n = 8;
+    }
+    if (n < 1)
+        n = 1;
+    if (n > VIT_STAGE_MAX_THREADS)
+        n = VIT_STAGE_MAX_THREADS;
+    return (int)n;
+}
+
+vit_stager *vit_stager_create(int threads)
+{
+    vit_stager *s = (vit_stager *)calloc(1, sizeof(*s));
+    if (!s)
+        return NULL;
+    pthread_mutex_init(&s->mu, NULL);
+    pthread_cond_init(&s->cv_job, NULL);
+    pthread_cond_init(&s->cv_done, NULL);
+    if (threads > VIT_STAGE_MAX_THREADS)
+        threads = VIT_STAGE_MAX_THREADS;
+    /* the caller copies too, so `threads` total means threads-1 workers; a failed
+     * pthread_create only lowers the count */
+    for (int i = 0; i < threads - 1; i++) {
+        if (pthread_create(&s->th[s->nth], NULL, worker, s) != 0)
+            break;
+        s->nth++;
+    }
+    return s;
+}
+
+void vit_stager_destroy(vit_stager *s)
+{
+    if (!s)
+        return;
+    pthread_mutex_lock(&s->mu);
+    s->stop = 1;
+    pthread_cond_broadcast(&s->cv_job);
+    pthread_mutex_unlock(&s->mu);
+    for (int i = 0; i < s->nth; i++)
+        pthread_join(s->th[i], NULL);
+    pthread_cond_destroy(&s->cv_job);
+    pthread_cond_destroy(&s->cv_done);
+    pthread_mutex_destroy(&s->mu);
+    free(s);
+}
+
+void vit_stager_copy(vit_stager *s, void *dst, const vitb200_image *structs, const void *contig, size_t bytes,
+                     int count)
+{
+    pthread_mutex_lock(&s->mu);
+    s->dst = (char *)dst;
+    s->structs = structs;
+    s->contig = (const char *)contig;
+    s->bytes = bytes;
+    s->count = count;
+    s->pieces = (int)((bytes + VIT_STAGE_PIECE - 1) / VIT_STAGE_PIECE);
+    atomic_store(&s->next, 0);
+    s->running = s->nth;
+    s->gen++;
+    pthread_cond_broadcast(&s->cv_job);
+    pthread_mutex_unlock(&s->mu);
+    run_job(s);
+    pthread_mutex_lock(&s->mu);
+    while (s->running)
+        pthread_cond_wait(&s->cv_done, &s->mu);
+    pthread_mutex_unlock(&s->mu);
+}
