@@ -21,7 +21,10 @@
  *    works; missing blobs are reported instead of dereferenced.
  *    Environment knobs: VITB200_PRECISION=fp32|bf16 (default fp32, the
  *    reference's arithmetic), VITB200_GPUS=<n> (default: 1 GPU per 256 images,
- *    capped by the visible devices), VITB200_BATCH=<images per chunk>.
+ *    capped by the visible devices), VITB200_BATCH=<images per chunk>,
+ *    VITB200_PERSIST=1 (keep the engines and the packed weights across calls;
+ *    weights are re-uploaded only when their signature changes; released by
+ *    vitb200_release_persistent()).
  *
  * 2. The engine API underneath it, for callers that keep the model resident
  *    (the bench, the tests, a serving loop).  The structs mirror the
@@ -63,6 +66,9 @@ typedef struct vitb200_engine vitb200_engine;
 /* the reference's entry point (R/ViT_opencl.h:6) */
 void ViT_opencl(vitb200_image *image, vitb200_blob *networks, float **prb);
 
+/* frees the engines VITB200_PERSIST=1 kept alive (no-op otherwise) */
+void vitb200_release_persistent(void);
+
 /* ---- engine API: every int function returns 0 or an error code whose text is
  * in vitb200_last_error(). ---- */
 const char *vitb200_last_error(void);
@@ -85,6 +91,12 @@ int vitb200_forward(vitb200_engine *e, const float *images_host, int n, float *p
 /* Same, from the reference's per-image structs into per-image rows (the
  * ViT_opencl calling convention). */
 int vitb200_forward_structs(vitb200_engine *e, const vitb200_image *images, int n, float **prb);
+
+/* Labels only: the k most probable classes of every image, most probable first, ties to the lower
+ * class index (k = 1 is the argmax scan of R/Main.c:59-72 without its pred_idx carried over from the
+ * previous image).  labels/probs are [n,k] host arrays; the 1000-way probabilities stay on the GPU. */
+#define VITB200_TOPK_MAX 8
+int vitb200_forward_topk(vitb200_engine *e, const float *images_host, int n, int k, int *labels, float *probs);
 
 /* Device-resident variant for kernel-only timing: stage n <= max_batch images
  * once, then run the forward on them any number of times. */

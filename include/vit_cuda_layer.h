@@ -176,6 +176,11 @@ int vitcu_attention_debug_timeline(unsigned long long *buffer);
  * oracle R/ViT_seq.c:372-397). */
 int vitcu_softmax_rows(const float *logits, float *probs, int rows, int n, vitcu_stream s);
 
+/* The k largest entries of every row, largest first, ties to the lower index: idx/val [rows,k]
+ * (device).  k = 1 is the argmax scan of R/Main.c:59-72 (first maximum wins) without its stale
+ * pred_idx carry-over between images. */
+int vitcu_topk_rows(const float *x, int rows, int cols, int k, int *idx, float *val, vitcu_stream s);
+
 #ifdef __cplusplus
 }
 #endif

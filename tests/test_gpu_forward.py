@@ -97,6 +97,35 @@ def test_vit_opencl_drop_in(pkg, lib, blobs224, case224, monkeypatch):
     assert np.abs(probs16 - ref["probs"][:3]).max() <= 0.01
 
 
+def test_vit_opencl_persistent_context(pkg, lib, blobs224, case224, monkeypatch):
+    """VITB200_PERSIST=1: later calls reuse the engine and the packed weights, notice
+    changed weights, and give the same rows as the default create/upload/destroy call"""
+    imgs, ref = case224
+    monkeypatch.setenv("VITB200_PRECISION", "fp32")
+    once = pkg.vit_opencl(imgs[:3], blobs224)
+    monkeypatch.setenv("VITB200_PERSIST", "1")
+    try:
+        a = pkg.vit_opencl(imgs[:3], blobs224)
+        b = pkg.vit_opencl(imgs[:3], blobs224)           # engine + weights reused
+        np.testing.assert_allclose(a, once, rtol=1e-5, atol=1e-9)
+        np.testing.assert_allclose(b, once, rtol=1e-5, atol=1e-9)
+        other = [w.copy() for w in blobs224]
+        other[151] = other[151][::-1].copy()             # head bias reversed: same shapes, other logits
+        c = pkg.vit_opencl(imgs[:3], other)
+        assert np.abs(c - once).max() > 1e-6
+        edited = blobs224[151].copy()
+        blobs224[151][0] += 1.0                          # in-place edit of a resident blob is noticed
+        try:
+            d = pkg.vit_opencl(imgs[:3], blobs224)
+        finally:
+            blobs224[151][...] = edited
+        assert np.abs(d - once).max() > 1e-6
+        e = pkg.vit_opencl(imgs[:3], blobs224)
+        np.testing.assert_allclose(e, once, rtol=1e-5, atol=1e-9)
+    finally:
+        lib.vitb200_release_persistent()
+
+
 def test_forward_structs_equals_contiguous(pkg, lib, blobs224, case224):
     imgs, _ = case224
     with pkg.Engine(0, 224, pkg.FP32, max_batch=4) as eng:
@@ -106,6 +135,53 @@ def test_forward_structs_equals_contiguous(pkg, lib, blobs224, case224):
     # same images, same kernels; at this small batch the residual GEMMs are split along K and meet
     # through TMA reduce-add, whose fp32 summation order is not fixed -> equal to rounding, not bitwise
     np.testing.assert_allclose(a, b, rtol=1e-5, atol=1e-9)
+
+
+def test_pageable_sources_match_pinned(pkg, lib, blobs224, monkeypatch):
+    """pageable images (one contiguous array, or the reference's per-image buffers, R/Network.c:84-105)
+    pass through the threaded pinned ring; a pinned source is DMA'd in place -- same results.
+    70 images over max_batch 32 and 1 MB slots: three chunks, ragged last chunk, ragged last group."""
+    monkeypatch.setenv("VITB200_STAGE_SLOT_MB", "1")
+    monkeypatch.setenv("VITB200_STAGE_THREADS", "3")
+    n = 70
+    imgs = pkg.synth.synthetic_images(n, 224, seed=5)
+    pin = pkg.PinnedArray(imgs.shape)
+    pin.array[...] = imgs
+    with pkg.Engine(0, 224, pkg.BF16, max_batch=32) as eng:
+        eng.load_weights(blobs224)
+        ref = eng.forward(pin.array)
+        a = eng.forward(imgs)
+        b = eng.forward_structs(imgs)
+        c = eng.forward(imgs)       # ring slots are reused across calls
+        monkeypatch.setenv("VITB200_NO_STAGER", "1")
+        d = eng.forward(imgs)       # driver-staged pageable copy
+    for got in (a, b, c, d):
+        # full chunks: same kernels in the same order -> bitwise equal, so every image landed in its slot
+        assert np.array_equal(got[:64], ref[:64])
+        # the ragged 6-image chunk splits its residual GEMMs along K (TMA reduce-add, unordered fp32
+        # sums), and one flipped bf16 rounding downstream moves a probability by up to ~1 %
+        np.testing.assert_allclose(got[64:], ref[64:], rtol=3e-2, atol=1e-7)
+        assert np.array_equal(got.argmax(1), ref.argmax(1))
+    assert len({tuple(ref[i].argsort()[-3:]) for i in range(n)}) > 1  # not all images alike
+
+
+def test_forward_topk_matches_host_argmax(pkg, lib, blobs224, case224):
+    """labels-only read-back: same top-1 as scanning the full probability rows the way
+    R/Main.c:59-72 does, and as the oracle's rows"""
+    imgs, ref = case224
+    with pkg.Engine(0, 224, pkg.FP32, max_batch=4) as eng:
+        eng.load_weights(blobs224)
+        probs = eng.forward(imgs)
+        labels, top = eng.forward_topk(imgs, 5)
+        l1, _ = eng.forward_topk(imgs, 1)
+        with pytest.raises(RuntimeError):
+            eng.forward_topk(imgs, 9)
+    n = imgs.shape[0]
+    assert np.array_equal(labels[:, 0], probs.argmax(1))
+    assert np.array_equal(l1[:, 0], labels[:, 0])
+    assert np.array_equal(labels[:, 0], ref["probs"][:n].argmax(1))
+    np.testing.assert_allclose(top, np.take_along_axis(probs, labels, 1), rtol=1e-5)
+    assert (np.diff(top, axis=1) <= 0).all()
 
 
 def test_golden_reference_vectors(pkg, lib, synth_blobs224):

@@ -235,6 +235,40 @@ def test_softmax_rows(pkg, lib, oracle):
     np.testing.assert_allclose(p.sum(1), 1.0, atol=1e-5)
 
 
+def _main_c_argmax(rows):
+    """the scan of R/Main.c:59-72, including pred_idx carried over from the previous image"""
+    out, pred = [], 0
+    for r in rows:
+        for j in range(1, r.size):
+            if r[j] > r[pred]:
+                pred = j
+        out.append(pred)
+    return np.array(out)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k", [1, 5, 8])
+def test_topk_rows(pkg, lib, k):
+    """integer/index work: exact.  Ties go to the lower index; duplicates are returned as separate entries."""
+    rng = np.random.default_rng(11)
+    x = rng.random((37, 1000), dtype=np.float32)
+    x[3, 10] = x[3, 700] = 2.0            # tied maxima
+    x[4, :] = 0.25                        # constant row: indices 0..k-1
+    x[5, 999] = 3.0                       # maximum in the last, partial 32-column group
+    dx = _dev(pkg, x)
+    di, dv = pkg.DeviceBuffer(37 * k * 4), pkg.DeviceBuffer(37 * k * 4)
+    pkg.layer_check(lib.vitcu_topk_rows(dx.ptr, 37, 1000, k, di.ptr, dv.ptr, None))
+    idx, val = di.to_numpy(np.int32, (37, k)), dv.to_numpy(np.float32, (37, k))
+    order = np.lexsort((np.arange(1000)[None, :].repeat(37, 0), -x), axis=1)[:, :k]
+    assert np.array_equal(idx, order)
+    assert np.array_equal(val, np.take_along_axis(x, order, 1))
+    if k == 1:  # rows without ties: the same label the reference's Main.c prints
+        keep = [i for i in range(37) if i not in (3, 4)]
+        assert np.array_equal(idx[keep, 0], _main_c_argmax(x[keep]))
+    assert lib.vitcu_topk_rows(dx.ptr, 37, 1000, 0, di.ptr, dv.ptr, None) != 0
+    assert lib.vitcu_topk_rows(dx.ptr, 37, 4, 5, di.ptr, dv.ptr, None) != 0
+
+
 # ---------------------------------------------------------------- weight packing
 def test_f32_to_bf16_bit_exact(pkg, lib):
     rng = np.random.default_rng(9)

@@ -80,6 +80,7 @@ def lib() -> C.CDLL:
         L.vitb200_load_weights.argtypes = [C.c_void_p, C.POINTER(Network)]
         L.vitb200_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.vitb200_forward_structs.argtypes = [C.c_void_p, C.POINTER(ImageData), C.c_int, C.POINTER(_f32p)]
+        L.vitb200_forward_topk.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.vitb200_stage_images.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.vitb200_forward_resident.argtypes = [C.c_void_p, C.c_int]
         L.vitb200_read_probs.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
@@ -93,6 +94,7 @@ def lib() -> C.CDLL:
         L.vitb200_tokens.argtypes = [C.c_void_p]
         L.ViT_opencl.argtypes = [C.POINTER(ImageData), C.POINTER(Network), C.POINTER(_f32p)]
         L.ViT_opencl.restype = None
+        L.vitb200_release_persistent.restype = None
         # device layer
         L.vitcu_malloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
         L.vitcu_free.argtypes = [C.c_void_p]
@@ -122,6 +124,8 @@ def lib() -> C.CDLL:
         L.vitcu_split3.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
         L.vitcu_attention.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.vitcu_softmax_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.vitcu_topk_rows.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.vitcu_host_is_pinned.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
         _lib = L
     return _lib
 
@@ -232,6 +236,15 @@ class Engine:
         rows = (_f32p * n)(*[out[i].ctypes.data_as(_f32p) for i in range(n)])
         _check(lib().vitb200_forward_structs(self.h, imgs, n, rows))
         return out
+
+    def forward_topk(self, images: np.ndarray, k: int = 1):
+        """labels [n,k] int32 and their probabilities [n,k], most probable first (vitb200_forward_topk)"""
+        assert images.dtype == np.float32 and images.flags["C_CONTIGUOUS"]
+        n = images.shape[0]
+        labels = np.zeros((n, k), np.int32)
+        probs = np.zeros((n, k), np.float32)
+        _check(lib().vitb200_forward_topk(self.h, images.ctypes.data, n, k, labels.ctypes.data, probs.ctypes.data))
+        return labels, probs
 
     def stage(self, images: np.ndarray):
         assert images.dtype == np.float32 and images.flags["C_CONTIGUOUS"]

@@ -194,6 +194,53 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float *__restri
         p[i] = expf(l[i] - m) / s;
 }
 
+// ---------------------------------------------------------------------------
+// top-k per row: the reference's host-side argmax scan (R/Main.c:59-72) moved to the device so a
+// caller that only wants labels reads k*8 bytes per image instead of 4 KB.  One warp per row; the
+// row lives in registers (<= 32 values per lane up to 1024 columns, strided beyond that); round r
+// picks the largest element that comes after round r-1's pick in the order (value descending,
+// index ascending) -- the first maximum wins, as in Main.c's strict `>` scan.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) topk_rows_kernel(const float *__restrict__ x, int rows, int cols, int k,
+                                                        int *__restrict__ idx, float *__restrict__ val)
+{
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows)
+        return;
+    const float *r = x + (size_t)row * cols;
+    float pv = INFINITY;
+    int pi = -1;
+    for (int t = 0; t < k; t++) {
+        float bv = -INFINITY;
+        int bi = 0x7fffffff;
+        for (int c = lane; c < cols; c += 32) {
+            const float v = r[c];
+            // NaNs never win; "after the previous pick": smaller value, or same value and larger index
+            const bool after = v < pv || (v == pv && c > pi);
+            if (after && (v > bv || (v == bv && c < bi))) {
+                bv = v;
+                bi = c;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) {
+                bv = ov;
+                bi = oi;
+            }
+        }
+        if (lane == 0) {
+            idx[(size_t)row * k + t] = bi == 0x7fffffff ? -1 : bi;
+            val[(size_t)row * k + t] = bv;
+        }
+        pv = bv;
+        pi = bi;
+    }
+}
+
 static inline int grid_for(size_t work_items, int block, int max_blocks = 148 * 16)
 {
     size_t g = (work_items + block - 1) / block;
@@ -271,6 +318,15 @@ int vitcu_softmax_rows(const float *logits, float *probs, int rows, int n, vitcu
 {
     VITCU_REQUIRE(logits && probs && rows > 0 && n > 0, "bad argument");
     softmax_rows_kernel<<<rows, 256, 0, as_stream(s)>>>(logits, probs, n);
+    VITCU_LAUNCHED();
+    return 0;
+}
+
+int vitcu_topk_rows(const float *x, int rows, int cols, int k, int *idx, float *val, vitcu_stream s)
+{
+    VITCU_REQUIRE(x && idx && val && rows > 0 && cols > 0, "bad argument");
+    VITCU_REQUIRE(k > 0 && k <= cols, "top-k needs 0 < k <= cols");
+    topk_rows_kernel<<<(rows + 7) / 8, 256, 0, as_stream(s)>>>(x, rows, cols, k, idx, val);
     VITCU_LAUNCHED();
     return 0;
 }

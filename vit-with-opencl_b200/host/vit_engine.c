@@ -212,6 +212,10 @@ void vitb200_destroy(vitb200_engine *e)
     vitcu_free(e->d_cls);
     vitcu_host_free(e->h_probs);
     vitcu_host_free(e->h_logits);
+    vitcu_free(e->d_topi);
+    vitcu_free(e->d_topv);
+    vitcu_host_free(e->h_topi);
+    vitcu_host_free(e->h_topv);
     vit_stager_destroy(e->stager);
     vitcu_host_free(e->h_stage);
     for (int i = 0; i < VIT_STAGE_SLOTS; i++)
@@ -495,7 +499,8 @@ static int upload_pageable(vitb200_engine *e, int buf, const float *contig, cons
  * chunk c-1's results out of pinned staging and the copy stream uploads chunk
  * c+1, so the GPU never waits for the host. */
 static int forward_pipeline(vitb200_engine *e, const float *images_host, const vitb200_image *structs, int n,
-                            float *probs_host, float **prob_rows, float *logits_host)
+                            float *probs_host, float **prob_rows, float *logits_host, int topk, int *top_idx,
+                            float *top_val)
 {
     const size_t img_elems = (size_t)3 * e->img * e->img;
     const size_t pbytes = (size_t)VITB200_CLASSES * sizeof(float);
@@ -530,7 +535,18 @@ static int forward_pipeline(vitb200_engine *e, const float *images_host, const v
             VIT_TRY(vitcu_stream_wait_event(e->stream, e->ev_h2d[buf]));
             VIT_TRY_RC(run_chunk(e, buf, b));
             VIT_TRY(vitcu_event_record(e->ev_done[buf], e->stream));
-            VIT_TRY(vitcu_memcpy_d2h(e->h_probs + buf * stage, e->d_probs[buf], (size_t)b * pbytes, e->stream));
+            if (probs_host || prob_rows)
+                VIT_TRY(vitcu_memcpy_d2h(e->h_probs + buf * stage, e->d_probs[buf], (size_t)b * pbytes, e->stream));
+            if (topk) {
+                /* labels only: k*8 bytes per image come back instead of 4 KB */
+                const size_t tk = (size_t)e->B * VITB200_TOPK_MAX;
+                VIT_TRY(vitcu_topk_rows(e->d_probs[buf], b, VITB200_CLASSES, topk, e->d_topi + buf * tk,
+                                        e->d_topv + buf * tk, e->stream));
+                VIT_TRY(vitcu_memcpy_d2h(e->h_topi + buf * tk, e->d_topi + buf * tk, (size_t)b * topk * sizeof(int),
+                                         e->stream));
+                VIT_TRY(vitcu_memcpy_d2h(e->h_topv + buf * tk, e->d_topv + buf * tk,
+                                         (size_t)b * topk * sizeof(float), e->stream));
+            }
             if (logits_host)
                 VIT_TRY(vitcu_memcpy_d2h(e->h_logits + buf * stage, e->d_logits[buf], (size_t)b * pbytes,
                                          e->stream));
@@ -547,6 +563,13 @@ static int forward_pipeline(vitb200_engine *e, const float *images_host, const v
             if (logits_host)
                 memcpy(logits_host + (size_t)pend_off * VITB200_CLASSES, e->h_logits + pend_buf * stage,
                        (size_t)pend_n * pbytes);
+            if (topk) {
+                const size_t tk = (size_t)e->B * VITB200_TOPK_MAX;
+                memcpy(top_idx + (size_t)pend_off * topk, e->h_topi + pend_buf * tk,
+                       (size_t)pend_n * topk * sizeof(int));
+                memcpy(top_val + (size_t)pend_off * topk, e->h_topv + pend_buf * tk,
+                       (size_t)pend_n * topk * sizeof(float));
+            }
             pend_n = 0;
         }
         if (b) {
@@ -569,7 +592,26 @@ int vitb200_forward(vitb200_engine *e, const float *images_host, int n, float *p
         return vit_fail(__FILE__, __LINE__, VITCU_E_ARG, "bad images/probs argument");
     if (n == 0)
         return 0;
-    return forward_pipeline(e, images_host, NULL, n, probs_host, NULL, logits_host);
+    return forward_pipeline(e, images_host, NULL, n, probs_host, NULL, logits_host, 0, NULL, NULL);
+}
+
+int vitb200_forward_topk(vitb200_engine *e, const float *images_host, int n, int k, int *labels, float *probs)
+{
+    VIT_TRY_RC(check_ready(e));
+    if (n < 0 || (n > 0 && (!images_host || !labels || !probs)))
+        return vit_fail(__FILE__, __LINE__, VITCU_E_ARG, "bad images/labels/probs argument");
+    if (k < 1 || k > VITB200_TOPK_MAX)
+        return vit_fail(__FILE__, __LINE__, VITCU_E_ARG, "k must be in 1..VITB200_TOPK_MAX");
+    if (n == 0)
+        return 0;
+    if (!e->d_topi) { /* first use */
+        const size_t tk = (size_t)e->B * VITB200_TOPK_MAX * 2;
+        VIT_TRY(vitcu_malloc((void **)&e->d_topi, tk * sizeof(int)));
+        VIT_TRY(vitcu_malloc((void **)&e->d_topv, tk * sizeof(float)));
+        VIT_TRY(vitcu_host_alloc((void **)&e->h_topi, tk * sizeof(int)));
+        VIT_TRY(vitcu_host_alloc((void **)&e->h_topv, tk * sizeof(float)));
+    }
+    return forward_pipeline(e, images_host, NULL, n, NULL, NULL, NULL, k, labels, probs);
 }
 
 int vitb200_forward_structs(vitb200_engine *e, const vitb200_image *images, int n, float **prb)
@@ -585,7 +627,7 @@ int vitb200_forward_structs(vitb200_engine *e, const vitb200_image *images, int 
     }
     if (n == 0)
         return 0;
-    return forward_pipeline(e, NULL, images, n, NULL, prb, NULL);
+    return forward_pipeline(e, NULL, images, n, NULL, prb, NULL, 0, NULL, NULL);
 }
 
 int vitb200_stage_images(vitb200_engine *e, const float *images_host, int n)

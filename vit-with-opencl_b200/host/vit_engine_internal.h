@@ -29,6 +29,8 @@ struct vitb200_engine {
     float *d_cls;                    /* [B,768] final-LN class tokens */
     float *d_logits[2], *d_probs[2]; /* [B,1000] */
     float *h_probs, *h_logits;       /* pinned staging [2][B,1000] */
+    int *d_topi, *h_topi;            /* [2][B,VITB200_TOPK_MAX] labels of vitb200_forward_topk (allocated on first use) */
+    float *d_topv, *h_topv;
     /* pageable sources: worker threads gather images into a ring of pinned slots (vit_stage.c) */
     struct vit_stager *stager;
     char *h_stage;                   /* [VIT_STAGE_SLOTS][stage_group images] pinned */

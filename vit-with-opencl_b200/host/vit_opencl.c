@@ -29,22 +29,116 @@ typedef struct {
     const vitb200_blob *networks;
     float **prb;
     int first, count;
+    int persist;
+    unsigned long long wsig;
     int rc;
     char msg[640];
 } shard_job;
 
+/* ---- persistent context (VITB200_PERSIST=1) --------------------------------------------------
+ * The reference rebuilds its OpenCL context, recompiles its kernels and re-uploads 346 MB of weights
+ * on every call (R/ViT_opencl.c:800-922) and tears all of it down before returning (:968-985).  That
+ * stays the default here.  With VITB200_PERSIST=1 the per-GPU engines outlive the call: a later
+ * ViT_opencl with the same image size and precision reuses the engine, and re-uploads the weights
+ * only when their signature changed.  vitb200_release_persistent() frees them. */
+#define MAX_CACHED 16
+typedef struct {
+    vitb200_engine *e;
+    int device, img, precision, batch, busy;
+    unsigned long long wsig;
+} cached_engine;
+static cached_engine g_cache[MAX_CACHED];
+static pthread_mutex_t g_cache_mu = PTHREAD_MUTEX_INITIALIZER;
+
+/* FNV-1a over every blob's address, size and a strided sample of its contents: cheap (~40 k floats
+ * read) against the ~40 ms a re-upload costs, and it notices both a different Network array and an
+ * in-place edit that touches the sampled elements, the first or the last element of a blob */
+static unsigned long long weights_signature(const vitb200_blob *net)
+{
+    unsigned long long h = 1469598103934665603ull;
+#define MIX(v)                                                                 \
+    do {                                                                       \
+        h ^= (unsigned long long)(v);                                          \
+        h *= 1099511628211ull;                                                 \
+    } while (0)
+    for (int i = 0; i < VITB200_NBLOBS; i++) {
+        MIX((size_t)net[i].data);
+        MIX(net[i].size);
+        if (!net[i].data || !net[i].size)
+            continue;
+        const unsigned *u = (const unsigned *)net[i].data;
+        const size_t step = net[i].size / 256 + 1;
+        for (size_t k = 0; k < net[i].size; k += step)
+            MIX(u[k]);
+        MIX(u[net[i].size - 1]);
+    }
+#undef MIX
+    return h;
+}
+
+static cached_engine *cache_acquire(const int device, int img, int precision, int batch)
+{
+    cached_engine *slot = NULL;
+    pthread_mutex_lock(&g_cache_mu);
+    for (int i = 0; i < MAX_CACHED && !slot; i++) {
+        cached_engine *c = &g_cache[i];
+        if (c->e && !c->busy && c->device == device && c->img == img && c->precision == precision &&
+            c->batch >= batch)
+            slot = c;
+    }
+    for (int i = 0; i < MAX_CACHED && !slot; i++)
+        if (!g_cache[i].e && !g_cache[i].busy)
+            slot = &g_cache[i];
+    if (slot)
+        slot->busy = 1;
+    pthread_mutex_unlock(&g_cache_mu);
+    return slot;
+}
+
+void vitb200_release_persistent(void)
+{
+    pthread_mutex_lock(&g_cache_mu);
+    for (int i = 0; i < MAX_CACHED; i++) {
+        if (g_cache[i].e && !g_cache[i].busy) {
+            vitb200_destroy(g_cache[i].e);
+            memset(&g_cache[i], 0, sizeof(g_cache[i]));
+        }
+    }
+    pthread_mutex_unlock(&g_cache_mu);
+}
+
 static void *shard_main(void *arg)
 {
     shard_job *j = (shard_job *)arg;
-    vitb200_engine *e = NULL;
-    j->rc = vitb200_create(&e, j->device, j->img, j->precision, j->batch);
-    if (!j->rc)
+    cached_engine *c = j->persist ? cache_acquire(j->device, j->img, j->precision, j->batch) : NULL;
+    vitb200_engine *e = c ? c->e : NULL;
+    if (!e) {
+        j->rc = vitb200_create(&e, j->device, j->img, j->precision, j->batch);
+        if (c && !j->rc) {
+            c->e = e;
+            c->device = j->device;
+            c->img = j->img;
+            c->precision = j->precision;
+            c->batch = j->batch;
+            c->wsig = 0;
+        }
+    }
+    if (!j->rc && (!c || c->wsig != j->wsig)) {
         j->rc = vitb200_load_weights(e, j->networks);
+        if (c)
+            c->wsig = j->rc ? 0 : j->wsig;
+    }
     if (!j->rc)
         j->rc = vitb200_forward_structs(e, j->images + j->first, j->count, j->prb + j->first);
     if (j->rc)
         snprintf(j->msg, sizeof(j->msg), "%s", vitb200_last_error());
-    vitb200_destroy(e);
+    if (c) {
+        pthread_mutex_lock(&g_cache_mu);
+        c->busy = 0;
+        pthread_mutex_unlock(&g_cache_mu);
+    } else {
+        vitb200_destroy(e);
+    }
     return NULL;
 }
 
@@ -95,6 +189,10 @@ void ViT_opencl(vitb200_image *image, vitb200_blob *networks, float **prb)
     if (batch > per)
         batch = per;
 
+    const char *pe = getenv("VITB200_PERSIST");
+    const int persist = pe && *pe && strcmp(pe, "0") != 0;
+    const unsigned long long wsig = persist ? weights_signature(networks) : 0;
+
     shard_job *jobs = (shard_job *)calloc((size_t)gpus, sizeof(shard_job));
     pthread_t *threads = (pthread_t *)calloc((size_t)gpus, sizeof(pthread_t));
     if (!jobs || !threads)
@@ -114,6 +212,8 @@ void ViT_opencl(vitb200_image *image, vitb200_blob *networks, float **prb)
         j->prb = prb;
         j->first = first;
         j->count = first + per <= n ? per : n - first;
+        j->persist = persist;
+        j->wsig = wsig;
         used++;
     }
     if (used == 1) {
@@ -130,8 +230,8 @@ void ViT_opencl(vitb200_image *image, vitb200_blob *networks, float **prb)
             die(jobs[g].msg);
     clock_gettime(CLOCK_MONOTONIC, &t1);
     /* the reference prints its own timings (R/ViT_opencl.c:910,964); keep one line */
-    printf("ViT_b200: %d images, %d GPU(s), %s, %.3f s wall (device bring-up + weight upload + forward)\n", n,
-           used, precision == VITB200_BF16 ? "bf16" : "fp32",
+    printf("ViT_b200: %d images, %d GPU(s), %s%s, %.3f s wall (device bring-up + weight upload + forward)\n", n,
+           used, precision == VITB200_BF16 ? "bf16" : "fp32", persist ? ", persistent context" : "",
            (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec));
     free(jobs);
     free(threads);
