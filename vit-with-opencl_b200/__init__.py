@@ -19,7 +19,7 @@ import subprocess
 
 import numpy as np
 
-from . import synth  # noqa: F401  (re-export)
+from . import compare, synth  # noqa: F401  (re-export)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libvit_b200.so")
