@@ -22,6 +22,9 @@
 // multiple of 128) is handled by TMA zero-fill on load and a row predicate on
 // store.  Every mbarrier wait is watchdog-guarded (tc_common.cuh).
 #include "tc_common.cuh"
+#ifndef VITCU_GELU_FORM
+#define VITCU_GELU_FORM 0 // 0 = (3,3) rational (default), 1 = MUFU.TANH form (measured: same fc1 time)
+#endif
 #ifndef VITCU_GELU_SCALAR
 #define VITCU_GELU_SCALAR 0
 #endif
@@ -152,7 +155,11 @@ __device__ __forceinline__ bool epilogue_tile(const EpiParams &p, void *C, const
                 for (int j = 0; j < 32; j++)
                     v[j] = gelu_erf(v[j]);
             } else {
-#if VITCU_GELU_SCALAR
+#if VITCU_GELU_FORM == 1
+#pragma unroll
+                for (int j = 0; j < 32; j++)
+                    v[j] = gelu_erf_tanh1(v[j]);
+#elif VITCU_GELU_SCALAR
 #pragma unroll
                 for (int j = 0; j < 32; j++)
                     v[j] = gelu_erf_fast1(v[j]);
