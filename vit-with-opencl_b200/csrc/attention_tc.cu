@@ -58,6 +58,7 @@ enum Bar { QK_FULL = 0, V_FULL = 2, SMEM_FREE = 4, S_FULL = 6, P_FULL = 8, O_FUL
 struct AttnParams {
     int batch, tokens, kp;     // kp = tokens rounded up to a multiple of 16
     int items;                 // batch * heads
+    int rev;                   // 1: walk the items from the last image down (the freshest QKV rows are still in L2)
     __nv_bfloat16 *out;        // [B*T, 768]
     unsigned long long *dbg;   // optional timeline of CTA 0 (clock64 stamps), see vitcu_attention_debug_timeline
 };
@@ -68,6 +69,8 @@ __device__ __forceinline__ float max3(float a, float b, float c)
     asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
     return d;
 }
+
+__device__ __forceinline__ int item_of(const AttnParams &p, int raw) { return p.rev ? p.items - 1 - raw : raw; }
 
 __device__ __forceinline__ void stamp(const AttnParams &p, int role, int k, int ev)
 {
@@ -228,7 +231,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             prefetch_tensormap(&tmap_kv);
         }
         for (int il = 0; il < n_items; il++) {
-            const int item = blockIdx.x + il * gridDim.x;
+            const int item = item_of(p, blockIdx.x + il * gridDim.x);
             const int img = item / kHeads, head = item - img * kHeads;
             const uint32_t s = il & 1;
             // stage s was last used by item il-2: wait until its MMAs have retired
@@ -329,7 +332,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             const float *xs = xsum + (j & 1) * 2 * QT;
             const float inv = 1.0f / (xs[row] + xs[QT + row]);
             const int il = j / ntiles, t = j - il * ntiles;
-            const int item = blockIdx.x + il * gridDim.x;
+            const int item = item_of(p, blockIdx.x + il * gridDim.x);
             const int img = item / kHeads, head = item - img * kHeads;
             // Row-per-thread 16-byte global stores touch 32 different lines per instruction (1 024 L1
             // wavefronts per unit, ~1 000-2 000 cycles on the timeline); instead every warp puts its
@@ -492,6 +495,8 @@ int attention_bf16_tc(const void *qkv, void *out, int batch, int tokens, cudaStr
     p.items = batch * kHeads;
     p.out = reinterpret_cast<__nv_bfloat16 *>(out);
     p.dbg = g_attn_dbg;
+    static const bool serp = !(getenv("VITCU_SERPENTINE") && atoi(getenv("VITCU_SERPENTINE")) == 0);
+    p.rev = serp;
     const int sms = device_sm_count();
     const int grid = p.items < sms ? p.items : sms;
     int dev = 0;

@@ -113,12 +113,14 @@ __global__ void __launch_bounds__(192) cls_rows_kernel(float *__restrict__ x, co
 template <int kOut> // 0: fp32, 1: bf16, 2: three bf16 pieces [rows, 3*768]
 __global__ void __launch_bounds__(256) layernorm_kernel(const float *__restrict__ x, size_t x_row_stride,
                                                         void *__restrict__ y, const float *__restrict__ gamma,
-                                                        const float *__restrict__ beta, int rows)
+                                                        const float *__restrict__ beta, int rows, int rev)
 {
     const int lane = threadIdx.x & 31;
-    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows)
         return;
+    if (rev) // last rows first: they are what the producing GEMM wrote most recently, still in L2
+        row = rows - 1 - row;
     const float4 *xr = reinterpret_cast<const float4 *>(x + (size_t)row * x_row_stride);
     float4 v[6];
     float s = 0.f;
@@ -304,12 +306,13 @@ int vitcu_layernorm(const float *x, size_t x_row_stride, void *y, int y_bf16, co
     VITCU_REQUIRE(x && y && gamma && beta && rows > 0, "bad argument");
     VITCU_REQUIRE(x_row_stride % 4 == 0 && x_row_stride >= (size_t)kEmbed, "row stride must be >= 768 and a multiple of 4");
     const int grid = (rows + 7) / 8;
+    static const int rev = !(getenv("VITCU_SERPENTINE") && atoi(getenv("VITCU_SERPENTINE")) == 0);
     if (y_bf16 == 1)
-        layernorm_kernel<1><<<grid, 256, 0, as_stream(s)>>>(x, x_row_stride, y, gamma, beta, rows);
+        layernorm_kernel<1><<<grid, 256, 0, as_stream(s)>>>(x, x_row_stride, y, gamma, beta, rows, rev);
     else if (y_bf16 == 2)
-        layernorm_kernel<2><<<grid, 256, 0, as_stream(s)>>>(x, x_row_stride, y, gamma, beta, rows);
+        layernorm_kernel<2><<<grid, 256, 0, as_stream(s)>>>(x, x_row_stride, y, gamma, beta, rows, rev);
     else
-        layernorm_kernel<0><<<grid, 256, 0, as_stream(s)>>>(x, x_row_stride, y, gamma, beta, rows);
+        layernorm_kernel<0><<<grid, 256, 0, as_stream(s)>>>(x, x_row_stride, y, gamma, beta, rows, rev);
     VITCU_LAUNCHED();
     return 0;
 }
