@@ -80,8 +80,9 @@ class Dist:
             self.backend = backend
             if backend == "nccl":
                 torch.cuda.set_device(self.local_rank)
-            dist.init_process_group(backend=backend)
             self.device = torch.device("cuda", self.local_rank) if backend == "nccl" else torch.device("cpu")
+            # naming the device binds the NCCL communicator to it (no rank -> GPU guessing in barrier())
+            dist.init_process_group(backend=backend, **({"device_id": self.device} if backend == "nccl" else {}))
 
     def barrier(self):
         if self.on:

@@ -169,7 +169,7 @@ int vitcu_attention(const void *qkv, void *out, int batch, int tokens, int is_bf
                     vitcu_stream s);
 
 /* Debug aid for the single-block attention kernel: record clock64 stamps of CTA 0's first 16 units
- * into `buffer` (device memory, 3*16*8 uint64); NULL switches it off.  See tools/attn_timeline.py. */
+ * into `buffer` (device memory, 4*16*8 uint64); NULL switches it off.  See tools/attn_timeline.py. */
 int vitcu_attention_debug_timeline(unsigned long long *buffer);
 
 /* Row softmax over `n` logits per row (replaces softMax, R/miniSoftMax.cl:1-50;

@@ -16,14 +16,18 @@
 //                    O(k)   = P(k) V         (M=128, N=64,  K=KP, A = P from TMEM, V MN-major)
 //                so the next unit's scores are ready when the softmax warps finish unit k
 //   warp 2       TMEM allocation: S buffers at columns 0 and 224, O at 448
-//   warps 4-7    softmax of the LEFT half of the key columns of every unit (thread = query row)
-//   warps 8-11   softmax of the RIGHT half; the two halves exchange the row maxima through shared
-//                memory (mbarrier-synchronised) and the row sums for the epilogue
-// P (bf16 pairs) is written back into TMEM over each half's own score columns (tcgen05.st), the
-// epilogue of unit k (O / row sum -> bf16 -> global) is deferred until after the softmax of unit
-// k+1 so the P V MMAs are hidden too.  Two warp groups on one tile halve the per-unit softmax
-// latency; the earlier one-tile-per-warp-group version was bound by the serial chain
-// S -> max -> exp -> P V -> epilogue (profiles/r01_v6_attention.md).
+//   warps 4-7    exponentials of the LEFT half of the key columns of every unit (thread = query row)
+//   warps 8-11   exponentials of the RIGHT half; row sums left in shared memory for the epilogue
+//   warps 12-15  statistics + epilogue: row maxima of S(k+1) while warps 4-11 work on unit k, then
+//                O(k-1) / row sum -> bf16 -> swizzled smem tile -> TMA store
+// P (bf16 pairs) is written back into TMEM over each half's own score columns (tcgen05.st).  Two
+// warp groups on one tile halve the per-unit exp latency; the fourth warp group takes the max pass,
+// the exchange of the half-row maxima and the ~900-cycle O read-out off their chain, so the period of
+// a unit is the MUFU-bound exp pass plus ~300 cycles instead of twice that
+// (profiles/r01_v6_attention.md).
+// Registers: the kernel starts with 128 per thread (512 threads); setmaxnreg moves them to where
+// the score rows live: warps 0-3 keep 40, the exp warp groups 168 each, the statistics warps 136
+// (40 + 136 + 2 x 168 = 4 x 128).
 //
 // Softmax (R/ViT_seq.c:204-234): scores are scaled by 1/sqrt(64) after the dot product;
 // p = exp(s/8 - max/8) is evaluated as exp2((s - max) * log2(e)/8); padded keys (j >= T) get
@@ -35,7 +39,7 @@ using namespace vitcu::tc;
 
 namespace {
 
-constexpr int kThreadsAttn = 384;
+constexpr int kThreadsAttn = 512;
 constexpr int QT = 128;                   // queries per tile
 constexpr uint32_t Q_BYTES = QT * 128;    // [128 x 64] bf16
 constexpr uint32_t S_STRIDE = 224;         // score buffers at columns 0 and 224 (<= 224 columns each)
@@ -48,16 +52,22 @@ constexpr uint32_t O_COL = 448;           // output accumulator, 64 columns
 #define VITCU_ATTN_POLY_MASK 0x00
 #endif
 constexpr uint32_t kPolyMask = VITCU_ATTN_POLY_MASK;
+#ifndef VITCU_ATTN_STAGGER_NS
+#define VITCU_ATTN_STAGGER_NS 0 // measured: no effect (the warp groups re-synchronise through P_FULL)
+#endif
 #ifndef VITCU_ATTN_SCALAR
 #define VITCU_ATTN_SCALAR 0
 #endif
 
-// barriers: per smem stage {QK_FULL, V_FULL, SMEM_FREE}; per score buffer {S_FULL}; P_FULL, O_FULL, O_FREE, XCHG
-enum Bar { QK_FULL = 0, V_FULL = 2, SMEM_FREE = 4, S_FULL = 6, P_FULL = 8, O_FULL = 9, O_FREE = 10, XCHG = 11, NUM_BARS = 12 };
+// barriers: per smem stage {QK_FULL, V_FULL, SMEM_FREE}; per score buffer {S_FULL, MAX_FULL}; P_FULL, O_FULL, O_FREE
+enum Bar { QK_FULL = 0, V_FULL = 2, SMEM_FREE = 4, S_FULL = 6, P_FULL = 8, O_FULL = 9, O_FREE = 10, MAX_FULL = 11, NUM_BARS = 13 };
 
 struct AttnParams {
     int batch, tokens, kp;     // kp = tokens rounded up to a multiple of 16
     int items;                 // batch * heads
+    int dbg_first, dbg_cta;    // timeline window: units [dbg_first, dbg_first + 16) of CTA dbg_cta
+    int order;                 // statistics warps: 0 = max(j) then whole epilogue(j-1); 1 = read O(j-2), max(j), store O(j-2)
+    int stagger_ns;            // head start of the left exp warp group
     int rev;                   // 1: walk the items from the last image down (the freshest QKV rows are still in L2)
     __nv_bfloat16 *out;        // [B*T, 768]
     unsigned long long *dbg;   // optional timeline of CTA 0 (clock64 stamps), see vitcu_attention_debug_timeline
@@ -74,45 +84,61 @@ __device__ __forceinline__ int item_of(const AttnParams &p, int raw) { return p.
 
 __device__ __forceinline__ void stamp(const AttnParams &p, int role, int k, int ev)
 {
-    // role 0..3 (0: left softmax warp 4, 1: right softmax warp 8, 2: MMA issuer), 16 units x 8 events each
-    if (p.dbg && blockIdx.x == 0 && k < 16 && (threadIdx.x & 31) == 0)
+    // role 0..3 (0: left exp warp 4, 1: right exp warp 8, 2: MMA issuer, 3: statistics/epilogue warp 12), 16 units x 8 events each
+    k -= p.dbg_first;
+    if (p.dbg && blockIdx.x == p.dbg_cta && k >= 0 && k < 16 && (threadIdx.x & 31) == 0)
         p.dbg[(role * 16 + k) * 8 + ev] = clock64();
 }
 
-// Softmax of one warp group's NC 16-column chunks of a unit.  Returns the partial row sum.
-// Pass 1 leaves the row maximum of the own columns in pmax; the caller exchanges it with the other
-// warp group between the passes through `exchange`.
-template <int NC, typename Exchange>
-__device__ __forceinline__ float softmax_half(uint32_t taddr_s, int valid_cols, float sl2, Exchange &&exchange)
+// Row maximum over NC 16-column chunks of a score row (thread = row), columns >= valid_cols excluded.
+// Four independent running maxima: one chain of 56 dependent 3-input max instructions would cost
+// ~300 cycles of pure latency per part.
+template <int NC>
+__device__ __forceinline__ float row_max_part(uint32_t taddr_s, int valid_cols, float mx)
 {
-    if (NC == 0) {
-        exchange(-INFINITY);
-        return 0.f;
-    }
-    // The whole half-row (<= 112 scores) is pulled into registers with back-to-back tcgen05.ld and ONE
-    // wait: the per-chunk load -> wait -> compute chain of the earlier versions paid the TMEM load
-    // latency (~200 cycles under MMA traffic) 14 times per unit and bounded the kernel
-    // (profiles/r01_v6_attention.md); both softmax passes now run from registers.
+    if (NC == 0)
+        return mx;
     uint32_t sc[NC > 0 ? NC : 1][16];
 #pragma unroll
     for (int c = 0; c < NC; c++)
         tmem_ld_32x32b_x16(taddr_s + c * 16, sc[c]);
     tmem_ld_wait();
-    float mx = -INFINITY;
+    float m4[4] = {mx, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
     for (int c = 0; c < NC; c++) {
-        if (c + 1 < NC) { // only the last chunk of a half can hold padded keys
+        if (c + 1 < NC) { // only the last chunk of a part can hold padded keys
 #pragma unroll
             for (int j = 0; j < 16; j += 2)
-                mx = max3(mx, __uint_as_float(sc[c][j]), __uint_as_float(sc[c][j + 1]));
+                m4[(j >> 1) & 3] = max3(m4[(j >> 1) & 3], __uint_as_float(sc[c][j]), __uint_as_float(sc[c][j + 1]));
         } else {
 #pragma unroll
             for (int j = 0; j < 16; j++)
                 if (c * 16 + j < valid_cols)
-                    mx = fmaxf(mx, __uint_as_float(sc[c][j]));
+                    m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(sc[c][j]));
         }
     }
-    mx = exchange(mx); // row maximum over BOTH halves
+    return max3(max3(m4[0], m4[1], m4[2]), m4[3], m4[3]);
+}
+
+// Exponentials of one warp group's NC 16-column chunks of a unit.  Returns the partial row sum.
+// The row maximum comes from the statistics warps (`row_max()` is called once the score loads are in
+// flight, so waiting for it overlaps the TMEM load latency).
+template <int NC, typename RowMax>
+__device__ __forceinline__ float softmax_half(uint32_t taddr_s, int valid_cols, float sl2, RowMax &&row_max)
+{
+    if (NC == 0) {
+        row_max();
+        return 0.f;
+    }
+    // The whole half-row (<= 112 scores) is pulled into registers with back-to-back tcgen05.ld and ONE
+    // wait: a per-chunk load -> wait -> compute chain pays the TMEM load latency (~200 cycles under
+    // MMA traffic) once per chunk (profiles/r01_v6_attention.md).
+    uint32_t sc[NC > 0 ? NC : 1][16];
+#pragma unroll
+    for (int c = 0; c < NC; c++)
+        tmem_ld_32x32b_x16(taddr_s + c * 16, sc[c]);
+    const float mx = row_max(); // row maximum over ALL key columns
+    tmem_ld_wait();
 #if VITCU_ATTN_SCALAR
     const float nm = -mx * sl2;
     float s0 = 0.f, s1 = 0.f;
@@ -190,11 +216,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     const uint32_t kv_bytes = static_cast<uint32_t>(p.kp) * 128u;
     const uint32_t stage_bytes = 2 * Q_BYTES + 2 * kv_bytes; // Q0 | Q1 | K | V
-    uint8_t *ostage = smem + 2 * stage_bytes;                   // [8 softmax warps][32 rows x 64 B], 64B-swizzled, 1 KB aligned
+    uint8_t *ostage = smem + 2 * stage_bytes;                   // [4 epilogue warps][32 rows x 128 B], 128B-swizzled, 1 KB aligned
     uint64_t *bars = reinterpret_cast<uint64_t *>(ostage + 8 * 2048);
-    float *xmax = reinterpret_cast<float *>(bars + NUM_BARS);   // [2 unit parity][2 halves][128 rows]
-    float *xsum = xmax + 2 * 2 * QT;                            // [2 unit parity][2 halves][128 rows]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(xsum + 2 * 2 * QT);
+    float *xmax = reinterpret_cast<float *>(bars + NUM_BARS);   // [2 unit parity][128 rows] (2 x 2 x 128 floats reserved)
+    // row sums: 3 slots.  Slot reuse is ordered by the MMA chain: S(k+3) is issued after P V(k+1), which
+    // waited for O_FREE(k), which the epilogue warps arrive on after reading the sums of unit k.
+    float *xsum = xmax + 2 * 2 * QT;                            // [unit % 3][2 halves][128 rows]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(xsum + 3 * 2 * QT);
     volatile uint32_t *cta_abort = tmem_slot + 1;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -211,8 +239,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         }
         mbar_init(&bars[P_FULL], 8);
         mbar_init(&bars[O_FULL], 1);
-        mbar_init(&bars[O_FREE], 8);
-        mbar_init(&bars[XCHG], 8);
+        mbar_init(&bars[O_FREE], 4);
+        mbar_init(&bars[MAX_FULL + 0], 4);
+        mbar_init(&bars[MAX_FULL + 1], 4);
         *cta_abort = 0;
         fence_barrier_init();
     }
@@ -224,7 +253,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     const uint32_t tmem_base = *tmem_slot;
     const Watchdog wd{cta_abort, watchdog_flag};
 
-    if (warp == 0) {
+    // register hand-over between the warp groups: every role branch below starts with its
+    // setmaxnreg (all four warps of a warp group take the same one)
+    if (warp < 4) {
+      setmaxnreg_dec<40>();
+      if (warp == 0) {
         // ===================== TMA producer =====================
         if (elect_one()) {
             prefetch_tensormap(&tmap_q);
@@ -249,7 +282,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             }
             __syncwarp();
         }
-    } else if (warp == 1) {
+      } else if (warp == 1) {
         // ===================== MMA issuer =====================
         const uint32_t idesc_s = umma_idesc_bf16(QT, p.kp, false, false);
         const uint32_t idesc_o = umma_idesc_bf16(QT, kHeadDim, false, true);
@@ -306,8 +339,104 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             __syncwarp();
             stamp(p, 2, k, 2); // PV(k) issued
         }
-    } else if (warp >= 4) {
-        // ===================== softmax + epilogue =====================
+      }
+    } else if (warp >= 12) {
+        setmaxnreg_inc<136>();
+        // ===================== statistics (row maxima) + epilogue (O / sum -> bf16 -> global) =====================
+        const int quad = warp & 3;          // TMEM lane quadrant of this warp
+        const int row = quad * 32 + lane;   // query row inside the tile
+        const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+        // Row-per-thread 16-byte global stores touch 32 different lines per instruction (1 024 L1
+        // wavefronts per unit); instead every warp puts its 32 rows x 128 B into a swizzled
+        // shared-memory tile and the TMA engine writes it, clipped at T by the 3-D tensor map.
+        uint8_t *tile = ostage + quad * 4096;
+        // The read-out of O(j) is split in two so that the row maxima (which the exp warps wait for) sit
+        // between the halves: o_read frees the accumulator for P V(j+1) within ~300 cycles of O_FULL and
+        // keeps the normalised row as 32 packed bf16 pairs; o_store writes them out after the max pass.
+        uint32_t pk[32];
+        auto o_read = [&](int j) -> bool {
+            // O_FULL(j) follows P_FULL(j), which the exp warps arrive on after writing their sums
+            if (!mbar_wait_warp(&bars[O_FULL], j & 1, wd, 7))
+                return false;
+            tcgen05_fence_after();
+            uint32_t vlo[32], vhi[32];
+            tmem_ld_32x32b_x32(lane_addr + O_COL, vlo);
+            tmem_ld_32x32b_x32(lane_addr + O_COL + 32, vhi);
+            const float *xs = xsum + (j % 3) * 2 * QT;
+            const float inv = 1.0f / (xs[row] + xs[QT + row]);
+            tmem_ld_wait();
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0)
+                mbar_arrive(&bars[O_FREE]); // O and this unit's sums have been read: P V(j+1) may overwrite O
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                pk[i] = pack_bf16x2(__uint_as_float(vlo[2 * i]) * inv, __uint_as_float(vlo[2 * i + 1]) * inv);
+                pk[16 + i] = pack_bf16x2(__uint_as_float(vhi[2 * i]) * inv, __uint_as_float(vhi[2 * i + 1]) * inv);
+            }
+            return true;
+        };
+        auto o_store = [&](int j) {
+            const int il = j / ntiles, t = j - il * ntiles;
+            const int item = item_of(p, blockIdx.x + il * gridDim.x);
+            const int img = item / kHeads, head = item - img * kHeads;
+            if (lane == 0)
+                tma_wait_group_read<0>(); // the previous unit's store has read this tile
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                *reinterpret_cast<uint4 *>(tile + lane * 128 + ((i ^ (lane & 7)) << 4)) =
+                    make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_3d(&tmap_out, tile, head * kHeadDim, t * QT + quad * 32, img);
+                tma_commit_group();
+            }
+            if (quad == 0)
+                stamp(p, 3, j, 6); // epilogue of unit j issued
+        };
+        // S(j) and O(j-2) complete at about the same time: both follow the issue of P V(j-2)
+        bool ok = true;
+        const int lag = p.order ? 2 : 1;
+        for (int j = 0; j < n_units && ok; j++) {
+            if (quad == 0)
+                stamp(p, 3, j, 0);
+            if (p.order && j > 1 && !(ok = o_read(j - 2)))
+                break;
+            // ---- row maxima of unit j (the exp warps are still on unit j-1) ----
+            if (!(ok = mbar_wait_warp(&bars[S_FULL + (j & 1)], (j >> 1) & 1, wd, 6)))
+                break;
+            tcgen05_fence_after();
+            const uint32_t ts = lane_addr + (j & 1) * S_STRIDE;
+            constexpr int R0 = (NCH + 2) / 3, R1 = (NCH - R0 + 1) / 2, R2 = NCH - R0 - R1; // three rounds of <= 5 chunks
+            float mx = row_max_part<R0>(ts, min(p.tokens, R0 * 16), -INFINITY);
+            mx = row_max_part<R1>(ts + R0 * 16, max(0, min(p.tokens - R0 * 16, R1 * 16)), mx);
+            mx = row_max_part<R2>(ts + (R0 + R1) * 16, max(0, min(p.tokens - (R0 + R1) * 16, R2 * 16)), mx);
+            // slot j & 1 was last read for unit j-2, whose P_FULL preceded the issue of S(j)
+            xmax[(j & 1) * QT + row] = mx;
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0)
+                mbar_arrive(&bars[MAX_FULL + (j & 1)]);
+            if (quad == 0)
+                stamp(p, 3, j, 1);
+            if (p.order) {
+                if (j > 1)
+                    o_store(j - 2);
+            } else if (j > 0 && (ok = o_read(j - 1))) {
+                o_store(j - 1);
+            }
+        }
+        for (int j = max(0, n_units - lag); j < n_units && ok; j++) {
+            if ((ok = o_read(j)))
+                o_store(j);
+        }
+        if (lane == 0)
+            tma_wait_group<0>(); // this warp's output stores have landed before the CTA retires
+    } else {
+        setmaxnreg_inc<168>();
+        // ===================== exponentials: P = exp2((S - max) * log2(e)/8), row sums =====================
         const int wg = (warp - 4) >> 2;     // 0: left half of the key columns, 1: right half
         const int quad = warp & 3;          // TMEM lane quadrant of this warp
         const int row = quad * 32 + lane;   // query row inside the tile
@@ -317,46 +446,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         const int valid_cols = max(0, min(p.tokens - col0, (wg ? NC1 : NC0) * 16));
         bool ok = true;
 
-        // epilogue of unit j: O / sum -> bf16; this warp group stores 32 of the 64 head dims
-        auto epilogue = [&](int j) {
-            if (!(ok = mbar_wait_warp(&bars[O_FULL], j & 1, wd, 7)))
-                return;
-            tcgen05_fence_after();
-            uint32_t v[32];
-            tmem_ld_32x32b_x32(lane_addr + O_COL + wg * 32, v);
-            tmem_ld_wait();
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0)
-                mbar_arrive(&bars[O_FREE]); // O may be overwritten by the next P V
-            const float *xs = xsum + (j & 1) * 2 * QT;
-            const float inv = 1.0f / (xs[row] + xs[QT + row]);
-            const int il = j / ntiles, t = j - il * ntiles;
-            const int item = item_of(p, blockIdx.x + il * gridDim.x);
-            const int img = item / kHeads, head = item - img * kHeads;
-            // Row-per-thread 16-byte global stores touch 32 different lines per instruction (1 024 L1
-            // wavefronts per unit, ~1 000-2 000 cycles on the timeline); instead every warp puts its
-            // 32 rows x 64 B into a swizzled shared-memory tile and the TMA engine writes it, clipped at
-            // T by the 3-D tensor map.
-            uint8_t *tile = ostage + (warp - 4) * 2048;
-            if (lane == 0)
-                tma_wait_group_read<0>(); // the previous unit's store has read this tile
-            __syncwarp();
-#pragma unroll
-            for (int i = 0; i < 4; i++)
-                *reinterpret_cast<uint4 *>(tile + lane * 64 + ((i ^ ((lane >> 1) & 3)) << 4)) = make_uint4(
-                    pack_bf16x2(__uint_as_float(v[8 * i + 0]) * inv, __uint_as_float(v[8 * i + 1]) * inv),
-                    pack_bf16x2(__uint_as_float(v[8 * i + 2]) * inv, __uint_as_float(v[8 * i + 3]) * inv),
-                    pack_bf16x2(__uint_as_float(v[8 * i + 4]) * inv, __uint_as_float(v[8 * i + 5]) * inv),
-                    pack_bf16x2(__uint_as_float(v[8 * i + 6]) * inv, __uint_as_float(v[8 * i + 7]) * inv));
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-                tma_store_3d(&tmap_out, tile, head * kHeadDim + wg * 32, t * QT + quad * 32, img);
-                tma_commit_group();
-            }
-        };
-
+        // Both halves share the MUFU of their sub-partition; started together they run their ~700 cycles
+        // of per-unit latency (publish, barrier waits, TMEM loads) at the same time and the MUFU idles.
+        // Half a period of head start for the left half interleaves the two.
+        if (wg == 1 && p.stagger_ns > 0)
+            __nanosleep(p.stagger_ns);
         for (int k = 0; k < n_units && ok; k++) {
             stamp(p, wg, k, 0); // start waiting for S(k)
             if (!(ok = mbar_wait_warp(&bars[S_FULL + (k & 1)], (k >> 1) & 1, wd, 6)))
@@ -364,27 +458,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             tcgen05_fence_after();
             if (quad == 0)
                 stamp(p, wg, k, 1); // S(k) ready
-            float *xm = xmax + (k & 1) * 2 * QT;
-            auto exchange = [&](float pmax) -> float {
+            auto row_max = [&]() -> float {
+                ok = mbar_wait_warp(&bars[MAX_FULL + (k & 1)], (k >> 1) & 1, wd, 8);
                 if (quad == 0)
-                    stamp(p, wg, k, 2); // pass 1 done
-                xm[wg * QT + row] = pmax;
-                __syncwarp();
-                if (lane == 0)
-                    mbar_arrive(&bars[XCHG]);
-                ok = mbar_wait_warp(&bars[XCHG], k & 1, wd, 8);
-                if (quad == 0)
-                    stamp(p, wg, k, 3); // exchange done
-                return ok ? fmaxf(pmax, xm[(1 - wg) * QT + row]) : pmax;
+                    stamp(p, wg, k, 3); // row maxima available
+                return ok ? xmax[(k & 1) * QT + row] : 0.f;
             };
             const uint32_t ts = lane_addr + (k & 1) * S_STRIDE + col0;
-            const float psum = wg == 0 ? softmax_half<NC0>(ts, valid_cols, sl2, exchange)
-                                       : softmax_half<NC1>(ts, valid_cols, sl2, exchange);
+            const float psum = wg == 0 ? softmax_half<NC0>(ts, valid_cols, sl2, row_max)
+                                       : softmax_half<NC1>(ts, valid_cols, sl2, row_max);
             if (!ok)
                 break;
             if (quad == 0)
                 stamp(p, wg, k, 4); // pass 2 issued
-            xsum[(k & 1) * 2 * QT + wg * QT + row] = psum;
+            xsum[(k % 3) * 2 * QT + wg * QT + row] = psum;
             tmem_st_wait();
             tcgen05_fence_before();
             __syncwarp();
@@ -392,21 +479,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                 mbar_arrive(&bars[P_FULL]);
             if (quad == 0)
                 stamp(p, wg, k, 5); // P(k) published
-            if (k > 0)
-                epilogue(k - 1); // deferred: the P V of unit k-1 ran under this unit's softmax
-            if (quad == 0)
-                stamp(p, wg, k, 6); // deferred epilogue done
         }
-        if (ok && n_units > 0) {
-            // the other half's row sums of the last unit: one more exchange round orders them
-            __syncwarp();
-            if (lane == 0)
-                mbar_arrive(&bars[XCHG]);
-            if (mbar_wait_warp(&bars[XCHG], n_units & 1, wd, 9))
-                epilogue(n_units - 1);
-        }
-        if (lane == 0)
-            tma_wait_group<0>(); // this warp's output stores have landed before the CTA retires
     }
 
     tcgen05_fence_before();
@@ -466,9 +539,9 @@ int attention_bf16_tc(const void *qkv, void *out, int batch, int tokens, cudaStr
     rc = make_qkv_map(&tkv, qkv, batch, tokens, (uint32_t)kp);
     if (rc)
         return rc;
-    const size_t smem = 2 * (2 * (size_t)Q_BYTES + 2 * (size_t)kp * 128) + NUM_BARS * 8 + 2 * 2 * 2 * QT * sizeof(float) +
-                        8 * 2048 + 16 + 1024;
-    CUtensorMap tout; // out viewed as [B][T][768]: box 32 rows x 32 columns, rows past T are clipped
+    const size_t smem = 2 * (2 * (size_t)Q_BYTES + 2 * (size_t)kp * 128) + NUM_BARS * 8 + (2 + 3) * 2 * QT * sizeof(float) +
+                        4 * 4096 + 16 + 1024;
+    CUtensorMap tout; // out viewed as [B][T][768]: box 32 rows x 64 columns (one head), rows past T are clipped
     {
         static EncodeTiledFn fn = nullptr;
         if (!fn) {
@@ -481,10 +554,10 @@ int attention_bf16_tc(const void *qkv, void *out, int batch, int tokens, cudaStr
         }
         cuuint64_t dims[3] = {kEmbed, (cuuint64_t)tokens, (cuuint64_t)batch};
         cuuint64_t strides[2] = {kEmbed * 2, (cuuint64_t)tokens * kEmbed * 2};
-        cuuint32_t box[3] = {32, 32, 1};
+        cuuint32_t box[3] = {kHeadDim, 32, 1};
         cuuint32_t estr[3] = {1, 1, 1};
         if (fn(&tout, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return set_error(VITCU_E_ARG, __FILE__, __LINE__, "cuTensorMapEncodeTiled rejected the output tensor");
     }
     VITCU_REQUIRE(smem <= 227 * 1024, "attention tile does not fit shared memory");
@@ -497,6 +570,12 @@ int attention_bf16_tc(const void *qkv, void *out, int batch, int tokens, cudaStr
     p.dbg = g_attn_dbg;
     static const bool serp = !(getenv("VITCU_SERPENTINE") && atoi(getenv("VITCU_SERPENTINE")) == 0);
     p.rev = serp;
+    static const int order = getenv("VITCU_ATTN_ORDER") ? atoi(getenv("VITCU_ATTN_ORDER")) : 1;
+    static const int stagger = getenv("VITCU_ATTN_STAGGER_NS") ? atoi(getenv("VITCU_ATTN_STAGGER_NS")) : VITCU_ATTN_STAGGER_NS;
+    p.order = order;
+    p.dbg_first = getenv("VITCU_ATTN_DBG_FIRST") ? atoi(getenv("VITCU_ATTN_DBG_FIRST")) : 0;
+    p.dbg_cta = getenv("VITCU_ATTN_DBG_CTA") ? atoi(getenv("VITCU_ATTN_DBG_CTA")) : 0;
+    p.stagger_ns = stagger;
     const int sms = device_sm_count();
     const int grid = p.items < sms ? p.items : sms;
     int dev = 0;
@@ -538,7 +617,7 @@ int attention_bf16_tc(const void *qkv, void *out, int batch, int tokens, cudaStr
 
 } // namespace vitcu
 
-// Debug aid: when `buffer` (device memory, 3*16*8 u64) is non-NULL the next launches of the
+// Debug aid: when `buffer` (device memory, 4*16*8 u64) is non-NULL the next launches of the
 // single-block attention kernel record clock64 stamps of CTA 0's first 16 units
 // (tools/attn_timeline.py prints them).  Pass NULL to switch it off.
 extern "C" int vitcu_attention_debug_timeline(unsigned long long *buffer)

@@ -418,6 +418,20 @@ __device__ __forceinline__ void exp2_poly2(f32x2 x, float &e0, float &e1)
     e1 = exp2_poly_finish(q1, t1);
 }
 
+// Warp-group register reallocation: a kernel launched with R registers per thread can hand registers
+// from its data-movement warp groups to the arithmetic ones.  Every warp of a warp group (4 consecutive
+// warps) must execute the same instruction; inc blocks until the registers have been released.
+template <uint32_t N>
+__device__ __forceinline__ void setmaxnreg_inc()
+{
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <uint32_t N>
+__device__ __forceinline__ void setmaxnreg_dec()
+{
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+
 // Exact-form (erf) GELU for bf16 outputs, two values at a time:
 //     erf(x / sqrt 2) = xc * P3(u) / Q3(u),   xc = clamp(x, +-A), A = 3.2 sqrt 2, u = 2 xc^2 / A^2 - 1,
 // a (3,3) rational minimax fit (tools/fit_gelu.py): max |erf error| 4.8e-6 (the clamp: 1 - erf(3.2) =
