@@ -86,6 +86,10 @@ attention_flash_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FlashP
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // every CTA holds its TMEM now: the next kernel may start its prologue; our own global-memory
+    // traffic (TMA loads, epilogue stores) waits for the previous kernel to complete
+    pdl_trigger();
+    pdl_wait();
     const Watchdog wd{cta_abort, watchdog_flag};
 
     // item -> (image, head, first query tile, tiles in this item)
@@ -366,7 +370,7 @@ int attention_bf16_flash_tc(const void *qkv, void *out, int batch, int tokens, c
     }
     const int sms = device_sm_count();
     const int grid = p.items < sms ? p.items : sms;
-    attention_flash_tc_kernel<<<grid, kThreadsFlash, smem, st>>>(map, p, watchdog_flag());
+    VITCU_TRY(launch_kernel(attention_flash_tc_kernel, grid, kThreadsFlash, smem, st, map, p, watchdog_flag()));
     VITCU_LAUNCHED();
     return 0;
 }

@@ -54,6 +54,8 @@ struct Elem<__nv_bfloat16> {
 template <typename T>
 __global__ void __launch_bounds__(256) attention_simt_kernel(const T *__restrict__ qkv, T *__restrict__ out, int tokens)
 {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ __align__(16) float smem[];
     const int nkb = (tokens + KB - 1) / KB;
     float *Qs = smem;                // [64 d][LDT]
@@ -212,13 +214,11 @@ extern "C" int vitcu_attention(const void *qkv, void *out, int batch, int tokens
     if (is_bf16) {
         auto k = attention_simt_kernel<__nv_bfloat16>;
         VITCU_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<grid, 256, smem, as_stream(s)>>>(reinterpret_cast<const __nv_bfloat16 *>(qkv),
-                                             reinterpret_cast<__nv_bfloat16 *>(out), tokens);
+        VITCU_TRY(launch_kernel(k, grid, 256, smem, as_stream(s), reinterpret_cast<const __nv_bfloat16 *>(qkv), reinterpret_cast<__nv_bfloat16 *>(out), tokens));
     } else {
         auto k = attention_simt_kernel<float>;
         VITCU_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<grid, 256, smem, as_stream(s)>>>(reinterpret_cast<const float *>(qkv), reinterpret_cast<float *>(out),
-                                             tokens);
+        VITCU_TRY(launch_kernel(k, grid, 256, smem, as_stream(s), reinterpret_cast<const float *>(qkv), reinterpret_cast<float *>(out), tokens));
     }
     VITCU_LAUNCHED();
     return 0;

@@ -251,6 +251,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // every CTA holds its TMEM now: the next kernel may start its prologue; our own global-memory
+    // traffic (TMA loads, epilogue stores) waits for the previous kernel to complete
+    pdl_trigger();
+    pdl_wait();
     const Watchdog wd{cta_abort, watchdog_flag};
 
     // register hand-over between the warp groups: every role branch below starts with its
@@ -589,7 +593,7 @@ int attention_bf16_tc(const void *qkv, void *out, int batch, int tokens, cudaStr
                                            (int)smem));                                                             \
             configured[dev] = (int)smem;                                                                            \
         }                                                                                                           \
-        attention_tc_kernel<N><<<grid, kThreadsAttn, smem, st>>>(tq, tkv, tout, p, watchdog_flag());                     \
+        VITCU_TRY(launch_kernel(attention_tc_kernel<N>, grid, kThreadsAttn, smem, st, tq, tkv, tout, p, watchdog_flag()));                     \
         break;                                                                                                      \
     }
     switch (nch) {

@@ -38,6 +38,37 @@ uint32_t *watchdog_flag();
 
 static inline cudaStream_t as_stream(vitcu_stream s) { return (cudaStream_t)s; }
 
+// ---------------------------------------------------------------------------
+// Programmatic dependent launch.  Every kernel of the layer starts with pdl_trigger() -- the next
+// kernel in the stream may be launched and run its prologue (barrier init, TMEM allocation,
+// descriptor prefetch) while this one is still working -- and calls pdl_wait() before its first
+// global-memory access, which returns once the preceding kernel has completed and its writes are
+// visible.  Nothing before pdl_wait() may touch global memory another kernel writes.  The forward
+// is 89 launches; at batch 1 the launch-to-launch latency is most of its time.
+// VITCU_PDL=0 launches everything with full stream serialisation (the wait is then a no-op).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool pdl_enabled(); // runtime.cu
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                 Args &&...args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 constexpr int kEmbed = 768;
 constexpr int kHeads = 12;
 constexpr int kHeadDim = 64;

@@ -14,6 +14,8 @@ __global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float4 *__restri
                                                           const float *__restrict__ src_tail,
                                                           __nv_bfloat16 *__restrict__ dst_tail, int tail)
 {
+    pdl_trigger();
+    pdl_wait();
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (; i < n4; i += stride) {
@@ -51,6 +53,8 @@ __device__ __forceinline__ void split3_store4(__nv_bfloat16 *row, int K, int col
 __global__ void __launch_bounds__(256) split3_kernel(const float *__restrict__ x, size_t ld, __nv_bfloat16 *__restrict__ out,
                                                      size_t rows, int K)
 {
+    pdl_trigger();
+    pdl_wait();
     const size_t k4 = K / 4, total = rows * k4;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -71,6 +75,8 @@ __global__ void __launch_bounds__(256) patch_gather_kernel(const float *__restri
                                                            void *__restrict__ patches, int batch,
                                                            int img, int side)
 {
+    pdl_trigger();
+    pdl_wait();
     const int P = side * side;
     const size_t total4 = (size_t)batch * P * (kEmbed / 4);
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -96,6 +102,8 @@ __global__ void __launch_bounds__(256) patch_gather_kernel(const float *__restri
 __global__ void __launch_bounds__(192) cls_rows_kernel(float *__restrict__ x, const float *__restrict__ cls,
                                                        const float *__restrict__ pos, int tokens)
 {
+    pdl_trigger();
+    pdl_wait();
     const int b = blockIdx.x, i = threadIdx.x; // 192 threads x float4 = 768
     const float4 c = reinterpret_cast<const float4 *>(cls)[i];
     const float4 p = reinterpret_cast<const float4 *>(pos)[i];
@@ -115,6 +123,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float *__restrict_
                                                         void *__restrict__ y, const float *__restrict__ gamma,
                                                         const float *__restrict__ beta, int rows, int rev)
 {
+    pdl_trigger();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows)
@@ -165,6 +175,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float *__restrict_
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const float *__restrict__ logits,
                                                            float *__restrict__ probs, int n)
 {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float red[8];
     const float *l = logits + (size_t)blockIdx.x * n;
     float *p = probs + (size_t)blockIdx.x * n;
@@ -206,6 +218,8 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float *__restri
 __global__ void __launch_bounds__(256) topk_rows_kernel(const float *__restrict__ x, int rows, int cols, int k,
                                                         int *__restrict__ idx, float *__restrict__ val)
 {
+    pdl_trigger();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows)
@@ -261,9 +275,7 @@ int vitcu_f32_to_bf16(const float *src, vitcu_bf16 *dst, size_t n, vitcu_stream 
     VITCU_REQUIRE(((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 7) == 0, "unaligned buffer");
     const size_t n4 = n / 4;
     const int tail = (int)(n - n4 * 4);
-    f32_to_bf16_kernel<<<grid_for(n4, 256), 256, 0, as_stream(s)>>>(
-        reinterpret_cast<const float4 *>(src), reinterpret_cast<uint2 *>(dst), n4, src + n4 * 4,
-        reinterpret_cast<__nv_bfloat16 *>(dst) + n4 * 4, tail);
+    VITCU_TRY(launch_kernel(f32_to_bf16_kernel, grid_for(n4, 256), 256, 0, as_stream(s), reinterpret_cast<const float4 *>(src), reinterpret_cast<uint2 *>(dst), n4, src + n4 * 4, reinterpret_cast<__nv_bfloat16 *>(dst) + n4 * 4, tail));
     VITCU_LAUNCHED();
     return 0;
 }
@@ -271,8 +283,7 @@ int vitcu_f32_to_bf16(const float *src, vitcu_bf16 *dst, size_t n, vitcu_stream 
 int vitcu_split3(const float *x, size_t ld, vitcu_bf16 *out, size_t rows, int K, vitcu_stream s)
 {
     VITCU_REQUIRE(x && out && rows > 0 && K > 0 && K % 4 == 0 && ld % 4 == 0 && ld >= (size_t)K, "bad argument");
-    split3_kernel<<<grid_for(rows * (size_t)(K / 4), 256, 148 * 32), 256, 0, as_stream(s)>>>(
-        x, ld, reinterpret_cast<__nv_bfloat16 *>(out), rows, K);
+    VITCU_TRY(launch_kernel(split3_kernel, grid_for(rows * (size_t)(K / 4), 256, 148 * 32), 256, 0, as_stream(s), x, ld, reinterpret_cast<__nv_bfloat16 *>(out), rows, K));
     VITCU_LAUNCHED();
     return 0;
 }
@@ -285,9 +296,9 @@ int vitcu_patch_gather(const float *images, void *patches, int batch, int img, i
     const size_t total4 = (size_t)batch * side * side * (kEmbed / 4);
     const int grid = grid_for(total4, 256, 148 * 32);
     if (out_bf16)
-        patch_gather_kernel<true><<<grid, 256, 0, as_stream(s)>>>(images, patches, batch, img, side);
+        VITCU_TRY(launch_kernel(patch_gather_kernel<true>, grid, 256, 0, as_stream(s), images, patches, batch, img, side));
     else
-        patch_gather_kernel<false><<<grid, 256, 0, as_stream(s)>>>(images, patches, batch, img, side);
+        VITCU_TRY(launch_kernel(patch_gather_kernel<false>, grid, 256, 0, as_stream(s), images, patches, batch, img, side));
     VITCU_LAUNCHED();
     return 0;
 }
@@ -295,7 +306,7 @@ int vitcu_patch_gather(const float *images, void *patches, int batch, int img, i
 int vitcu_cls_rows(float *x, const float *cls, const float *pos, int batch, int tokens, vitcu_stream s)
 {
     VITCU_REQUIRE(x && cls && pos && batch > 0 && tokens > 0, "bad argument");
-    cls_rows_kernel<<<batch, 192, 0, as_stream(s)>>>(x, cls, pos, tokens);
+    VITCU_TRY(launch_kernel(cls_rows_kernel, batch, 192, 0, as_stream(s), x, cls, pos, tokens));
     VITCU_LAUNCHED();
     return 0;
 }
@@ -308,11 +319,11 @@ int vitcu_layernorm(const float *x, size_t x_row_stride, void *y, int y_bf16, co
     const int grid = (rows + 7) / 8;
     static const int rev = !(getenv("VITCU_SERPENTINE") && atoi(getenv("VITCU_SERPENTINE")) == 0);
     if (y_bf16 == 1)
-        layernorm_kernel<1><<<grid, 256, 0, as_stream(s)>>>(x, x_row_stride, y, gamma, beta, rows, rev);
+        VITCU_TRY(launch_kernel(layernorm_kernel<1>, grid, 256, 0, as_stream(s), x, x_row_stride, y, gamma, beta, rows, rev));
     else if (y_bf16 == 2)
-        layernorm_kernel<2><<<grid, 256, 0, as_stream(s)>>>(x, x_row_stride, y, gamma, beta, rows, rev);
+        VITCU_TRY(launch_kernel(layernorm_kernel<2>, grid, 256, 0, as_stream(s), x, x_row_stride, y, gamma, beta, rows, rev));
     else
-        layernorm_kernel<0><<<grid, 256, 0, as_stream(s)>>>(x, x_row_stride, y, gamma, beta, rows, rev);
+        VITCU_TRY(launch_kernel(layernorm_kernel<0>, grid, 256, 0, as_stream(s), x, x_row_stride, y, gamma, beta, rows, rev));
     VITCU_LAUNCHED();
     return 0;
 }
@@ -320,7 +331,7 @@ int vitcu_layernorm(const float *x, size_t x_row_stride, void *y, int y_bf16, co
 int vitcu_softmax_rows(const float *logits, float *probs, int rows, int n, vitcu_stream s)
 {
     VITCU_REQUIRE(logits && probs && rows > 0 && n > 0, "bad argument");
-    softmax_rows_kernel<<<rows, 256, 0, as_stream(s)>>>(logits, probs, n);
+    VITCU_TRY(launch_kernel(softmax_rows_kernel, rows, 256, 0, as_stream(s), logits, probs, n));
     VITCU_LAUNCHED();
     return 0;
 }
@@ -329,7 +340,7 @@ int vitcu_topk_rows(const float *x, int rows, int cols, int k, int *idx, float *
 {
     VITCU_REQUIRE(x && idx && val && rows > 0 && cols > 0, "bad argument");
     VITCU_REQUIRE(k > 0 && k <= cols, "top-k needs 0 < k <= cols");
-    topk_rows_kernel<<<(rows + 7) / 8, 256, 0, as_stream(s)>>>(x, rows, cols, k, idx, val);
+    VITCU_TRY(launch_kernel(topk_rows_kernel, (rows + 7) / 8, 256, 0, as_stream(s), x, rows, cols, k, idx, val));
     VITCU_LAUNCHED();
     return 0;
 }

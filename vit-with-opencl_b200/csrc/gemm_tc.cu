@@ -285,6 +285,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // every CTA holds its TMEM now: the next kernel may start its prologue; our own global-memory
+    // traffic (TMA loads, epilogue stores) waits for the previous kernel to complete
+    pdl_trigger();
+    pdl_wait();
     const Watchdog wd{cta_abort, watchdog_flag};
 
     const int num_m = (p.M + BM - 1) / BM, num_n = p.N / BN;
@@ -466,6 +470,10 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     cluster_sync_all(); // both CTAs' barriers are initialised before any remote arrive / TMA signal
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // every CTA holds its TMEM now: the next kernel may start its prologue; our own global-memory
+    // traffic (TMA loads, epilogue stores) waits for the previous kernel to complete
+    pdl_trigger();
+    pdl_wait();
     const Watchdog wd{cta_abort, watchdog_flag};
 
     const int num_m = (p.M + BM2 - 1) / BM2, num_n = p.N / BN;
@@ -602,7 +610,7 @@ int launch(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &tc, 
     }
     const int num_tiles = ((p.M + BM - 1) / BM) * (p.N / BN) * p.splits;
     const int grid = num_tiles < sms ? num_tiles : sms;
-    kernel<<<grid, kThreads, L::TOTAL, st>>>(ta, tb, tc, C, p, watchdog_flag());
+    VITCU_TRY(launch_kernel(kernel, grid, kThreads, L::TOTAL, st, ta, tb, tc, C, p, watchdog_flag()));
     VITCU_LAUNCHED();
     return 0;
 }
@@ -622,7 +630,7 @@ int launch_pair(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap 
     }
     const int num_tiles = ((p.M + 255) / 256) * (p.N / 256);
     const int pairs = num_tiles < sms / 2 ? num_tiles : sms / 2;
-    kernel<<<2 * pairs, 64 + 32 * EW, L::TOTAL, st>>>(ta, tb, tc, C, p, watchdog_flag());
+    VITCU_TRY(launch_kernel(kernel, 2 * pairs, 64 + 32 * EW, L::TOTAL, st, ta, tb, tc, C, p, watchdog_flag()));
     VITCU_LAUNCHED();
     return 0;
 }

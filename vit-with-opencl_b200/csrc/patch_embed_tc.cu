@@ -113,6 +113,10 @@ patch_embed_tc_kernel(const __grid_constant__ CUtensorMap tmap_img, const __grid
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // every CTA holds its TMEM now: the next kernel may start its prologue; our own global-memory
+    // traffic (TMA loads, epilogue stores) waits for the previous kernel to complete
+    pdl_trigger();
+    pdl_wait();
     const Watchdog wd{cta_abort, watchdog_flag};
 
     constexpr int NUM_N = kEmbed / BN; // 3
@@ -293,8 +297,8 @@ extern "C" int vitcu_patch_embed_tc(const float *images, const float *conv_w, co
     }
     const int num_tiles = batch * p.tiles_per_img * (kEmbed / BN);
     const int sms = device_sm_count();
-    patch_embed_tc_kernel<<<num_tiles < sms ? num_tiles : sms, kThreadsPE, SMEM_TOTAL, as_stream(s)>>>(timg, tw, p,
-                                                                                                     watchdog_flag());
+    VITCU_TRY(launch_kernel(patch_embed_tc_kernel, num_tiles < sms ? num_tiles : sms, kThreadsPE, SMEM_TOTAL, as_stream(s),
+                            timg, tw, p, watchdog_flag()));
     VITCU_LAUNCHED();
     return 0;
 }

@@ -5,6 +5,7 @@
 #include "common.cuh"
 
 #include <atomic>
+#include <stdlib.h>
 #include <string.h>
 
 namespace vitcu {
@@ -18,6 +19,12 @@ int set_error(int code, const char *file, int line, const char *what)
     snprintf(g_err, sizeof(g_err), "[%s:%d] CUDA error %d (%s)", base ? base + 1 : file, line, code,
              what ? what : "?");
     return code;
+}
+
+bool pdl_enabled()
+{
+    static const bool on = !(getenv("VITCU_PDL") && atoi(getenv("VITCU_PDL")) == 0);
+    return on;
 }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 

@@ -71,6 +71,8 @@ template <int BM, int BN, int TM, int TN>
 __global__ void __launch_bounds__(256) sgemm_kernel(const float *__restrict__ A, const float *__restrict__ W,
                                                     void *__restrict__ C, const EpiParams p)
 {
+    pdl_trigger();
+    pdl_wait();
     static_assert(BM / TM * (BN / TN) == 256, "256 threads");
     static_assert(TM % 4 == 0 && TN % 4 == 0, "float4 register tiles");
     constexpr int PAD = 4;
@@ -181,6 +183,8 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float *__restrict__ A,
 __global__ void __launch_bounds__(256) gemv_rows_kernel(const float *__restrict__ A, const float *__restrict__ W,
                                                         float *__restrict__ C, const EpiParams p)
 {
+    pdl_trigger();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (n >= p.N)
@@ -228,7 +232,7 @@ extern "C" int vitcu_sgemm(const float *A, const float *W, void *C, const vitcu_
     p.tokens = d->tokens;
     p.out_bf16 = d->out_bf16;
     if (p.M <= 8 && p.epilogue == VITCU_EPI_BIAS && !p.out_bf16) {
-        gemv_rows_kernel<<<(p.N + 7) / 8, 256, 0, as_stream(s)>>>(A, W, reinterpret_cast<float *>(C), p);
+        VITCU_TRY(launch_kernel(gemv_rows_kernel, (p.N + 7) / 8, 256, 0, as_stream(s), A, W, reinterpret_cast<float *>(C), p));
         VITCU_LAUNCHED();
         return 0;
     }
@@ -237,10 +241,10 @@ extern "C" int vitcu_sgemm(const float *A, const float *W, void *C, const vitcu_
     const long big_ctas = (long)((p.M + 127) / 128) * ((p.N + 127) / 128);
     if (big_ctas >= 148) {
         dim3 grid((p.N + 127) / 128, (p.M + 127) / 128);
-        sgemm_kernel<128, 128, 8, 8><<<grid, 256, 0, as_stream(s)>>>(A, W, C, p);
+        VITCU_TRY(launch_kernel(sgemm_kernel<128, 128, 8, 8>, grid, 256, 0, as_stream(s), A, W, C, p));
     } else {
         dim3 grid((p.N + 63) / 64, (p.M + 63) / 64);
-        sgemm_kernel<64, 64, 4, 4><<<grid, 256, 0, as_stream(s)>>>(A, W, C, p);
+        VITCU_TRY(launch_kernel(sgemm_kernel<64, 64, 4, 4>, grid, 256, 0, as_stream(s), A, W, C, p));
     }
     VITCU_LAUNCHED();
     return 0;
