@@ -24,9 +24,10 @@ using namespace vitcu;
 
 namespace {
 
-constexpr int QT = 64;      // queries per CTA
-constexpr int KB = 64;      // keys per staged block
-constexpr int LDT = QT + 4; // padded row of the transposed tiles
+// QT queries per CTA; 256 threads hold 4x4 register tiles of S, so a staged key block has
+// KB = 4096 / QT keys.  QT = 64 (KB = 64) is the throughput shape; QT = 16 (KB = 256) gives a small
+// batch four times as many CTAs (batch 1: 13 x 12 = 156 instead of 48, one wave on 148 SMs).
+__host__ __device__ constexpr int kKeysPerBlock(int qt) { return 4096 / qt; }
 
 template <typename T>
 struct Elem;
@@ -51,45 +52,52 @@ struct Elem<__nv_bfloat16> {
     }
 };
 
-template <typename T>
+template <typename T, int QT>
 __global__ void __launch_bounds__(256) attention_simt_kernel(const T *__restrict__ qkv, T *__restrict__ out, int tokens)
 {
+    constexpr int KB = kKeysPerBlock(QT);
+    constexpr int LDQ = QT + 4;       // padded row of the [d][q] / [key][q] tiles
+    constexpr int LDK = KB + 4;       // padded row of the transposed K block [d][key]
+    constexpr int LDV = kHeadDim + 4; // padded row of the V block [key][d]
+    constexpr int KVF = kHeadDim * LDK > KB * LDV ? kHeadDim * LDK : KB * LDV;
+    constexpr int NTX = QT / 4;       // threads along the query axis of the S tile
+    constexpr int PARTS = 256 / QT;   // key-interleaved softmax parts per query
+    constexpr int OQ = QT / 16;       // queries per thread in the P V phase
     pdl_trigger();
     pdl_wait();
     extern __shared__ __align__(16) float smem[];
     const int nkb = (tokens + KB - 1) / KB;
-    float *Qs = smem;                // [64 d][LDT]
-    float *KV = Qs + kHeadDim * LDT; // K block transposed [64 d][LDT], later V block [64 key][LDT]
-    float *St = KV + KB * LDT;       // [nkb*KB keys][LDT]
-    float *red = St + (size_t)nkb * KB * LDT; // [4][QT]
+    float *Qs = smem;                // [64 d][LDQ]
+    float *KV = Qs + kHeadDim * LDQ; // K block transposed [64 d][LDK], later V block [KB key][LDV]
+    float *St = KV + KVF;            // [nkb*KB keys][LDQ]
+    float *red = St + (size_t)nkb * KB * LDQ; // [PARTS][QT]
 
     const int tid = threadIdx.x;
     const int q0 = blockIdx.x * QT, head = blockIdx.y, img = blockIdx.z;
     const size_t ld = 3 * kEmbed;
     const T *base = qkv + (size_t)img * tokens * ld + head * kHeadDim;
 
-    // each thread moves 4 x (4 consecutive d) of a 64x64 tile: rows r, d4
-    auto load_transposed = [&](float *dst, const T *src, int row0) {
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const int f = tid + i * 256, r = f >> 4, d4 = (f & 15) * 4;
+    // ROWS x 64 tile -> dst[d][row]; each thread moves (4 consecutive d) of ROWS*16/256 rows
+    auto load_transposed = [&](float *dst, int ldd, const T *src, int row0, int rows) {
+        for (int f = tid; f < rows * 16; f += 256) {
+            const int r = f >> 4, d4 = (f & 15) * 4;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (row0 + r < tokens)
                 v = Elem<T>::load4(src + (size_t)(row0 + r) * ld + d4);
-            dst[(d4 + 0) * LDT + r] = v.x;
-            dst[(d4 + 1) * LDT + r] = v.y;
-            dst[(d4 + 2) * LDT + r] = v.z;
-            dst[(d4 + 3) * LDT + r] = v.w;
+            dst[(d4 + 0) * ldd + r] = v.x;
+            dst[(d4 + 1) * ldd + r] = v.y;
+            dst[(d4 + 2) * ldd + r] = v.z;
+            dst[(d4 + 3) * ldd + r] = v.w;
         }
     };
 
-    load_transposed(Qs, base, q0);
+    load_transposed(Qs, LDQ, base, q0, QT);
 
     // ---- phase 2: S = Q K^T / 8 ------------------------------------------------
-    const int tx = tid & 15, ty = tid >> 4; // tx -> 4 queries, ty -> 4 keys
+    const int tx = tid % NTX, ty = tid / NTX; // tx -> 4 queries, ty -> 4 keys
     for (int kb = 0; kb < nkb; kb++) {
         __syncthreads(); // previous block's readers are done with KV (and Qs is visible)
-        load_transposed(KV, base + kEmbed, kb * KB);
+        load_transposed(KV, LDK, base + kEmbed, kb * KB, KB);
         __syncthreads();
         float acc[4][4];
 #pragma unroll
@@ -99,8 +107,8 @@ __global__ void __launch_bounds__(256) attention_simt_kernel(const T *__restrict
                 acc[i][j] = 0.f;
 #pragma unroll 16
         for (int d = 0; d < kHeadDim; d++) {
-            const float4 a = *reinterpret_cast<const float4 *>(&Qs[d * LDT + tx * 4]);
-            const float4 b = *reinterpret_cast<const float4 *>(&KV[d * LDT + ty * 4]);
+            const float4 a = *reinterpret_cast<const float4 *>(&Qs[d * LDQ + tx * 4]);
+            const float4 b = *reinterpret_cast<const float4 *>(&KV[d * LDK + ty * 4]);
             const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
             for (int j = 0; j < 4; j++)
@@ -110,7 +118,7 @@ __global__ void __launch_bounds__(256) attention_simt_kernel(const T *__restrict
         }
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            float *row = St + (size_t)(kb * KB + ty * 4 + j) * LDT + tx * 4;
+            float *row = St + (size_t)(kb * KB + ty * 4 + j) * LDQ + tx * 4;
             *reinterpret_cast<float4 *>(row) =
                 make_float4(acc[j][0] * 0.125f, acc[j][1] * 0.125f, acc[j][2] * 0.125f, acc[j][3] * 0.125f);
         }
@@ -119,53 +127,74 @@ __global__ void __launch_bounds__(256) attention_simt_kernel(const T *__restrict
 
     // ---- phase 3: softmax down each query column -------------------------------
     {
-        const int q = tid & 63, part = tid >> 6; // 4 key-interleaved parts per query
+        const int q = tid % QT, part = tid / QT; // PARTS key-interleaved parts per query
         float m = -INFINITY;
-        for (int j = part; j < tokens; j += 4)
-            m = fmaxf(m, St[(size_t)j * LDT + q]);
+        for (int j = part; j < tokens; j += PARTS)
+            m = fmaxf(m, St[(size_t)j * LDQ + q]);
         red[part * QT + q] = m;
         __syncthreads();
-        m = fmaxf(fmaxf(red[q], red[QT + q]), fmaxf(red[2 * QT + q], red[3 * QT + q]));
+        m = red[q];
+#pragma unroll
+        for (int i = 1; i < PARTS; i++)
+            m = fmaxf(m, red[i * QT + q]);
         __syncthreads();
         float s = 0.f;
-        for (int j = part; j < tokens; j += 4) {
-            const float e = expf(St[(size_t)j * LDT + q] - m);
-            St[(size_t)j * LDT + q] = e;
+        for (int j = part; j < tokens; j += PARTS) {
+            const float e = expf(St[(size_t)j * LDQ + q] - m);
+            St[(size_t)j * LDQ + q] = e;
             s += e;
         }
         red[part * QT + q] = s;
         __syncthreads();
-        s = (red[q] + red[QT + q]) + (red[2 * QT + q] + red[3 * QT + q]);
-        for (int j = part; j < tokens; j += 4)
-            St[(size_t)j * LDT + q] /= s;
+        s = 0.f;
+        if (PARTS == 4) { // the summation order the 64-query version has always used
+            s = (red[q] + red[QT + q]) + (red[2 * QT + q] + red[3 * QT + q]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < PARTS; i++)
+                s += red[i * QT + q];
+        }
+        for (int j = part; j < tokens; j += PARTS)
+            St[(size_t)j * LDQ + q] /= s;
     }
 
     // ---- phase 4: O = P V -------------------------------------------------------
-    // tx -> 4 head dims, ty -> 4 queries
-    float o[4][4];
+    // px -> 4 head dims, py -> OQ queries
+    const int px = tid & 15, py = tid >> 4;
+    float o[OQ][4];
 #pragma unroll
-    for (int i = 0; i < 4; i++)
+    for (int i = 0; i < OQ; i++)
 #pragma unroll
         for (int j = 0; j < 4; j++)
             o[i][j] = 0.f;
     for (int kb = 0; kb < nkb; kb++) {
         __syncthreads(); // softmax writes visible / previous V block consumed
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const int f = tid + i * 256, r = f >> 4, d4 = (f & 15) * 4;
+        for (int f = tid; f < KB * 16; f += 256) {
+            const int r = f >> 4, d4 = (f & 15) * 4;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (kb * KB + r < tokens)
                 v = Elem<T>::load4(base + 2 * kEmbed + (size_t)(kb * KB + r) * ld + d4);
-            *reinterpret_cast<float4 *>(&KV[r * LDT + d4]) = v;
+            *reinterpret_cast<float4 *>(&KV[r * LDV + d4]) = v;
         }
         __syncthreads();
         const int jmax = min(KB, tokens - kb * KB);
         for (int j = 0; j < jmax; j++) {
-            const float4 a = *reinterpret_cast<const float4 *>(&St[(size_t)(kb * KB + j) * LDT + ty * 4]);
-            const float4 b = *reinterpret_cast<const float4 *>(&KV[j * LDT + tx * 4]);
-            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+            float av[OQ];
+            if (OQ == 4) {
+                const float4 a = *reinterpret_cast<const float4 *>(&St[(size_t)(kb * KB + j) * LDQ + py * 4]);
+                av[0] = a.x;
+                av[OQ > 1 ? 1 : 0] = a.y;
+                av[OQ > 2 ? 2 : 0] = a.z;
+                av[OQ > 3 ? 3 : 0] = a.w;
+            } else {
 #pragma unroll
-            for (int i = 0; i < 4; i++)
+                for (int i = 0; i < OQ; i++)
+                    av[i] = St[(size_t)(kb * KB + j) * LDQ + py * OQ + i];
+            }
+            const float4 b = *reinterpret_cast<const float4 *>(&KV[j * LDV + px * 4]);
+            const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < OQ; i++)
 #pragma unroll
                 for (int d = 0; d < 4; d++)
                     o[i][d] = fmaf(av[i], bv[d], o[i][d]);
@@ -174,18 +203,33 @@ __global__ void __launch_bounds__(256) attention_simt_kernel(const T *__restrict
 
     // ---- phase 5 ------------------------------------------------------------------
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const int q = q0 + ty * 4 + i;
+    for (int i = 0; i < OQ; i++) {
+        const int q = q0 + py * OQ + i;
         if (q < tokens)
-            Elem<T>::store4(out + ((size_t)img * tokens + q) * kEmbed + head * kHeadDim + tx * 4,
+            Elem<T>::store4(out + ((size_t)img * tokens + q) * kEmbed + head * kHeadDim + px * 4,
                             make_float4(o[i][0], o[i][1], o[i][2], o[i][3]));
     }
 }
 
+template <int QT>
 size_t attention_simt_smem(int tokens)
 {
+    constexpr int KB = kKeysPerBlock(QT), LDQ = QT + 4, LDK = KB + 4, LDV = kHeadDim + 4;
+    constexpr int KVF = kHeadDim * LDK > KB * LDV ? kHeadDim * LDK : KB * LDV;
     const int nkb = (tokens + KB - 1) / KB;
-    return sizeof(float) * ((size_t)kHeadDim * LDT + (size_t)KB * LDT + (size_t)nkb * KB * LDT + 4 * QT);
+    return sizeof(float) * ((size_t)kHeadDim * LDQ + KVF + (size_t)nkb * KB * LDQ + 256);
+}
+
+template <typename T, int QT>
+int launch_attention_simt(const void *qkv, void *out, int batch, int tokens, cudaStream_t st)
+{
+    const size_t smem = attention_simt_smem<QT>(tokens);
+    VITCU_REQUIRE(smem <= 227 * 1024, "token count too large for the shared-memory score tile");
+    auto k = attention_simt_kernel<T, QT>;
+    VITCU_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((tokens + QT - 1) / QT, kHeads, batch);
+    VITCU_TRY(launch_kernel(k, grid, 256, smem, st, reinterpret_cast<const T *>(qkv), reinterpret_cast<T *>(out), tokens));
+    return 0;
 }
 
 } // namespace
@@ -208,18 +252,17 @@ extern "C" int vitcu_attention(const void *qkv, void *out, int batch, int tokens
             return attention_bf16_tc(qkv, out, batch, tokens, as_stream(s));
         return attention_bf16_flash_tc(qkv, out, batch, tokens, as_stream(s));
     }
-    const size_t smem = attention_simt_smem(tokens);
-    VITCU_REQUIRE(smem <= 227 * 1024, "token count too large for the shared-memory score tile");
-    dim3 grid((tokens + QT - 1) / QT, kHeads, batch);
-    if (is_bf16) {
-        auto k = attention_simt_kernel<__nv_bfloat16>;
-        VITCU_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        VITCU_TRY(launch_kernel(k, grid, 256, smem, as_stream(s), reinterpret_cast<const __nv_bfloat16 *>(qkv), reinterpret_cast<__nv_bfloat16 *>(out), tokens));
-    } else {
-        auto k = attention_simt_kernel<float>;
-        VITCU_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        VITCU_TRY(launch_kernel(k, grid, 256, smem, as_stream(s), reinterpret_cast<const float *>(qkv), reinterpret_cast<float *>(out), tokens));
-    }
+    // 16-query tiles when 64-query tiles would leave most of the 148 SMs idle (small batches)
+    const bool small = (long)batch * kHeads * ((tokens + 63) / 64) < 148 && attention_simt_smem<16>(tokens) <= 227 * 1024;
+    int rc;
+    if (is_bf16)
+        rc = small ? launch_attention_simt<__nv_bfloat16, 16>(qkv, out, batch, tokens, as_stream(s))
+                   : launch_attention_simt<__nv_bfloat16, 64>(qkv, out, batch, tokens, as_stream(s));
+    else
+        rc = small ? launch_attention_simt<float, 16>(qkv, out, batch, tokens, as_stream(s))
+                   : launch_attention_simt<float, 64>(qkv, out, batch, tokens, as_stream(s));
+    if (rc)
+        return rc;
     VITCU_LAUNCHED();
     return 0;
 }
