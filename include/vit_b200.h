@@ -75,11 +75,29 @@ const char *vitb200_last_error(void);
 int vitb200_device_count(void);
 
 /* One engine = one GPU, one image size, one precision.  max_batch = images per
- * forward chunk (activation buffers are sized for it). */
+ * forward chunk (activation buffers are sized for it).  vitb200_create builds the
+ * reference's model, ViT-B/16 (R/ViT_seq.c:10-17). */
 int vitb200_create(vitb200_engine **out, int device, int img, int precision, int max_batch);
+
+/* Other members of the family with the same blob order: the values of the
+ * reference's macros img_size, patch_size, embed_dim, depth, num_heads and embed_dim * mlp_ratio
+ * (R/ViT_seq.c:10-17) as run-time numbers.  Supported: patch 16 or 32; embed 384, 768 or 1024 with
+ * heads = embed / 64; depth 1..32; hidden a multiple of 128; img a multiple of patch.  The model
+ * has 8 + 12 * depth blobs (152 for depth 12): cls, conv w [embed, 3*patch*patch], conv b,
+ * pos [(img/patch)^2 + 1, embed], 12 per layer, final LN, head. */
+typedef struct {
+    int img, patch, embed, depth, heads, hidden;
+} vitb200_model;
+int vitb200_create_model(vitb200_engine **out, int device, const vitb200_model *model, int precision, int max_batch);
+/* Reads the dims of a 152-blob (depth 12) model off the blob sizes: embed from the class token,
+ * patch from the conv filters, hidden from the fc1 bias, heads = embed / 64; img from `image` (or,
+ * when image is NULL, from the position table).  Falls back to ViT-B/16 when the sizes are
+ * inconsistent, so that vitb200_load_weights names the offending blob.  ViT_opencl uses this, which
+ * makes ViT-B/32 or ViT-S/16 weights work through the unchanged Main.c. */
+int vitb200_model_from_blobs(const vitb200_blob *networks, const vitb200_image *image, vitb200_model *model);
 void vitb200_destroy(vitb200_engine *e);
 
-/* Upload + pack the 152 blobs (validates presence and sizes). */
+/* Upload + pack the 8 + 12 * depth blobs (152 for the reference's model; validates presence and sizes). */
 int vitb200_load_weights(vitb200_engine *e, const vitb200_blob *networks);
 
 /* Forward n images from a contiguous host array [n,3,img,img] (pinned memory

@@ -101,6 +101,9 @@ int vitcu_split3(const float *x, size_t ld, vitcu_bf16 *out, size_t rows, int K,
  * bf16 or fp32 output. */
 int vitcu_patch_gather(const float *images, void *patches, int batch, int img,
                        int out_bf16, vitcu_stream s);
+/* same with a patch side of 16 or 32: patches [B*P, 3*patch*patch] (the /32 variants of the model) */
+int vitcu_patch_gather_ex(const float *images, void *patches, int batch, int img, int patch,
+                          int out_bf16, vitcu_stream s);
 
 /* Patch embedding as one TF32 tensor-core GEMM whose patch gather is staged by TMA (5-D tensor map
  * over the NCHW image; replaces conv2d_kernel + postprocess, R/conv2d.cl:1-80): for every image b
@@ -108,11 +111,17 @@ int vitcu_patch_gather(const float *images, void *patches, int batch, int img,
  * conv_w [768, 3*16*16] fp32.  Class-token rows are left to vitcu_cls_rows. */
 int vitcu_patch_embed_tc(const float *images, const float *conv_w, const float *conv_b, const float *pos,
                          float *x, int batch, int img, vitcu_stream s);
+/* same for an embedding width other than 768 (a multiple of 256; 16x16 patches) */
+int vitcu_patch_embed_tc_ex(const float *images, const float *conv_w, const float *conv_b, const float *pos,
+                            float *x, int batch, int img, int embed, vitcu_stream s);
 
 /* Row 0 of every image: x[b*T + 0, :] = cls + pos[0, :]  (R/conv2d.cl:39-80 t==0
  * branch; R/ViT_seq.c:83-118). */
 int vitcu_cls_rows(float *x, const float *cls, const float *pos, int batch, int tokens,
                    vitcu_stream s);
+/* same for rows of `cols` features (a multiple of 4, at most 1024) */
+int vitcu_cls_rows_ex(float *x, const float *cls, const float *pos, int batch, int tokens, int cols,
+                      vitcu_stream s);
 
 /* LayerNorm over 768 features (replaces layerNorm, R/layer_norm.cl:3-53; oracle
  * R/ViT_seq.c:120-142).  rows = number of rows normalised; row r is read at
@@ -121,6 +130,9 @@ int vitcu_cls_rows(float *x, const float *cls, const float *pos, int batch, int 
  * pieces [rows,3*768] (see vitcu_split3). */
 int vitcu_layernorm(const float *x, size_t x_row_stride, void *y, int y_bf16,
                     const float *gamma, const float *beta, int rows, vitcu_stream s);
+/* same over `cols` features: 384, 768 or 1024 (embed_dim of the model variants, R/ViT_seq.c:14) */
+int vitcu_layernorm_ex(const float *x, size_t x_row_stride, void *y, int y_bf16, const float *gamma,
+                       const float *beta, int rows, int cols, vitcu_stream s);
 
 /* Epilogue selector for both GEMM families */
 enum {
@@ -167,6 +179,9 @@ int vitcu_gemm_bf16x3(const vitcu_bf16 *A3, const vitcu_bf16 *W3, void *C, const
  * qkv/out: fp32 (is_bf16 = 0) or bf16 (is_bf16 = 1; softmax stays fp32). */
 int vitcu_attention(const void *qkv, void *out, int batch, int tokens, int is_bf16,
                     vitcu_stream s);
+/* same with `heads` heads of 64 (num_heads, R/ViT_seq.c:16): qkv [B*T, 3*heads*64], out [B*T, heads*64] */
+int vitcu_attention_ex(const void *qkv, void *out, int batch, int tokens, int heads, int is_bf16,
+                       vitcu_stream s);
 
 /* Debug aid for the single-block attention kernel: record clock64 stamps of CTA 0's first 16 units
  * into `buffer` (device memory, 4*16*8 uint64); NULL switches it off.  See tools/attn_timeline.py. */

@@ -83,10 +83,17 @@ def make_prob_rows(n: int, classes: int = 1000):
 class Oracle:
     """Our restatement (oracle/vit_oracle.c)."""
 
-    def __init__(self):
-        if not os.path.exists(ORACLE_SO):
+    # -D variants built by oracle/Makefile: name -> (patch, embed, heads, hidden)
+    VARIANTS = {None: (16, 768, 12, 3072, 12), "b16": (16, 768, 12, 3072, 12), "b32": (32, 768, 12, 3072, 12),
+                "s16": (16, 384, 6, 1536, 12), "l16": (16, 1024, 16, 4096, 24)}
+
+    def __init__(self, variant=None):
+        self.patch, self.embed, self.heads, self.hidden, self.depth = self.VARIANTS[variant]
+        self.nblobs = 8 + 12 * self.depth
+        so = ORACLE_SO if variant in (None, "b16") else ORACLE_SO.replace("libvit_oracle.so", f"libvit_oracle_{variant}.so")
+        if not os.path.exists(so):
             build()
-        self.lib = C.CDLL(ORACLE_SO)
+        self.lib = C.CDLL(so)
         L = self.lib
         L.vit_oracle_tokens.restype = C.c_int
         L.vit_oracle_forward.restype = C.c_int
@@ -115,12 +122,12 @@ class Oracle:
         images = np.ascontiguousarray(images, dtype=np.float32)
         n, c, h, w = images.shape
         assert c == 3 and h == w
-        if len(weights) != NBLOBS:
-            raise ValueError(f"need {NBLOBS} weight blobs, got {len(weights)}")
+        if len(weights) != self.nblobs:
+            raise ValueError(f"need {self.nblobs} weight blobs, got {len(weights)}")
         T = self.lib.vit_oracle_tokens(h)
         probs = np.zeros((n, 1000), np.float32)
         logits = np.zeros((n, 1000), np.float32) if want_logits else None
-        stages = np.zeros((13, T, 768), np.float32) if want_stages else None
+        stages = np.zeros((self.depth + 1, T, self.embed), np.float32) if want_stages else None
         wp, keep = self._wptrs(weights)
         rc = self.lib.vit_oracle_forward(_fp(images), n, h, wp, _fp(probs),
                                          _fp(logits) if want_logits else None,
@@ -164,7 +171,7 @@ class Oracle:
         image = np.ascontiguousarray(image, np.float32)
         img = image.shape[-1]
         T = self.lib.vit_oracle_tokens(img)
-        out = np.empty((T, 768), np.float32)
+        out = np.empty((T, self.embed), np.float32)
         args = [np.ascontiguousarray(a, np.float32) for a in (cls, conv_w, conv_b, pos)]
         self.lib.vit_oracle_patch_embed(_fp(image), C.c_int(img), *[_fp(a) for a in args], _fp(out))
         return out
@@ -186,8 +193,9 @@ class Oracle:
 class Reference:
     """The reference's own ViT_seq.c, compiled unmodified into oracle/_ref."""
 
-    def __init__(self, img: int = 224):
-        path = os.path.join(REF_DIR, f"libvit_ref{img}.so")
+    def __init__(self, img: int = 224, variant=None):
+        """variant: None (the unmodified macros), "b32" (patch_size 32) or "s16" (embed_dim 384, num_heads 6)"""
+        path = os.path.join(REF_DIR, f"libvit_ref{img}.so" if variant in (None, "b16") else f"libvit_ref{img}_{variant}.so")
         if not os.path.exists(path):
             raise FileNotFoundError(path)
         self.img = img
@@ -196,8 +204,9 @@ class Reference:
         self.lib.ViT_seq.restype = None
 
     @staticmethod
-    def available(img: int = 224) -> bool:
-        return os.path.exists(os.path.join(REF_DIR, f"libvit_ref{img}.so"))
+    def available(img: int = 224, variant=None) -> bool:
+        name = f"libvit_ref{img}.so" if variant in (None, "b16") else f"libvit_ref{img}_{variant}.so"
+        return os.path.exists(os.path.join(REF_DIR, name))
 
     def forward(self, images: np.ndarray, weights) -> np.ndarray:
         """ViT_seq(image, networks, probabilities) -> probs [n,1000]."""

@@ -323,8 +323,9 @@ int vit_oracle_forward(const float *images, int n, int img, const float *const *
             if (stage_dump && im == 0)
                 memcpy(stage_dump + (size_t)(l + 1) * tok, a, tok * sizeof(float));
         }
-        vit_oracle_layer_norm(a, b, T, w[148], w[149]);
-        vit_oracle_linear(b, lg, 1, D, NCLS, w[150], w[151], 0);
+        const int hb = 4 + 12 * VIT_ORACLE_DEPTH; /* 148: final LN gamma/beta, head weight/bias */
+        vit_oracle_layer_norm(a, b, T, w[hb], w[hb + 1]);
+        vit_oracle_linear(b, lg, 1, D, NCLS, w[hb + 2], w[hb + 3], 0);
         if (logits)
             memcpy(logits + (size_t)im * NCLS, lg, NCLS * sizeof(float));
         vit_oracle_softmax(lg, probs + (size_t)im * NCLS, NCLS);

@@ -28,13 +28,30 @@
 extern "C" {
 #endif
 
+/* The reference fixes the model with macros (ViT_seq.c:10-17); so does this file.  oracle/Makefile
+ * builds the default (ViT-B/16) and, with -D overrides, the variants the reference can express by
+ * editing those macros (its 12 encoder calls and blob indices 148-151 are written out, so depth
+ * stays 12): libvit_oracle_b32.so (patch_size 32) and libvit_oracle_s16.so (embed_dim 384,
+ * num_heads 6).  Each is pinned against the reference compiled with the same macro edit.
+ * libvit_oracle_l16.so (embed 1024, 16 heads, depth 24) has no reference build to be pinned to: it
+ * is the same per-layer code, pinned through the other builds, run in a longer loop. */
+#ifndef VIT_ORACLE_EMBED
 #define VIT_ORACLE_EMBED 768
+#endif
+#ifndef VIT_ORACLE_HEADS
 #define VIT_ORACLE_HEADS 12
-#define VIT_ORACLE_DEPTH 12
-#define VIT_ORACLE_HIDDEN 3072
+#endif
+#ifndef VIT_ORACLE_DEPTH
+#define VIT_ORACLE_DEPTH 12 /* other depths only extend the loop: the reference writes its 12 calls out */
+#endif
+#ifndef VIT_ORACLE_HIDDEN
+#define VIT_ORACLE_HIDDEN (4 * VIT_ORACLE_EMBED)
+#endif
 #define VIT_ORACLE_CLASSES 1000
+#ifndef VIT_ORACLE_PATCH
 #define VIT_ORACLE_PATCH 16
-#define VIT_ORACLE_NBLOBS 152
+#endif
+#define VIT_ORACLE_NBLOBS (8 + 12 * VIT_ORACLE_DEPTH) /* 152 */
 
 /* tokens for a square image of side img (multiple of 16): (img/16)^2 + 1 */
 int vit_oracle_tokens(int img);

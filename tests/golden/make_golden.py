@@ -77,5 +77,23 @@ def main():
         print(k, v.shape, float(np.abs(v).max()))
 
 
+def variants():
+    """model variants the reference expresses by editing its macros (oracle/Makefile streams the edit
+    into gcc): ViT-B/32 (patch_size 32) and ViT-S/16 (embed_dim 384, num_heads 6), 2 synthetic images each"""
+    binding.build()
+    out = {}
+    for name in ("b32", "s16"):
+        ref = binding.Reference(224, name)
+        blobs = synth.variant_blobs(name, 224, seed=7)
+        imgs = synth.synthetic_images(2, 224, seed=1234)
+        out[f"{name}_probs"] = ref.forward(imgs, blobs)
+    np.savez_compressed(os.path.join(HERE, "variant_vectors.npz"), **out)
+    for k, v in out.items():
+        print(k, v.shape, float(np.abs(v).max()), v.argmax(1))
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "variants":
+        variants()
+    else:
+        main()

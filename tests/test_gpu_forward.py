@@ -6,6 +6,7 @@ Stated tolerances (BASELINE.json north_star):
   FP32 path : max|logit - ref| <= 1e-4 * max|ref logit|
   BF16 path : max|logit - ref| <= 2e-2 (absolute) and identical top-1 on every image
 """
+import ctypes as C
 import os
 import subprocess
 
@@ -182,6 +183,57 @@ def test_forward_topk_matches_host_argmax(pkg, lib, blobs224, case224):
     assert np.array_equal(labels[:, 0], ref["probs"][:n].argmax(1))
     np.testing.assert_allclose(top, np.take_along_axis(probs, labels, 1), rtol=1e-5)
     assert (np.diff(top, axis=1) <= 0).all()
+
+
+# ---------------------------------------------------------------- model variants
+@pytest.mark.parametrize("variant,img,nimg", [("b32", 224, 3), ("s16", 224, 3), ("b32", 384, 2), ("l16", 224, 1)])
+def test_model_variants_match_oracle(pkg, lib, variant, img, nimg):
+    """other members of the family through run-time dims: ViT-B/32 (patch_size 32: gather + GEMM patch
+    embedding, 50 tokens), ViT-S/16 (embed_dim 384, 6 heads: 1-CTA GEMM tiles, 3-vector LayerNorm),
+    ViT-L/16 (1024 wide, 16 heads, 24 layers, 296 blobs).  Oracle = the -D build of the restatement
+    (b32 / s16 pinned against the reference compiled with the same macro edit, tests/test_oracle.py)."""
+    from oracle import binding
+    blobs = pkg.synth.variant_blobs(variant, img, seed=7)
+    imgs = pkg.synth.synthetic_images(nimg, img, seed=1234)
+    ref = binding.Oracle(variant).forward(imgs, blobs)
+    scale = np.abs(ref["logits"]).max()
+    with pkg.Engine(0, img, pkg.FP32, max_batch=2, model=variant) as eng:
+        eng.load_weights(blobs)
+        probs, logits = eng.forward(imgs, want_logits=True)
+    assert np.abs(logits - ref["logits"]).max() <= FP32_REL * scale
+    assert np.array_equal(probs.argmax(1), ref["probs"].argmax(1))
+    with pkg.Engine(0, img, pkg.BF16, max_batch=4, model=variant) as eng:
+        eng.load_weights(blobs)
+        probs16, logits16 = eng.forward(imgs, want_logits=True)
+        assert lib.vitcu_watchdog_check() == 0
+    assert np.abs(logits16 - ref["logits"]).max() <= BF16_ABS
+    assert np.array_equal(probs16.argmax(1), ref["probs"].argmax(1))
+
+
+def test_vit_opencl_infers_variant_from_blobs(pkg, lib, monkeypatch):
+    """the unchanged drop-in call with ViT-B/32 weights: patch side, width and MLP width are read off the
+    blob sizes (vitb200_model_from_blobs), the image side off the ImageData struct"""
+    from oracle import binding
+    blobs = pkg.synth.variant_blobs("b32", 224, seed=7)
+    imgs = pkg.synth.synthetic_images(2, 224, seed=1234)
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "variant_vectors.npz"))
+    monkeypatch.setenv("VITB200_PRECISION", "fp32")
+    probs = pkg.vit_opencl(imgs, blobs)
+    assert np.abs(probs - gold["b32_probs"]).max() <= 1e-6      # the reference's own output (patch_size 32 build)
+    assert np.array_equal(probs.argmax(1), gold["b32_probs"].argmax(1))
+    m = pkg.Model()
+    nets, keep = pkg.make_network_structs(blobs)
+    assert lib.vitb200_model_from_blobs(nets, None, C.byref(m)) == 0
+    assert (m.img, m.patch, m.embed, m.depth, m.heads, m.hidden) == (224, 32, 768, 12, 12, 3072)
+
+
+def test_model_rejects_unsupported_dims(pkg, lib):
+    for bad in (dict(patch=8), dict(embed=512, heads=8), dict(heads=8), dict(depth=0), dict(hidden=100), dict(img=200)):
+        m = pkg.Model.variant("b16", 224)
+        for k, v in bad.items():
+            setattr(m, k, v)
+        h = C.c_void_p()
+        assert lib.vitb200_create_model(C.byref(h), 0, C.byref(m), pkg.FP32, 1) != 0, bad
 
 
 def test_golden_reference_vectors(pkg, lib, synth_blobs224):

@@ -332,6 +332,13 @@ def test_gemm_bf16_narrow_tiles(pkg, lib, M, N, K):
     _bf16_gemm_case(pkg, lib, M, N, K, pkg.EPI_BIAS, seed=M + K)
 
 
+@pytest.mark.parametrize("M,N,K", [(197, 1024, 4096), (591, 384, 1536), (197, 1024, 1024), (50, 768, 3072), (197, 384, 384)])
+def test_gemm_bf16_split_k_residual(pkg, lib, M, N, K):
+    """small-M residual GEMMs are split along K; slice counts that do not divide the k-blocks (64 k-blocks
+    over 9 slices left the ninth empty and its epilogue waiting) and the widths of the S/16 and L/16 models"""
+    _bf16_gemm_case(pkg, lib, M, N, K, pkg.EPI_BIAS_RESIDUAL, seed=M + K)
+
+
 @pytest.mark.parametrize("M,N,K,epi", [(6304, 2304, 768, 0), (6304, 3072, 768, 1), (6400, 768, 3072, 2),
                                        (12608, 768, 768, 2), (19001, 2304, 768, 0)])
 def test_gemm_bf16_wide_tiles(pkg, lib, M, N, K, epi):

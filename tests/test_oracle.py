@@ -80,6 +80,22 @@ def test_forward_384_bit_exact(oracle, pkg):
     assert np.array_equal(r["probs"], GOLD["synth384_probs"])
 
 
+@pytest.mark.parametrize("variant", ["b32", "s16"])
+def test_variant_oracles_bit_exact(pkg, variant):
+    """the -D builds of the restatement (ViT-B/32: patch_size 32; ViT-S/16: embed_dim 384, num_heads 6)
+    against vectors from the reference compiled with the same macro edit (make_golden.py variants),
+    and against that build run live where oracle/_ref travelled"""
+    from oracle import binding
+    gold = np.load(os.path.join(HERE, "golden", "variant_vectors.npz"))
+    blobs = pkg.synth.variant_blobs(variant, 224, seed=7)
+    imgs = pkg.synth.synthetic_images(2, 224, seed=1234)
+    got = binding.Oracle(variant).forward(imgs, blobs)["probs"]
+    assert np.array_equal(got, gold[f"{variant}_probs"])
+    if binding.Reference.available(224, variant):
+        live = binding.Reference(224, variant).forward(imgs[:1], blobs)
+        assert np.array_equal(live, got[:1])
+
+
 def test_live_reference_matches_oracle(oracle, pkg):
     """the compiled reference itself, on a fresh seed (skipped where oracle/_ref did not travel)"""
     from oracle import binding

@@ -75,6 +75,8 @@ def lib() -> C.CDLL:
         L.vitcu_last_error.restype = C.c_char_p
         L.vitb200_device_count.restype = C.c_int
         L.vitb200_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int]
+        L.vitb200_create_model.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int, C.c_int]
+        L.vitb200_model_from_blobs.argtypes = [C.POINTER(Network), C.c_void_p, C.c_void_p]
         L.vitb200_destroy.argtypes = [C.c_void_p]
         L.vitb200_destroy.restype = None
         L.vitb200_load_weights.argtypes = [C.c_void_p, C.POINTER(Network)]
@@ -116,6 +118,11 @@ def lib() -> C.CDLL:
         L.vitcu_patch_embed_tc.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                            C.c_void_p]
         L.vitcu_cls_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.vitcu_layernorm_ex.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                         C.c_int, C.c_void_p]
+        L.vitcu_attention_ex.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.vitcu_patch_gather_ex.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.vitcu_cls_rows_ex.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.vitcu_layernorm.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                       C.c_void_p]
         L.vitcu_sgemm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(GemmDesc), C.c_void_p]
@@ -142,7 +149,7 @@ def device_count() -> int:
 
 
 def make_network_structs(blobs):
-    arr = (Network * NBLOBS)()
+    arr = (Network * max(NBLOBS, len(blobs)))()
     keep = []
     for i, b in enumerate(blobs):
         if b is None:
@@ -179,6 +186,17 @@ def vit_opencl(images: np.ndarray, blobs) -> np.ndarray:
     return out
 
 
+class Model(C.Structure):
+    """vitb200_model (include/vit_b200.h): run-time values of the reference's model macros"""
+    _fields_ = [("img", C.c_int), ("patch", C.c_int), ("embed", C.c_int), ("depth", C.c_int), ("heads", C.c_int),
+                ("hidden", C.c_int)]
+
+    @classmethod
+    def variant(cls, name: str, img: int = 224):
+        patch, embed, depth, heads, hidden = synth.VARIANTS[name]
+        return cls(img, patch, embed, depth, heads, hidden)
+
+
 class PinnedArray:
     """float32 numpy view over pinned host memory (vitb200_host_alloc)."""
 
@@ -206,10 +224,15 @@ class PinnedArray:
 class Engine:
     """Resident engine on one GPU (include/vit_b200.h)."""
 
-    def __init__(self, device: int = 0, img: int = 224, precision: int = BF16, max_batch: int = 256):
+    def __init__(self, device: int = 0, img: int = 224, precision: int = BF16, max_batch: int = 256, model=None):
         self.h = C.c_void_p()
         self.img, self.precision, self.max_batch = img, precision, max_batch
-        _check(lib().vitb200_create(C.byref(self.h), device, img, precision, max_batch))
+        if model is None:
+            _check(lib().vitb200_create(C.byref(self.h), device, img, precision, max_batch))
+        else:  # a Model, or a variant name from synth.VARIANTS
+            m = Model.variant(model, img) if isinstance(model, str) else model
+            self.img = m.img
+            _check(lib().vitb200_create_model(C.byref(self.h), device, C.byref(m), precision, max_batch))
         self.tokens = lib().vitb200_tokens(self.h)
 
     def load_weights(self, blobs):

@@ -41,6 +41,7 @@ struct FlashParams {
     int qpairs;   // ceil(qtiles / 2)
     int kblocks;  // ceil(T / 128)
     int items;    // batch * heads * qpairs
+    int heads, embed; // embed = heads * 64: Q | K | V column blocks of qkv start at 0, embed, 2 * embed
     __nv_bfloat16 *out;
 };
 
@@ -96,8 +97,8 @@ attention_flash_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FlashP
     auto decode = [&](int item, int &img, int &head, int &q0, int &nt) {
         const int pair = item % p.qpairs;
         const int bh = item / p.qpairs;
-        img = bh / kHeads;
-        head = bh - img * kHeads;
+        img = bh / p.heads;
+        head = bh - img * p.heads;
         q0 = pair * 2;
         nt = p.qtiles - q0 >= 2 ? 2 : 1;
     };
@@ -127,8 +128,8 @@ attention_flash_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FlashP
                 if (elect_one()) {
                     uint8_t *dst = sKV + s * 2 * TILE_BYTES;
                     mbar_arrive_expect_tx(&bars[KV_FULL + s], 2 * TILE_BYTES);
-                    tma_load_3d(dst, &tmap, &bars[KV_FULL + s], kEmbed + head * kHeadDim, j * KB, img);
-                    tma_load_3d(dst + TILE_BYTES, &tmap, &bars[KV_FULL + s], 2 * kEmbed + head * kHeadDim, j * KB, img);
+                    tma_load_3d(dst, &tmap, &bars[KV_FULL + s], p.embed + head * kHeadDim, j * KB, img);
+                    tma_load_3d(dst + TILE_BYTES, &tmap, &bars[KV_FULL + s], 2 * p.embed + head * kHeadDim, j * KB, img);
                 }
                 __syncwarp();
             }
@@ -299,7 +300,7 @@ attention_flash_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FlashP
             const int q = (q0 + tile) * QT + row;
             if (q < p.tokens) {
                 const float inv = 1.0f / l;
-                __nv_bfloat16 *dst = p.out + (static_cast<size_t>(img) * p.tokens + q) * kEmbed + head * kHeadDim;
+                __nv_bfloat16 *dst = p.out + (static_cast<size_t>(img) * p.tokens + q) * p.embed + head * kHeadDim;
 #pragma unroll
                 for (int i = 0; i < 8; i++)
                     reinterpret_cast<uint4 *>(dst)[i] =
@@ -328,7 +329,7 @@ namespace vitcu {
 int device_sm_count(); // gemm_tc.cu
 
 // qkv [B*T, 2304] bf16 -> out [B*T, 768] bf16; any token count
-int attention_bf16_flash_tc(const void *qkv, void *out, int batch, int tokens, cudaStream_t st)
+int attention_bf16_flash_tc(const void *qkv, void *out, int batch, int tokens, int heads, cudaStream_t st)
 {
     VITCU_REQUIRE(((uintptr_t)qkv & 15) == 0 && ((uintptr_t)out & 15) == 0, "buffers must be 16-byte aligned");
     static EncodeTiledFn fn = nullptr;
@@ -342,7 +343,7 @@ int attention_bf16_flash_tc(const void *qkv, void *out, int batch, int tokens, c
     }
     // one 3-D map over qkv [B][T][2304], box = 128 rows x 64 columns (Q tiles, K blocks and V blocks alike)
     CUtensorMap map;
-    const cuuint64_t ld = 3 * kEmbed;
+    const cuuint64_t ld = 3 * (cuuint64_t)(heads * kHeadDim);
     cuuint64_t dims[3] = {ld, (cuuint64_t)tokens, (cuuint64_t)batch};
     cuuint64_t strides[2] = {ld * 2, ld * 2 * (cuuint64_t)tokens};
     cuuint32_t box[3] = {kHeadDim, 128, 1};
@@ -358,7 +359,9 @@ int attention_bf16_flash_tc(const void *qkv, void *out, int batch, int tokens, c
     p.qtiles = (tokens + QT - 1) / QT;
     p.qpairs = (p.qtiles + 1) / 2;
     p.kblocks = (tokens + KB - 1) / KB;
-    p.items = batch * kHeads * p.qpairs;
+    p.items = batch * heads * p.qpairs;
+    p.heads = heads;
+    p.embed = heads * kHeadDim;
     p.out = reinterpret_cast<__nv_bfloat16 *>(out);
     const size_t smem = (4 + 2 * NS) * (size_t)TILE_BYTES + NUM_BARS * 8 + 16 + 1024;
     static bool configured[64] = {false};

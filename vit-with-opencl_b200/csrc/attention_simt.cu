@@ -53,7 +53,7 @@ struct Elem<__nv_bfloat16> {
 };
 
 template <typename T, int QT>
-__global__ void __launch_bounds__(256) attention_simt_kernel(const T *__restrict__ qkv, T *__restrict__ out, int tokens)
+__global__ void __launch_bounds__(256) attention_simt_kernel(const T *__restrict__ qkv, T *__restrict__ out, int tokens, int embed)
 {
     constexpr int KB = kKeysPerBlock(QT);
     constexpr int LDQ = QT + 4;       // padded row of the [d][q] / [key][q] tiles
@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(256) attention_simt_kernel(const T *__restrict
 
     const int tid = threadIdx.x;
     const int q0 = blockIdx.x * QT, head = blockIdx.y, img = blockIdx.z;
-    const size_t ld = 3 * kEmbed;
+    const size_t ld = 3 * (size_t)embed; // embed = heads * 64 (768 for ViT-B)
     const T *base = qkv + (size_t)img * tokens * ld + head * kHeadDim;
 
     // ROWS x 64 tile -> dst[d][row]; each thread moves (4 consecutive d) of ROWS*16/256 rows
@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(256) attention_simt_kernel(const T *__restrict
     const int tx = tid % NTX, ty = tid / NTX; // tx -> 4 queries, ty -> 4 keys
     for (int kb = 0; kb < nkb; kb++) {
         __syncthreads(); // previous block's readers are done with KV (and Qs is visible)
-        load_transposed(KV, LDK, base + kEmbed, kb * KB, KB);
+        load_transposed(KV, LDK, base + embed, kb * KB, KB);
         __syncthreads();
         float acc[4][4];
 #pragma unroll
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(256) attention_simt_kernel(const T *__restrict
             const int r = f >> 4, d4 = (f & 15) * 4;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (kb * KB + r < tokens)
-                v = Elem<T>::load4(base + 2 * kEmbed + (size_t)(kb * KB + r) * ld + d4);
+                v = Elem<T>::load4(base + 2 * embed + (size_t)(kb * KB + r) * ld + d4);
             *reinterpret_cast<float4 *>(&KV[r * LDV + d4]) = v;
         }
         __syncthreads();
@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(256) attention_simt_kernel(const T *__restrict
     for (int i = 0; i < OQ; i++) {
         const int q = q0 + py * OQ + i;
         if (q < tokens)
-            Elem<T>::store4(out + ((size_t)img * tokens + q) * kEmbed + head * kHeadDim + px * 4,
+            Elem<T>::store4(out + ((size_t)img * tokens + q) * embed + head * kHeadDim + px * 4,
                             make_float4(o[i][0], o[i][1], o[i][2], o[i][3]));
     }
 }
@@ -221,27 +221,29 @@ size_t attention_simt_smem(int tokens)
 }
 
 template <typename T, int QT>
-int launch_attention_simt(const void *qkv, void *out, int batch, int tokens, cudaStream_t st)
+int launch_attention_simt(const void *qkv, void *out, int batch, int tokens, int heads, cudaStream_t st)
 {
     const size_t smem = attention_simt_smem<QT>(tokens);
     VITCU_REQUIRE(smem <= 227 * 1024, "token count too large for the shared-memory score tile");
     auto k = attention_simt_kernel<T, QT>;
     VITCU_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((tokens + QT - 1) / QT, kHeads, batch);
-    VITCU_TRY(launch_kernel(k, grid, 256, smem, st, reinterpret_cast<const T *>(qkv), reinterpret_cast<T *>(out), tokens));
+    dim3 grid((tokens + QT - 1) / QT, heads, batch);
+    VITCU_TRY(launch_kernel(k, grid, 256, smem, st, reinterpret_cast<const T *>(qkv), reinterpret_cast<T *>(out), tokens,
+                            heads * kHeadDim));
     return 0;
 }
 
 } // namespace
 
 namespace vitcu {
-int attention_bf16_tc(const void *qkv, void *out, int batch, int tokens, cudaStream_t st);       // attention_tc.cu
-int attention_bf16_flash_tc(const void *qkv, void *out, int batch, int tokens, cudaStream_t st); // attention_flash_tc.cu
+int attention_bf16_tc(const void *qkv, void *out, int batch, int tokens, int heads, cudaStream_t st);       // attention_tc.cu
+int attention_bf16_flash_tc(const void *qkv, void *out, int batch, int tokens, int heads, cudaStream_t st); // attention_flash_tc.cu
 }
 
-extern "C" int vitcu_attention(const void *qkv, void *out, int batch, int tokens, int is_bf16, vitcu_stream s)
+extern "C" int vitcu_attention_ex(const void *qkv, void *out, int batch, int tokens, int heads, int is_bf16, vitcu_stream s)
 {
     VITCU_REQUIRE(qkv && out && batch > 0 && tokens > 0, "bad argument");
+    VITCU_REQUIRE(heads > 0 && heads <= 32, "head count must be 1..32 (head dimension is 64)");
     // BF16 storage: tensor-core kernels -- all keys in one TMEM score buffer when they fit (<= 224),
     // key-blocked online softmax otherwise.  (VITCU_ATTN_SIMT=1 forces the CUDA-core kernel and
     // VITCU_ATTN_FLASH=1 the key-blocked kernel, for A/B measurements.)
@@ -249,20 +251,25 @@ extern "C" int vitcu_attention(const void *qkv, void *out, int batch, int tokens
     static const bool force_flash = getenv("VITCU_ATTN_FLASH") != nullptr;
     if (is_bf16 && !force_simt) {
         if (tokens <= 224 && !force_flash)
-            return attention_bf16_tc(qkv, out, batch, tokens, as_stream(s));
-        return attention_bf16_flash_tc(qkv, out, batch, tokens, as_stream(s));
+            return attention_bf16_tc(qkv, out, batch, tokens, heads, as_stream(s));
+        return attention_bf16_flash_tc(qkv, out, batch, tokens, heads, as_stream(s));
     }
     // 16-query tiles when 64-query tiles would leave most of the 148 SMs idle (small batches)
-    const bool small = (long)batch * kHeads * ((tokens + 63) / 64) < 148 && attention_simt_smem<16>(tokens) <= 227 * 1024;
+    const bool small = (long)batch * heads * ((tokens + 63) / 64) < 148 && attention_simt_smem<16>(tokens) <= 227 * 1024;
     int rc;
     if (is_bf16)
-        rc = small ? launch_attention_simt<__nv_bfloat16, 16>(qkv, out, batch, tokens, as_stream(s))
-                   : launch_attention_simt<__nv_bfloat16, 64>(qkv, out, batch, tokens, as_stream(s));
+        rc = small ? launch_attention_simt<__nv_bfloat16, 16>(qkv, out, batch, tokens, heads, as_stream(s))
+                   : launch_attention_simt<__nv_bfloat16, 64>(qkv, out, batch, tokens, heads, as_stream(s));
     else
-        rc = small ? launch_attention_simt<float, 16>(qkv, out, batch, tokens, as_stream(s))
-                   : launch_attention_simt<float, 64>(qkv, out, batch, tokens, as_stream(s));
+        rc = small ? launch_attention_simt<float, 16>(qkv, out, batch, tokens, heads, as_stream(s))
+                   : launch_attention_simt<float, 64>(qkv, out, batch, tokens, heads, as_stream(s));
     if (rc)
         return rc;
     VITCU_LAUNCHED();
     return 0;
+}
+
+extern "C" int vitcu_attention(const void *qkv, void *out, int batch, int tokens, int is_bf16, vitcu_stream s)
+{
+    return vitcu_attention_ex(qkv, out, batch, tokens, kHeads, is_bf16, s);
 }

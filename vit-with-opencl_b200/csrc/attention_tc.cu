@@ -65,6 +65,7 @@ enum Bar { QK_FULL = 0, V_FULL = 2, SMEM_FREE = 4, S_FULL = 6, P_FULL = 8, O_FUL
 struct AttnParams {
     int batch, tokens, kp;     // kp = tokens rounded up to a multiple of 16
     int items;                 // batch * heads
+    int heads, embed;          // embed = heads * 64: Q | K | V column blocks of qkv start at 0, embed, 2 * embed
     int dbg_first, dbg_cta;    // timeline window: units [dbg_first, dbg_first + 16) of CTA dbg_cta
     int order;                 // statistics warps: 0 = max(j) then whole epilogue(j-1); 1 = read O(j-2), max(j), store O(j-2)
     int stagger_ns;            // head start of the left exp warp group
@@ -269,7 +270,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         }
         for (int il = 0; il < n_items; il++) {
             const int item = item_of(p, blockIdx.x + il * gridDim.x);
-            const int img = item / kHeads, head = item - img * kHeads;
+            const int img = item / p.heads, head = item - img * p.heads;
             const uint32_t s = il & 1;
             // stage s was last used by item il-2: wait until its MMAs have retired
             if (il >= 2 && !mbar_wait_warp(&bars[SMEM_FREE + s], ((il >> 1) - 1) & 1, wd, 1))
@@ -280,9 +281,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                 mbar_arrive_expect_tx(&bars[QK_FULL + s], ntiles * Q_BYTES + kv_bytes);
                 for (int t = 0; t < ntiles; t++)
                     tma_load_3d(sq + t * Q_BYTES, &tmap_q, &bars[QK_FULL + s], head * kHeadDim, t * QT, img);
-                tma_load_3d(sk, &tmap_kv, &bars[QK_FULL + s], kEmbed + head * kHeadDim, 0, img);
+                tma_load_3d(sk, &tmap_kv, &bars[QK_FULL + s], p.embed + head * kHeadDim, 0, img);
                 mbar_arrive_expect_tx(&bars[V_FULL + s], kv_bytes);
-                tma_load_3d(sk + kv_bytes, &tmap_kv, &bars[V_FULL + s], 2 * kEmbed + head * kHeadDim, 0, img);
+                tma_load_3d(sk + kv_bytes, &tmap_kv, &bars[V_FULL + s], 2 * p.embed + head * kHeadDim, 0, img);
             }
             __syncwarp();
         }
@@ -383,7 +384,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         auto o_store = [&](int j) {
             const int il = j / ntiles, t = j - il * ntiles;
             const int item = item_of(p, blockIdx.x + il * gridDim.x);
-            const int img = item / kHeads, head = item - img * kHeads;
+            const int img = item / p.heads, head = item - img * p.heads;
             if (lane == 0)
                 tma_wait_group_read<0>(); // the previous unit's store has read this tile
             __syncwarp();
@@ -498,7 +499,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int make_qkv_map(CUtensorMap *map, const void *qkv, int batch, int tokens, uint32_t box_rows)
+int make_qkv_map(CUtensorMap *map, const void *qkv, int batch, int tokens, int embed, uint32_t box_rows)
 {
     static EncodeTiledFn fn = nullptr;
     if (!fn) {
@@ -509,7 +510,7 @@ int make_qkv_map(CUtensorMap *map, const void *qkv, int batch, int tokens, uint3
             return set_error(VITCU_E_NODEVICE, __FILE__, __LINE__, "cuTensorMapEncodeTiled is unavailable");
         fn = reinterpret_cast<EncodeTiledFn>(sym);
     }
-    const cuuint64_t ld = 3 * kEmbed;
+    const cuuint64_t ld = 3 * (cuuint64_t)embed;
     cuuint64_t dims[3] = {ld, (cuuint64_t)tokens, (cuuint64_t)batch};
     cuuint64_t strides[2] = {ld * 2, ld * 2 * (cuuint64_t)tokens};
     cuuint32_t box[3] = {kHeadDim, box_rows, 1};
@@ -531,16 +532,17 @@ int device_sm_count(); // gemm_tc.cu
 unsigned long long *g_attn_dbg = nullptr; // set by vitcu_attention_debug_timeline
 
 // qkv [B*T, 2304] bf16 -> out [B*T, 768] bf16; tokens <= 224 (two score buffers of <= 224 columns)
-int attention_bf16_tc(const void *qkv, void *out, int batch, int tokens, cudaStream_t st)
+int attention_bf16_tc(const void *qkv, void *out, int batch, int tokens, int heads, cudaStream_t st)
 {
+    const int embed = heads * kHeadDim;
     const int kp = (tokens + 15) / 16 * 16;
     VITCU_REQUIRE(kp <= 224, "single-block tensor-core attention handles at most 224 tokens");
     VITCU_REQUIRE(((uintptr_t)qkv & 15) == 0 && ((uintptr_t)out & 15) == 0, "buffers must be 16-byte aligned");
     CUtensorMap tq, tkv;
-    int rc = make_qkv_map(&tq, qkv, batch, tokens, QT);
+    int rc = make_qkv_map(&tq, qkv, batch, tokens, embed, QT);
     if (rc)
         return rc;
-    rc = make_qkv_map(&tkv, qkv, batch, tokens, (uint32_t)kp);
+    rc = make_qkv_map(&tkv, qkv, batch, tokens, embed, (uint32_t)kp);
     if (rc)
         return rc;
     const size_t smem = 2 * (2 * (size_t)Q_BYTES + 2 * (size_t)kp * 128) + NUM_BARS * 8 + (2 + 3) * 2 * QT * sizeof(float) +
@@ -556,8 +558,8 @@ int attention_bf16_tc(const void *qkv, void *out, int batch, int tokens, cudaStr
                 return set_error(VITCU_E_NODEVICE, __FILE__, __LINE__, "cuTensorMapEncodeTiled is unavailable");
             fn = reinterpret_cast<EncodeTiledFn>(sym);
         }
-        cuuint64_t dims[3] = {kEmbed, (cuuint64_t)tokens, (cuuint64_t)batch};
-        cuuint64_t strides[2] = {kEmbed * 2, (cuuint64_t)tokens * kEmbed * 2};
+        cuuint64_t dims[3] = {(cuuint64_t)embed, (cuuint64_t)tokens, (cuuint64_t)batch};
+        cuuint64_t strides[2] = {(cuuint64_t)embed * 2, (cuuint64_t)tokens * embed * 2};
         cuuint32_t box[3] = {kHeadDim, 32, 1};
         cuuint32_t estr[3] = {1, 1, 1};
         if (fn(&tout, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -569,7 +571,9 @@ int attention_bf16_tc(const void *qkv, void *out, int batch, int tokens, cudaStr
     p.batch = batch;
     p.tokens = tokens;
     p.kp = kp;
-    p.items = batch * kHeads;
+    p.items = batch * heads;
+    p.heads = heads;
+    p.embed = embed;
     p.out = reinterpret_cast<__nv_bfloat16 *>(out);
     p.dbg = g_attn_dbg;
     static const bool serp = !(getenv("VITCU_SERPENTINE") && atoi(getenv("VITCU_SERPENTINE")) == 0);

@@ -66,30 +66,31 @@ __global__ void __launch_bounds__(256) split3_kernel(const float *__restrict__ x
 }
 
 // ---------------------------------------------------------------------------
-// patch gather: [B,3,img,img] -> [B*P, 768], column = (c*16 + kh)*16 + kw, the
-// accumulation order of Conv2d_seq (R/ViT_seq.c:37-48).  One thread moves one
-// 16-byte chunk (4 kw values): 4 threads cover a contiguous 64-byte image run.
+// patch gather: [B,3,img,img] -> [B*P, 3*ps*ps], column = (c*ps + kh)*ps + kw (ps = patch side, 16 or
+// 32), the accumulation order of Conv2d_seq (R/ViT_seq.c:37-48).  One thread moves one 16-byte
+// chunk (4 kw values): ps/4 threads cover a contiguous image run of one patch row.
 // ---------------------------------------------------------------------------
 template <bool kBf16>
 __global__ void __launch_bounds__(256) patch_gather_kernel(const float *__restrict__ images,
                                                            void *__restrict__ patches, int batch,
-                                                           int img, int side)
+                                                           int img, int side, int ps)
 {
     pdl_trigger();
     pdl_wait();
     const int P = side * side;
-    const size_t total4 = (size_t)batch * P * (kEmbed / 4);
+    const int K4 = 3 * ps * ps / 4, ps4 = ps / 4; // float4 chunks per patch row of the output / per kernel row
+    const size_t total4 = (size_t)batch * P * K4;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (; i < total4; i += stride) {
-        const int col4 = (int)(i % (kEmbed / 4));
-        const size_t row = i / (kEmbed / 4);
+        const int col4 = (int)(i % K4);
+        const size_t row = i / K4;
         const int p = (int)(row % P);
         const int b = (int)(row / P);
-        const int c = col4 >> 6, kh = (col4 >> 2) & 15, kw4 = col4 & 3;
+        const int c = col4 / (ps * ps4), kh = (col4 / ps4) % ps, kw4 = col4 % ps4;
         const int ph = p / side, pw = p % side;
         const float4 v = *reinterpret_cast<const float4 *>(
-            images + (((size_t)b * 3 + c) * img + ph * kPatch + kh) * img + pw * kPatch + kw4 * 4);
+            images + (((size_t)b * 3 + c) * img + ph * ps + kh) * img + pw * ps + kw4 * 4);
         if (kBf16) {
             reinterpret_cast<uint2 *>(patches)[i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
         } else {
@@ -99,26 +100,27 @@ __global__ void __launch_bounds__(256) patch_gather_kernel(const float *__restri
 }
 
 // x[b*T, :] = cls + pos[0, :]   (R/ViT_seq.c:83-118; R/conv2d.cl:39-80, t == 0)
-__global__ void __launch_bounds__(192) cls_rows_kernel(float *__restrict__ x, const float *__restrict__ cls,
-                                                       const float *__restrict__ pos, int tokens)
+__global__ void __launch_bounds__(256) cls_rows_kernel(float *__restrict__ x, const float *__restrict__ cls,
+                                                       const float *__restrict__ pos, int tokens, int cols)
 {
     pdl_trigger();
     pdl_wait();
-    const int b = blockIdx.x, i = threadIdx.x; // 192 threads x float4 = 768
+    const int b = blockIdx.x, i = threadIdx.x; // cols/4 threads x float4 (192 for the 768-wide model)
     const float4 c = reinterpret_cast<const float4 *>(cls)[i];
     const float4 p = reinterpret_cast<const float4 *>(pos)[i];
-    reinterpret_cast<float4 *>(x + (size_t)b * tokens * kEmbed)[i] =
+    reinterpret_cast<float4 *>(x + (size_t)b * tokens * cols)[i] =
         make_float4(c.x + p.x, c.y + p.y, c.z + p.z, c.w + p.w);
 }
 
 // ---------------------------------------------------------------------------
-// LayerNorm, one warp per 768-wide row: 6 x float4 per lane held in registers,
+// LayerNorm, one warp per row of NV*128 columns (NV = 6 for the 768-wide model, 3 / 8 for 384 / 1024):
+// NV x float4 per lane held in registers,
 // shuffle reductions, statistics in fp32 (mean first, then centred variance,
 // which is at least as accurate as the reference's E[x^2]-mean^2 single pass,
 // R/ViT_seq.c:126-135), eps 1e-6, output fp32 or bf16.
 // Algorithmic bytes per row: 768*4 read + 768*(4|2) written.
 // ---------------------------------------------------------------------------
-template <int kOut> // 0: fp32, 1: bf16, 2: three bf16 pieces [rows, 3*768]
+template <int kOut, int NV> // kOut 0: fp32, 1: bf16, 2: three bf16 pieces [rows, 3*cols]
 __global__ void __launch_bounds__(256) layernorm_kernel(const float *__restrict__ x, size_t x_row_stride,
                                                         void *__restrict__ y, const float *__restrict__ gamma,
                                                         const float *__restrict__ beta, int rows, int rev)
@@ -132,26 +134,27 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float *__restrict_
     if (rev) // last rows first: they are what the producing GEMM wrote most recently, still in L2
         row = rows - 1 - row;
     const float4 *xr = reinterpret_cast<const float4 *>(x + (size_t)row * x_row_stride);
-    float4 v[6];
+    constexpr int kCols = NV * 128;
+    float4 v[NV];
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < 6; i++) {
+    for (int i = 0; i < NV; i++) {
         v[i] = xr[lane + 32 * i];
         s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     }
-    const float mean = warp_sum(s) * (1.0f / kEmbed);
+    const float mean = warp_sum(s) * (1.0f / kCols);
     float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < 6; i++) {
+    for (int i = 0; i < NV; i++) {
         const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
         q += (a * a + b * b) + (c * c + d * d);
     }
-    const float var = warp_sum(q) * (1.0f / kEmbed);
+    const float var = warp_sum(q) * (1.0f / kCols);
     const float inv_std = 1.0f / sqrtf(var + 1e-6f);
     const float4 *g4 = reinterpret_cast<const float4 *>(gamma);
     const float4 *b4 = reinterpret_cast<const float4 *>(beta);
 #pragma unroll
-    for (int i = 0; i < 6; i++) {
+    for (int i = 0; i < NV; i++) {
         const float4 g = g4[lane + 32 * i], bb = b4[lane + 32 * i];
         float4 o;
         o.x = (v[i].x - mean) * inv_std * g.x + bb.x;
@@ -159,12 +162,12 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float *__restrict_
         o.z = (v[i].z - mean) * inv_std * g.z + bb.z;
         o.w = (v[i].w - mean) * inv_std * g.w + bb.w;
         if (kOut == 1) {
-            reinterpret_cast<uint2 *>(reinterpret_cast<__nv_bfloat16 *>(y) + (size_t)row * kEmbed)[lane + 32 * i] =
+            reinterpret_cast<uint2 *>(reinterpret_cast<__nv_bfloat16 *>(y) + (size_t)row * kCols)[lane + 32 * i] =
                 make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
         } else if (kOut == 2) {
-            split3_store4(reinterpret_cast<__nv_bfloat16 *>(y) + (size_t)row * 3 * kEmbed, kEmbed, (lane + 32 * i) * 4, o);
+            split3_store4(reinterpret_cast<__nv_bfloat16 *>(y) + (size_t)row * 3 * kCols, kCols, (lane + 32 * i) * 4, o);
         } else {
-            reinterpret_cast<float4 *>(reinterpret_cast<float *>(y) + (size_t)row * kEmbed)[lane + 32 * i] = o;
+            reinterpret_cast<float4 *>(reinterpret_cast<float *>(y) + (size_t)row * kCols)[lane + 32 * i] = o;
         }
     }
 }
@@ -288,44 +291,78 @@ int vitcu_split3(const float *x, size_t ld, vitcu_bf16 *out, size_t rows, int K,
     return 0;
 }
 
-int vitcu_patch_gather(const float *images, void *patches, int batch, int img, int out_bf16, vitcu_stream s)
+int vitcu_patch_gather_ex(const float *images, void *patches, int batch, int img, int patch, int out_bf16,
+                          vitcu_stream s)
 {
     VITCU_REQUIRE(images && patches, "NULL buffer");
-    VITCU_REQUIRE(batch > 0 && img > 0 && img % kPatch == 0, "image side must be a positive multiple of 16");
-    const int side = img / kPatch;
-    const size_t total4 = (size_t)batch * side * side * (kEmbed / 4);
+    VITCU_REQUIRE(patch == 16 || patch == 32, "patch side must be 16 or 32");
+    VITCU_REQUIRE(batch > 0 && img > 0 && img % patch == 0, "image side must be a positive multiple of the patch side");
+    const int side = img / patch;
+    const size_t total4 = (size_t)batch * side * side * (3 * patch * patch / 4);
     const int grid = grid_for(total4, 256, 148 * 32);
     if (out_bf16)
-        VITCU_TRY(launch_kernel(patch_gather_kernel<true>, grid, 256, 0, as_stream(s), images, patches, batch, img, side));
+        VITCU_TRY(launch_kernel(patch_gather_kernel<true>, grid, 256, 0, as_stream(s), images, patches, batch, img, side, patch));
     else
-        VITCU_TRY(launch_kernel(patch_gather_kernel<false>, grid, 256, 0, as_stream(s), images, patches, batch, img, side));
+        VITCU_TRY(launch_kernel(patch_gather_kernel<false>, grid, 256, 0, as_stream(s), images, patches, batch, img, side, patch));
     VITCU_LAUNCHED();
     return 0;
 }
+int vitcu_patch_gather(const float *images, void *patches, int batch, int img, int out_bf16, vitcu_stream s)
+{
+    return vitcu_patch_gather_ex(images, patches, batch, img, kPatch, out_bf16, s);
+}
 
-int vitcu_cls_rows(float *x, const float *cls, const float *pos, int batch, int tokens, vitcu_stream s)
+int vitcu_cls_rows_ex(float *x, const float *cls, const float *pos, int batch, int tokens, int cols, vitcu_stream s)
 {
     VITCU_REQUIRE(x && cls && pos && batch > 0 && tokens > 0, "bad argument");
-    VITCU_TRY(launch_kernel(cls_rows_kernel, batch, 192, 0, as_stream(s), x, cls, pos, tokens));
+    VITCU_REQUIRE(cols > 0 && cols % 4 == 0 && cols <= 1024, "row width must be a multiple of 4, at most 1024");
+    VITCU_TRY(launch_kernel(cls_rows_kernel, batch, cols / 4, 0, as_stream(s), x, cls, pos, tokens, cols));
     VITCU_LAUNCHED();
     return 0;
 }
-
-int vitcu_layernorm(const float *x, size_t x_row_stride, void *y, int y_bf16, const float *gamma,
-                    const float *beta, int rows, vitcu_stream s)
+int vitcu_cls_rows(float *x, const float *cls, const float *pos, int batch, int tokens, vitcu_stream s)
 {
-    VITCU_REQUIRE(x && y && gamma && beta && rows > 0, "bad argument");
-    VITCU_REQUIRE(x_row_stride % 4 == 0 && x_row_stride >= (size_t)kEmbed, "row stride must be >= 768 and a multiple of 4");
+    return vitcu_cls_rows_ex(x, cls, pos, batch, tokens, kEmbed, s);
+}
+
+extern "C++" {
+template <int NV>
+static int launch_layernorm(const float *x, size_t x_row_stride, void *y, int y_bf16, const float *gamma, const float *beta,
+                            int rows, vitcu_stream s)
+{
     const int grid = (rows + 7) / 8;
     static const int rev = !(getenv("VITCU_SERPENTINE") && atoi(getenv("VITCU_SERPENTINE")) == 0);
     if (y_bf16 == 1)
-        VITCU_TRY(launch_kernel(layernorm_kernel<1>, grid, 256, 0, as_stream(s), x, x_row_stride, y, gamma, beta, rows, rev));
+        VITCU_TRY(launch_kernel(layernorm_kernel<1, NV>, grid, 256, 0, as_stream(s), x, x_row_stride, y, gamma, beta, rows, rev));
     else if (y_bf16 == 2)
-        VITCU_TRY(launch_kernel(layernorm_kernel<2>, grid, 256, 0, as_stream(s), x, x_row_stride, y, gamma, beta, rows, rev));
+        VITCU_TRY(launch_kernel(layernorm_kernel<2, NV>, grid, 256, 0, as_stream(s), x, x_row_stride, y, gamma, beta, rows, rev));
     else
-        VITCU_TRY(launch_kernel(layernorm_kernel<0>, grid, 256, 0, as_stream(s), x, x_row_stride, y, gamma, beta, rows, rev));
+        VITCU_TRY(launch_kernel(layernorm_kernel<0, NV>, grid, 256, 0, as_stream(s), x, x_row_stride, y, gamma, beta, rows, rev));
     VITCU_LAUNCHED();
     return 0;
+}
+} // extern "C++"
+
+int vitcu_layernorm_ex(const float *x, size_t x_row_stride, void *y, int y_bf16, const float *gamma, const float *beta,
+                       int rows, int cols, vitcu_stream s)
+{
+    VITCU_REQUIRE(x && y && gamma && beta && rows > 0, "bad argument");
+    VITCU_REQUIRE(x_row_stride % 4 == 0 && x_row_stride >= (size_t)cols, "row stride must be >= the row width and a multiple of 4");
+    switch (cols) {
+    case 384:
+        return launch_layernorm<3>(x, x_row_stride, y, y_bf16, gamma, beta, rows, s);
+    case 768:
+        return launch_layernorm<6>(x, x_row_stride, y, y_bf16, gamma, beta, rows, s);
+    case 1024:
+        return launch_layernorm<8>(x, x_row_stride, y, y_bf16, gamma, beta, rows, s);
+    default:
+        return set_error(VITCU_E_ARG, __FILE__, __LINE__, "LayerNorm row width must be 384, 768 or 1024");
+    }
+}
+int vitcu_layernorm(const float *x, size_t x_row_stride, void *y, int y_bf16, const float *gamma,
+                    const float *beta, int rows, vitcu_stream s)
+{
+    return vitcu_layernorm_ex(x, x_row_stride, y, y_bf16, gamma, beta, rows, kEmbed, s);
 }
 
 int vitcu_softmax_rows(const float *logits, float *probs, int rows, int n, vitcu_stream s)

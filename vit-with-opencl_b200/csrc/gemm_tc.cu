@@ -772,7 +772,12 @@ static int gemm_dispatch(const vitcu_bf16 *A, const vitcu_bf16 *W, void *C, cons
         int splits = sms / tiles;
         if (splits > total_kb / 2)
             splits = total_kb / 2;
-        p.splits = splits < 1 ? 1 : splits;
+        if (splits < 1)
+            splits = 1;
+        // no empty slice: a work item without k-blocks would never commit its accumulator and its
+        // epilogue would wait forever (K = 4096 over 9 slices of 8 k-blocks leaves the ninth empty)
+        const int kb_per = (total_kb + splits - 1) / splits;
+        p.splits = (total_kb + kb_per - 1) / kb_per;
     }
     rc = make_tensor_map_2d(&tb, W, 2, (uint64_t)d->N, kphys, kphys * 2, wide ? 256 : 128, BK);
     if (rc)

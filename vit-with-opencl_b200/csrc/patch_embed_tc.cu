@@ -35,6 +35,7 @@ constexpr uint32_t SMEM_TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;
 struct PEParams {
     int batch, side, tokens;   // side = S/16 patches per image row, tokens = side*side + 1
     int ph_box, tiles_per_img; // patch rows per tile, tiles per image
+    int embed, num_n;          // output features (768 for ViT-B) and embed / BN column tiles
     uint32_t a_box_bytes;      // bytes one A box delivers
     const float *bias;         // [768]
     const float *pos;          // [tokens, 768]
@@ -119,7 +120,7 @@ patch_embed_tc_kernel(const __grid_constant__ CUtensorMap tmap_img, const __grid
     pdl_wait();
     const Watchdog wd{cta_abort, watchdog_flag};
 
-    constexpr int NUM_N = kEmbed / BN; // 3
+    const int NUM_N = p.num_n; // 3 for the 768-wide model
     constexpr int NUM_KB = 3 * kPatch; // (channel, kernel row) slices
     const int num_tiles = p.batch * p.tiles_per_img * NUM_N;
 
@@ -198,8 +199,8 @@ patch_embed_tc_kernel(const __grid_constant__ CUtensorMap tmap_img, const __grid
             const int r = quad * 32 + lane;
             const int patch = ph0 * p.side + r;
             const bool valid = r < rows_here;
-            float *dst = p.x + (static_cast<size_t>(img) * p.tokens + 1 + patch) * kEmbed + n_blk * BN;
-            const float *pos = p.pos + static_cast<size_t>(1 + patch) * kEmbed + n_blk * BN;
+            float *dst = p.x + (static_cast<size_t>(img) * p.tokens + 1 + patch) * p.embed + n_blk * BN;
+            const float *pos = p.pos + static_cast<size_t>(1 + patch) * p.embed + n_blk * BN;
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
 #pragma unroll 1
             for (int c = 0; c < BN / 32; c++) {
@@ -243,10 +244,11 @@ int device_sm_count(); // gemm_tc.cu
 }
 
 // images [B,3,S,S] fp32, conv_w [768, 3*16*16] fp32 -> x[b*T + 1 + p, :] = conv + bias + pos[1 + p, :]
-extern "C" int vitcu_patch_embed_tc(const float *images, const float *conv_w, const float *conv_b, const float *pos,
-                                    float *x, int batch, int img, vitcu_stream s)
+extern "C" int vitcu_patch_embed_tc_ex(const float *images, const float *conv_w, const float *conv_b, const float *pos,
+                                       float *x, int batch, int img, int embed, vitcu_stream s)
 {
     VITCU_REQUIRE(images && conv_w && conv_b && pos && x, "NULL argument");
+    VITCU_REQUIRE(embed > 0 && embed % BN == 0, "embedding width must be a multiple of the 256-column tile");
     VITCU_REQUIRE(batch > 0 && img > 0 && img % kPatch == 0, "image side must be a positive multiple of 16");
     const int side = img / kPatch;
     VITCU_REQUIRE(side <= 128, "image too large for one 128-row tile per patch row");
@@ -271,6 +273,8 @@ extern "C" int vitcu_patch_embed_tc(const float *images, const float *conv_w, co
     p.bias = conv_b;
     p.pos = pos;
     p.x = x;
+    p.embed = embed;
+    p.num_n = embed / BN;
 
     CUtensorMap timg, tw;
     {
@@ -285,7 +289,7 @@ extern "C" int vitcu_patch_embed_tc(const float *images, const float *conv_w, co
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return set_error(VITCU_E_ARG, __FILE__, __LINE__, "cuTensorMapEncodeTiled rejected the image tensor");
     }
-    int rc = make_tensor_map_2d(&tw, conv_w, 4, kEmbed, 3 * kPatch * kPatch, 3 * kPatch * kPatch * sizeof(float), BN, kPatch, 64);
+    int rc = make_tensor_map_2d(&tw, conv_w, 4, embed, 3 * kPatch * kPatch, 3 * kPatch * kPatch * sizeof(float), BN, kPatch, 64);
     if (rc)
         return rc;
     static bool configured[64] = {false};
@@ -295,10 +299,16 @@ extern "C" int vitcu_patch_embed_tc(const float *images, const float *conv_w, co
         VITCU_TRY(cudaFuncSetAttribute(patch_embed_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TOTAL));
         configured[dev] = true;
     }
-    const int num_tiles = batch * p.tiles_per_img * (kEmbed / BN);
+    const int num_tiles = batch * p.tiles_per_img * (embed / BN);
     const int sms = device_sm_count();
     VITCU_TRY(launch_kernel(patch_embed_tc_kernel, num_tiles < sms ? num_tiles : sms, kThreadsPE, SMEM_TOTAL, as_stream(s),
                             timg, tw, p, watchdog_flag()));
     VITCU_LAUNCHED();
     return 0;
+}
+
+extern "C" int vitcu_patch_embed_tc(const float *images, const float *conv_w, const float *conv_b, const float *pos,
+                                    float *x, int batch, int img, vitcu_stream s)
+{
+    return vitcu_patch_embed_tc_ex(images, conv_w, conv_b, pos, x, batch, img, kEmbed, s);
 }

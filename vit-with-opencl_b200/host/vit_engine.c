@@ -50,59 +50,127 @@ int vitb200_host_free(void *ptr)
     return 0;
 }
 
-/* expected element count of blob idx (index map: R/ViT_seq.c:437-513) */
-static size_t blob_elems(int idx, int tokens)
+/* expected element count of blob idx (index map: R/ViT_seq.c:437-513; torchvision state_dict() order) */
+static size_t blob_elems(const vitb200_engine *e, int idx)
 {
+    const size_t D = (size_t)e->D, HID = (size_t)e->HID;
+    const int head0 = e->nblobs - 4;
     if (idx == 0 || idx == 2)
-        return VIT_D;
+        return D;
     if (idx == 1)
-        return (size_t)VIT_D * 3 * 16 * 16;
+        return D * 3 * e->patch * e->patch;
     if (idx == 3)
-        return (size_t)tokens * VIT_D;
-    if (idx >= 4 && idx < 148) {
+        return (size_t)e->T * D;
+    if (idx >= 4 && idx < head0) {
         switch ((idx - 4) % 12) {
         case 2:
-            return (size_t)3 * VIT_D * VIT_D;
+            return 3 * D * D;
         case 3:
-            return 3 * VIT_D;
+            return 3 * D;
         case 4:
-            return (size_t)VIT_D * VIT_D;
+            return D * D;
         case 8:
-            return (size_t)VIT_HID * VIT_D;
+            return HID * D;
         case 9:
-            return VIT_HID;
+            return HID;
         case 10:
-            return (size_t)VIT_D * VIT_HID;
+            return D * HID;
         default:
-            return VIT_D;
+            return D;
         }
     }
-    if (idx == 148 || idx == 149)
-        return VIT_D;
-    if (idx == 150)
-        return (size_t)VITB200_CLASSES * VIT_D;
+    if (idx == head0 || idx == head0 + 1)
+        return D;
+    if (idx == head0 + 2)
+        return (size_t)VITB200_CLASSES * D;
     return VITB200_CLASSES;
 }
 
 /* GEMM weight matrices (everything else stays fp32 in both precisions) */
-static int is_gemm_weight(int idx)
+static int is_gemm_weight(const vitb200_engine *e, int idx)
 {
     if (idx == 1)
         return 1;
-    if (idx >= 4 && idx < 148) {
+    if (idx >= 4 && idx < e->nblobs - 4) {
         int k = (idx - 4) % 12;
         return k == 2 || k == 4 || k == 8 || k == 10;
     }
     return 0;
 }
 
+/* K (row length) of GEMM weight idx */
+static int gemm_weight_k(const vitb200_engine *e, int idx)
+{
+    if (idx == 1)
+        return 3 * e->patch * e->patch;
+    return (idx - 4) % 12 == 10 ? e->HID : e->D;
+}
+
+int vitb200_model_from_blobs(const vitb200_blob *net, const vitb200_image *image, vitb200_model *m)
+{
+    if (!net || !m)
+        return vit_fail(__FILE__, __LINE__, VITCU_E_ARG, "NULL argument");
+    /* class token = embed_dim; conv filters = embed * 3 * patch^2; fc1 bias = hidden; 64 per head;
+     * position rows = (img / patch)^2 + 1.  Anything absent or inconsistent -> the ViT-B/16 defaults,
+     * so that load_weights reports exactly which blob is wrong. */
+    m->img = image ? image->h : 224;
+    m->patch = 16;
+    m->embed = 768;
+    m->depth = 12;
+    m->heads = 12;
+    m->hidden = 3072;
+    if (!net[0].data || !net[1].data || !net[3].data || !net[13].data)
+        return 0;
+    const size_t D = net[0].size;
+    if (D == 0 || D % 64 != 0 || net[1].size % (3 * D) != 0)
+        return 0;
+    const size_t pp = net[1].size / (3 * D);
+    int patch = 0;
+    while ((size_t)patch * patch < pp)
+        patch++;
+    if ((size_t)patch * patch != pp || net[3].size % D != 0 || net[13].size == 0)
+        return 0;
+    m->patch = patch;
+    m->embed = (int)D;
+    m->heads = (int)(D / 64);
+    m->hidden = (int)net[13].size;
+    if (!image) { /* image side from the position table */
+        const size_t P = net[3].size / D - 1;
+        int side = 0;
+        while ((size_t)side * side < P)
+            side++;
+        if ((size_t)side * side == P)
+            m->img = side * patch;
+    }
+    return 0;
+}
+
 int vitb200_create(vitb200_engine **out, int device, int img, int precision, int max_batch)
+{
+    const vitb200_model m = {img, 16, 768, 12, 12, 3072}; /* ViT-B/16, the reference's macros (R/ViT_seq.c:10-17) */
+    return vitb200_create_model(out, device, &m, precision, max_batch);
+}
+
+int vitb200_create_model(vitb200_engine **out, int device, const vitb200_model *m, int precision, int max_batch)
 {
     if (!out)
         return vit_fail(__FILE__, __LINE__, VITCU_E_ARG, "engine out-pointer is NULL");
     *out = NULL;
-    if (img <= 0 || img % 16 != 0)
+    if (!m)
+        return vit_fail(__FILE__, __LINE__, VITCU_E_ARG, "model description is NULL");
+    const int img = m->img;
+    if (m->patch != 16 && m->patch != 32)
+        return vit_fail(__FILE__, __LINE__, VITCU_E_ARG, "patch side must be 16 or 32");
+    if (img <= 0 || img % m->patch != 0)
         return vit_fail(__FILE__, __LINE__, VITCU_E_ARG, "image side must be a positive multiple of 16");
+    if (m->embed != 384 && m->embed != 768 && m->embed != 1024)
+        return vit_fail(__FILE__, __LINE__, VITCU_E_ARG, "embedding width must be 384, 768 or 1024");
+    if (m->heads * 64 != m->embed)
+        return vit_fail(__FILE__, __LINE__, VITCU_E_ARG, "heads must be embed / 64 (head dimension 64)");
+    if (m->depth < 1 || m->depth > VIT_MAX_DEPTH)
+        return vit_fail(__FILE__, __LINE__, VITCU_E_ARG, "depth must be 1..32");
+    if (m->hidden <= 0 || m->hidden % 128 != 0)
+        return vit_fail(__FILE__, __LINE__, VITCU_E_ARG, "MLP width must be a positive multiple of 128");
     if (precision != VITB200_FP32 && precision != VITB200_BF16)
         return vit_fail(__FILE__, __LINE__, VITCU_E_ARG, "precision must be VITB200_FP32 or VITB200_BF16");
     if (max_batch <= 0)
@@ -123,7 +191,13 @@ int vitb200_create(vitb200_engine **out, int device, int img, int precision, int
         return vit_fail(__FILE__, __LINE__, VITCU_E_ARG, "out of host memory");
     e->device = device;
     e->img = img;
-    e->side = img / 16;
+    e->patch = m->patch;
+    e->D = m->embed;
+    e->HID = m->hidden;
+    e->depth = m->depth;
+    e->heads = m->heads;
+    e->nblobs = 8 + 12 * m->depth;
+    e->side = img / m->patch;
     e->P = e->side * e->side;
     e->T = e->P + 1;
     e->precision = precision;
@@ -134,7 +208,7 @@ int vitb200_create(vitb200_engine **out, int device, int img, int precision, int
      * VITB200_FP32_SIMT=1 selects the CUDA-core FFMA GEMM instead */
     e->fp32_tc = precision == VITB200_FP32 && getenv("VITB200_FP32_SIMT") == NULL;
     /* VITB200_PE_GATHER=1: separate gather kernel + BF16 GEMM instead of the TMA-gather TF32 GEMM */
-    e->pe_gather = getenv("VITB200_PE_GATHER") != NULL;
+    e->pe_gather = getenv("VITB200_PE_GATHER") != NULL || e->patch != 16 || e->D % 256 != 0;
     const int bf = precision == VITB200_BF16;
     const size_t act = bf ? 2 : 4;
     const size_t rows = (size_t)e->B * e->T;
@@ -162,15 +236,15 @@ int vitb200_create(vitb200_engine **out, int device, int img, int precision, int
     }
     ENG_TRY(vitcu_event_create(&e->ev_t0));
     ENG_TRY(vitcu_event_create(&e->ev_t1));
-    ENG_TRY(vitcu_malloc(&e->d_patches, (size_t)e->B * e->P * VIT_D * act));
-    ENG_TRY(vitcu_malloc((void **)&e->d_x, rows * VIT_D * sizeof(float)));
-    ENG_TRY(vitcu_malloc(&e->d_ln, rows * VIT_D * (e->fp32_tc ? 6 : act)));
+    ENG_TRY(vitcu_malloc(&e->d_patches, (size_t)e->B * e->P * 3 * e->patch * e->patch * act));
+    ENG_TRY(vitcu_malloc((void **)&e->d_x, rows * e->D * sizeof(float)));
+    ENG_TRY(vitcu_malloc(&e->d_ln, rows * e->D * (e->fp32_tc ? 6 : act)));
     if (e->fp32_tc)
-        ENG_TRY(vitcu_malloc((void **)&e->d_a3, rows * VIT_HID * 3 * sizeof(vitcu_bf16)));
-    ENG_TRY(vitcu_malloc(&e->d_qkv, rows * 3 * VIT_D * act));
-    ENG_TRY(vitcu_malloc(&e->d_att, rows * VIT_D * act));
-    ENG_TRY(vitcu_malloc(&e->d_hid, rows * VIT_HID * act));
-    ENG_TRY(vitcu_malloc((void **)&e->d_cls, (size_t)e->B * VIT_D * sizeof(float)));
+        ENG_TRY(vitcu_malloc((void **)&e->d_a3, rows * (size_t)(e->HID > 3 * e->patch * e->patch ? e->HID : 3 * e->patch * e->patch) * 3 * sizeof(vitcu_bf16)));
+    ENG_TRY(vitcu_malloc(&e->d_qkv, rows * 3 * e->D * act));
+    ENG_TRY(vitcu_malloc(&e->d_att, rows * e->D * act));
+    ENG_TRY(vitcu_malloc(&e->d_hid, rows * e->HID * act));
+    ENG_TRY(vitcu_malloc((void **)&e->d_cls, (size_t)e->B * e->D * sizeof(float)));
     ENG_TRY(vitcu_host_alloc((void **)&e->h_probs, (size_t)e->B * VITB200_CLASSES * sizeof(float) * 2));
     ENG_TRY(vitcu_host_alloc((void **)&e->h_logits, (size_t)e->B * VITB200_CLASSES * sizeof(float) * 2));
 #undef ENG_TRY
@@ -235,16 +309,16 @@ int vitb200_load_weights(vitb200_engine *e, const vitb200_blob *net)
     VIT_TRY(vitcu_set_device(e->device));
     /* validate first: the reference would dereference a NULL blob (R/Network.c:144-148
      * leaves absent files as {NULL,0}) */
-    for (int i = 0; i < VITB200_NBLOBS; i++) {
+    for (int i = 0; i < e->nblobs; i++) {
         if (!net[i].data || net[i].size == 0) {
             char what[96];
             snprintf(what, sizeof(what), "weight blob %d is missing", i);
             return vit_fail(__FILE__, __LINE__, VITCU_E_ARG, what);
         }
-        if (net[i].size != blob_elems(i, e->T)) {
+        if (net[i].size != blob_elems(e, i)) {
             char what[128];
             snprintf(what, sizeof(what), "weight blob %d has %zu elements, expected %zu", i, net[i].size,
-                     blob_elems(i, e->T));
+                     blob_elems(e, i));
             return vit_fail(__FILE__, __LINE__, VITCU_E_ARG, what);
         }
     }
@@ -254,10 +328,10 @@ int vitb200_load_weights(vitb200_engine *e, const vitb200_blob *net)
      * to the packed form: bf16 [N,K] on the BF16 path, three bf16 pieces [N,3K] on the FP32
      * tensor-core path.  Everything else (biases, LayerNorm, class token, position embedding, head,
      * and the conv filters of the TF32 patch embedding) stays fp32. */
-    size_t off32[VITB200_NBLOBS], off16[VITB200_NBLOBS], total = 0, scratch_elems = 0;
-    for (int i = 0; i < VITB200_NBLOBS; i++) {
+    size_t off32[VIT_MAX_BLOBS], off16[VIT_MAX_BLOBS], total = 0, scratch_elems = 0;
+    for (int i = 0; i < e->nblobs; i++) {
         const size_t n = net[i].size;
-        const int packed = is_gemm_weight(i) && (bf || e->fp32_tc);
+        const int packed = is_gemm_weight(e, i) && (bf || e->fp32_tc);
         const int keep32 = !packed || (bf && i == 1 && !e->pe_gather);
         const int need16 = packed && !(bf && i == 1 && !e->pe_gather);
         off32[i] = off16[i] = (size_t)-1;
@@ -282,7 +356,7 @@ int vitb200_load_weights(vitb200_engine *e, const vitb200_blob *net)
         for (int k = 0; k < 2; k++)
             VIT_TRY(vitcu_malloc((void **)&scratch[k], scratch_elems * sizeof(float)));
     int k = 0, rc = 0;
-    for (int i = 0; i < VITB200_NBLOBS && !rc; i++) {
+    for (int i = 0; i < e->nblobs && !rc; i++) {
         const size_t n = net[i].size;
         e->w32[i] = off32[i] == (size_t)-1 ? NULL : (float *)((char *)e->w_arena + off32[i]);
         e->w16[i] = off16[i] == (size_t)-1 ? NULL : (vitcu_bf16 *)((char *)e->w_arena + off16[i]);
@@ -297,7 +371,7 @@ int vitb200_load_weights(vitb200_engine *e, const vitb200_blob *net)
             if (!rc && bf)
                 rc = vitcu_f32_to_bf16(src, e->w16[i], n, e->stream);
             if (!rc && e->fp32_tc) { /* [N,K] fp32 -> [N,3K] bf16 pieces */
-                const int K = (i == 1 || (i - 4) % 12 != 10) ? VIT_D : VIT_HID;
+                const int K = gemm_weight_k(e, i);
                 rc = vitcu_split3(src, (size_t)K, e->w16[i], n / (size_t)K, K, e->stream);
             }
         }
@@ -365,50 +439,50 @@ static int enqueue_forward(vitb200_engine *e, int buf, int b)
      * tensor-core GEMM that gathers the patches by TMA straight from the NCHW image; FP32 path:
      * gather kernel + FP32-accurate GEMM with the class/position epilogue */
     if (bf && !e->pe_gather) {
-        VIT_TRY(vitcu_patch_embed_tc(e->d_images[buf], e->w32[1], e->w32[2], e->w32[3], e->d_x, b, e->img, s));
+        VIT_TRY(vitcu_patch_embed_tc_ex(e->d_images[buf], e->w32[1], e->w32[2], e->w32[3], e->d_x, b, e->img, e->D, s));
         e->launches++;
     } else {
-        VIT_TRY(vitcu_patch_gather(e->d_images[buf], e->d_patches, b, e->img, bf, s));
+        VIT_TRY(vitcu_patch_gather_ex(e->d_images[buf], e->d_patches, b, e->img, e->patch, bf, s));
         e->launches++;
-        VIT_TRY(gemm(e, e->d_patches, 0, 1, 2, e->d_x, b * e->P, VIT_D, VIT_D, VITCU_EPI_PATCH_EMBED, 0));
+        VIT_TRY(gemm(e, e->d_patches, 0, 1, 2, e->d_x, b * e->P, e->D, 3 * e->patch * e->patch, VITCU_EPI_PATCH_EMBED, 0));
     }
-    VIT_TRY(vitcu_cls_rows(e->d_x, e->w32[0], e->w32[3], b, e->T, s));
+    VIT_TRY(vitcu_cls_rows_ex(e->d_x, e->w32[0], e->w32[3], b, e->T, e->D, s));
     e->launches++;
 
-    const int layers = e->stop_after < 0 ? VIT_DEPTH : (e->stop_after < VIT_DEPTH ? e->stop_after : VIT_DEPTH);
+    const int layers = e->stop_after < 0 ? e->depth : (e->stop_after < e->depth ? e->stop_after : e->depth);
     for (int l = 0; l < layers; l++) {
         const int w = 4 + 12 * l; /* blob base of the layer (R/ViT_seq.c:446-504) */
         /* x -> LN1 -> QKV -> attention -> out-proj (+x)  (R/ViT_opencl.c:710-730) */
-        VIT_TRY(vitcu_layernorm(e->d_x, VIT_D, e->d_ln, ln_mode, e->w32[w + 0], e->w32[w + 1], M, s));
+        VIT_TRY(vitcu_layernorm_ex(e->d_x, e->D, e->d_ln, ln_mode, e->w32[w + 0], e->w32[w + 1], M, e->D, s));
         e->launches++;
-        VIT_TRY(gemm(e, e->d_ln, 1, w + 2, w + 3, e->d_qkv, M, 3 * VIT_D, VIT_D, VITCU_EPI_BIAS, bf));
-        VIT_TRY(vitcu_attention(e->d_qkv, e->d_att, b, e->T, bf, s));
+        VIT_TRY(gemm(e, e->d_ln, 1, w + 2, w + 3, e->d_qkv, M, 3 * e->D, e->D, VITCU_EPI_BIAS, bf));
+        VIT_TRY(vitcu_attention_ex(e->d_qkv, e->d_att, b, e->T, e->heads, bf, s));
         e->launches++;
-        VIT_TRY(gemm(e, e->d_att, 0, w + 4, w + 5, e->d_x, M, VIT_D, VIT_D, VITCU_EPI_BIAS_RESIDUAL, 0));
+        VIT_TRY(gemm(e, e->d_att, 0, w + 4, w + 5, e->d_x, M, e->D, e->D, VITCU_EPI_BIAS_RESIDUAL, 0));
         /* -> LN2 -> fc1+GELU -> fc2 (+r1)  (R/ViT_opencl.c:732-746) */
-        VIT_TRY(vitcu_layernorm(e->d_x, VIT_D, e->d_ln, ln_mode, e->w32[w + 6], e->w32[w + 7], M, s));
+        VIT_TRY(vitcu_layernorm_ex(e->d_x, e->D, e->d_ln, ln_mode, e->w32[w + 6], e->w32[w + 7], M, e->D, s));
         e->launches++;
-        VIT_TRY(gemm(e, e->d_ln, 1, w + 8, w + 9, e->d_hid, M, VIT_HID, VIT_D, VITCU_EPI_BIAS_GELU, bf));
-        VIT_TRY(gemm(e, e->d_hid, 0, w + 10, w + 11, e->d_x, M, VIT_D, VIT_HID, VITCU_EPI_BIAS_RESIDUAL, 0));
+        VIT_TRY(gemm(e, e->d_ln, 1, w + 8, w + 9, e->d_hid, M, e->HID, e->D, VITCU_EPI_BIAS_GELU, bf));
+        VIT_TRY(gemm(e, e->d_hid, 0, w + 10, w + 11, e->d_x, M, e->D, e->HID, VITCU_EPI_BIAS_RESIDUAL, 0));
     }
     if (e->stop_after >= 0)
         return 0;
 
     /* final LN on the class-token rows only, head, softmax
      * (R/ViT_opencl.c:951-959; R/ViT_seq.c:506-515 normalises all rows but uses row 0) */
-    VIT_TRY(vitcu_layernorm(e->d_x, (size_t)e->T * VIT_D, e->d_cls, 0, e->w32[148], e->w32[149], b, s));
+    VIT_TRY(vitcu_layernorm_ex(e->d_x, (size_t)e->T * e->D, e->d_cls, 0, e->w32[e->nblobs - 4], e->w32[e->nblobs - 3], b, e->D, s));
     e->launches++;
     vitcu_gemm_desc d;
     memset(&d, 0, sizeof(d));
     d.M = b;
     d.N = VITB200_CLASSES;
-    d.K = VIT_D;
-    d.lda = VIT_D;
+    d.K = e->D;
+    d.lda = e->D;
     d.ldc = VITB200_CLASSES;
     d.epilogue = VITCU_EPI_BIAS;
-    d.bias = e->w32[151];
+    d.bias = e->w32[e->nblobs - 1];
     /* the head stays FP32 on both paths: 0.004 % of the FLOPs, all of the logit precision */
-    const float *head_w = e->w32[150];
+    const float *head_w = e->w32[e->nblobs - 2];
     VIT_TRY(vitcu_sgemm(e->d_cls, head_w, e->d_logits[buf], &d, s));
     e->launches++;
     VIT_TRY(vitcu_softmax_rows(e->d_logits[buf], e->d_probs[buf], b, VITB200_CLASSES, s));
@@ -693,7 +767,7 @@ int vitb200_read_probs(vitb200_engine *e, int n, float *probs_host, float *logit
 
 int vitb200_set_stop_after_layer(vitb200_engine *e, int layer)
 {
-    if (!e || layer < -1 || layer > VIT_DEPTH)
+    if (!e || layer < -1 || layer > e->depth)
         return vit_fail(__FILE__, __LINE__, VITCU_E_ARG, "stop_after_layer must be in [-1,12]");
     e->stop_after = layer;
     return 0;
@@ -704,7 +778,7 @@ int vitb200_read_tokens(vitb200_engine *e, int n, float *x_host)
     VIT_TRY_RC(check_ready(e));
     if (n <= 0 || n > e->B || !x_host)
         return vit_fail(__FILE__, __LINE__, VITCU_E_ARG, "read_tokens: bad argument");
-    VIT_TRY(vitcu_memcpy_d2h(x_host, e->d_x, (size_t)n * e->T * VIT_D * sizeof(float), e->stream));
+    VIT_TRY(vitcu_memcpy_d2h(x_host, e->d_x, (size_t)n * e->T * e->D * sizeof(float), e->stream));
     VIT_TRY(vitcu_stream_sync(e->stream));
     return 0;
 }

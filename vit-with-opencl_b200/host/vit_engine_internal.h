@@ -5,12 +5,14 @@
 #include "../../include/vit_b200.h"
 #include "../../include/vit_cuda_layer.h"
 
-#define VIT_D 768
-#define VIT_HID 3072
-#define VIT_DEPTH 12
+/* blob slots: 4 embedding blobs + 12 per encoder layer + 4 head blobs (R/ViT_seq.c:437-513 for depth 12) */
+#define VIT_MAX_DEPTH 32
+#define VIT_MAX_BLOBS (8 + 12 * VIT_MAX_DEPTH)
 
 struct vitb200_engine {
     int device, img, side, P, T, precision, B;
+    int patch, D, HID, depth, heads; /* model dims (ViT-B/16: 16, 768, 3072, 12, 12) */
+    int nblobs;                      /* 8 + 12 * depth */
     int weights_loaded, stop_after, no_graph, warmed;
     int pe_gather;                   /* BF16 path: use the gather kernel + BF16 GEMM for the patch embedding */
     int fp32_tc;                     /* FP32 precision computed as split-bf16 (x3 pieces, 6 products) on the tensor cores */
@@ -19,8 +21,8 @@ struct vitb200_engine {
     vitcu_event ev_h2d[2], ev_done[2], ev_out[2], ev_t0, ev_t1;
     vitcu_graph graph[2];
     void *w_arena;                   /* one device allocation holding every weight below */
-    float *w32[VITB200_NBLOBS];      /* fp32 blobs on the device (pointers into w_arena) */
-    vitcu_bf16 *w16[VITB200_NBLOBS]; /* BF16 path: bf16 GEMM weights [N,K]; FP32 tensor-core path: three bf16 pieces [N,3K] */
+    float *w32[VIT_MAX_BLOBS];         /* fp32 blobs on the device (pointers into w_arena) */
+    vitcu_bf16 *w16[VIT_MAX_BLOBS]; /* BF16 path: bf16 GEMM weights [N,K]; FP32 tensor-core path: three bf16 pieces [N,3K] */
     vitcu_bf16 *d_a3;                /* FP32 tensor-core path: split form [rows,3K] of the current GEMM A operand */
     float *d_images[2];              /* double-buffered input chunk [B,3,img,img] */
     void *d_patches;                 /* [B*P,768] gathered patches */

@@ -25,6 +25,7 @@
 
 typedef struct {
     int device, precision, batch, img;
+    vitb200_model model;
     const vitb200_image *images;
     const vitb200_blob *networks;
     float **prb;
@@ -45,6 +46,7 @@ typedef struct {
 typedef struct {
     vitb200_engine *e;
     int device, img, precision, batch, busy;
+    vitb200_model model;
     unsigned long long wsig;
 } cached_engine;
 static cached_engine g_cache[MAX_CACHED];
@@ -76,13 +78,13 @@ static unsigned long long weights_signature(const vitb200_blob *net)
     return h;
 }
 
-static cached_engine *cache_acquire(const int device, int img, int precision, int batch)
+static cached_engine *cache_acquire(const int device, const vitb200_model *m, int precision, int batch)
 {
     cached_engine *slot = NULL;
     pthread_mutex_lock(&g_cache_mu);
     for (int i = 0; i < MAX_CACHED && !slot; i++) {
         cached_engine *c = &g_cache[i];
-        if (c->e && !c->busy && c->device == device && c->img == img && c->precision == precision &&
+        if (c->e && !c->busy && c->device == device && !memcmp(&c->model, m, sizeof(*m)) && c->precision == precision &&
             c->batch >= batch)
             slot = c;
     }
@@ -110,14 +112,15 @@ void vitb200_release_persistent(void)
 static void *shard_main(void *arg)
 {
     shard_job *j = (shard_job *)arg;
-    cached_engine *c = j->persist ? cache_acquire(j->device, j->img, j->precision, j->batch) : NULL;
+    cached_engine *c = j->persist ? cache_acquire(j->device, &j->model, j->precision, j->batch) : NULL;
     vitb200_engine *e = c ? c->e : NULL;
     if (!e) {
-        j->rc = vitb200_create(&e, j->device, j->img, j->precision, j->batch);
+        j->rc = vitb200_create_model(&e, j->device, &j->model, j->precision, j->batch);
         if (c && !j->rc) {
             c->e = e;
             c->device = j->device;
             c->img = j->img;
+            c->model = j->model;
             c->precision = j->precision;
             c->batch = j->batch;
             c->wsig = 0;
@@ -168,6 +171,9 @@ void ViT_opencl(vitb200_image *image, vitb200_blob *networks, float **prb)
         return;
     if (image->c != 3 || image->h != image->w || image->h % 16 != 0)
         die("[vit_opencl.c] CUDA error 90001 (ViT_opencl: images must be 3 x S x S with S a multiple of 16)");
+    /* ViT-B/16 unless the blob sizes say /32 patches or another width (same 152-blob order) */
+    vitb200_model model;
+    vitb200_model_from_blobs(networks, image, &model);
 
     struct timespec t0, t1;
     clock_gettime(CLOCK_MONOTONIC, &t0);
@@ -207,6 +213,7 @@ void ViT_opencl(vitb200_image *image, vitb200_blob *networks, float **prb)
         j->precision = precision;
         j->batch = batch;
         j->img = image->h;
+        j->model = model;
         j->images = image;
         j->networks = networks;
         j->prb = prb;

@@ -27,15 +27,40 @@ def tokens(img: int) -> int:
     return (img // PATCH) ** 2 + 1
 
 
-def blob_shapes(img: int = 224):
-    """Shapes of the 152 blobs (index use: ViT_seq.c:437-513)."""
-    shapes = [(EMBED,), (EMBED, 3, PATCH, PATCH), (EMBED,), (tokens(img), EMBED)]
-    for _ in range(DEPTH):
-        shapes += [(EMBED,), (EMBED,), (3 * EMBED, EMBED), (3 * EMBED,), (EMBED, EMBED), (EMBED,),
-                   (EMBED,), (EMBED,), (HIDDEN, EMBED), (HIDDEN,), (EMBED, HIDDEN), (EMBED,)]
-    shapes += [(EMBED,), (EMBED,), (CLASSES, EMBED), (CLASSES,)]
-    assert len(shapes) == NBLOBS
+# model variants with the reference's blob order: name -> (patch, embed, depth, heads, hidden)
+VARIANTS = {
+    "b16": (16, 768, 12, 12, 3072),   # the reference's macros (ViT_seq.c:10-17)
+    "b32": (32, 768, 12, 12, 3072),   # patch_size 32
+    "s16": (16, 384, 12, 6, 1536),    # embed_dim 384, num_heads 6
+    "l16": (16, 1024, 24, 16, 4096),  # depth 24: beyond what the reference's unrolled encoder calls express
+}
+
+
+def blob_shapes(img: int = 224, variant: str = "b16"):
+    """Shapes of the 8 + 12*depth blobs (152 for depth 12; index use: ViT_seq.c:437-513)."""
+    patch, embed, depth, _heads, hidden = VARIANTS[variant]
+    t = (img // patch) ** 2 + 1
+    shapes = [(embed,), (embed, 3, patch, patch), (embed,), (t, embed)]
+    for _ in range(depth):
+        shapes += [(embed,), (embed,), (3 * embed, embed), (3 * embed,), (embed, embed), (embed,),
+                   (embed,), (embed,), (hidden, embed), (hidden,), (embed, hidden), (embed,)]
+    shapes += [(embed,), (embed,), (CLASSES, embed), (CLASSES,)]
+    assert len(shapes) == 8 + 12 * depth
     return shapes
+
+
+def variant_blobs(variant: str, img: int = 224, seed: int = 0, std: float = 0.02):
+    """fully synthetic blobs of a model variant: N(0, std^2), LayerNorm gammas 1 + N(0, std^2), 6-decimal rounding"""
+    rng = np.random.default_rng(seed)
+    shapes = blob_shapes(img, variant)
+    n = len(shapes)
+    out = []
+    for idx, shp in enumerate(shapes):
+        a = rng.standard_normal(int(np.prod(shp)), dtype=np.float32) * np.float32(std)
+        if idx == n - 4 or (4 <= idx < n - 4 and (idx - 4) % 12 in (0, 6)):
+            a = a + np.float32(1.0)
+        out.append(round6(a))
+    return out
 
 
 def is_ln_gamma(idx: int) -> bool:
