@@ -317,6 +317,28 @@ def test_full_batch_properties_bf16(pkg, lib, blobs224):
     assert np.array_equal(p4.argmax(1), p1[:16].argmax(1))
 
 
+def test_4096_images_replica_property_bf16(pkg, lib, blobs224):
+    """BASELINE config 4 size on one GPU (4096 images, 16 chunks of 256) through a size-independent
+    property: 64 distinct images tiled 64 times -- every replica must give bit-identical rows (same
+    position inside a full chunk -> same kernels, same tiles), the 64 distinct rows must match a
+    64-image run to rounding, and nothing may be lost between chunks, staging slots or graph replays"""
+    base = pkg.synth.synthetic_images(64, 224, seed=99)
+    imgs = np.ascontiguousarray(np.tile(base, (64, 1, 1, 1)))
+    with pkg.Engine(0, 224, pkg.BF16, max_batch=256) as eng:
+        eng.load_weights(blobs224)
+        probs = eng.forward(imgs)               # pageable source: threaded pinned staging
+        labels, top = eng.forward_topk(imgs, 1)
+        small = eng.forward(base)
+        assert lib.vitcu_watchdog_check() == 0
+    assert probs.shape == (4096, 1000) and np.isfinite(probs).all()
+    np.testing.assert_allclose(probs.sum(1), 1.0, atol=1e-5)
+    tiles = probs.reshape(64, 64, 1000)
+    assert np.array_equal(tiles, np.broadcast_to(tiles[0], tiles.shape))
+    assert np.array_equal(labels[:, 0], probs.argmax(1))
+    assert np.array_equal(small.argmax(1), tiles[0].argmax(1))
+    assert np.abs(small - tiles[0]).max() <= 1e-4
+
+
 def test_main_c_drop_in(pkg, lib, oracle, blobs224, ref_dir, tmp_path):
     """The reference's UNMODIFIED Main.c + Network.c + comparator.c (objects built by
     oracle/Makefile) linked against libvit_b200.so instead of ViT_opencl.c: the
