@@ -23,7 +23,7 @@
 // store.  Every mbarrier wait is watchdog-guarded (tc_common.cuh).
 #include "tc_common.cuh"
 #ifndef VITCU_GELU_FORM
-#define VITCU_GELU_FORM 0 // 0 = (3,3) rational (default), 1 = MUFU.TANH form (measured: same fc1 time)
+#define VITCU_GELU_FORM 0 // 0 = (3,3) rational (default: smallest error), 1 = MUFU.TANH form, scalar, 2 = MUFU.TANH form, packed fp32x2
 #endif
 #ifndef VITCU_GELU_SCALAR
 #define VITCU_GELU_SCALAR 0
@@ -155,7 +155,11 @@ __device__ __forceinline__ bool epilogue_tile(const EpiParams &p, void *C, const
                 for (int j = 0; j < 32; j++)
                     v[j] = gelu_erf(v[j]);
             } else {
-#if VITCU_GELU_FORM == 1
+#if VITCU_GELU_FORM == 2
+#pragma unroll
+                for (int j = 0; j < 32; j += 2)
+                    unpack2(gelu_erf_tanh2(pack2(v[j], v[j + 1])), v[j], v[j + 1]);
+#elif VITCU_GELU_FORM == 1
 #pragma unroll
                 for (int j = 0; j < 32; j++)
                     v[j] = gelu_erf_tanh1(v[j]);
