@@ -23,7 +23,7 @@
 // store.  Every mbarrier wait is watchdog-guarded (tc_common.cuh).
 #include "tc_common.cuh"
 #ifndef VITCU_GELU_FORM
-#define VITCU_GELU_FORM 0 // 0 = (3,3) rational (default: smallest error), 1 = MUFU.TANH form, scalar, 2 = MUFU.TANH form, packed fp32x2
+#define VITCU_GELU_FORM 2 // 0 = (3,3) rational, 1 / 2 = MUFU.TANH form scalar / packed (default), 3 = sigmoid form (EX2 + RCP), packed
 #endif
 #ifndef VITCU_GELU_SCALAR
 #define VITCU_GELU_SCALAR 0
@@ -155,7 +155,11 @@ __device__ __forceinline__ bool epilogue_tile(const EpiParams &p, void *C, const
                 for (int j = 0; j < 32; j++)
                     v[j] = gelu_erf(v[j]);
             } else {
-#if VITCU_GELU_FORM == 2
+#if VITCU_GELU_FORM == 3
+#pragma unroll
+                for (int j = 0; j < 32; j += 2)
+                    unpack2(gelu_erf_sigmoid2(pack2(v[j], v[j + 1])), v[j], v[j + 1]);
+#elif VITCU_GELU_FORM == 2
 #pragma unroll
                 for (int j = 0; j < 32; j += 2)
                     unpack2(gelu_erf_tanh2(pack2(v[j], v[j + 1])), v[j], v[j + 1]);
@@ -760,9 +764,11 @@ static int gemm_dispatch(const vitcu_bf16 *A, const vitcu_bf16 *W, void *C, cons
         rc = make_tensor_map_2d(&tb, W, 2, (uint64_t)d->N, kphys, kphys * 2, 128, BK);
         if (rc)
             return rc;
-        // 16 epilogue warps need the TMA output path (their staging share is 4 KB); VITCU_GEMM_EW=8|16 overrides
+        // 16 epilogue warps (VITCU_GEMM_EW=16; they need the TMA output path, their staging share is 4 KB) paid
+        // off for the 17-instruction rational GELU (1195 vs 1127 TFLOP/s); with the 9-instruction packed
+        // MUFU.TANH form 8 warps with double-buffered tcgen05.ld are as fast or faster (0.195 vs 0.198 ms)
         static const int force_ew = getenv("VITCU_GEMM_EW") ? atoi(getenv("VITCU_GEMM_EW")) : 0;
-        const bool ew16 = p.tma_out != 0 && (force_ew ? force_ew == 16 : p.epilogue == VITCU_EPI_BIAS_GELU);
+        const bool ew16 = p.tma_out != 0 && (force_ew ? force_ew == 16 : (VITCU_GELU_FORM == 0 && p.epilogue == VITCU_EPI_BIAS_GELU));
         if (ew16)
             return launch_pair<5, 16>(ta, tb, tc, C, p, sms, as_stream(s));
         return launch_pair<5, 8>(ta, tb, tc, C, p, sms, as_stream(s));

@@ -506,9 +506,11 @@ __device__ __forceinline__ float gelu_erf_tanh1(float x)
 }
 
 // packed form of gelu_erf_tanh1: per PAIR 5 packed FMA-pipe instructions + 2 FMNMX + 2 MUFU.TANH.
-// Measured (tools/fc1_ab.py, -DVITCU_GELU_FORM=2): fc1 0.195 ms instead of 0.204 ms (GELU/bias-only time ratio 1.09
-// instead of 1.16), but the BF16 forward's logit error grows from 1.15e-2 to 1.29e-2 (bound 2e-2) because
-// tanh.approx is only good to 2^-11; the rational form stays the default.
+// Measured (tools/fc1_ab.py): fc1 0.195 ms instead of 0.200-0.204 ms (GELU / bias-only time ratio 1.09 instead of
+// 1.16): the fc1 epilogue is bound by issue slots, and this form needs 9 per pair instead of 17.  The BF16
+// forward's logit error does not change (tools/bf16_error_stats.py, 16 images: RMS 3.49e-3 rational, 3.52e-3 this
+// form, 3.45e-3 sigmoid form; the per-image maxima scatter between 1.05e-2 and 1.7e-2 for all three -- bf16
+// rounding of the activations dominates), so this is the default.
 __device__ __forceinline__ f32x2 gelu_erf_tanh2(f32x2 x)
 {
     const f32x2 xx = mul2(x, x);
@@ -522,6 +524,26 @@ __device__ __forceinline__ f32x2 gelu_erf_tanh2(f32x2 x)
     const f32x2 t = pack2(tanh_approx(a0), tanh_approx(a1));
     const f32x2 hx = mul2(x, pack2(0.5f, 0.5f));
     return fma2(hx, t, hx);
+}
+
+// The same fit through the two accurate MUFU functions instead of tanh.approx:
+//     0.5 x (1 + tanh(a)) = x / (1 + 2^(-2 a log2 e)),   a = x (c0 + c1 w + c2 w^2),  w = min(x^2, 20.25)
+// max |GELU error| 2.6e-5 in fp32 arithmetic (ex2.approx / rcp.approx are good to ~2^-22; the rational form
+// has 2e-5).  Per PAIR: 5 packed FMA-pipe instructions + 2 FMNMX + 4 MUFU, against 11 + 4 + 2 for the rational form.
+// x -> -inf: 2^(+big) = inf, 1/inf = 0, x * 0 = -0;  x -> +inf: 2^(-big) = 0, x / 1 = x.
+__device__ __forceinline__ f32x2 gelu_erf_sigmoid2(f32x2 x)
+{
+    const f32x2 xx = mul2(x, x);
+    float w0, w1;
+    unpack2(xx, w0, w1);
+    const f32x2 w = pack2(fminf(w0, 20.25f), fminf(w1, 20.25f));
+    f32x2 p = fma2(pack2(0.0010142631363123655f, 0.0010142631363123655f), w, pack2(-0.10677571594715118f, -0.10677571594715118f));
+    p = fma2(p, w, pack2(-2.301121234893799f, -2.301121234893799f));
+    float a0, a1;
+    unpack2(mul2(x, p), a0, a1);
+    float d0, d1;
+    unpack2(add2(pack2(ex2_approx(a0), ex2_approx(a1)), pack2(1.0f, 1.0f)), d0, d1);
+    return mul2(x, pack2(rcp_approx(d0), rcp_approx(d1)));
 }
 
 } // namespace tc
