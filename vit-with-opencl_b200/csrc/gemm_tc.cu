@@ -422,13 +422,13 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 //   tfull[a]   one per CTA, multicast commit when the accumulator is complete
 //   tempty[a]  leader's barrier, 16 arrivals (8 epilogue warps of each CTA)
 // ---------------------------------------------------------------------------
-template <int STAGES>
+template <int STAGES, uint32_t EPI_BYTES = 65536>
 struct SmemLayout2 {
     static constexpr uint32_t A_BYTES = BM * BK * 2;       // this CTA's 128 A rows
     static constexpr uint32_t B_BYTES = 128 * BK * 2;      // this CTA's half of the 256-row W tile
     static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr uint32_t EPI_OFFSET = STAGES * STAGE_BYTES;
-    static constexpr uint32_t BAR_OFFSET = EPI_OFFSET + kEpiWarps * kStageFloats * 4;
+    static constexpr uint32_t BAR_OFFSET = EPI_OFFSET + EPI_BYTES; // epilogue staging, split evenly over the warps
     static constexpr uint32_t NUM_BARS = 2 * STAGES + 4;
     static constexpr uint32_t TOTAL = BAR_OFFSET + NUM_BARS * 8 + 16 + 1024;
     static_assert(TOTAL <= 227 * 1024, "shared memory budget");
@@ -437,12 +437,14 @@ struct SmemLayout2 {
 // EW = epilogue warps per CTA: 8 (two per TMEM lane quadrant, 128 columns each, 168 registers) or
 // 16 (four per quadrant, 64 columns each, 96 registers): the heavier epilogues (GELU) are bound by
 // the latency of one warp's chunk chain, which more warps overlap
-template <int STAGES, int EW>
+// EPI_BYTES = epilogue staging per CTA: 64 KB with 5 operand stages, or 32 KB (4 KB per warp: two bf16 tiles
+// or one fp32 tile, TMA output path only) which makes room for a sixth stage
+template <int STAGES, int EW, uint32_t EPI_BYTES = 65536>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EW, 1)
 gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                      const __grid_constant__ CUtensorMap tmap_c, void *C, const EpiParams p, uint32_t *watchdog_flag)
 {
-    using L = SmemLayout2<STAGES>;
+    using L = SmemLayout2<STAGES, EPI_BYTES>;
     constexpr int BN = 256, BM2 = 256;
     constexpr uint32_t TMEM_COLS = 512;
     constexpr uint32_t IDESC = umma_idesc_bf16(BM2, BN, false, false);
@@ -496,20 +498,33 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         }
         uint32_t stage = 0, phase = 0;
         bool ok = true;
+        // the leader's full barriers as shared::cluster addresses (consecutive 8-byte slots)
+        const uint32_t full_leader0 = mapa_u32(smem_u32(&full_bar[0]), 0);
         for (int tile = pair; tile < num_tiles && ok; tile += num_pairs) {
             const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
+            const int arow = m_blk * BM2 + (int)rank * BM, brow = n_blk * BN + (int)rank * 128;
+            // running (segment, column) instead of a division per k-block: this warp's instruction
+            // stream is what feeds the tensor core (the MMA issuer spends most of its time on the full barrier)
+            int seg = 0, kin = 0, acol = p.a_seg[0], bcol = p.b_seg[0];
             for (int kb = 0; kb < num_kb; kb++) {
                 if (!(ok = mbar_wait_warp(&empty_bar[stage], phase ^ 1, wd, 1)))
                     break;
                 if (elect_one()) {
                     uint8_t *sa = smem + stage * L::STAGE_BYTES;
-                    const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
+                    const uint32_t full_leader = full_leader0 + stage * 8;
                     mbar_arrive_expect_tx_cluster(full_leader, L::STAGE_BYTES);
-                    const int seg = kb / p.seg_kb, kk = (kb - seg * p.seg_kb) * BK;
-                    tma_load_2d_2sm(sa, &tmap_a, full_leader, p.a_seg[seg] + kk, m_blk * BM2 + (int)rank * BM);
-                    tma_load_2d_2sm(sa + L::A_BYTES, &tmap_b, full_leader, p.b_seg[seg] + kk, n_blk * BN + (int)rank * 128);
+                    tma_load_2d_2sm(sa, &tmap_a, full_leader, acol, arow);
+                    tma_load_2d_2sm(sa + L::A_BYTES, &tmap_b, full_leader, bcol, brow);
                 }
                 __syncwarp();
+                acol += BK;
+                bcol += BK;
+                if (++kin == p.seg_kb && kb + 1 < num_kb) {
+                    kin = 0;
+                    seg++;
+                    acol = p.a_seg[seg];
+                    bcol = p.b_seg[seg];
+                }
                 if (++stage == STAGES) {
                     stage = 0;
                     phase ^= 1;
@@ -553,7 +568,7 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     } else {
         // ===================== epilogue (warps 2.., both CTAs) =====================
         constexpr int CW = BN / (EW / 4);          // columns per warp
-        constexpr int SBW = 65536 / EW;            // staging bytes per warp
+        constexpr int SBW = EPI_BYTES / EW;        // staging bytes per warp
         const int quad = warp & 3;
         const int cgrp = (warp - 2) >> 2;
         uint32_t it = 0, chunk_ctr = 0;
@@ -623,12 +638,12 @@ int launch(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &tc, 
     return 0;
 }
 
-template <int STAGES, int EW>
+template <int STAGES, int EW, uint32_t EPI_BYTES = 65536>
 int launch_pair(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &tc, void *C, const EpiParams &p, int sms,
                 cudaStream_t st)
 {
-    using L = SmemLayout2<STAGES>;
-    auto kernel = gemm_bf16_tc2_kernel<STAGES, EW>;
+    using L = SmemLayout2<STAGES, EPI_BYTES>;
+    auto kernel = gemm_bf16_tc2_kernel<STAGES, EW, EPI_BYTES>;
     static bool configured[64] = {false};
     int dev = 0;
     VITCU_TRY(cudaGetDevice(&dev));
@@ -771,6 +786,11 @@ static int gemm_dispatch(const vitcu_bf16 *A, const vitcu_bf16 *W, void *C, cons
         const bool ew16 = p.tma_out != 0 && (force_ew ? force_ew == 16 : (VITCU_GELU_FORM == 0 && p.epilogue == VITCU_EPI_BIAS_GELU));
         if (ew16)
             return launch_pair<5, 16>(ta, tb, tc, C, p, sms, as_stream(s));
+        // VITCU_GEMM_STAGES=6: a sixth operand stage in exchange for single-buffered epilogue staging (A/B)
+        // measured (M=50432): bf16-output launches unchanged, fp32 reduce-add launches (out_proj, fc2) +1.5 %
+        static const int stages = getenv("VITCU_GEMM_STAGES") ? atoi(getenv("VITCU_GEMM_STAGES")) : 0;
+        if (p.tma_out != 0 && (stages == 6 || (stages == 0 && p.tma_out == 2)))
+            return launch_pair<6, 8, 32768>(ta, tb, tc, C, p, sms, as_stream(s));
         return launch_pair<5, 8>(ta, tb, tc, C, p, sms, as_stream(s));
     }
     // 128x256 tiles when they divide N and still give every SM work; else 128x128
