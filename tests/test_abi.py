@@ -92,3 +92,53 @@ def test_bf16_helpers_roundtrip(pkg):
     # round-to-nearest-even on a tie
     tie = np.array([np.uint32(0x3F808000)], np.uint32).view(np.float32)
     assert pkg.f32_to_bf16_bits(tie)[0] == 0x3F80
+
+
+# ---------------------------------------------------------------- host logic that needs no GPU
+def test_stager_gathers_blocks_on_all_threads(pkg):
+    """host/vit_stage.c: the thread pool that gathers the reference's per-image buffers (R/Network.c:84-105)
+    into pinned staging -- here into plain memory: byte-exact for block sizes that are not a multiple of
+    the 128 KB piece, for per-image pointers and for one contiguous source, and reusable job after job"""
+    L = pkg.lib()
+    L.vit_stager_create.restype = C.c_void_p
+    L.vit_stager_create.argtypes = [C.c_int]
+    L.vit_stager_destroy.argtypes = [C.c_void_p]
+    L.vit_stager_copy.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+    L.vit_stager_copy.restype = None
+    rng = np.random.default_rng(5)
+    for threads in (1, 4):
+        st = L.vit_stager_create(threads)
+        assert st
+        try:
+            for elems, count in ((150528, 9), (33333, 37), (7, 3), (150528, 1)):
+                blocks = [rng.standard_normal(elems, dtype=np.float32) for _ in range(count)]
+                structs, keep = pkg.make_image_structs(np.stack(blocks).reshape(count, 1, 1, elems))
+                for i, b in enumerate(blocks):          # separate allocations, like load_image_data
+                    structs[i].data = b.ctypes.data_as(C.POINTER(C.c_float))
+                dst = np.zeros((count, elems), np.float32)
+                L.vit_stager_copy(st, dst.ctypes.data, structs, None, elems * 4, count)
+                assert np.array_equal(dst, np.stack(blocks))
+                src = np.ascontiguousarray(np.stack(blocks))
+                dst2 = np.zeros_like(dst)
+                L.vit_stager_copy(st, dst2.ctypes.data, None, src.ctypes.data, elems * 4, count)
+                assert np.array_equal(dst2, src)
+        finally:
+            L.vit_stager_destroy(st)
+
+
+def test_model_from_blobs_reads_dims_off_sizes(pkg):
+    """vitb200_model_from_blobs (host logic, no device): B/16, B/32 and S/16 blob sets, and the fall-back"""
+    L = pkg.lib()
+    for variant, img in (("b16", 224), ("b32", 224), ("s16", 224), ("b32", 384)):
+        shapes = pkg.synth.blob_shapes(img, variant)
+        blobs = [np.zeros(int(np.prod(s)), np.float32) for s in shapes]
+        nets, keep = pkg.make_network_structs(blobs)
+        m = pkg.Model()
+        assert L.vitb200_model_from_blobs(nets, None, C.byref(m)) == 0
+        patch, embed, depth, heads, hidden = pkg.synth.VARIANTS[variant]
+        assert (m.img, m.patch, m.embed, m.depth, m.heads, m.hidden) == (img, patch, embed, depth, heads, hidden)
+    blobs[1] = None  # conv filters absent (Network.c:144-148 leaves {NULL,0}): ViT-B/16 defaults, load_weights names the blob
+    nets, keep = pkg.make_network_structs(blobs)
+    m = pkg.Model()
+    assert L.vitb200_model_from_blobs(nets, None, C.byref(m)) == 0
+    assert (m.patch, m.embed, m.hidden) == (16, 768, 3072)
