@@ -103,56 +103,107 @@ class Dist:
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled every 200 ms during the timed region"""
+    """SM clock, power and throttle reasons sampled DURING the timed region: NVML every 5 ms from a
+    thread (the timed calls are ctypes calls, which release the GIL); nvidia-smi -lms 200 when the
+    NVML binding is unavailable."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+            0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, gpu_index: int):
         self.idx = gpu_index
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+        self.p = self.f = self.thread = None
+        self.rows = []          # (sm_mhz, sm_max_mhz, power_w, reason_bits)
+        self.stop_flag = False
+        self.source = None
+
+    def _nvml_loop(self, nv, h):
+        smax = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                try:
+                    bits = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except AttributeError:
+                    bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append((float(sm), float(smax), pw, int(bits)))
+            except Exception:
+                break
+            time.sleep(0.005)
 
     def start(self):
         try:
+            import pynvml as nv
+            nv.nvmlInit()
+            # NVML enumerates all GPUs of the box; CUDA_VISIBLE_DEVICES may renumber what this process sees
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            phys = self.idx
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if self.idx < len(ids) and ids[self.idx].isdigit():
+                    phys = int(ids[self.idx])
+            h = nv.nvmlDeviceGetHandleByIndex(phys)
+            import threading
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self.thread.start()
+            self.source = "nvml 5 ms"
+            return
+        except Exception:
+            self.thread = None
+        try:
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                        "-lms", "200", "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
+            self.source = "nvidia-smi 200 ms"
         except OSError:
             self.p = None
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.p is None:
-            return out
-        time.sleep(0.25)
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.p.kill()
-        self.f.flush()
-        self.f.seek(0)
         sm, smax, power, reasons = [], [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.f.read().splitlines():
-            c = [x.strip() for x in line.split(",")]
-            if len(c) < 9:
-                continue
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            for s_, m_, p_, bits in self.rows:
+                sm.append(s_)
+                smax.append(m_)
+                power.append(p_)
+                for bit, name in self.BITS.items():
+                    if bits & bit:
+                        reasons.add(name)
+        elif self.p is not None:
+            time.sleep(0.25)
+            self.p.terminate()
             try:
-                sm.append(float(c[1]))
-                smax.append(float(c[2]))
-                power.append(float(c[3]))
-            except ValueError:
-                continue
-            for name, v in zip(names, c[5:9]):
-                if v.lower() == "active":
-                    reasons.add(name)
-        self.f.close()
-        os.unlink(self.f.name)
+                self.p.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.p.kill()
+            self.f.flush()
+            self.f.seek(0)
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for line in self.f.read().splitlines():
+                c = [x.strip() for x in line.split(",")]
+                if len(c) < 9:
+                    continue
+                try:
+                    sm.append(float(c[1]))
+                    smax.append(float(c[2]))
+                    power.append(float(c[3]))
+                except ValueError:
+                    continue
+                for name, v in zip(names, c[5:9]):
+                    if v.lower() == "active":
+                        reasons.add(name)
+            self.f.close()
+            os.unlink(self.f.name)
+        else:
+            return out
         if sm:
-            busy = [s for s, p in zip(sm, power) if p > 300.0] or sm
-            out.update(sm_mhz=statistics.median(busy), sm_max_mhz=max(smax), reasons=sorted(reasons),
-                       samples=len(sm), power_w_max=max(power))
+            out.update(sm_mhz=statistics.median(sm), sm_min_mhz=min(sm), sm_max_mhz=max(smax), reasons=sorted(reasons),
+                       samples=len(sm), power_w_max=max(power), source=self.source)
         return out
 
 
