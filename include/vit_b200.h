@@ -127,6 +127,16 @@ int vitb200_last_forward_ms(vitb200_engine *e, float *ms);
 /* times `iters` back-to-back resident forwards with one event pair */
 int vitb200_time_resident(vitb200_engine *e, int n, int iters, float *total_ms);
 
+/* in-situ time of the dense-layer (GEMM) launches: runs `iters` eager forwards of the n staged images
+ * with one CUDA-event pair around every GEMM launch on the compute stream and returns the summed GEMM
+ * time per forward (bench.py's roofline: same data, cache state and clocks as the timed forward) */
+int vitb200_profile_gemms(vitb200_engine *e, int n, int iters, float *gemm_ms_per_forward, int *gemm_launches);
+
+/* whole-forward timeline: one eager forward of the n staged images with an event in front of every
+ * launch; the span up to the next launch (kernel + gap) is booked under 0 = GEMM, 1 = attention,
+ * 2 = LayerNorm, 3 = everything else (patch embedding, class rows, split kernels, final LN + head + softmax) */
+int vitb200_profile_timeline(vitb200_engine *e, int n, float ms_by_kind[4], int launches_by_kind[4]);
+
 /* debugging / per-stage parity: copy an internal activation of the last
  * resident forward to the host.  what: 0 = residual stream x [n*T,768] fp32
  * after the last executed stage; stop_after_layer (set before the forward)

@@ -87,6 +87,7 @@ def lib() -> C.CDLL:
         L.vitb200_forward_resident.argtypes = [C.c_void_p, C.c_int]
         L.vitb200_read_probs.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.vitb200_last_forward_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+        L.vitb200_profile_gemms.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int)]
         L.vitb200_time_resident.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]
         L.vitb200_set_stop_after_layer.argtypes = [C.c_void_p, C.c_int]
         L.vitb200_read_tokens.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
@@ -278,6 +279,12 @@ class Engine:
         ms = C.c_float()
         _check(lib().vitb200_last_forward_ms(self.h, C.byref(ms)))
         return ms.value
+
+    def profile_gemms(self, n: int, iters: int = 3):
+        """(summed GEMM ms per forward, GEMM launches per forward), CUDA events around every launch in situ"""
+        ms, k = C.c_float(), C.c_int()
+        _check(lib().vitb200_profile_gemms(self.h, n, iters, C.byref(ms), C.byref(k)))
+        return ms.value, k.value
 
     def time_resident(self, n: int, iters: int) -> float:
         ms = C.c_float()

@@ -390,6 +390,16 @@ int vitb200_load_weights(vitb200_engine *e, const vitb200_blob *net)
 
 /* one GEMM of the chain, dispatched on the engine precision.  a_split: A already holds the three
  * bf16 pieces (FP32 tensor-core path; the LayerNorm kernel emits them directly). */
+/* timeline profiling: an event in front of the next launch, tagged with what that launch is */
+static int mark(vitb200_engine *e, int kind)
+{
+    if (!e->mark_ev || e->mark_n >= e->mark_cap)
+        return 0;
+    VIT_TRY(vitcu_event_record(e->mark_ev[e->mark_n], e->stream));
+    e->mark_kind[e->mark_n++] = (unsigned char)kind;
+    return 0;
+}
+
 static int gemm(vitb200_engine *e, const void *A, int a_split, int widx, int bidx, void *C, int M, int N, int K, int epi,
                 int out_bf16)
 {
@@ -411,22 +421,32 @@ static int gemm(vitb200_engine *e, const void *A, int a_split, int widx, int bid
         d.tokens = e->T;
     }
     e->launches++;
-    if (e->precision == VITB200_BF16)
-        return vitcu_gemm_bf16((const vitcu_bf16 *)A, e->w16[widx], C, &d, e->stream);
-    if (e->fp32_tc) {
-        if (!a_split) {
-            int rc = vitcu_split3((const float *)A, (size_t)K, e->d_a3, (size_t)M, K, e->stream);
-            if (rc)
-                return rc;
-            e->launches++;
-            A = e->d_a3;
-        }
-        return vitcu_gemm_bf16x3((const vitcu_bf16 *)A, e->w16[widx], C, &d, e->stream);
+    if (e->fp32_tc && !a_split) {
+        VIT_TRY_RC(mark(e, VIT_K_OTHER));
+        int rc = vitcu_split3((const float *)A, (size_t)K, e->d_a3, (size_t)M, K, e->stream);
+        if (rc)
+            return rc;
+        e->launches++;
+        A = e->d_a3;
     }
-    return vitcu_sgemm((const float *)A, e->w32[widx], C, &d, e->stream);
+    VIT_TRY_RC(mark(e, VIT_K_GEMM));
+    const int prof = e->prof_ev && e->prof_n < e->prof_cap;
+    if (prof)
+        VIT_TRY(vitcu_event_record(e->prof_ev[2 * e->prof_n], e->stream));
+    int rc;
+    if (e->precision == VITB200_BF16)
+        rc = vitcu_gemm_bf16((const vitcu_bf16 *)A, e->w16[widx], C, &d, e->stream);
+    else if (e->fp32_tc)
+        rc = vitcu_gemm_bf16x3((const vitcu_bf16 *)A, e->w16[widx], C, &d, e->stream);
+    else
+        rc = vitcu_sgemm((const float *)A, e->w32[widx], C, &d, e->stream);
+    if (!rc && prof)
+        VIT_TRY(vitcu_event_record(e->prof_ev[2 * e->prof_n++ + 1], e->stream));
+    return rc;
 }
 
 /* Enqueue the forward of b images resident in d_images[buf] on e->stream. */
+#define MARK(kind) VIT_TRY_RC(mark(e, kind))
 static int enqueue_forward(vitb200_engine *e, int buf, int b)
 {
     const int bf = e->precision == VITB200_BF16;
@@ -438,6 +458,7 @@ static int enqueue_forward(vitb200_engine *e, int buf, int b)
     /* patch embedding (Conv2d + postConv2d, R/ViT_opencl.c:361-442).  BF16 path: one TF32
      * tensor-core GEMM that gathers the patches by TMA straight from the NCHW image; FP32 path:
      * gather kernel + FP32-accurate GEMM with the class/position epilogue */
+    MARK(VIT_K_OTHER);
     if (bf && !e->pe_gather) {
         VIT_TRY(vitcu_patch_embed_tc_ex(e->d_images[buf], e->w32[1], e->w32[2], e->w32[3], e->d_x, b, e->img, e->D, s));
         e->launches++;
@@ -446,6 +467,7 @@ static int enqueue_forward(vitb200_engine *e, int buf, int b)
         e->launches++;
         VIT_TRY(gemm(e, e->d_patches, 0, 1, 2, e->d_x, b * e->P, e->D, 3 * e->patch * e->patch, VITCU_EPI_PATCH_EMBED, 0));
     }
+    MARK(VIT_K_OTHER);
     VIT_TRY(vitcu_cls_rows_ex(e->d_x, e->w32[0], e->w32[3], b, e->T, e->D, s));
     e->launches++;
 
@@ -453,13 +475,16 @@ static int enqueue_forward(vitb200_engine *e, int buf, int b)
     for (int l = 0; l < layers; l++) {
         const int w = 4 + 12 * l; /* blob base of the layer (R/ViT_seq.c:446-504) */
         /* x -> LN1 -> QKV -> attention -> out-proj (+x)  (R/ViT_opencl.c:710-730) */
+        MARK(VIT_K_LAYERNORM);
         VIT_TRY(vitcu_layernorm_ex(e->d_x, e->D, e->d_ln, ln_mode, e->w32[w + 0], e->w32[w + 1], M, e->D, s));
         e->launches++;
         VIT_TRY(gemm(e, e->d_ln, 1, w + 2, w + 3, e->d_qkv, M, 3 * e->D, e->D, VITCU_EPI_BIAS, bf));
+        MARK(VIT_K_ATTENTION);
         VIT_TRY(vitcu_attention_ex(e->d_qkv, e->d_att, b, e->T, e->heads, bf, s));
         e->launches++;
         VIT_TRY(gemm(e, e->d_att, 0, w + 4, w + 5, e->d_x, M, e->D, e->D, VITCU_EPI_BIAS_RESIDUAL, 0));
         /* -> LN2 -> fc1+GELU -> fc2 (+r1)  (R/ViT_opencl.c:732-746) */
+        MARK(VIT_K_LAYERNORM);
         VIT_TRY(vitcu_layernorm_ex(e->d_x, e->D, e->d_ln, ln_mode, e->w32[w + 6], e->w32[w + 7], M, e->D, s));
         e->launches++;
         VIT_TRY(gemm(e, e->d_ln, 1, w + 8, w + 9, e->d_hid, M, e->HID, e->D, VITCU_EPI_BIAS_GELU, bf));
@@ -470,6 +495,7 @@ static int enqueue_forward(vitb200_engine *e, int buf, int b)
 
     /* final LN on the class-token rows only, head, softmax
      * (R/ViT_opencl.c:951-959; R/ViT_seq.c:506-515 normalises all rows but uses row 0) */
+    MARK(VIT_K_OTHER); /* final LN + head + softmax: one 'other' span */
     VIT_TRY(vitcu_layernorm_ex(e->d_x, (size_t)e->T * e->D, e->d_cls, 0, e->w32[e->nblobs - 4], e->w32[e->nblobs - 3], b, e->D, s));
     e->launches++;
     vitcu_gemm_desc d;
@@ -740,6 +766,98 @@ int vitb200_time_resident(vitb200_engine *e, int n, int iters, float *total_ms)
     VIT_TRY(vitcu_stream_sync(e->stream));
     VIT_TRY(vitcu_event_elapsed_ms(e->ev_t0, e->ev_t1, total_ms));
     VIT_TRY(vitcu_watchdog_check());
+    return 0;
+}
+
+int vitb200_profile_gemms(vitb200_engine *e, int n, int iters, float *gemm_ms_per_forward, int *gemm_launches)
+{
+    VIT_TRY_RC(check_ready(e));
+    if (n <= 0 || n > e->B || iters <= 0 || !gemm_ms_per_forward)
+        return vit_fail(__FILE__, __LINE__, VITCU_E_ARG, "profile_gemms: bad argument");
+    const int cap = 4 * e->depth + 1; /* qkv, out_proj, fc1, fc2 per layer (+ the gather-path patch embedding) */
+    vitcu_event *ev = (vitcu_event *)calloc((size_t)2 * cap, sizeof(vitcu_event));
+    if (!ev)
+        return vit_fail(__FILE__, __LINE__, VITCU_E_ARG, "out of host memory");
+    int rc = 0;
+    for (int i = 0; i < 2 * cap && !rc; i++)
+        rc = vitcu_event_create(&ev[i]);
+    double total = 0.0;
+    int launches = 0;
+    for (int it = 0; it < iters && !rc; it++) {
+        e->prof_ev = ev;
+        e->prof_cap = cap;
+        e->prof_n = 0;
+        rc = enqueue_forward(e, 0, n); /* eager: events cannot sit inside the captured graph */
+        e->prof_ev = NULL;
+        if (!rc)
+            rc = vitcu_stream_sync(e->stream);
+        launches = e->prof_n;
+        for (int k = 0; k < launches && !rc; k++) {
+            float ms = 0.f;
+            rc = vitcu_event_elapsed_ms(ev[2 * k], ev[2 * k + 1], &ms);
+            total += ms;
+        }
+    }
+    for (int i = 0; i < 2 * cap; i++)
+        if (ev[i])
+            vitcu_event_destroy(ev[i]);
+    free(ev);
+    if (rc)
+        return vit_fail(__FILE__, __LINE__, rc, NULL);
+    *gemm_ms_per_forward = (float)(total / iters);
+    if (gemm_launches)
+        *gemm_launches = launches;
+    VIT_TRY(vitcu_watchdog_check());
+    return 0;
+}
+
+int vitb200_profile_timeline(vitb200_engine *e, int n, float ms_by_kind[4], int launches_by_kind[4])
+{
+    VIT_TRY_RC(check_ready(e));
+    if (n <= 0 || n > e->B || !ms_by_kind)
+        return vit_fail(__FILE__, __LINE__, VITCU_E_ARG, "profile_timeline: bad argument");
+    const int cap = 16 * e->depth + 16;
+    vitcu_event *ev = (vitcu_event *)calloc((size_t)cap, sizeof(vitcu_event));
+    unsigned char *kind = (unsigned char *)calloc((size_t)cap, 1);
+    if (!ev || !kind) {
+        free(ev);
+        free(kind);
+        return vit_fail(__FILE__, __LINE__, VITCU_E_ARG, "out of host memory");
+    }
+    int rc = 0;
+    for (int i = 0; i < cap && !rc; i++)
+        rc = vitcu_event_create(&ev[i]);
+    e->mark_ev = ev;
+    e->mark_kind = kind;
+    e->mark_cap = cap - 1;
+    e->mark_n = 0;
+    if (!rc)
+        rc = enqueue_forward(e, 0, n);
+    const int marks = e->mark_n;
+    if (!rc)
+        rc = vitcu_event_record(ev[marks], e->stream); /* end of the last span */
+    e->mark_ev = NULL;
+    if (!rc)
+        rc = vitcu_stream_sync(e->stream);
+    for (int k = 0; k < 4; k++) {
+        ms_by_kind[k] = 0.f;
+        if (launches_by_kind)
+            launches_by_kind[k] = 0;
+    }
+    for (int k = 0; k < marks && !rc; k++) {
+        float ms = 0.f;
+        rc = vitcu_event_elapsed_ms(ev[k], ev[k + 1], &ms);
+        ms_by_kind[kind[k] & 3] += ms;
+        if (launches_by_kind)
+            launches_by_kind[kind[k] & 3]++;
+    }
+    for (int i = 0; i < cap; i++)
+        if (ev[i])
+            vitcu_event_destroy(ev[i]);
+    free(ev);
+    free(kind);
+    if (rc)
+        return vit_fail(__FILE__, __LINE__, rc, NULL);
     return 0;
 }
 

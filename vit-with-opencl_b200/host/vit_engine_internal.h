@@ -33,6 +33,13 @@ struct vitb200_engine {
     float *h_probs, *h_logits;       /* pinned staging [2][B,1000] */
     int *d_topi, *h_topi;            /* [2][B,VITB200_TOPK_MAX] labels of vitb200_forward_topk (allocated on first use) */
     float *d_topv, *h_topv;
+    /* in-situ GEMM timing (vitb200_profile_gemms): one event pair per GEMM launch of an eager forward */
+    vitcu_event *prof_ev;            /* [2 * prof_cap], NULL when not profiling */
+    int prof_cap, prof_n;
+    /* whole-timeline variant (vitb200_profile_timeline): one event before every launch, tagged by kind */
+    vitcu_event *mark_ev;
+    unsigned char *mark_kind;
+    int mark_cap, mark_n;
     /* pageable sources: worker threads gather images into a ring of pinned slots (vit_stage.c) */
     struct vit_stager *stager;
     char *h_stage;                   /* [VIT_STAGE_SLOTS][stage_group images] pinned */
@@ -40,6 +47,7 @@ struct vitb200_engine {
     vitcu_event ev_slot[4];
 };
 
+enum { VIT_K_GEMM = 0, VIT_K_ATTENTION = 1, VIT_K_LAYERNORM = 2, VIT_K_OTHER = 3 };
 #define VIT_STAGE_SLOTS 3
 typedef struct vit_stager vit_stager;
 int vit_stager_threads_default(void);
