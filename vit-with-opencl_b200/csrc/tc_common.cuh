@@ -506,8 +506,9 @@ __device__ __forceinline__ float gelu_erf_tanh1(float x)
 }
 
 // packed form of gelu_erf_tanh1: per PAIR 5 packed FMA-pipe instructions + 2 FMNMX + 2 MUFU.TANH.
-// Measured (tools/fc1_ab.py): fc1 0.195 ms instead of 0.200-0.204 ms (GELU / bias-only time ratio 1.09 instead of
-// 1.16): the fc1 epilogue is bound by issue slots, and this form needs 9 per pair instead of 17.  The BF16
+// Measured on one box, builds alternating (tools/gemm_bench.py): fc1 191.7 us with this form and 8 epilogue warps,
+// 195.4 us with the rational form and 16 (the best configuration of each): the fc1 epilogue is bound by issue
+// slots, and this form needs 9 per pair instead of 17.  The BF16
 // forward's logit error does not change (tools/bf16_error_stats.py, 16 images: RMS 3.49e-3 rational, 3.52e-3 this
 // form, 3.45e-3 sigmoid form; the per-image maxima scatter between 1.05e-2 and 1.7e-2 for all three -- bf16
 // rounding of the activations dominates), so this is the default.
