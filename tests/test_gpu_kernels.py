@@ -6,6 +6,9 @@ summation order differs); BF16 tensor-core kernels are compared (a) tightly
 against an exact float64 product of the SAME bf16-rounded operands, which
 isolates kernel bugs from rounding, and (b) loosely against the fp32 oracle."""
 import ctypes as C
+import os
+import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -200,6 +203,27 @@ def test_attention_tensor_core(pkg, lib, oracle, T, batch):
         tol = 3 * 2.0 ** -8 * np.abs(ref).max() + 1e-3  # P and O are rounded to bf16
         err = np.abs(out[i] - ref)
         assert err.max() <= tol, f"image {i}: max err {err.max()} at {np.unravel_index(err.argmax(), err.shape)} tol {tol}"
+
+
+@pytest.mark.parametrize("scale", [0.05, 0.4, 3.0, 12.0])
+def test_attention_tensor_core_score_ranges(pkg, lib, oracle, scale):
+    """score magnitudes from nearly uniform attention (scale 0.05) to one-hot rows (scale 12: |s|/8 up to
+    ~1000, exp2 arguments down to -180): the max subtraction keeps every row finite and within tolerance"""
+    T, batch = 197, 3
+    rng = np.random.default_rng(77)
+    bits = pkg.f32_to_bf16_bits((rng.standard_normal((batch, T, 2304), dtype=np.float32) * scale).astype(np.float32))
+    qkv = pkg.bf16_bits_to_f32(bits).reshape(batch, T, 2304)
+    dq = _dev(pkg, bits)
+    do = pkg.DeviceBuffer(batch * T * 768 * 2)
+    pkg.layer_check(lib.vitcu_memset(do.ptr, 0xFF, batch * T * 768 * 2, None))
+    pkg.layer_check(lib.vitcu_attention(dq.ptr, do.ptr, batch, T, 1, None))
+    assert lib.vitcu_watchdog_check() == 0
+    out = pkg.bf16_bits_to_f32(do.to_numpy(np.uint16, (batch, T, 768)))
+    assert np.isfinite(out).all()
+    for i in range(batch):
+        ref = oracle.attention_core(qkv[i, :, :768], qkv[i, :, 768:1536], qkv[i, :, 1536:])
+        tol = 3 * 2.0 ** -8 * np.abs(ref).max() + 1e-3
+        assert np.abs(out[i] - ref).max() <= tol
 
 
 @pytest.mark.parametrize("T,batch", [(577, 2), (300, 1), (257, 1), (640, 1), (1025, 1), (577, 20)])

@@ -61,10 +61,33 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
     return ok != 0;
 }
 
+// The same with a suspend-time hint: the thread is parked by the hardware until the phase completes or the hint
+// (ns) runs out, instead of coming back to the issue port every few cycles.  Warps that wait most of the time
+// (TMA producer, MMA issuer, statistics warps) otherwise take issue slots from the arithmetic warps of their
+// sub-partition.  -DVITCU_MBAR_SUSPEND_NS=0 restores the plain polling loop.
+#ifndef VITCU_MBAR_SUSPEND_NS
+#define VITCU_MBAR_SUSPEND_NS 1000
+#endif
+__device__ __forceinline__ bool mbar_try_wait_suspend(uint64_t *bar, uint32_t parity)
+{
+#if VITCU_MBAR_SUSPEND_NS > 0
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, P;\n\t}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)VITCU_MBAR_SUSPEND_NS)
+                 : "memory");
+    return ok != 0;
+#else
+    return mbar_try_wait(bar, parity);
+#endif
+}
+
 // Watchdog-guarded wait.  A pipeline bug must never hang the GPU: after
 // kWatchdogNs without progress the waiter raises the CTA-wide abort flag and a
 // device-global diagnostic word, and every role falls through to teardown.
 constexpr uint64_t kWatchdogNs = 2000000000ull;
+// the clock is read every 1024 polls of the plain loop, every 16 of the suspending one (each up to 1 us long)
+constexpr uint32_t kWatchdogPollMask = VITCU_MBAR_SUSPEND_NS > 0 ? 15u : 1023u;
 struct Watchdog {
     volatile uint32_t *cta_abort; // shared memory
     uint32_t *global_flag;        // device memory (vitcu_watchdog_check)
@@ -75,8 +98,8 @@ __device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, const 
         return true;
     uint32_t spins = 0;
     uint64_t t0 = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if ((++spins & 1023u) == 0) {
+    while (!mbar_try_wait_suspend(bar, parity)) {
+        if ((++spins & kWatchdogPollMask) == 0) {
             if (*wd.cta_abort)
                 return false;
             const uint64_t now = globaltimer_ns();
