@@ -179,7 +179,9 @@ int vitcu_gemm_bf16x3(const vitcu_bf16 *A3, const vitcu_bf16 *W3, void *C, const
  * qkv/out: fp32 (is_bf16 = 0) or bf16 (is_bf16 = 1; softmax stays fp32). */
 int vitcu_attention(const void *qkv, void *out, int batch, int tokens, int is_bf16,
                     vitcu_stream s);
-/* same with `heads` heads of 64 (num_heads, R/ViT_seq.c:16): qkv [B*T, 3*heads*64], out [B*T, heads*64] */
+/* same with `heads` heads of 64 (num_heads, R/ViT_seq.c:16): qkv [B*T, 3*heads*64], out [B*T, heads*64].
+ * is_bf16 = 2: fp32 qkv, fp32 math, output as three bf16 pieces [B*T, 3*heads*64] (the A operand of
+ * vitcu_gemm_bf16x3, see vitcu_split3) */
 int vitcu_attention_ex(const void *qkv, void *out, int batch, int tokens, int heads, int is_bf16,
                        vitcu_stream s);
 

@@ -184,6 +184,23 @@ def test_attention_simt(pkg, lib, oracle, T, batch, bf16):
         assert np.abs(out[i] - ref).max() <= tol
 
 
+@pytest.mark.parametrize("T,batch", [(197, 1), (197, 5), (50, 2)])
+def test_attention_simt_split_output(pkg, lib, oracle, T, batch):
+    """mode 2: fp32 math, output as three bf16 pieces [rows, 3*768] whose sum is the fp32 result to 24 bits"""
+    rng = np.random.default_rng(T * 7 + batch)
+    qkv = (rng.standard_normal((batch, T, 2304), dtype=np.float32) * 1.5).astype(np.float32)
+    dq = _dev(pkg, qkv)
+    d32 = pkg.DeviceBuffer(batch * T * 768 * 4)
+    d3 = pkg.DeviceBuffer(batch * T * 768 * 6)
+    pkg.layer_check(lib.vitcu_attention(dq.ptr, d32.ptr, batch, T, 0, None))
+    pkg.layer_check(lib.vitcu_attention(dq.ptr, d3.ptr, batch, T, 2, None))
+    want = d32.to_numpy(np.float32, (batch * T, 768))
+    pieces = pkg.bf16_bits_to_f32(d3.to_numpy(np.uint16, (batch * T, 3, 768)))
+    got = pieces[:, 0].astype(np.float64) + pieces[:, 1] + pieces[:, 2]
+    assert np.abs(got - want).max() <= 2.0 ** -22 * np.abs(want).max()
+    assert np.array_equal(pieces[:, 0], pkg.bf16_bits_to_f32(pkg.f32_to_bf16_bits(want)))  # first piece = bf16(x)
+
+
 @pytest.mark.parametrize("T,batch", [(197, 3), (50, 2), (128, 1), (129, 1), (256, 2), (16, 1), (197, 40)])
 def test_attention_tensor_core(pkg, lib, oracle, T, batch):
     """tcgen05 attention (bf16 storage, tokens <= 256): one and two query tiles, ragged key counts,

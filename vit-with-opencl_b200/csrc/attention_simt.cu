@@ -52,8 +52,10 @@ struct Elem<__nv_bfloat16> {
     }
 };
 
-template <typename T, int QT>
-__global__ void __launch_bounds__(256) attention_simt_kernel(const T *__restrict__ qkv, T *__restrict__ out, int tokens, int embed)
+// kSplit: write the output as three bf16 pieces [rows, 3*embed] (the A operand form of the FP32 tensor-core GEMM,
+// vitcu_gemm_bf16x3) instead of T -- saves the separate split kernel in front of the output projection
+template <typename T, int QT, bool kSplit = false>
+__global__ void __launch_bounds__(256) attention_simt_kernel(const T *__restrict__ qkv, void *__restrict__ out_, int tokens, int embed)
 {
     constexpr int KB = kKeysPerBlock(QT);
     constexpr int LDQ = QT + 4;       // padded row of the [d][q] / [key][q] tiles
@@ -205,9 +207,14 @@ __global__ void __launch_bounds__(256) attention_simt_kernel(const T *__restrict
 #pragma unroll
     for (int i = 0; i < OQ; i++) {
         const int q = q0 + py * OQ + i;
-        if (q < tokens)
-            Elem<T>::store4(out + ((size_t)img * tokens + q) * embed + head * kHeadDim + px * 4,
-                            make_float4(o[i][0], o[i][1], o[i][2], o[i][3]));
+        if (q < tokens) {
+            const float4 v = make_float4(o[i][0], o[i][1], o[i][2], o[i][3]);
+            if (kSplit)
+                split3_store4(reinterpret_cast<__nv_bfloat16 *>(out_) + ((size_t)img * tokens + q) * 3 * embed, embed,
+                              head * kHeadDim + px * 4, v);
+            else
+                Elem<T>::store4(reinterpret_cast<T *>(out_) + ((size_t)img * tokens + q) * embed + head * kHeadDim + px * 4, v);
+        }
     }
 }
 
@@ -220,15 +227,15 @@ size_t attention_simt_smem(int tokens)
     return sizeof(float) * ((size_t)kHeadDim * LDQ + KVF + (size_t)nkb * KB * LDQ + 256);
 }
 
-template <typename T, int QT>
+template <typename T, int QT, bool kSplit = false>
 int launch_attention_simt(const void *qkv, void *out, int batch, int tokens, int heads, cudaStream_t st)
 {
     const size_t smem = attention_simt_smem<QT>(tokens);
     VITCU_REQUIRE(smem <= 227 * 1024, "token count too large for the shared-memory score tile");
-    auto k = attention_simt_kernel<T, QT>;
+    auto k = attention_simt_kernel<T, QT, kSplit>;
     VITCU_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((tokens + QT - 1) / QT, heads, batch);
-    VITCU_TRY(launch_kernel(k, grid, 256, smem, st, reinterpret_cast<const T *>(qkv), reinterpret_cast<T *>(out), tokens,
+    VITCU_TRY(launch_kernel(k, grid, 256, smem, st, reinterpret_cast<const T *>(qkv), out, tokens,
                             heads * kHeadDim));
     return 0;
 }
@@ -249,7 +256,7 @@ extern "C" int vitcu_attention_ex(const void *qkv, void *out, int batch, int tok
     // VITCU_ATTN_FLASH=1 the key-blocked kernel, for A/B measurements.)
     static const bool force_simt = getenv("VITCU_ATTN_SIMT") != nullptr;
     static const bool force_flash = getenv("VITCU_ATTN_FLASH") != nullptr;
-    if (is_bf16 && !force_simt) {
+    if (is_bf16 == 1 && !force_simt) {
         if (tokens <= 224 && !force_flash)
             return attention_bf16_tc(qkv, out, batch, tokens, heads, as_stream(s));
         return attention_bf16_flash_tc(qkv, out, batch, tokens, heads, as_stream(s));
@@ -257,7 +264,10 @@ extern "C" int vitcu_attention_ex(const void *qkv, void *out, int batch, int tok
     // 16-query tiles when 64-query tiles would leave most of the 148 SMs idle (small batches)
     const bool small = (long)batch * heads * ((tokens + 63) / 64) < 148 && attention_simt_smem<16>(tokens) <= 227 * 1024;
     int rc;
-    if (is_bf16)
+    if (is_bf16 == 2)
+        rc = small ? launch_attention_simt<float, 16, true>(qkv, out, batch, tokens, heads, as_stream(s))
+                   : launch_attention_simt<float, 64, true>(qkv, out, batch, tokens, heads, as_stream(s));
+    else if (is_bf16)
         rc = small ? launch_attention_simt<__nv_bfloat16, 16>(qkv, out, batch, tokens, heads, as_stream(s))
                    : launch_attention_simt<__nv_bfloat16, 64>(qkv, out, batch, tokens, heads, as_stream(s));
     else

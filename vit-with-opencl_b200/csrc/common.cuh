@@ -101,4 +101,25 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi)
     return *reinterpret_cast<uint32_t *>(&v);
 }
 
+// fp32 -> three bf16 pieces, x = p1 + p2 + p3 to 24 mantissa bits (see elementwise.cu: split3_kernel); a row of the
+// split form is [p1 | p2 | p3], each K wide
+__device__ __forceinline__ void split3(float x, __nv_bfloat16 &p1, __nv_bfloat16 &p2, __nv_bfloat16 &p3)
+{
+    p1 = __float2bfloat16_rn(x);
+    const float r1 = x - __bfloat162float(p1);
+    p2 = __float2bfloat16_rn(r1);
+    p3 = __float2bfloat16_rn(r1 - __bfloat162float(p2));
+}
+__device__ __forceinline__ void split3_store4(__nv_bfloat16 *row, int K, int col, float4 v)
+{
+    __nv_bfloat16 a[4], b[4], c[4];
+    split3(v.x, a[0], b[0], c[0]);
+    split3(v.y, a[1], b[1], c[1]);
+    split3(v.z, a[2], b[2], c[2]);
+    split3(v.w, a[3], b[3], c[3]);
+    *reinterpret_cast<uint2 *>(row + col) = *reinterpret_cast<const uint2 *>(a);
+    *reinterpret_cast<uint2 *>(row + K + col) = *reinterpret_cast<const uint2 *>(b);
+    *reinterpret_cast<uint2 *>(row + 2 * K + col) = *reinterpret_cast<const uint2 *>(c);
+}
+
 } // namespace vitcu

@@ -242,7 +242,7 @@ int vitb200_create_model(vitb200_engine **out, int device, const vitb200_model *
     if (e->fp32_tc)
         ENG_TRY(vitcu_malloc((void **)&e->d_a3, rows * (size_t)(e->HID > 3 * e->patch * e->patch ? e->HID : 3 * e->patch * e->patch) * 3 * sizeof(vitcu_bf16)));
     ENG_TRY(vitcu_malloc(&e->d_qkv, rows * 3 * e->D * act));
-    ENG_TRY(vitcu_malloc(&e->d_att, rows * e->D * act));
+    ENG_TRY(vitcu_malloc(&e->d_att, rows * e->D * (e->fp32_tc ? 6 : act)));
     ENG_TRY(vitcu_malloc(&e->d_hid, rows * e->HID * act));
     ENG_TRY(vitcu_malloc((void **)&e->d_cls, (size_t)e->B * e->D * sizeof(float)));
     ENG_TRY(vitcu_host_alloc((void **)&e->h_probs, (size_t)e->B * VITB200_CLASSES * sizeof(float) * 2));
@@ -480,9 +480,10 @@ static int enqueue_forward(vitb200_engine *e, int buf, int b)
         e->launches++;
         VIT_TRY(gemm(e, e->d_ln, 1, w + 2, w + 3, e->d_qkv, M, 3 * e->D, e->D, VITCU_EPI_BIAS, bf));
         MARK(VIT_K_ATTENTION);
-        VIT_TRY(vitcu_attention_ex(e->d_qkv, e->d_att, b, e->T, e->heads, bf, s));
+        /* FP32 tensor-core path: the attention kernel writes its output already split into three bf16 pieces */
+        VIT_TRY(vitcu_attention_ex(e->d_qkv, e->d_att, b, e->T, e->heads, e->fp32_tc ? 2 : bf, s));
         e->launches++;
-        VIT_TRY(gemm(e, e->d_att, 0, w + 4, w + 5, e->d_x, M, e->D, e->D, VITCU_EPI_BIAS_RESIDUAL, 0));
+        VIT_TRY(gemm(e, e->d_att, e->fp32_tc, w + 4, w + 5, e->d_x, M, e->D, e->D, VITCU_EPI_BIAS_RESIDUAL, 0));
         /* -> LN2 -> fc1+GELU -> fc2 (+r1)  (R/ViT_opencl.c:732-746) */
         MARK(VIT_K_LAYERNORM);
         VIT_TRY(vitcu_layernorm_ex(e->d_x, e->D, e->d_ln, ln_mode, e->w32[w + 6], e->w32[w + 7], M, e->D, s));
