@@ -1,5 +1,5 @@
 // csrc/attention_tc.cu -- fused multi-head attention on the 5th-gen tensor cores
-// (BF16 operands, FP32 accumulation and softmax), for token counts <= 256.
+// (BF16 operands, FP32 accumulation and softmax), for token counts <= 224.
 //
 // Replaces QKV_TO_SCOREV (R/multihead.cl:65-137); oracle R/ViT_seq.c:192-262.
 // R/ = /root/reference/MulticoreMainProject/.  S = Q K^T, the row softmax and
@@ -18,13 +18,15 @@
 //   warp 2       TMEM allocation: S buffers at columns 0 and 224, O at 448
 //   warps 4-7    exponentials of the LEFT half of the key columns of every unit (thread = query row)
 //   warps 8-11   exponentials of the RIGHT half; row sums left in shared memory for the epilogue
-//   warps 12-15  statistics + epilogue: row maxima of S(k+1) while warps 4-11 work on unit k, then
-//                O(k-1) / row sum -> bf16 -> swizzled smem tile -> TMA store
+//   warps 12-15  statistics + epilogue: read O(k-2) and free the accumulator, row maxima of S(k) while
+//                warps 4-11 are still on unit k-1, then O(k-2) / row sum -> bf16 -> swizzled smem
+//                tile -> TMA store
 // P (bf16 pairs) is written back into TMEM over each half's own score columns (tcgen05.st).  Two
 // warp groups on one tile halve the per-unit exp latency; the fourth warp group takes the max pass,
-// the exchange of the half-row maxima and the ~900-cycle O read-out off their chain, so the period of
-// a unit is the MUFU-bound exp pass plus ~300 cycles instead of twice that
-// (profiles/r01_v6_attention.md).
+// the exchange of the half-row maxima and the ~900-cycle O read-out off their chain.  Measured on one
+// box this layout is exactly as fast as the three-warp-group version it replaced (the warps of a
+// sub-partition stretch each other's phases); it is kept because the roles are cleaner, not because
+// it is faster (profiles/r01_v6_attention.md has the A/B and two further experiments).
 // Registers: the kernel starts with 128 per thread (512 threads); setmaxnreg moves them to where
 // the score rows live: warps 0-3 keep 40, the exp warp groups 168 each, the statistics warps 136
 // (40 + 136 + 2 x 168 = 4 x 128).
