@@ -490,6 +490,8 @@ def run_engine_arm(args, dist: Dist):
             T = (IMG // 16) ** 2 + 1
             gemm_flops_fwd = 12 * 2.0 * BATCH * T * 768 * (2304 + 768 + 3072 + 3072)
             insitu_ms, insitu_launches = eng.profile_gemms(BATCH, 5)
+            tl = eng.profile_timeline(BATCH, 3)             # spans between launches of an eager forward, by kind
+            line["forward_breakdown_ms"] = {k: {"ms": round(v[0], 4), "launches": v[1]} for k, v in tl.items()}
             per, flops, ms = time_gemms(pkg, L, BATCH * T)   # the four launches of a layer timed alone
             achieved = gemm_flops_fwd / insitu_ms / 1e9
             traffic = None

@@ -14,7 +14,6 @@ batch = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 prec = pkg.FP32 if (len(sys.argv) > 2 and sys.argv[2] == "fp32") else pkg.BF16
 blobs = pkg.synth.model_blobs(None, 224, seed=7)
 x = pkg.synth.synthetic_images(batch, 224, seed=1)
-L.vitb200_profile_timeline.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int)]
 with pkg.Engine(0, 224, prec, max_batch=batch) as e:
     e.load_weights(blobs)
     e.stage(x)

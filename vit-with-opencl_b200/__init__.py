@@ -87,6 +87,7 @@ def lib() -> C.CDLL:
         L.vitb200_forward_resident.argtypes = [C.c_void_p, C.c_int]
         L.vitb200_read_probs.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.vitb200_last_forward_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+        L.vitb200_profile_timeline.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int)]
         L.vitb200_profile_gemms.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int)]
         L.vitb200_time_resident.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]
         L.vitb200_set_stop_after_layer.argtypes = [C.c_void_p, C.c_int]
@@ -285,6 +286,16 @@ class Engine:
         ms, k = C.c_float(), C.c_int()
         _check(lib().vitb200_profile_gemms(self.h, n, iters, C.byref(ms), C.byref(k)))
         return ms.value, k.value
+
+    def profile_timeline(self, n: int, iters: int = 3):
+        """in-situ spans (kernel + gap to the next launch) of one eager forward, averaged over `iters`:
+        {kind: (ms per forward, launches)} for gemm / attention / layernorm / other"""
+        ms, cnt = (C.c_float * 4)(), (C.c_int * 4)()
+        acc = [0.0] * 4
+        for _ in range(iters):
+            _check(lib().vitb200_profile_timeline(self.h, n, ms, cnt))
+            acc = [a + m for a, m in zip(acc, ms)]
+        return {k: (acc[i] / iters, cnt[i]) for i, k in enumerate(("gemm", "attention", "layernorm", "other"))}
 
     def time_resident(self, n: int, iters: int) -> float:
         ms = C.c_float()
