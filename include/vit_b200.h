@@ -66,6 +66,18 @@ typedef struct vitb200_engine vitb200_engine;
 /* the reference's entry point (R/ViT_opencl.h:6) */
 void ViT_opencl(vitb200_image *image, vitb200_blob *networks, float **prb);
 
+/* The image split ViT_opencl uses over several GPUs: contiguous shards first[g] .. first[g] + count[g]
+ * of the n images (arrays of at least `gpus` entries); returns the number of shards (<= gpus). */
+int vitb200_shard_plan(int n, int gpus, int *first, int *count);
+
+/* what the last ViT_opencl call of this process spent where: wall time of the whole call and, per
+ * phase, the slowest shard's time (the shards run concurrently, one host thread per GPU) */
+typedef struct {
+    int images, gpus;
+    double wall_s, create_s, weights_s, forward_s;
+} vitb200_call_stats;
+void vitb200_last_call_stats(vitb200_call_stats *out);
+
 /* frees the engines VITB200_PERSIST=1 kept alive (no-op otherwise) */
 void vitb200_release_persistent(void);
 
@@ -151,6 +163,8 @@ int vitb200_host_free(void *ptr);
 /* kernels launched per forward chunk of the current configuration */
 int vitb200_kernels_per_forward(const vitb200_engine *e);
 int vitb200_tokens(const vitb200_engine *e);
+/* embedding width of the engine's model (row length of vitb200_read_tokens) */
+int vitb200_embed(const vitb200_engine *e);
 
 #ifdef __cplusplus
 }

@@ -142,3 +142,25 @@ def test_model_from_blobs_reads_dims_off_sizes(pkg):
     m = pkg.Model()
     assert L.vitb200_model_from_blobs(nets, None, C.byref(m)) == 0
     assert (m.patch, m.embed, m.hidden) == (16, 768, 3072)
+
+
+def test_shard_plan_covers_every_image_once():
+    """host logic of the multi-GPU split (vit_opencl.c): contiguous, disjoint, complete"""
+    import __graft_entry__ as g
+    pkg = g.load_package()
+    L = pkg.lib()
+    L.vitb200_shard_plan.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    for n in (1, 2, 7, 100, 256, 600, 4096, 4097):
+        for gpus in (1, 2, 3, 4, 8, 64):
+            first, count = (C.c_int * 64)(), (C.c_int * 64)()
+            used = L.vitb200_shard_plan(n, gpus, first, count)
+            assert 1 <= used <= min(gpus, n)
+            nxt = 0
+            for k in range(used):
+                assert first[k] == nxt and count[k] > 0
+                nxt += count[k]
+            assert nxt == n
+            assert max(count[:used]) - min(count[:used]) <= max(count[:used])  # last shard may be short
+            assert max(count[:used]) == -(-n // min(gpus, n))
+    assert L.vitb200_shard_plan(0, 4, (C.c_int * 4)(), (C.c_int * 4)()) == 0
+    assert L.vitb200_shard_plan(4096, 8, (C.c_int * 8)(), (C.c_int * 8)()) == 8

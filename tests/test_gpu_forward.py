@@ -123,8 +123,51 @@ def test_vit_opencl_persistent_context(pkg, lib, blobs224, case224, monkeypatch)
         assert np.abs(d - once).max() > 1e-6
         e = pkg.vit_opencl(imgs[:3], blobs224)
         np.testing.assert_allclose(e, once, rtol=1e-5, atol=1e-9)
+        # one element in the middle of a 2.36 M-element matrix (a sampled signature would miss it)
+        k = blobs224[12].size // 2 + 12345
+        keep = blobs224[12][k]
+        blobs224[12][k] = keep + np.float32(8.0)
+        try:
+            f = pkg.vit_opencl(imgs[:3], blobs224)
+        finally:
+            blobs224[12][k] = keep
+        assert np.abs(f - once).max() > 1e-7
+        g = pkg.vit_opencl(imgs[:3], blobs224)
+        np.testing.assert_allclose(g, once, rtol=1e-5, atol=1e-9)
     finally:
         lib.vitb200_release_persistent()
+
+
+def test_reload_weights_drops_captured_graphs(pkg, lib, blobs224):
+    """a second vitb200_load_weights on an engine whose forward is already captured in CUDA graphs:
+    the graphs hold the old arena's addresses, so they must be dropped with it.  The new arena is built
+    beside the old one (a failed reload keeps the old weights), so its address always differs."""
+    imgs = pkg.synth.synthetic_images(32, 224, seed=21)
+    other = [w.copy() for w in blobs224]
+    other[6] = (other[6] * np.float32(0.5)).astype(np.float32)   # layer-0 in_proj weight: changes every logit
+    other[151] = other[151][::-1].copy()
+    with pkg.Engine(0, 224, pkg.BF16, max_batch=32) as fresh:   # M = 6304: no split-K, deterministic sums
+        fresh.load_weights(other)
+        want = fresh.forward(imgs, want_logits=True)[1]
+    with pkg.Engine(0, 224, pkg.BF16, max_batch=32) as eng:
+        eng.load_weights(blobs224)
+        first = eng.forward(imgs, want_logits=True)[1]         # eager
+        eng.forward(imgs)                                       # captured
+        eng.forward(imgs)                                       # replayed
+        eng.load_weights(other)
+        got = [eng.forward(imgs, want_logits=True)[1] for _ in range(3)]  # eager, capture, replay
+        bad = list(other)
+        bad[3] = bad[3][:-768]
+        with pytest.raises(pkg.VitError, match="blob 3"):
+            eng.load_weights(bad)                               # rejected: the engine keeps serving `other`
+        still = eng.forward(imgs, want_logits=True)[1]
+        eng.load_weights(blobs224)
+        back = eng.forward(imgs, want_logits=True)[1]
+        assert lib.vitcu_watchdog_check() == 0
+    for g in got + [still]:
+        assert np.array_equal(g, want)
+    assert np.abs(want - first).max() > 1e-3
+    assert np.array_equal(back, first)
 
 
 def test_forward_structs_equals_contiguous(pkg, lib, blobs224, case224):
@@ -371,3 +414,41 @@ def test_main_c_drop_in(pkg, lib, oracle, blobs224, ref_dir, tmp_path):
     out = subprocess.run([str(exe)], cwd=tmp_path, env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "good" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_vit_opencl_multi_gpu_split(pkg, lib, blobs224, monkeypatch):
+    """the product's own multi-GPU path (vit_opencl.c: one host thread per GPU, contiguous shards,
+    replicated weights, host-side gather into the caller's rows; reference loop R/ViT_opencl.c:926-965):
+    one ViT_opencl call over G GPUs must return the rows a 1-GPU call returns -- bit for bit when the
+    shards are whole chunks (same position in a full chunk -> same kernels, same tiles), to rounding and
+    with the same labels for a ragged split -- cold and with the persistent context."""
+    ndev = pkg.device_count()
+    if ndev < 2:
+        pytest.skip("needs at least 2 GPUs (run with gpurun --gpus 2)")
+    gpus = min(ndev, 4)
+    monkeypatch.setenv("VITB200_PRECISION", "bf16")
+    monkeypatch.setenv("VITB200_BATCH", "64")
+    base = pkg.synth.synthetic_images(96, 224, seed=11)
+    n = 64 * 2 * gpus
+    imgs = np.ascontiguousarray(base[np.arange(n) % 96])
+    monkeypatch.setenv("VITB200_GPUS", "1")
+    one = pkg.vit_opencl(imgs, blobs224)
+    stats = pkg.CallStats()
+    lib.vitb200_last_call_stats(C.byref(stats))
+    assert (stats.images, stats.gpus) == (n, 1)
+    monkeypatch.setenv("VITB200_GPUS", str(gpus))
+    cold = pkg.vit_opencl(imgs, blobs224)
+    lib.vitb200_last_call_stats(C.byref(stats))
+    assert (stats.images, stats.gpus) == (n, gpus)
+    assert np.array_equal(cold, one)
+    monkeypatch.setenv("VITB200_PERSIST", "1")
+    try:
+        warm1 = pkg.vit_opencl(imgs, blobs224)
+        warm2 = pkg.vit_opencl(imgs, blobs224)
+        ragged = pkg.vit_opencl(imgs[:n - 37], blobs224)
+    finally:
+        lib.vitb200_release_persistent()
+    assert np.array_equal(warm1, one) and np.array_equal(warm2, one)
+    assert np.array_equal(ragged.argmax(1), one[:n - 37].argmax(1))
+    np.testing.assert_allclose(ragged, one[:n - 37], rtol=3e-2, atol=1e-7)
+    assert lib.vitcu_watchdog_check() == 0

@@ -96,9 +96,12 @@ def lib() -> C.CDLL:
         L.vitb200_host_free.argtypes = [C.c_void_p]
         L.vitb200_kernels_per_forward.argtypes = [C.c_void_p]
         L.vitb200_tokens.argtypes = [C.c_void_p]
+        L.vitb200_embed.argtypes = [C.c_void_p]
         L.ViT_opencl.argtypes = [C.POINTER(ImageData), C.POINTER(Network), C.POINTER(_f32p)]
         L.ViT_opencl.restype = None
         L.vitb200_release_persistent.restype = None
+        L.vitb200_last_call_stats.restype = None
+        L.vitb200_last_call_stats.argtypes = [C.c_void_p]
         # device layer
         L.vitcu_malloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
         L.vitcu_free.argtypes = [C.c_void_p]
@@ -115,6 +118,9 @@ def lib() -> C.CDLL:
         L.vitcu_event_sync.argtypes = [C.c_void_p]
         L.vitcu_event_elapsed_ms.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
         L.vitcu_launch_count.restype = C.c_ulonglong
+        L.vitcu_launch_count_of.restype = C.c_ulonglong
+        L.vitcu_launch_count_of.argtypes = [C.c_char_p]
+        L.vitcu_launch_count_reset.restype = None
         L.vitcu_f32_to_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.vitcu_patch_gather.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.vitcu_patch_embed_tc.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
@@ -148,6 +154,14 @@ def _check(rc: int, layer: bool = False):
 
 def device_count() -> int:
     return lib().vitb200_device_count()
+
+
+def launch_counts() -> dict:
+    """launches per kernel family since the last vitcu_launch_count_reset (a captured launch counts once)"""
+    L = lib()
+    names = ("gemm_bf16_tc2_kernel", "gemm_bf16_tc_kernel", "attention_tc_kernel", "attention_flash_tc_kernel",
+             "attention_simt_kernel", "sgemm_kernel", "layernorm_kernel", "patch_embed_tc_kernel")
+    return {n: int(L.vitcu_launch_count_of(n.encode())) for n in names}
 
 
 def make_network_structs(blobs):
@@ -186,6 +200,12 @@ def vit_opencl(images: np.ndarray, blobs) -> np.ndarray:
     rows = (_f32p * n)(*[out[i].ctypes.data_as(_f32p) for i in range(n)])
     lib().ViT_opencl(imgs, nets, rows)
     return out
+
+
+class CallStats(C.Structure):
+    """vitb200_call_stats (include/vit_b200.h): where the last ViT_opencl call spent its time"""
+    _fields_ = [("images", C.c_int), ("gpus", C.c_int), ("wall_s", C.c_double), ("create_s", C.c_double),
+                ("weights_s", C.c_double), ("forward_s", C.c_double)]
 
 
 class Model(C.Structure):
@@ -236,6 +256,7 @@ class Engine:
             self.img = m.img
             _check(lib().vitb200_create_model(C.byref(self.h), device, C.byref(m), precision, max_batch))
         self.tokens = lib().vitb200_tokens(self.h)
+        self.embed = lib().vitb200_embed(self.h)
 
     def load_weights(self, blobs):
         nets, keep = make_network_structs(blobs)
@@ -312,7 +333,7 @@ class Engine:
         _check(lib().vitb200_set_stop_after_layer(self.h, layer))
 
     def read_tokens(self, n: int) -> np.ndarray:
-        x = np.empty((n, self.tokens, 768), np.float32)
+        x = np.empty((n, self.tokens, self.embed), np.float32)
         _check(lib().vitb200_read_tokens(self.h, n, x.ctypes.data))
         return x
 

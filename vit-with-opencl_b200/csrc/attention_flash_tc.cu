@@ -374,7 +374,7 @@ int attention_bf16_flash_tc(const void *qkv, void *out, int batch, int tokens, i
     const int sms = device_sm_count();
     const int grid = p.items < sms ? p.items : sms;
     VITCU_TRY(launch_kernel(attention_flash_tc_kernel, grid, kThreadsFlash, smem, st, map, p, watchdog_flag()));
-    VITCU_LAUNCHED();
+    VITCU_LAUNCHED_KIND(LK_ATTN_FLASH);
     return 0;
 }
 

@@ -262,7 +262,9 @@ extern "C" int vitcu_attention_ex(const void *qkv, void *out, int batch, int tok
         return attention_bf16_flash_tc(qkv, out, batch, tokens, heads, as_stream(s));
     }
     // 16-query tiles when 64-query tiles would leave most of the 148 SMs idle (small batches)
-    const bool small = (long)batch * heads * ((tokens + 63) / 64) < 148 && attention_simt_smem<16>(tokens) <= 227 * 1024;
+    // ... or when the 64-query score tile does not fit shared memory (more than ~620 tokens: 448x448 images)
+    const bool small = ((long)batch * heads * ((tokens + 63) / 64) < 148 || attention_simt_smem<64>(tokens) > 227 * 1024) &&
+                       attention_simt_smem<16>(tokens) <= 227 * 1024;
     int rc;
     if (is_bf16 == 2)
         rc = small ? launch_attention_simt<float, 16, true>(qkv, out, batch, tokens, heads, as_stream(s))
@@ -275,7 +277,7 @@ extern "C" int vitcu_attention_ex(const void *qkv, void *out, int batch, int tok
                    : launch_attention_simt<float, 64>(qkv, out, batch, tokens, heads, as_stream(s));
     if (rc)
         return rc;
-    VITCU_LAUNCHED();
+    VITCU_LAUNCHED_KIND(LK_ATTN_SIMT);
     return 0;
 }
 

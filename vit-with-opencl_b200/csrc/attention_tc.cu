@@ -621,7 +621,7 @@ int attention_bf16_tc(const void *qkv, void *out, int batch, int tokens, int hea
         return set_error(VITCU_E_ARG, __FILE__, __LINE__, "unsupported key count");
     }
 #undef VITCU_ATTN_CASE
-    VITCU_LAUNCHED();
+    VITCU_LAUNCHED_KIND(LK_ATTN_TC);
     return 0;
 }
 

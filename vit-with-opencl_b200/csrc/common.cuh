@@ -12,6 +12,10 @@ namespace vitcu {
 // Records file:line + message for vitcu_last_error(); returns the code.
 int set_error(int code, const char *file, int line, const char *what);
 void count_launch();
+// per-kernel-family launch counters (vitcu_launch_count_of): the tests assert which kernel a shape dispatched to
+enum LaunchKind { LK_GEMM_PAIR = 0, LK_GEMM_1CTA, LK_ATTN_TC, LK_ATTN_FLASH, LK_ATTN_SIMT, LK_SGEMM, LK_LAYERNORM,
+                  LK_PATCH_EMBED_TC, LK_OTHER, LK_COUNT };
+void count_launch_kind(int kind);
 // device flag raised by kernels whose mbarrier wait ran out of patience
 uint32_t *watchdog_flag();
 
@@ -30,11 +34,13 @@ uint32_t *watchdog_flag();
     } while (0)
 
 // after a <<<>>> launch
-#define VITCU_LAUNCHED()                                                       \
+#define VITCU_LAUNCHED_KIND(kind)                                              \
     do {                                                                       \
         ::vitcu::count_launch();                                               \
+        ::vitcu::count_launch_kind(kind);                                      \
         VITCU_TRY(cudaGetLastError());                                         \
     } while (0)
+#define VITCU_LAUNCHED() VITCU_LAUNCHED_KIND(::vitcu::LK_OTHER)
 
 static inline cudaStream_t as_stream(vitcu_stream s) { return (cudaStream_t)s; }
 

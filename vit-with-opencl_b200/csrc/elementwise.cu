@@ -320,7 +320,7 @@ static int launch_layernorm(const float *x, size_t x_row_stride, void *y, int y_
         VITCU_TRY(launch_kernel(layernorm_kernel<2, NV>, grid, 256, 0, as_stream(s), x, x_row_stride, y, gamma, beta, rows, rev));
     else
         VITCU_TRY(launch_kernel(layernorm_kernel<0, NV>, grid, 256, 0, as_stream(s), x, x_row_stride, y, gamma, beta, rows, rev));
-    VITCU_LAUNCHED();
+    VITCU_LAUNCHED_KIND(LK_LAYERNORM);
     return 0;
 }
 } // extern "C++"

@@ -634,7 +634,7 @@ int launch(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &tc, 
     const int num_tiles = ((p.M + BM - 1) / BM) * (p.N / BN) * p.splits;
     const int grid = num_tiles < sms ? num_tiles : sms;
     VITCU_TRY(launch_kernel(kernel, grid, kThreads, L::TOTAL, st, ta, tb, tc, C, p, watchdog_flag()));
-    VITCU_LAUNCHED();
+    VITCU_LAUNCHED_KIND(LK_GEMM_1CTA);
     return 0;
 }
 
@@ -654,7 +654,7 @@ int launch_pair(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap 
     const int num_tiles = ((p.M + 255) / 256) * (p.N / 256);
     const int pairs = num_tiles < sms / 2 ? num_tiles : sms / 2;
     VITCU_TRY(launch_kernel(kernel, 2 * pairs, 64 + 32 * EW, L::TOTAL, st, ta, tb, tc, C, p, watchdog_flag()));
-    VITCU_LAUNCHED();
+    VITCU_LAUNCHED_KIND(LK_GEMM_PAIR);
     return 0;
 }
 

@@ -303,7 +303,7 @@ extern "C" int vitcu_patch_embed_tc_ex(const float *images, const float *conv_w,
     const int sms = device_sm_count();
     VITCU_TRY(launch_kernel(patch_embed_tc_kernel, num_tiles < sms ? num_tiles : sms, kThreadsPE, SMEM_TOTAL, as_stream(s),
                             timg, tw, p, watchdog_flag()));
-    VITCU_LAUNCHED();
+    VITCU_LAUNCHED_KIND(LK_PATCH_EMBED_TC);
     return 0;
 }
 

@@ -27,6 +27,15 @@ bool pdl_enabled()
     return on;
 }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+static std::atomic<unsigned long long> g_kind_launches[LK_COUNT];
+void count_launch_kind(int kind)
+{
+    if (kind >= 0 && kind < LK_COUNT)
+        g_kind_launches[kind].fetch_add(1, std::memory_order_relaxed);
+}
+static const char *const kKindNames[LK_COUNT] = {"gemm_bf16_tc2_kernel", "gemm_bf16_tc_kernel", "attention_tc_kernel",
+                                                 "attention_flash_tc_kernel", "attention_simt_kernel", "sgemm_kernel",
+                                                 "layernorm_kernel", "patch_embed_tc_kernel", "other"};
 
 // one flag per device, lazily allocated
 static uint32_t *g_watchdog[64] = {nullptr};
@@ -240,7 +249,19 @@ int vitcu_graph_destroy(vitcu_graph g)
     return 0;
 }
 
-void vitcu_launch_count_reset(void) { g_launches.store(0); }
+void vitcu_launch_count_reset(void)
+{
+    g_launches.store(0);
+    for (int k = 0; k < LK_COUNT; k++)
+        g_kind_launches[k].store(0);
+}
+unsigned long long vitcu_launch_count_of(const char *kernel)
+{
+    for (int k = 0; kernel && k < LK_COUNT; k++)
+        if (!strcmp(kernel, kKindNames[k]))
+            return g_kind_launches[k].load();
+    return 0;
+}
 unsigned long long vitcu_launch_count(void) { return g_launches.load(); }
 
 int vitcu_watchdog_check(void)

@@ -233,7 +233,7 @@ extern "C" int vitcu_sgemm(const float *A, const float *W, void *C, const vitcu_
     p.out_bf16 = d->out_bf16;
     if (p.M <= 8 && p.epilogue == VITCU_EPI_BIAS && !p.out_bf16) {
         VITCU_TRY(launch_kernel(gemv_rows_kernel, (p.N + 7) / 8, 256, 0, as_stream(s), A, W, reinterpret_cast<float *>(C), p));
-        VITCU_LAUNCHED();
+        VITCU_LAUNCHED_KIND(LK_SGEMM);
         return 0;
     }
     // Big tile when it still fills the 148 SMs, small tile for the batch-1 /
@@ -246,6 +246,6 @@ extern "C" int vitcu_sgemm(const float *A, const float *W, void *C, const vitcu_
         dim3 grid((p.N + 63) / 64, (p.M + 63) / 64);
         VITCU_TRY(launch_kernel(sgemm_kernel<64, 64, 4, 4>, grid, 256, 0, as_stream(s), A, W, C, p));
     }
-    VITCU_LAUNCHED();
+    VITCU_LAUNCHED_KIND(LK_SGEMM);
     return 0;
 }

@@ -510,8 +510,8 @@ __device__ __forceinline__ f32x2 gelu_erf_fast2(f32x2 x)
 // (tools/fit_gelu_tanh.py: max |erf error| 1.0e-4, max |GELU error| 2.5e-5 before the 2^-11 relative
 // error of tanh.approx -- together under 1/8 of a bf16 half-ulp of the result).  7 FMA-pipe
 // instructions + 1 MUFU per value against 14 + 1 for the rational form.  Measured on B200 (M=50432):
-// fc1 0.2066 ms with either form -- with 16 epilogue warps the GELU arithmetic is no longer what
-// bounds fc1, so the more accurate rational form stays the default (-DVITCU_GELU_FORM=1 selects this).
+// fc1 0.2066 ms with either scalar form and 16 epilogue warps (-DVITCU_GELU_FORM=1 selects this scalar
+// form; the default is the packed variant gelu_erf_tanh2 below, VITCU_GELU_FORM=2).
 __device__ __forceinline__ float tanh_approx(float x)
 {
     float y;

@@ -346,46 +346,67 @@ int vitb200_load_weights(vitb200_engine *e, const vitb200_blob *net)
                 scratch_elems = n;
         }
     }
-    if (e->w_arena) {
-        VIT_TRY(vitcu_free(e->w_arena));
-        e->w_arena = NULL;
-    }
-    VIT_TRY(vitcu_malloc(&e->w_arena, total));
+    /* The new arena is built beside the old one and swapped in only when the whole upload succeeded: a
+     * failed reload leaves the engine serving its previous weights.  A successful one invalidates
+     * everything that holds the old arena's addresses -- the captured graphs have device pointers and
+     * tensor maps baked into their kernel nodes -- so they are dropped with it. */
+    void *arena = NULL;
     float *scratch[2] = {NULL, NULL};
-    if (scratch_elems)
-        for (int k = 0; k < 2; k++)
-            VIT_TRY(vitcu_malloc((void **)&scratch[k], scratch_elems * sizeof(float)));
-    int k = 0, rc = 0;
+    float **w32 = (float **)calloc(VIT_MAX_BLOBS, sizeof(float *));
+    vitcu_bf16 **w16 = (vitcu_bf16 **)calloc(VIT_MAX_BLOBS, sizeof(vitcu_bf16 *));
+    int rc = (w32 && w16) ? 0 : VITCU_E_ARG;
+    if (rc)
+        vit_fail(__FILE__, __LINE__, rc, "out of host memory");
+    if (!rc && (rc = vitcu_malloc(&arena, total)) != 0)
+        vit_fail(__FILE__, __LINE__, rc, NULL);
+    for (int k = 0; k < 2 && !rc && scratch_elems; k++)
+        if ((rc = vitcu_malloc((void **)&scratch[k], scratch_elems * sizeof(float))) != 0)
+            vit_fail(__FILE__, __LINE__, rc, NULL);
+    int k = 0;
     for (int i = 0; i < e->nblobs && !rc; i++) {
         const size_t n = net[i].size;
-        e->w32[i] = off32[i] == (size_t)-1 ? NULL : (float *)((char *)e->w_arena + off32[i]);
-        e->w16[i] = off16[i] == (size_t)-1 ? NULL : (vitcu_bf16 *)((char *)e->w_arena + off16[i]);
-        if (e->w32[i])
-            rc = vitcu_memcpy_h2d(e->w32[i], net[i].data, n * sizeof(float), e->stream);
-        if (!rc && e->w16[i]) {
+        w32[i] = off32[i] == (size_t)-1 ? NULL : (float *)((char *)arena + off32[i]);
+        w16[i] = off16[i] == (size_t)-1 ? NULL : (vitcu_bf16 *)((char *)arena + off16[i]);
+        if (w32[i])
+            rc = vitcu_memcpy_h2d(w32[i], net[i].data, n * sizeof(float), e->stream);
+        if (!rc && w16[i]) {
             /* stream order makes the scratch reuse safe: the conversion that read it two blobs ago
              * precedes this copy on the same stream */
-            float *src = e->w32[i] ? e->w32[i] : scratch[k++ & 1];
-            if (src != e->w32[i])
+            float *src = w32[i] ? w32[i] : scratch[k++ & 1];
+            if (src != w32[i])
                 rc = vitcu_memcpy_h2d(src, net[i].data, n * sizeof(float), e->stream);
             if (!rc && bf)
-                rc = vitcu_f32_to_bf16(src, e->w16[i], n, e->stream);
+                rc = vitcu_f32_to_bf16(src, w16[i], n, e->stream);
             if (!rc && e->fp32_tc) { /* [N,K] fp32 -> [N,3K] bf16 pieces */
                 const int K = gemm_weight_k(e, i);
-                rc = vitcu_split3(src, (size_t)K, e->w16[i], n / (size_t)K, K, e->stream);
+                rc = vitcu_split3(src, (size_t)K, w16[i], n / (size_t)K, K, e->stream);
             }
         }
+        if (rc)
+            vit_fail(__FILE__, __LINE__, rc, NULL);
     }
-    if (!rc)
-        rc = vitcu_stream_sync(e->stream);
-    if (rc)
+    if (!rc && (rc = vitcu_stream_sync(e->stream)) != 0)
         vit_fail(__FILE__, __LINE__, rc, NULL);
     vitcu_free(scratch[0]);
     vitcu_free(scratch[1]);
-    if (rc)
-        return rc;
-    e->weights_loaded = 1;
-    return 0;
+    if (!rc) {
+        for (int i = 0; i < 2; i++) {
+            if (e->graph[i])
+                vitcu_graph_destroy(e->graph[i]);
+            e->graph[i] = NULL;
+        }
+        e->warmed = 0;
+        vitcu_free(e->w_arena); /* the sync above also covers every forward that read it */
+        e->w_arena = arena;
+        memcpy(e->w32, w32, sizeof(e->w32));
+        memcpy(e->w16, w16, sizeof(e->w16));
+        e->weights_loaded = 1;
+    } else {
+        vitcu_free(arena);
+    }
+    free(w32);
+    free(w16);
+    return rc;
 }
 
 /* one GEMM of the chain, dispatched on the engine precision.  a_split: A already holds the three
@@ -572,9 +593,12 @@ static int upload_pageable(vitb200_engine *e, int buf, const float *contig, cons
             e->stage_group = 1;
         if (e->stage_group > e->B)
             e->stage_group = e->B;
-        VIT_TRY(vitcu_host_alloc((void **)&e->h_stage, (size_t)VIT_STAGE_SLOTS * e->stage_group * img_bytes));
+        /* a retry after a partial failure reuses what the first attempt got (nothing is allocated twice) */
+        if (!e->h_stage)
+            VIT_TRY(vitcu_host_alloc((void **)&e->h_stage, (size_t)VIT_STAGE_SLOTS * e->stage_group * img_bytes));
         for (int i = 0; i < VIT_STAGE_SLOTS; i++)
-            VIT_TRY(vitcu_event_create(&e->ev_slot[i]));
+            if (!e->ev_slot[i])
+                VIT_TRY(vitcu_event_create(&e->ev_slot[i]));
         e->stager = vit_stager_create(vit_stager_threads_default());
         if (!e->stager)
             return vit_fail(__FILE__, __LINE__, VITCU_E_ARG, "out of host memory");
@@ -705,12 +729,28 @@ int vitb200_forward_topk(vitb200_engine *e, const float *images_host, int n, int
         return vit_fail(__FILE__, __LINE__, VITCU_E_ARG, "k must be in 1..VITB200_TOPK_MAX");
     if (n == 0)
         return 0;
-    if (!e->d_topi) { /* first use */
+    if (!e->h_topv) { /* first use: all four buffers or none (h_topv is committed last) */
         const size_t tk = (size_t)e->B * VITB200_TOPK_MAX * 2;
-        VIT_TRY(vitcu_malloc((void **)&e->d_topi, tk * sizeof(int)));
-        VIT_TRY(vitcu_malloc((void **)&e->d_topv, tk * sizeof(float)));
-        VIT_TRY(vitcu_host_alloc((void **)&e->h_topi, tk * sizeof(int)));
-        VIT_TRY(vitcu_host_alloc((void **)&e->h_topv, tk * sizeof(float)));
+        int *di = NULL, *hi = NULL;
+        float *dv = NULL, *hv = NULL;
+        int rc = vitcu_malloc((void **)&di, tk * sizeof(int));
+        if (!rc)
+            rc = vitcu_malloc((void **)&dv, tk * sizeof(float));
+        if (!rc)
+            rc = vitcu_host_alloc((void **)&hi, tk * sizeof(int));
+        if (!rc)
+            rc = vitcu_host_alloc((void **)&hv, tk * sizeof(float));
+        if (rc) {
+            vit_fail(__FILE__, __LINE__, rc, NULL);
+            vitcu_free(di);
+            vitcu_free(dv);
+            vitcu_host_free(hi);
+            return rc;
+        }
+        e->d_topi = di;
+        e->d_topv = dv;
+        e->h_topi = hi;
+        e->h_topv = hv;
     }
     return forward_pipeline(e, images_host, NULL, n, NULL, NULL, NULL, k, labels, probs);
 }
@@ -904,3 +944,4 @@ int vitb200_read_tokens(vitb200_engine *e, int n, float *x_host)
 
 int vitb200_kernels_per_forward(const vitb200_engine *e) { return e ? e->kernels_per_forward : 0; }
 int vitb200_tokens(const vitb200_engine *e) { return e ? e->T : 0; }
+int vitb200_embed(const vitb200_engine *e) { return e ? e->D : 0; }

@@ -18,10 +18,12 @@
 #include "vit_engine_internal.h"
 
 #include <pthread.h>
+#include <stdatomic.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#include <unistd.h>
 
 typedef struct {
     int device, precision, batch, img;
@@ -33,8 +35,16 @@ typedef struct {
     int persist;
     unsigned long long wsig;
     int rc;
+    double t_create, t_weights, t_forward; /* seconds spent in each phase by this shard's thread */
     char msg[640];
 } shard_job;
+
+static double now_s(void)
+{
+    struct timespec t;
+    clock_gettime(CLOCK_MONOTONIC, &t);
+    return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec;
+}
 
 /* ---- persistent context (VITB200_PERSIST=1) --------------------------------------------------
  * The reference rebuilds its OpenCL context, recompiles its kernels and re-uploads 346 MB of weights
@@ -52,30 +62,103 @@ typedef struct {
 static cached_engine g_cache[MAX_CACHED];
 static pthread_mutex_t g_cache_mu = PTHREAD_MUTEX_INITIALIZER;
 
-/* FNV-1a over every blob's address, size and a strided sample of its contents: cheap (~40 k floats
- * read) against the ~40 ms a re-upload costs, and it notices both a different Network array and an
- * in-place edit that touches the sampled elements, the first or the last element of a blob */
-static unsigned long long weights_signature(const vitb200_blob *net)
+/* Signature of the weights: every byte of every blob is hashed (plus address and size), so any
+ * in-place edit of a resident blob -- a partial fine-tune, one row of one matrix -- is noticed; a
+ * sampled signature would serve stale device weights for edits that miss the samples.  346 MB in
+ * 1 MB pieces over a few threads (four independent multiply-xor lanes per piece, ~10 GB/s per
+ * core): a few ms against the ~40 ms a re-upload costs.  Piece hashes are combined in blob order,
+ * so the value does not depend on the thread count. */
+#define SIG_PIECE ((size_t)1 << 20)
+#define SIG_MAX_THREADS 8
+typedef struct {
+    const vitb200_blob *net;
+    int nblobs;
+    size_t first_piece[VIT_MAX_BLOBS + 1]; /* prefix sum of pieces per blob */
+    unsigned long long *piece_hash;
+    atomic_size_t next;
+} sig_job;
+
+static unsigned long long hash_bytes(const unsigned char *p, size_t n)
 {
+    unsigned long long h[4] = {0x9E3779B97F4A7C15ull, 0xC2B2AE3D27D4EB4Full, 0x165667B19E3779F9ull, 0x27D4EB2F165667C5ull};
+    size_t i = 0;
+    for (; i + 32 <= n; i += 32) {
+        unsigned long long w[4];
+        memcpy(w, p + i, 32);
+        for (int k = 0; k < 4; k++) {
+            h[k] = (h[k] ^ w[k]) * 0x100000001B3ull;
+            h[k] ^= h[k] >> 29;
+        }
+    }
+    unsigned long long t = 0x1469598103934665ull ^ (unsigned long long)n;
+    for (; i < n; i++)
+        t = (t ^ p[i]) * 0x100000001B3ull;
+    for (int k = 0; k < 4; k++)
+        t = (t ^ h[k]) * 0x9FB21C651E98DF25ull, t ^= t >> 32;
+    return t;
+}
+
+static void *sig_worker(void *arg)
+{
+    sig_job *j = (sig_job *)arg;
+    const size_t total = j->first_piece[j->nblobs];
+    int b = 0;
+    for (;;) {
+        const size_t u = atomic_fetch_add(&j->next, 1);
+        if (u >= total)
+            break;
+        while (u >= j->first_piece[b + 1])
+            b++;
+        const size_t off = (u - j->first_piece[b]) * SIG_PIECE, bytes = j->net[b].size * sizeof(float);
+        j->piece_hash[u] = hash_bytes((const unsigned char *)j->net[b].data + off,
+                                      bytes - off < SIG_PIECE ? bytes - off : SIG_PIECE);
+    }
+    return NULL;
+}
+
+static unsigned long long weights_signature(const vitb200_blob *net, int nblobs)
+{
+    sig_job j;
+    memset(&j, 0, sizeof(j));
+    j.net = net;
+    j.nblobs = nblobs;
+    for (int i = 0; i < nblobs; i++) {
+        const size_t bytes = net[i].data ? net[i].size * sizeof(float) : 0;
+        j.first_piece[i + 1] = j.first_piece[i] + (bytes + SIG_PIECE - 1) / SIG_PIECE;
+    }
+    const size_t total = j.first_piece[nblobs];
+    j.piece_hash = (unsigned long long *)calloc(total ? total : 1, sizeof(unsigned long long));
+    if (!j.piece_hash)
+        return 0; /* never equals a stored signature's odd value below: forces a re-upload */
+    atomic_init(&j.next, 0);
+    long nth = sysconf(_SC_NPROCESSORS_ONLN) / 2;
+    if (nth > SIG_MAX_THREADS)
+        nth = SIG_MAX_THREADS;
+    if (nth < 1 || total < 8)
+        nth = 1;
+    pthread_t th[SIG_MAX_THREADS];
+    int started = 0;
+    for (int t = 1; t < nth; t++)
+        if (pthread_create(&th[started], NULL, sig_worker, &j) == 0)
+            started++;
+    sig_worker(&j);
+    for (int t = 0; t < started; t++)
+        pthread_join(th[t], NULL);
     unsigned long long h = 1469598103934665603ull;
 #define MIX(v)                                                                 \
     do {                                                                       \
         h ^= (unsigned long long)(v);                                          \
         h *= 1099511628211ull;                                                 \
     } while (0)
-    for (int i = 0; i < VITB200_NBLOBS; i++) {
+    for (int i = 0; i < nblobs; i++) {
         MIX((size_t)net[i].data);
         MIX(net[i].size);
-        if (!net[i].data || !net[i].size)
-            continue;
-        const unsigned *u = (const unsigned *)net[i].data;
-        const size_t step = net[i].size / 256 + 1;
-        for (size_t k = 0; k < net[i].size; k += step)
-            MIX(u[k]);
-        MIX(u[net[i].size - 1]);
+        for (size_t u = j.first_piece[i]; u < j.first_piece[i + 1]; u++)
+            MIX(j.piece_hash[u]);
     }
 #undef MIX
-    return h;
+    free(j.piece_hash);
+    return h | 1ull;
 }
 
 static cached_engine *cache_acquire(const int device, const vitb200_model *m, int precision, int batch)
@@ -112,6 +195,7 @@ void vitb200_release_persistent(void)
 static void *shard_main(void *arg)
 {
     shard_job *j = (shard_job *)arg;
+    const double t0 = now_s();
     cached_engine *c = j->persist ? cache_acquire(j->device, &j->model, j->precision, j->batch) : NULL;
     vitb200_engine *e = c ? c->e : NULL;
     if (!e) {
@@ -126,13 +210,18 @@ static void *shard_main(void *arg)
             c->wsig = 0;
         }
     }
+    const double t1 = now_s();
     if (!j->rc && (!c || c->wsig != j->wsig)) {
         j->rc = vitb200_load_weights(e, j->networks);
         if (c)
             c->wsig = j->rc ? 0 : j->wsig;
     }
+    const double t2 = now_s();
     if (!j->rc)
         j->rc = vitb200_forward_structs(e, j->images + j->first, j->count, j->prb + j->first);
+    j->t_create = t1 - t0;
+    j->t_weights = t2 - t1;
+    j->t_forward = now_s() - t2;
     if (j->rc)
         snprintf(j->msg, sizeof(j->msg), "%s", vitb200_last_error());
     if (c) {
@@ -143,6 +232,35 @@ static void *shard_main(void *arg)
         vitb200_destroy(e);
     }
     return NULL;
+}
+
+/* Contiguous shards of n independent images over `gpus` devices (the images share only the
+ * read-only weights, R/ViT_opencl.c:926): ceil(n / gpus) images each, the last shard takes what is
+ * left, devices that would get nothing are not used.  Returns the number of shards. */
+int vitb200_shard_plan(int n, int gpus, int *first, int *count)
+{
+    if (n <= 0 || gpus <= 0 || !first || !count)
+        return 0;
+    if (gpus > n)
+        gpus = n;
+    const int per = (n + gpus - 1) / gpus;
+    int used = 0;
+    for (int g = 0; g < gpus; g++) {
+        const int f = g * per;
+        if (f >= n)
+            break;
+        first[used] = f;
+        count[used] = f + per <= n ? per : n - f;
+        used++;
+    }
+    return used;
+}
+
+static vitb200_call_stats g_last_call;
+void vitb200_last_call_stats(vitb200_call_stats *out)
+{
+    if (out)
+        *out = g_last_call;
 }
 
 static int env_int(const char *name, int dflt)
@@ -190,25 +308,24 @@ void ViT_opencl(vitb200_image *image, vitb200_blob *networks, float **prb)
         gpus = n;
     if (gpus < 1)
         gpus = 1;
-    const int per = (n + gpus - 1) / gpus;
+    int first_of[64], count_of[64];
+    if (gpus > 64)
+        gpus = 64;
+    const int used = vitb200_shard_plan(n, gpus, first_of, count_of);
     int batch = env_int("VITB200_BATCH", precision == VITB200_BF16 ? 256 : 64);
-    if (batch > per)
-        batch = per;
+    if (batch > count_of[0])
+        batch = count_of[0];
 
     const char *pe = getenv("VITB200_PERSIST");
     const int persist = pe && *pe && strcmp(pe, "0") != 0;
-    const unsigned long long wsig = persist ? weights_signature(networks) : 0;
+    const unsigned long long wsig = persist ? weights_signature(networks, 8 + 12 * model.depth) : 0;
 
     shard_job *jobs = (shard_job *)calloc((size_t)gpus, sizeof(shard_job));
     pthread_t *threads = (pthread_t *)calloc((size_t)gpus, sizeof(pthread_t));
     if (!jobs || !threads)
         die("[vit_opencl.c] CUDA error 90001 (ViT_opencl: out of host memory)");
-    int used = 0;
-    for (int g = 0; g < gpus; g++) {
-        const int first = g * per;
-        if (first >= n)
-            break;
-        shard_job *j = &jobs[used];
+    for (int g = 0; g < used; g++) {
+        shard_job *j = &jobs[g];
         j->device = g;
         j->precision = precision;
         j->batch = batch;
@@ -217,11 +334,10 @@ void ViT_opencl(vitb200_image *image, vitb200_blob *networks, float **prb)
         j->images = image;
         j->networks = networks;
         j->prb = prb;
-        j->first = first;
-        j->count = first + per <= n ? per : n - first;
+        j->first = first_of[g];
+        j->count = count_of[g];
         j->persist = persist;
         j->wsig = wsig;
-        used++;
     }
     if (used == 1) {
         shard_main(&jobs[0]);
@@ -236,10 +352,24 @@ void ViT_opencl(vitb200_image *image, vitb200_blob *networks, float **prb)
         if (jobs[g].rc)
             die(jobs[g].msg);
     clock_gettime(CLOCK_MONOTONIC, &t1);
-    /* the reference prints its own timings (R/ViT_opencl.c:910,964); keep one line */
-    printf("ViT_b200: %d images, %d GPU(s), %s%s, %.3f s wall (device bring-up + weight upload + forward)\n", n,
-           used, precision == VITB200_BF16 ? "bf16" : "fp32", persist ? ", persistent context" : "",
-           (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec));
+    /* the reference prints its own timings (R/ViT_opencl.c:910,964); keep one line, with the slowest
+     * shard's share of each phase (the shards run concurrently, one host thread per GPU) */
+    double mc = 0, mw = 0, mf = 0;
+    for (int g = 0; g < used; g++) {
+        mc = jobs[g].t_create > mc ? jobs[g].t_create : mc;
+        mw = jobs[g].t_weights > mw ? jobs[g].t_weights : mw;
+        mf = jobs[g].t_forward > mf ? jobs[g].t_forward : mf;
+    }
+    printf("ViT_b200: %d images, %d GPU(s), %s%s, %.3f s wall (device bring-up %.3f + weight upload %.3f + forward %.3f, "
+           "slowest shard each)\n", n, used, precision == VITB200_BF16 ? "bf16" : "fp32",
+           persist ? ", persistent context" : "",
+           (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec), mc, mw, mf);
+    g_last_call.images = n;
+    g_last_call.gpus = used;
+    g_last_call.wall_s = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+    g_last_call.create_s = mc;
+    g_last_call.weights_s = mw;
+    g_last_call.forward_s = mf;
     free(jobs);
     free(threads);
 }
