@@ -84,7 +84,7 @@ int vitcu_graph_destroy(vitcu_graph g);
 void vitcu_launch_count_reset(void);
 unsigned long long vitcu_launch_count(void);
 /* launches of one kernel family since the last reset, by kernel name: "gemm_bf16_tc2_kernel" (CTA-pair GEMM),
- * "gemm_bf16_tc_kernel", "attention_tc_kernel", "attention_flash_tc_kernel", "attention_simt_kernel",
+ * "gemm_bf16_tc_kernel", "attention_tc_kernel", "attention_duo_tc_kernel", "attention_flash_tc_kernel", "attention_simt_kernel",
  * "sgemm_kernel", "layernorm_kernel", "patch_embed_tc_kernel".  A launch captured into a graph counts once. */
 unsigned long long vitcu_launch_count_of(const char *kernel);
 /* device-side watchdog flag set by a kernel whose mbarrier wait timed out */

@@ -51,7 +51,7 @@ def test_bf16_batch256_pair_gemm_graph_vs_oracle(pkg, lib, blobs224, bench_case)
     # the kernels the bench times are the ones checked here
     assert counts["gemm_bf16_tc2_kernel"] == 48, counts           # qkv, out_proj, fc1, fc2 x 12 as CTA pairs
     assert counts["gemm_bf16_tc_kernel"] == 0, counts
-    assert counts["attention_tc_kernel"] == 12, counts
+    assert counts["attention_duo_tc_kernel"] + counts["attention_tc_kernel"] == 12, counts
     assert counts["patch_embed_tc_kernel"] == 1, counts
     assert np.array_equal(l_eager, l_graph) and np.array_equal(l_graph, l_again)
     assert np.array_equal(p_eager, p_graph)

@@ -201,10 +201,13 @@ def test_attention_simt_split_output(pkg, lib, oracle, T, batch):
     assert np.array_equal(pieces[:, 0], pkg.bf16_bits_to_f32(pkg.f32_to_bf16_bits(want)))  # first piece = bf16(x)
 
 
-@pytest.mark.parametrize("T,batch", [(197, 3), (50, 2), (128, 1), (129, 1), (256, 2), (16, 1), (197, 40)])
-def test_attention_tensor_core(pkg, lib, oracle, T, batch):
+@pytest.mark.parametrize("kernel", ["duo", "solo"])
+@pytest.mark.parametrize("T,batch", [(197, 3), (50, 2), (128, 1), (129, 1), (256, 2), (16, 1), (197, 40), (224, 26), (160, 30)])
+def test_attention_tensor_core(pkg, lib, oracle, T, batch, kernel, monkeypatch):
     """tcgen05 attention (bf16 storage, tokens <= 256): one and two query tiles, ragged key counts,
-    more work items than SMs (persistent loop, barrier phases flip)"""
+    more work items than CTAs (persistent loop, barrier phases flip), for both single-block kernels:
+    "duo" (two co-resident CTAs per SM, default) and "solo" (one software-pipelined CTA per SM)"""
+    monkeypatch.setenv("VITCU_ATTN_KERNEL", kernel)
     rng = np.random.default_rng(1000 + T + batch)
     bits = pkg.f32_to_bf16_bits((rng.standard_normal((batch, T, 2304), dtype=np.float32) * 1.5).astype(np.float32))
     qkv = pkg.bf16_bits_to_f32(bits).reshape(batch, T, 2304)
@@ -222,10 +225,12 @@ def test_attention_tensor_core(pkg, lib, oracle, T, batch):
         assert err.max() <= tol, f"image {i}: max err {err.max()} at {np.unravel_index(err.argmax(), err.shape)} tol {tol}"
 
 
+@pytest.mark.parametrize("kernel", ["duo", "solo"])
 @pytest.mark.parametrize("scale", [0.05, 0.4, 3.0, 12.0])
-def test_attention_tensor_core_score_ranges(pkg, lib, oracle, scale):
+def test_attention_tensor_core_score_ranges(pkg, lib, oracle, scale, kernel, monkeypatch):
     """score magnitudes from nearly uniform attention (scale 0.05) to one-hot rows (scale 12: |s|/8 up to
     ~1000, exp2 arguments down to -180): the max subtraction keeps every row finite and within tolerance"""
+    monkeypatch.setenv("VITCU_ATTN_KERNEL", kernel)
     T, batch = 197, 3
     rng = np.random.default_rng(77)
     bits = pkg.f32_to_bf16_bits((rng.standard_normal((batch, T, 2304), dtype=np.float32) * scale).astype(np.float32))

@@ -160,7 +160,8 @@ def launch_counts() -> dict:
     """launches per kernel family since the last vitcu_launch_count_reset (a captured launch counts once)"""
     L = lib()
     names = ("gemm_bf16_tc2_kernel", "gemm_bf16_tc_kernel", "attention_tc_kernel", "attention_flash_tc_kernel",
-             "attention_simt_kernel", "sgemm_kernel", "layernorm_kernel", "patch_embed_tc_kernel")
+             "attention_simt_kernel", "sgemm_kernel", "layernorm_kernel", "patch_embed_tc_kernel",
+             "attention_duo_tc_kernel")
     return {n: int(L.vitcu_launch_count_of(n.encode())) for n in names}
 
 

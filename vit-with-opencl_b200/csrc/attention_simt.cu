@@ -18,6 +18,7 @@
 //   phase 4  per 64-key block: V block -> smem; 4x4 register tiles of O += P V
 //   phase 5  O -> out[(b*T + q), h*64 + d]
 #include "common.cuh"
+#include <string.h>
 #include <stdlib.h>
 
 using namespace vitcu;
@@ -245,6 +246,7 @@ int launch_attention_simt(const void *qkv, void *out, int batch, int tokens, int
 namespace vitcu {
 int attention_bf16_tc(const void *qkv, void *out, int batch, int tokens, int heads, cudaStream_t st);       // attention_tc.cu
 int attention_bf16_flash_tc(const void *qkv, void *out, int batch, int tokens, int heads, cudaStream_t st); // attention_flash_tc.cu
+int attention_bf16_duo_tc(const void *qkv, void *out, int batch, int tokens, int heads, cudaStream_t st);   // attention_duo_tc.cu
 }
 
 extern "C" int vitcu_attention_ex(const void *qkv, void *out, int batch, int tokens, int heads, int is_bf16, vitcu_stream s)
@@ -256,9 +258,14 @@ extern "C" int vitcu_attention_ex(const void *qkv, void *out, int batch, int tok
     // VITCU_ATTN_FLASH=1 the key-blocked kernel, for A/B measurements.)
     static const bool force_simt = getenv("VITCU_ATTN_SIMT") != nullptr;
     static const bool force_flash = getenv("VITCU_ATTN_FLASH") != nullptr;
+    // single-block kernels (all keys in one TMEM score buffer): "duo" = two co-resident CTAs per SM, each running
+    // its units serially (default); VITCU_ATTN_KERNEL=solo selects the one-CTA software-pipelined kernel
+    const char *which = getenv("VITCU_ATTN_KERNEL"); // read per call: the tests exercise both kernels in one process
+    const bool solo = which && !strcmp(which, "solo");
     if (is_bf16 == 1 && !force_simt) {
         if (tokens <= 224 && !force_flash)
-            return attention_bf16_tc(qkv, out, batch, tokens, heads, as_stream(s));
+            return solo ? attention_bf16_tc(qkv, out, batch, tokens, heads, as_stream(s))
+                        : attention_bf16_duo_tc(qkv, out, batch, tokens, heads, as_stream(s));
         return attention_bf16_flash_tc(qkv, out, batch, tokens, heads, as_stream(s));
     }
     // 16-query tiles when 64-query tiles would leave most of the 148 SMs idle (small batches)

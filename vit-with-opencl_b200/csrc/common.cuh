@@ -14,7 +14,7 @@ int set_error(int code, const char *file, int line, const char *what);
 void count_launch();
 // per-kernel-family launch counters (vitcu_launch_count_of): the tests assert which kernel a shape dispatched to
 enum LaunchKind { LK_GEMM_PAIR = 0, LK_GEMM_1CTA, LK_ATTN_TC, LK_ATTN_FLASH, LK_ATTN_SIMT, LK_SGEMM, LK_LAYERNORM,
-                  LK_PATCH_EMBED_TC, LK_OTHER, LK_COUNT };
+                  LK_PATCH_EMBED_TC, LK_ATTN_DUO, LK_OTHER, LK_COUNT };
 void count_launch_kind(int kind);
 // device flag raised by kernels whose mbarrier wait ran out of patience
 uint32_t *watchdog_flag();

@@ -35,7 +35,7 @@ void count_launch_kind(int kind)
 }
 static const char *const kKindNames[LK_COUNT] = {"gemm_bf16_tc2_kernel", "gemm_bf16_tc_kernel", "attention_tc_kernel",
                                                  "attention_flash_tc_kernel", "attention_simt_kernel", "sgemm_kernel",
-                                                 "layernorm_kernel", "patch_embed_tc_kernel", "other"};
+                                                 "layernorm_kernel", "patch_embed_tc_kernel", "attention_duo_tc_kernel", "other"};
 
 // one flag per device, lazily allocated
 static uint32_t *g_watchdog[64] = {nullptr};
