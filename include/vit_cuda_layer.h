@@ -156,6 +156,19 @@ typedef struct {
     int patches, tokens;  /* P and T (EPI_PATCH_EMBED)                          */
     int out_bf16;         /* output element type: 0 fp32, 1 bf16                */
     size_t ldc;           /* output row stride in elements                      */
+    /* LayerNorm folded into the GEMM (BF16 path; 0 / NULL = off).  Consumer (the GEMM that follows a
+     * LayerNorm, R/ViT_opencl.c:718,736): A holds bf16(x), the un-normalised fp32 rows; W holds
+     * bf16(gamma * W) and bias holds b + W beta (vitcu_ln_fold_weights); the epilogue computes
+     * y = rstd * acc - rstd * mean * ln_colsum[n] + bias[n] with mean / rstd of row r from the partial
+     * sums ln_stats[slot][r] = (sum x, sum x^2), slot = 0 .. ln_slots-1 (float2, [ln_slots][M]). */
+    const void *ln_stats;
+    int ln_slots;
+    const float *ln_colsum; /* [N] column sums of the folded bf16 weight                */
+    /* Producer (EPI_BIAS_RESIDUAL in place, CTA-pair kernel only: vitcu_gemm_bf16_emit_supported): besides
+     * x += acc + bias the epilogue writes bf16(x) to emit_bf16 [M,N] and the partial sums of every row
+     * over each block of 128 columns to emit_stats (float2, [N / 128][M]). */
+    void *emit_bf16;
+    void *emit_stats;
 } vitcu_gemm_desc;
 
 /* FP32 SIMT GEMM (replaces linear_layer, R/ll.cl:7-70 and QKV, R/multihead.cl:3-63
@@ -168,6 +181,19 @@ int vitcu_sgemm(const float *A, const float *W, void *C, const vitcu_gemm_desc *
  * A [M,K] bf16 (lda == K), W [N,K] bf16.  Requires K % 64 == 0, N % 16 == 0. */
 int vitcu_gemm_bf16(const vitcu_bf16 *A, const vitcu_bf16 *W, void *C,
                     const vitcu_gemm_desc *d, vitcu_stream s);
+
+/* 1 when vitcu_gemm_bf16 can run the LayerNorm-producer epilogue (emit_bf16 / emit_stats) for an [M,N] output */
+int vitcu_gemm_bf16_emit_supported(int M, int N);
+
+/* One-time weight folding for a GEMM that follows a LayerNorm (gamma, beta over the K input features):
+ *   w_folded[n,k] = bf16(gamma[k] * W[n,k]),  colsum[n] = sum_k w_folded[n,k],  bias_folded[n] = bias[n] + sum_k beta[k] W[n,k]
+ * so that LN(x) W^T + bias = rstd * (x w_folded^T) - rstd * mean * colsum + bias_folded. */
+int vitcu_ln_fold_weights(const float *W, const float *gamma, const float *beta, const float *bias, vitcu_bf16 *w_folded,
+                          float *colsum, float *bias_folded, int N, int K, vitcu_stream s);
+
+/* Entry of the folded-LayerNorm chain (the rows the patch embedding wrote): xb = bf16(x) and the row sums
+ * (sum x, sum x^2) into slot 0 of stats (float2, [slots][rows]; the other slots are zeroed).  cols % 128 == 0, <= 1024. */
+int vitcu_rowstats_cast(const float *x, vitcu_bf16 *xb, void *stats, int rows, int cols, int slots, vitcu_stream s);
 
 /* FP32-accurate GEMM on the BF16 tensor cores: A3 [M,3K] and W3 [N,3K] hold the three bf16 pieces
  * of the fp32 operands (vitcu_split3); C = sum of the six significant piece products, FP32

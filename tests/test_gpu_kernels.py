@@ -465,3 +465,89 @@ def test_gemm_bf16x3_is_fp32_accurate(pkg, lib, oracle, M, N, K, epi):
     assert np.abs(y - ref).max() <= 5e-6 * np.abs(ref).max()  # fp32 accumulation over up to 6*3072 products
     if M <= 400 and epi == 0:  # and against the sequential fp32 oracle itself
         assert _rel_err(y, oracle.linear(x, w, b)) <= 2e-5
+
+
+# ---------------------------------------------------------------- LayerNorm folded into the GEMMs
+@pytest.mark.parametrize("M,N,gelu", [(300, 2304, 0), (6500, 2304, 0), (6304, 3072, 1), (12611, 3072, 1)])
+def test_gemm_layernorm_fold_consumer(pkg, lib, oracle, M, N, gelu):
+    """qkv / fc1 with the preceding LayerNorm folded in (vitcu_ln_fold_weights + vitcu_rowstats_cast +
+    ln_stats epilogue), against the oracle's layer_norm_seq + linear_layer_seq (R/ViT_seq.c:120-142, 295-309)
+    and against the unfused GPU chain (layernorm kernel -> bf16 -> GEMM), whose rounding it must match in size"""
+    K = 768
+    rng = np.random.default_rng(M + N)
+    x = (rng.standard_normal((M, K), dtype=np.float32) * 1.7 + 0.3).astype(np.float32)   # mean / sigma ~ 0.18
+    w = (rng.standard_normal((N, K), dtype=np.float32) * 0.03).astype(np.float32)
+    g = (1.0 + 0.2 * rng.standard_normal(K, dtype=np.float32)).astype(np.float32)
+    be = (0.1 * rng.standard_normal(K, dtype=np.float32)).astype(np.float32)
+    b = rng.standard_normal(N, dtype=np.float32)
+    dx, dw, dg, dbe, db = (_dev(pkg, a) for a in (x, w, g, be, b))
+    slots = K // 128
+    dwf, dcs, dbf = pkg.DeviceBuffer(N * K * 2), pkg.DeviceBuffer(N * 4), pkg.DeviceBuffer(N * 4)
+    dxb, dst = pkg.DeviceBuffer(M * K * 2), pkg.DeviceBuffer(slots * M * 8)
+    pkg.layer_check(lib.vitcu_ln_fold_weights(dw.ptr, dg.ptr, dbe.ptr, db.ptr, dwf.ptr, dcs.ptr, dbf.ptr, N, K, None))
+    pkg.layer_check(lib.vitcu_rowstats_cast(dx.ptr, dxb.ptr, dst.ptr, M, K, slots, None))
+    # the folding itself
+    wf = pkg.bf16_bits_to_f32(dwf.to_numpy(np.uint16, (N, K)))
+    assert np.array_equal(wf, pkg.bf16_bits_to_f32(pkg.f32_to_bf16_bits(w * g[None, :])))
+    np.testing.assert_allclose(dcs.to_numpy(np.float32, (N,)), wf.astype(np.float64).sum(1), rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(dbf.to_numpy(np.float32, (N,)), b + w.astype(np.float64) @ be, rtol=1e-5, atol=1e-5)
+    st = dst.to_numpy(np.float32, (slots, M, 2))
+    np.testing.assert_allclose(st[0, :, 0], x.astype(np.float64).sum(1), rtol=1e-5, atol=1e-3)
+    np.testing.assert_allclose(st[0, :, 1], (x.astype(np.float64) ** 2).sum(1), rtol=1e-5)
+    assert np.all(st[1:] == 0)
+    assert np.array_equal(dxb.to_numpy(np.uint16, (M, K)), pkg.f32_to_bf16_bits(x))
+    # folded GEMM
+    dy = pkg.DeviceBuffer(M * N * 2)
+    d = _gemm_desc(pkg, M, N, K, pkg.EPI_BIAS_GELU if gelu else pkg.EPI_BIAS, dbf, out_bf16=1)
+    d.ln_stats, d.ln_slots, d.ln_colsum = dst.ptr.value, slots, dcs.ptr.value
+    pkg.layer_check(lib.vitcu_gemm_bf16(dxb.ptr, dwf.ptr, dy.ptr, C.byref(d), None))
+    y = pkg.bf16_bits_to_f32(dy.to_numpy(np.uint16, (M, N)))
+    # unfused chain on the GPU
+    dln, dwb, dy0 = pkg.DeviceBuffer(M * K * 2), _dev(pkg, pkg.f32_to_bf16_bits(w)), pkg.DeviceBuffer(M * N * 2)
+    pkg.layer_check(lib.vitcu_layernorm(dx.ptr, K, dln.ptr, 1, dg.ptr, dbe.ptr, M, None))
+    d0 = _gemm_desc(pkg, M, N, K, pkg.EPI_BIAS_GELU if gelu else pkg.EPI_BIAS, db, out_bf16=1)
+    pkg.layer_check(lib.vitcu_gemm_bf16(dln.ptr, dwb.ptr, dy0.ptr, C.byref(d0), None))
+    y0 = pkg.bf16_bits_to_f32(dy0.to_numpy(np.uint16, (M, N)))
+    assert lib.vitcu_watchdog_check() == 0
+    rows = np.r_[0:64, M - 64:M]
+    ref = oracle.linear(oracle.layer_norm(x[rows], g, be), w, b, gelu=bool(gelu))
+    scale = np.abs(ref).max()
+    e_fold, e_base = np.abs(y[rows] - ref).max() / scale, np.abs(y0[rows] - ref).max() / scale
+    print(f"\nLN-fold GEMM M={M} N={N}: rel err folded {e_fold:.3e}, unfused {e_base:.3e}")
+    assert e_fold <= 1.2e-2 and e_fold <= 1.5 * e_base + 2.0 ** -8
+    assert np.isfinite(y).all()
+
+
+@pytest.mark.parametrize("M,K", [(6304, 768), (12611, 3072), (50432, 768)])
+def test_gemm_layernorm_fold_producer(pkg, lib, M, K):
+    """out-proj / fc2 residual epilogue that also emits bf16(x) and the row partial sums: x must equal what the plain
+    TMA reduce-add epilogue gives, bit for bit (the same fp32 add), xb = bf16(x) exactly, partials sum to the row sums"""
+    N = 768
+    assert lib.vitcu_gemm_bf16_emit_supported(M, N) == 1
+    assert lib.vitcu_gemm_bf16_emit_supported(197, N) == 0
+    rng = np.random.default_rng(M + K)
+    a_bits = pkg.f32_to_bf16_bits(rng.standard_normal((M, K), dtype=np.float32))
+    w_bits = pkg.f32_to_bf16_bits((rng.standard_normal((N, K), dtype=np.float32) * 0.03).astype(np.float32))
+    b = rng.standard_normal(N, dtype=np.float32)
+    r = rng.standard_normal((M, N), dtype=np.float32)
+    da, dw, db = _dev(pkg, a_bits), _dev(pkg, w_bits), _dev(pkg, b)
+    d_plain, d_emit = _dev(pkg, r), _dev(pkg, r)
+    d = _gemm_desc(pkg, M, N, K, pkg.EPI_BIAS_RESIDUAL, db, residual=d_plain)
+    pkg.layer_check(lib.vitcu_gemm_bf16(da.ptr, dw.ptr, d_plain.ptr, C.byref(d), None))
+    slots = N // 128
+    dxb, dst = pkg.DeviceBuffer(M * N * 2), pkg.DeviceBuffer(slots * M * 8)
+    pkg.layer_check(lib.vitcu_memset(dxb.ptr, 0xFF, M * N * 2, None))
+    pkg.layer_check(lib.vitcu_memset(dst.ptr, 0xFF, slots * M * 8, None))
+    d2 = _gemm_desc(pkg, M, N, K, pkg.EPI_BIAS_RESIDUAL, db, residual=d_emit)
+    d2.emit_bf16, d2.emit_stats = dxb.ptr.value, dst.ptr.value
+    for _ in range(2):  # twice: staging buffers and barrier phases carry over between tiles and launches
+        pkg.layer_check(lib.vitcu_memcpy_h2d(d_emit.ptr, r.ctypes.data, r.nbytes, None))
+        pkg.layer_check(lib.vitcu_gemm_bf16(da.ptr, dw.ptr, d_emit.ptr, C.byref(d2), None))
+    assert lib.vitcu_watchdog_check() == 0
+    x_plain, x_emit = d_plain.to_numpy(np.float32, (M, N)), d_emit.to_numpy(np.float32, (M, N))
+    assert np.array_equal(x_emit, x_plain)
+    assert np.array_equal(dxb.to_numpy(np.uint16, (M, N)), pkg.f32_to_bf16_bits(x_emit))
+    st = dst.to_numpy(np.float32, (slots, M, 2)).astype(np.float64)
+    blocks = x_emit.astype(np.float64).reshape(M, slots, 128)
+    np.testing.assert_allclose(st[:, :, 0].T, blocks.sum(2), rtol=1e-5, atol=1e-3)
+    np.testing.assert_allclose(st[:, :, 1].T, (blocks ** 2).sum(2), rtol=1e-5, atol=1e-3)

@@ -50,7 +50,9 @@ class GemmDesc(C.Structure):
     """vitcu_gemm_desc, include/vit_cuda_layer.h."""
     _fields_ = [("M", C.c_int), ("N", C.c_int), ("K", C.c_int), ("lda", C.c_size_t), ("epilogue", C.c_int),
                 ("bias", C.c_void_p), ("residual", C.c_void_p), ("pos", C.c_void_p), ("patches", C.c_int),
-                ("tokens", C.c_int), ("out_bf16", C.c_int), ("ldc", C.c_size_t)]
+                ("tokens", C.c_int), ("out_bf16", C.c_int), ("ldc", C.c_size_t),
+                ("ln_stats", C.c_void_p), ("ln_slots", C.c_int), ("ln_colsum", C.c_void_p),
+                ("emit_bf16", C.c_void_p), ("emit_stats", C.c_void_p)]
 
 
 def build(verbose: bool = False) -> str:
@@ -136,6 +138,9 @@ def lib() -> C.CDLL:
         L.vitcu_sgemm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(GemmDesc), C.c_void_p]
         L.vitcu_gemm_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(GemmDesc), C.c_void_p]
         L.vitcu_gemm_bf16x3.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(GemmDesc), C.c_void_p]
+        L.vitcu_ln_fold_weights.argtypes = [C.c_void_p] * 7 + [C.c_int, C.c_int, C.c_void_p]
+        L.vitcu_rowstats_cast.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.vitcu_gemm_bf16_emit_supported.argtypes = [C.c_int, C.c_int]
         L.vitcu_split3.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
         L.vitcu_attention.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.vitcu_softmax_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]

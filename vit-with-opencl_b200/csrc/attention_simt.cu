@@ -264,8 +264,8 @@ extern "C" int vitcu_attention_ex(const void *qkv, void *out, int batch, int tok
     const bool solo = which && !strcmp(which, "solo");
     if (is_bf16 == 1 && !force_simt) {
         if (tokens <= 224 && !force_flash)
-            return solo ? attention_bf16_tc(qkv, out, batch, tokens, heads, as_stream(s))
-                        : attention_bf16_duo_tc(qkv, out, batch, tokens, heads, as_stream(s));
+            return solo || tokens > 208 ? attention_bf16_tc(qkv, out, batch, tokens, heads, as_stream(s))
+                                        : attention_bf16_duo_tc(qkv, out, batch, tokens, heads, as_stream(s));
         return attention_bf16_flash_tc(qkv, out, batch, tokens, heads, as_stream(s));
     }
     // 16-query tiles when 64-query tiles would leave most of the 148 SMs idle (small batches)

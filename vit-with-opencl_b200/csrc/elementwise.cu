@@ -155,6 +155,71 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float *__restrict_
 }
 
 // ---------------------------------------------------------------------------
+// LayerNorm folded into the GEMM that follows it (BF16 path; include/vit_cuda_layer.h: vitcu_gemm_desc).
+// One-time weight folding, one warp per output feature n:
+//   w_folded[n,k] = bf16(gamma[k] W[n,k]);  colsum[n] = sum_k w_folded[n,k] (of the ROUNDED values: it multiplies
+//   the mean that the tensor core's product of the rounded values contains);  bias_folded[n] = bias[n] + sum_k beta[k] W[n,k]
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ln_fold_weights_kernel(const float *__restrict__ W, const float *__restrict__ gamma,
+                                                              const float *__restrict__ beta, const float *__restrict__ bias,
+                                                              __nv_bfloat16 *__restrict__ wf, float *__restrict__ colsum,
+                                                              float *__restrict__ bias_f, int N, int K)
+{
+    pdl_trigger();
+    pdl_wait();
+    const int lane = threadIdx.x & 31;
+    const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (n >= N)
+        return;
+    const float4 *w4 = reinterpret_cast<const float4 *>(W + (size_t)n * K);
+    const float4 *g4 = reinterpret_cast<const float4 *>(gamma), *b4 = reinterpret_cast<const float4 *>(beta);
+    uint2 *o = reinterpret_cast<uint2 *>(wf + (size_t)n * K);
+    float cs = 0.f, bs = 0.f;
+    for (int i = lane; i < K / 4; i += 32) {
+        const float4 w = w4[i], g = g4[i], b = b4[i];
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(w.x * g.x, w.y * g.y), hi = __floats2bfloat162_rn(w.z * g.z, w.w * g.w);
+        o[i] = make_uint2(*reinterpret_cast<const uint32_t *>(&lo), *reinterpret_cast<const uint32_t *>(&hi));
+        cs += (__low2float(lo) + __high2float(lo)) + (__low2float(hi) + __high2float(hi));
+        bs += (w.x * b.x + w.y * b.y) + (w.z * b.z + w.w * b.w);
+    }
+    cs = warp_sum(cs);
+    bs = warp_sum(bs);
+    if (lane == 0) {
+        colsum[n] = cs;
+        bias_f[n] = bias[n] + bs;
+    }
+}
+
+// Entry of the folded chain: xb = bf16(x) and (sum x, sum x^2) of every row into slot 0 of the partial-sum table
+// (the other slots are zeroed), one warp per row.  6 bytes per element like the LayerNorm kernel it replaces, but
+// only once per forward: the out-proj / fc2 epilogues produce the same outputs for all later LayerNorms.
+template <int NV>
+__global__ void __launch_bounds__(256) rowstats_cast_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ xb,
+                                                            float2 *__restrict__ stats, int rows, int slots)
+{
+    pdl_trigger();
+    pdl_wait();
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows)
+        return;
+    constexpr int kCols = NV * 128;
+    const float4 *xr = reinterpret_cast<const float4 *>(x + (size_t)row * kCols);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+        const float4 v = xr[lane + 32 * i];
+        s1 += (v.x + v.y) + (v.z + v.w);
+        s2 += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+        reinterpret_cast<uint2 *>(xb + (size_t)row * kCols)[lane + 32 * i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane < slots)
+        stats[(size_t)lane * rows + row] = lane == 0 ? make_float2(s1, s2) : make_float2(0.f, 0.f);
+}
+
+// ---------------------------------------------------------------------------
 // row softmax (R/ViT_seq.c:372-397): one 256-thread block per row
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const float *__restrict__ logits,
@@ -345,6 +410,42 @@ int vitcu_layernorm(const float *x, size_t x_row_stride, void *y, int y_bf16, co
                     const float *beta, int rows, vitcu_stream s)
 {
     return vitcu_layernorm_ex(x, x_row_stride, y, y_bf16, gamma, beta, rows, kEmbed, s);
+}
+
+int vitcu_ln_fold_weights(const float *W, const float *gamma, const float *beta, const float *bias, vitcu_bf16 *w_folded,
+                          float *colsum, float *bias_folded, int N, int K, vitcu_stream s)
+{
+    VITCU_REQUIRE(W && gamma && beta && bias && w_folded && colsum && bias_folded && N > 0 && K > 0 && K % 4 == 0, "bad argument");
+    VITCU_TRY(launch_kernel(ln_fold_weights_kernel, (N + 7) / 8, 256, 0, as_stream(s), W, gamma, beta, bias,
+                            reinterpret_cast<__nv_bfloat16 *>(w_folded), colsum, bias_folded, N, K));
+    VITCU_LAUNCHED();
+    return 0;
+}
+
+int vitcu_rowstats_cast(const float *x, vitcu_bf16 *xb, void *stats, int rows, int cols, int slots, vitcu_stream s)
+{
+    VITCU_REQUIRE(x && xb && stats && rows > 0 && slots > 0 && slots <= 32, "bad argument");
+    float2 *st = reinterpret_cast<float2 *>(stats);
+    __nv_bfloat16 *o = reinterpret_cast<__nv_bfloat16 *>(xb);
+    const int grid = (rows + 7) / 8;
+    switch (cols) {
+    case 768:
+        VITCU_TRY(launch_kernel(rowstats_cast_kernel<6>, grid, 256, 0, as_stream(s), x, o, st, rows, slots));
+        break;
+    case 1024:
+        VITCU_TRY(launch_kernel(rowstats_cast_kernel<8>, grid, 256, 0, as_stream(s), x, o, st, rows, slots));
+        break;
+    case 256:
+        VITCU_TRY(launch_kernel(rowstats_cast_kernel<2>, grid, 256, 0, as_stream(s), x, o, st, rows, slots));
+        break;
+    case 512:
+        VITCU_TRY(launch_kernel(rowstats_cast_kernel<4>, grid, 256, 0, as_stream(s), x, o, st, rows, slots));
+        break;
+    default:
+        return set_error(VITCU_E_ARG, __FILE__, __LINE__, "row width must be 256, 512, 768 or 1024");
+    }
+    VITCU_LAUNCHED();
+    return 0;
 }
 
 int vitcu_softmax_rows(const float *logits, float *probs, int rows, int n, vitcu_stream s)

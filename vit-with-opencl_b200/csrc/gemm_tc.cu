@@ -51,6 +51,13 @@ struct EpiParams {
     // K loop as a list of segments (split-bf16 FP32 path: six piece products over one K range)
     int nseg, seg_kb;        // segments, k-blocks per segment
     int a_seg[6], b_seg[6];  // column offset (elements) of each segment in A and in W
+    // LayerNorm folded into the GEMM (BF16 path, see vitcu_gemm_desc): consumer side
+    const float2 *ln_stats;  // [ln_slots][M] partial (sum, sum of squares) of the fp32 rows the A operand was cast from
+    const float *ln_colsum;  // [N] column sums of the folded weight
+    int ln_slots;
+    float ln_inv_d;          // 1 / row length
+    // ... and producer side (tma_out == 4): the residual epilogue also emits bf16(x_new) and the row partials
+    float2 *emit_stats;      // [N / 128][M]
 };
 
 constexpr int BM = 128;
@@ -116,6 +123,23 @@ __device__ __forceinline__ bool epilogue_tile(const EpiParams &p, void *C, const
         }
     };
     fetch_add(0); // does not depend on the accumulator: in flight during the wait below
+    // LayerNorm folded into this GEMM: y = rstd * acc - rstd * mean * colsum[n] + bias'[n], with the statistics of
+    // this thread's row summed from the producer's partials in slot order (deterministic), R/ViT_seq.c:126-135
+    float rstd = 1.0f, nrm = 0.0f;
+    if (p.ln_stats) {
+        const int row = row0 + lane;
+        float s1 = 0.f, s2 = 0.f;
+        if (row < p.M)
+            for (int sl = 0; sl < p.ln_slots; sl++) {
+                const float2 v = __ldg(p.ln_stats + static_cast<size_t>(sl) * p.M + row);
+                s1 += v.x;
+                s2 += v.y;
+            }
+        const float mu = s1 * p.ln_inv_d;
+        const float var = fmaxf(s2 * p.ln_inv_d - mu * mu, 0.0f);
+        rstd = 1.0f / sqrtf(var + 1e-6f);
+        nrm = -rstd * mu;
+    }
 
     bool ok = mbar_wait(tfull, parity, wd, 4);
     ok = __all_sync(0xffffffffu, ok);
@@ -141,13 +165,26 @@ __device__ __forceinline__ bool epilogue_tile(const EpiParams &p, void *C, const
         const int col0 = col_base + c * 32;
         // ---- row-per-thread part: bias (+ GELU), then into the staging tile ----
         float v[32];
+        if (p.ln_stats) {
+            const f32x2 r2 = pack2(rstd, rstd), n2 = pack2(nrm, nrm);
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-            const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + col0 + j));
-            v[j + 0] = fmaf(b.x, bias_on, __uint_as_float(acc[c % NACC][j + 0]));
-            v[j + 1] = fmaf(b.y, bias_on, __uint_as_float(acc[c % NACC][j + 1]));
-            v[j + 2] = fmaf(b.z, bias_on, __uint_as_float(acc[c % NACC][j + 2]));
-            v[j + 3] = fmaf(b.w, bias_on, __uint_as_float(acc[c % NACC][j + 3]));
+            for (int j = 0; j < 32; j += 4) {
+                const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + col0 + j));
+                const float4 cs = __ldg(reinterpret_cast<const float4 *>(p.ln_colsum + col0 + j));
+                unpack2(fma2(pack2(__uint_as_float(acc[c % NACC][j + 0]), __uint_as_float(acc[c % NACC][j + 1])), r2,
+                             fma2(pack2(cs.x, cs.y), n2, pack2(b.x, b.y))), v[j + 0], v[j + 1]);
+                unpack2(fma2(pack2(__uint_as_float(acc[c % NACC][j + 2]), __uint_as_float(acc[c % NACC][j + 3])), r2,
+                             fma2(pack2(cs.z, cs.w), n2, pack2(b.z, b.w))), v[j + 2], v[j + 3]);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + col0 + j));
+                v[j + 0] = fmaf(b.x, bias_on, __uint_as_float(acc[c % NACC][j + 0]));
+                v[j + 1] = fmaf(b.y, bias_on, __uint_as_float(acc[c % NACC][j + 1]));
+                v[j + 2] = fmaf(b.z, bias_on, __uint_as_float(acc[c % NACC][j + 2]));
+                v[j + 3] = fmaf(b.w, bias_on, __uint_as_float(acc[c % NACC][j + 3]));
+            }
         }
         if (p.epilogue == VITCU_EPI_BIAS_GELU) {
             if (p.exact_gelu) {
@@ -250,6 +287,99 @@ __device__ __forceinline__ bool epilogue_tile(const EpiParams &p, void *C, const
         }
         __syncwarp(); // the staging tile is reused by the next chunk
     }
+    return true;
+}
+
+// Producer side of the folded LayerNorm (tma_out == 4; out-proj and fc2 of the BF16 path): the residual update
+//     x_new = x_old + acc + bias
+// is computed in registers instead of by TMA reduce-add, because the row is needed twice more: as bf16(x_new), the
+// A operand of the next GEMM (which applies the LayerNorm in its own epilogue), and in the row's partial sums
+// (sum x, sum x^2) over this warp's 128 columns -> emit_stats[col_base / 128][row].  x_old arrives by TMA (a 32 x 32
+// fp32 tile per chunk, same tensor map as the store), the thread that owns the row adds its accumulators, puts
+// x_new back IN PLACE and the TMA engine stores the tile; a second, bf16 tile goes out beside it.  The layernorm
+// kernel's launch and its re-read of the fp32 stream (4 of its 6 bytes per element) disappear.
+// Per-warp staging (12 KB): R[2] fp32 in/out tiles at 0 / 4096, B[2] bf16 tiles at 8192 / 10240; rbar[2] signal the loads.
+template <int NCHUNK>
+__device__ __forceinline__ bool epilogue_tile_emit(const EpiParams &p, const CUtensorMap *tmap_c, const CUtensorMap *tmap_d,
+                                                   uint8_t *stage, uint64_t *rbar, uint32_t (&rphase)[2], int lane, int row0,
+                                                   int col_base, uint32_t taddr, uint64_t *tfull, uint32_t parity,
+                                                   const Watchdog &wd)
+{
+    const bool rows_exist = row0 < p.M; // warp-uniform
+    if (rows_exist && lane == 0) {
+        tma_wait_group_read<0>(); // this warp's stores of the previous tile have read the staging buffers
+        for (int c = 0; c < 2 && c < NCHUNK; c++) {
+            mbar_arrive_expect_tx(&rbar[c], 4096);
+            tma_load_2d(stage + c * 4096, tmap_c, &rbar[c], col_base + c * 32, row0);
+        }
+    }
+    __syncwarp();
+    bool ok = mbar_wait(tfull, parity, wd, 4);
+    ok = __all_sync(0xffffffffu, ok);
+    if (!ok)
+        return false;
+    tcgen05_fence_after();
+    uint32_t acc[2][32];
+    tmem_ld_32x32b_x32(taddr, acc[0]);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCHUNK; c++) {
+        tmem_ld_wait();
+        if (c + 1 < NCHUNK)
+            tmem_ld_32x32b_x32(taddr + (c + 1) * 32, acc[(c + 1) & 1]);
+        if (!rows_exist)
+            continue;
+        const int col0 = col_base + c * 32, b = c & 1;
+        uint8_t *R = stage + b * 4096, *B = stage + 8192 + b * 2048;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            const float4 bb = __ldg(reinterpret_cast<const float4 *>(p.bias + col0 + j));
+            v[j + 0] = __uint_as_float(acc[c & 1][j + 0]) + bb.x;
+            v[j + 1] = __uint_as_float(acc[c & 1][j + 1]) + bb.y;
+            v[j + 2] = __uint_as_float(acc[c & 1][j + 2]) + bb.z;
+            v[j + 3] = __uint_as_float(acc[c & 1][j + 3]) + bb.w;
+        }
+        // the residual tile of this chunk has landed
+        ok = mbar_wait(&rbar[b], rphase[b], wd, 9);
+        ok = __all_sync(0xffffffffu, ok);
+        if (!ok)
+            return false;
+        rphase[b] ^= 1;
+#pragma unroll
+        for (int q = 0; q < 8; q++) { // 32 x 128 B rows, 128-byte swizzle: 16-byte chunk ^= row % 8
+            float4 *slot = reinterpret_cast<float4 *>(R + lane * 128 + ((q ^ (lane & 7)) << 4));
+            const float4 xo = *slot;
+            const float a0 = xo.x + v[4 * q + 0], a1 = xo.y + v[4 * q + 1], a2 = xo.z + v[4 * q + 2], a3 = xo.w + v[4 * q + 3];
+            v[4 * q + 0] = a0;
+            v[4 * q + 1] = a1;
+            v[4 * q + 2] = a2;
+            v[4 * q + 3] = a3;
+            *slot = make_float4(a0, a1, a2, a3);
+            s1 += (a0 + a1) + (a2 + a3);
+            s2 = fmaf(a0, a0, fmaf(a1, a1, fmaf(a2, a2, fmaf(a3, a3, s2))));
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) // 32 x 64 B rows, 64-byte swizzle: 16-byte chunk ^= (row / 2) % 4
+            *reinterpret_cast<uint4 *>(B + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) =
+                make_uint4(pack_bf16x2(v[8 * q + 0], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
+                           pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            tma_store_2d(tmap_c, R, col0, row0);
+            tma_store_2d(tmap_d, B, col0, row0);
+            tma_commit_group();
+            if (c + 2 < NCHUNK) { // the buffers are reloaded once the stores just issued have read them
+                tma_wait_group_read<0>();
+                mbar_arrive_expect_tx(&rbar[b], 4096);
+                tma_load_2d(R, tmap_c, &rbar[b], col_base + (c + 2) * 32, row0);
+            }
+        }
+        __syncwarp();
+    }
+    if (rows_exist && row0 + lane < p.M)
+        p.emit_stats[static_cast<size_t>(col_base / (32 * NCHUNK)) * p.M + row0 + lane] = make_float2(s1, s2);
     return true;
 }
 
@@ -429,7 +559,7 @@ struct SmemLayout2 {
     static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr uint32_t EPI_OFFSET = STAGES * STAGE_BYTES;
     static constexpr uint32_t BAR_OFFSET = EPI_OFFSET + EPI_BYTES; // epilogue staging, split evenly over the warps
-    static constexpr uint32_t NUM_BARS = 2 * STAGES + 4;
+    static constexpr uint32_t NUM_BARS = 2 * STAGES + 4 + 2 * 16; // + two residual-tile barriers per epilogue warp (emit mode)
     static constexpr uint32_t TOTAL = BAR_OFFSET + NUM_BARS * 8 + 16 + 1024;
     static_assert(TOTAL <= 227 * 1024, "shared memory budget");
 };
@@ -439,10 +569,12 @@ struct SmemLayout2 {
 // the latency of one warp's chunk chain, which more warps overlap
 // EPI_BYTES = epilogue staging per CTA: 64 KB with 5 operand stages, or 32 KB (4 KB per warp: two bf16 tiles
 // or one fp32 tile, TMA output path only) which makes room for a sixth stage
-template <int STAGES, int EW, uint32_t EPI_BYTES = 65536>
+// EMIT = residual epilogue that also emits bf16(x) and the row partial sums for the folded LayerNorm (epilogue_tile_emit)
+template <int STAGES, int EW, uint32_t EPI_BYTES = 65536, bool EMIT = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EW, 1)
 gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                     const __grid_constant__ CUtensorMap tmap_c, void *C, const EpiParams p, uint32_t *watchdog_flag)
+                     const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_d, void *C,
+                     const EpiParams p, uint32_t *watchdog_flag)
 {
     using L = SmemLayout2<STAGES, EPI_BYTES>;
     constexpr int BN = 256, BM2 = 256;
@@ -455,7 +587,8 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     uint64_t *empty_bar = full_bar + STAGES;
     uint64_t *tfull_bar = empty_bar + STAGES;
     uint64_t *tempty_bar = tfull_bar + 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty_bar + 2);
+    uint64_t *res_bar = tempty_bar + 2; // [EW][2] residual-tile barriers (emit mode)
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(res_bar + 2 * 16);
     volatile uint32_t *cta_abort = tmem_slot + 1;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -471,6 +604,8 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             mbar_init(&tfull_bar[i], 1);
             mbar_init(&tempty_bar[i], 2 * EW);
         }
+        for (int i = 0; i < 2 * 16; i++)
+            mbar_init(&res_bar[i], 1);
         *cta_abort = 0;
         fence_barrier_init();
     }
@@ -572,16 +707,30 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         const int quad = warp & 3;
         const int cgrp = (warp - 2) >> 2;
         uint32_t it = 0, chunk_ctr = 0;
-        if (warp == 2 && lane == 0)
+        uint32_t rphase[2] = {0, 0};
+        if (warp == 2 && lane == 0) {
             prefetch_tensormap(&tmap_c);
+            if (EMIT)
+                prefetch_tensormap(&tmap_d);
+        }
         for (int tile = pair; tile < num_tiles; tile += num_pairs, it++) {
             const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
             const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
             float *stage_tile = reinterpret_cast<float *>(smem + L::EPI_OFFSET + (warp - 2) * SBW);
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + cgrp * CW;
-            if (!epilogue_tile<CW / 32, SBW, EW == 8>(p, C, &tmap_c, chunk_ctr, stage_tile, lane,
-                                                     m_blk * BM2 + (int)rank * BM + quad * 32, n_blk * BN + cgrp * CW, taddr,
-                                                     &tfull_bar[acc], acc_phase, wd))
+            bool tile_ok;
+            if (EMIT) {
+                static_assert(!EMIT || SBW >= 12288, "emit mode needs 12 KB of staging per epilogue warp");
+                tile_ok = epilogue_tile_emit<CW / 32>(p, &tmap_c, &tmap_d, reinterpret_cast<uint8_t *>(stage_tile),
+                                                      &res_bar[2 * (warp - 2)], rphase, lane,
+                                                      m_blk * BM2 + (int)rank * BM + quad * 32, n_blk * BN + cgrp * CW, taddr,
+                                                      &tfull_bar[acc], acc_phase, wd);
+            } else {
+                tile_ok = epilogue_tile<CW / 32, SBW, EW == 8>(p, C, &tmap_c, chunk_ctr, stage_tile, lane,
+                                                               m_blk * BM2 + (int)rank * BM + quad * 32, n_blk * BN + cgrp * CW,
+                                                               taddr, &tfull_bar[acc], acc_phase, wd);
+            }
+            if (!tile_ok)
                 break;
             tcgen05_fence_before();
             __syncwarp();
@@ -638,12 +787,12 @@ int launch(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &tc, 
     return 0;
 }
 
-template <int STAGES, int EW, uint32_t EPI_BYTES = 65536>
-int launch_pair(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &tc, void *C, const EpiParams &p, int sms,
-                cudaStream_t st)
+template <int STAGES, int EW, uint32_t EPI_BYTES = 65536, bool EMIT = false>
+int launch_pair(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &tc, const CUtensorMap &td, void *C,
+                const EpiParams &p, int sms, cudaStream_t st)
 {
     using L = SmemLayout2<STAGES, EPI_BYTES>;
-    auto kernel = gemm_bf16_tc2_kernel<STAGES, EW, EPI_BYTES>;
+    auto kernel = gemm_bf16_tc2_kernel<STAGES, EW, EPI_BYTES, EMIT>;
     static bool configured[64] = {false};
     int dev = 0;
     VITCU_TRY(cudaGetDevice(&dev));
@@ -653,7 +802,7 @@ int launch_pair(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap 
     }
     const int num_tiles = ((p.M + 255) / 256) * (p.N / 256);
     const int pairs = num_tiles < sms / 2 ? num_tiles : sms / 2;
-    VITCU_TRY(launch_kernel(kernel, 2 * pairs, 64 + 32 * EW, L::TOTAL, st, ta, tb, tc, C, p, watchdog_flag()));
+    VITCU_TRY(launch_kernel(kernel, 2 * pairs, 64 + 32 * EW, L::TOTAL, st, ta, tb, tc, td, C, p, watchdog_flag()));
     VITCU_LAUNCHED_KIND(LK_GEMM_PAIR);
     return 0;
 }
@@ -700,6 +849,15 @@ int device_sm_count()
 
 } // namespace vitcu
 
+// CTA pairs on 256x256 tiles when N allows and every pair gets work
+static bool pair_eligible(int M, int N)
+{
+    static const bool force_1cta = getenv("VITCU_GEMM_MODE") && !strcmp(getenv("VITCU_GEMM_MODE"), "1cta");
+    return !force_1cta && N % 256 == 0 && ((M + 255) / 256) * (N / 256) >= device_sm_count() / 2;
+}
+
+extern "C" int vitcu_gemm_bf16_emit_supported(int M, int N) { return M > 0 && N > 0 && pair_eligible(M, N) ? 1 : 0; }
+
 static int gemm_dispatch(const vitcu_bf16 *A, const vitcu_bf16 *W, void *C, const vitcu_gemm_desc *d, bool split3,
                          vitcu_stream s)
 {
@@ -725,6 +883,23 @@ static int gemm_dispatch(const vitcu_bf16 *A, const vitcu_bf16 *W, void *C, cons
     p.tokens = d->tokens;
     p.out_bf16 = d->out_bf16;
     p.exact_gelu = split3 && !d->out_bf16;
+    // LayerNorm folded into the GEMM (see vitcu_gemm_desc)
+    if (d->ln_stats) {
+        VITCU_REQUIRE(!split3 && d->ln_colsum && d->ln_slots > 0, "LayerNorm-folded GEMM needs bf16 operands, column sums and slots");
+        VITCU_REQUIRE(d->epilogue == VITCU_EPI_BIAS || d->epilogue == VITCU_EPI_BIAS_GELU, "LayerNorm fold applies to bias / GELU epilogues");
+        p.ln_stats = reinterpret_cast<const float2 *>(d->ln_stats);
+        p.ln_colsum = d->ln_colsum;
+        p.ln_slots = d->ln_slots;
+        p.ln_inv_d = 1.0f / (float)d->K;
+    }
+    const bool emit = d->emit_bf16 != nullptr;
+    if (emit) {
+        VITCU_REQUIRE(!split3 && d->emit_stats && d->epilogue == VITCU_EPI_BIAS_RESIDUAL && d->residual == (const float *)C &&
+                          !d->out_bf16 && ((uintptr_t)C & 15) == 0 && ((uintptr_t)d->emit_bf16 & 15) == 0,
+                      "emit mode needs the in-place fp32 residual epilogue");
+        VITCU_REQUIRE(vitcu_gemm_bf16_emit_supported(d->M, d->N), "emit mode needs the CTA-pair kernel (N % 256 == 0, enough tiles)");
+        p.emit_stats = reinterpret_cast<float2 *>(d->emit_stats);
+    }
     VITCU_REQUIRE(p.ldc % 8 == 0, "ldc must be a multiple of 8");
     const uint64_t kphys = split3 ? 3 * (uint64_t)d->K : (uint64_t)d->K; // physical operand width
     const size_t lda = split3 ? (size_t)kphys : (d->lda ? d->lda : (size_t)d->K);
@@ -746,7 +921,6 @@ static int gemm_dispatch(const vitcu_bf16 *A, const vitcu_bf16 *W, void *C, cons
 
     const int sms = device_sm_count();
     // VITCU_GEMM_MODE=1cta forces the single-CTA kernels, VITCU_GEMM_EPI=lsu the LSU-store epilogue (A/B measurements)
-    static const bool force_1cta = getenv("VITCU_GEMM_MODE") && !strcmp(getenv("VITCU_GEMM_MODE"), "1cta");
     static const bool force_lsu = getenv("VITCU_GEMM_EPI") && !strcmp(getenv("VITCU_GEMM_EPI"), "lsu");
     // Output through the TMA engine: bf16 / fp32 tiles are stored; the in-place residual update
     // C = C + (acc + bias) becomes a TMA reduce-add, so the fp32 residual stream is never read by the SMs.
@@ -760,8 +934,15 @@ static int gemm_dispatch(const vitcu_bf16 *A, const vitcu_bf16 *W, void *C, cons
         else if (!p.out_bf16 && plain)
             p.tma_out = 3;
     }
-    CUtensorMap ta, tb, tc;
+    CUtensorMap ta, tb, tc, td;
+    memset(&td, 0, sizeof(td));
     int rc = 0;
+    if (emit) {
+        p.tma_out = 4;
+        rc = make_tensor_map_2d(&td, d->emit_bf16, 2, (uint64_t)d->M, (uint64_t)d->N, (size_t)d->N * 2, 32, 32, 64);
+        if (rc)
+            return rc;
+    }
     if (p.tma_out == 1)
         rc = make_tensor_map_2d(&tc, C, 2, (uint64_t)d->M, (uint64_t)d->N, p.ldc * 2, 32, 32, 64);
     else if (p.tma_out >= 2)
@@ -771,7 +952,7 @@ static int gemm_dispatch(const vitcu_bf16 *A, const vitcu_bf16 *W, void *C, cons
     if (rc)
         return rc;
     // CTA pairs on 256x256 tiles when N allows and every pair gets work
-    const bool pair = !force_1cta && d->N % 256 == 0 && ((d->M + 255) / 256) * (d->N / 256) >= sms / 2;
+    const bool pair = pair_eligible(d->M, d->N);
     rc = make_tensor_map_2d(&ta, A, 2, (uint64_t)d->M, kphys, lda * 2, BM, BK);
     if (rc)
         return rc;
@@ -779,19 +960,21 @@ static int gemm_dispatch(const vitcu_bf16 *A, const vitcu_bf16 *W, void *C, cons
         rc = make_tensor_map_2d(&tb, W, 2, (uint64_t)d->N, kphys, kphys * 2, 128, BK);
         if (rc)
             return rc;
+        if (emit) // 4 operand stages: the emit epilogue stages 12 KB per warp
+            return launch_pair<4, 8, 98304, true>(ta, tb, tc, td, C, p, sms, as_stream(s));
         // 16 epilogue warps (VITCU_GEMM_EW=16; they need the TMA output path, their staging share is 4 KB) paid
         // off for the 17-instruction rational GELU (1195 vs 1127 TFLOP/s); with the 9-instruction packed
         // MUFU.TANH form 8 warps with double-buffered tcgen05.ld are as fast or faster (0.195 vs 0.198 ms)
         static const int force_ew = getenv("VITCU_GEMM_EW") ? atoi(getenv("VITCU_GEMM_EW")) : 0;
         const bool ew16 = p.tma_out != 0 && (force_ew ? force_ew == 16 : (VITCU_GELU_FORM == 0 && p.epilogue == VITCU_EPI_BIAS_GELU));
         if (ew16)
-            return launch_pair<5, 16>(ta, tb, tc, C, p, sms, as_stream(s));
+            return launch_pair<5, 16>(ta, tb, tc, td, C, p, sms, as_stream(s));
         // VITCU_GEMM_STAGES=6: a sixth operand stage in exchange for single-buffered epilogue staging (A/B)
         // measured (M=50432): bf16-output launches unchanged, fp32 reduce-add launches (out_proj, fc2) +1.5 %
         static const int stages = getenv("VITCU_GEMM_STAGES") ? atoi(getenv("VITCU_GEMM_STAGES")) : 0;
         if (p.tma_out != 0 && (stages == 6 || (stages == 0 && p.tma_out == 2)))
-            return launch_pair<6, 8, 32768>(ta, tb, tc, C, p, sms, as_stream(s));
-        return launch_pair<5, 8>(ta, tb, tc, C, p, sms, as_stream(s));
+            return launch_pair<6, 8, 32768>(ta, tb, tc, td, C, p, sms, as_stream(s));
+        return launch_pair<5, 8>(ta, tb, tc, td, C, p, sms, as_stream(s));
     }
     // 128x256 tiles when they divide N and still give every SM work; else 128x128
     const bool wide = d->N % 256 == 0 && ((d->M + BM - 1) / BM) * (d->N / 256) >= sms;

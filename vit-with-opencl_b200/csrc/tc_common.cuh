@@ -116,6 +116,40 @@ __device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, const 
     return true;
 }
 
+// Spinning flavour for SHORT waits on a latency-critical chain (a few hundred cycles for an MMA batch to
+// retire): plain try_wait polling, no suspend hint -- a parked thread wakes up late.
+__device__ __forceinline__ bool mbar_wait_spin(uint64_t *bar, uint32_t parity, const Watchdog &wd, uint32_t tag)
+{
+    uint32_t spins = 0;
+    uint64_t t0 = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 4095u) == 0) {
+            if (*wd.cta_abort)
+                return false;
+            const uint64_t now = globaltimer_ns();
+            if (t0 == 0) {
+                t0 = now;
+            } else if (now - t0 > kWatchdogNs) {
+                *wd.cta_abort = 1;
+                if (wd.global_flag)
+                    atomicCAS(wd.global_flag, 0u, 0x80000000u | (tag << 16) | (blockIdx.x & 0xffffu));
+                return false;
+            }
+        }
+    }
+    return true;
+}
+__device__ __forceinline__ bool mbar_wait_spin_warp(uint64_t *bar, uint32_t parity, const Watchdog &wd, uint32_t tag)
+{
+    const bool ok = mbar_wait_spin(bar, parity, wd, tag);
+    return __all_sync(0xffffffffu, ok);
+}
+// named barrier over `threads` threads of the CTA (id 1..15; 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t threads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
 // warp-collective flavour: every lane polls the same barrier (converged warp => same
 // answer); the slow path votes so the whole warp leaves together on an abort
 __device__ __forceinline__ bool mbar_wait_warp(uint64_t *bar, uint32_t parity, const Watchdog &wd, uint32_t tag)

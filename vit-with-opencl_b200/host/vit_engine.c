@@ -98,6 +98,16 @@ static int is_gemm_weight(const vitb200_engine *e, int idx)
     return 0;
 }
 
+/* GEMM weights whose input is a LayerNorm output: in_proj (LN1) and fc1 (LN2) of every layer (R/ViT_opencl.c:718,736) */
+static int follows_layernorm(const vitb200_engine *e, int idx)
+{
+    if (idx >= 4 && idx < e->nblobs - 4) {
+        int k = (idx - 4) % 12;
+        return k == 2 || k == 8;
+    }
+    return 0;
+}
+
 /* K (row length) of GEMM weight idx */
 static int gemm_weight_k(const vitb200_engine *e, int idx)
 {
@@ -210,6 +220,9 @@ int vitb200_create_model(vitb200_engine **out, int device, const vitb200_model *
     /* VITB200_PE_GATHER=1: separate gather kernel + BF16 GEMM instead of the TMA-gather TF32 GEMM */
     e->pe_gather = getenv("VITB200_PE_GATHER") != NULL || e->patch != 16 || e->D % 256 != 0;
     const int bf = precision == VITB200_BF16;
+    /* LayerNorm folded into the qkv / fc1 GEMMs and produced by the out-proj / fc2 epilogues: BF16 path, widths the
+     * CTA-pair GEMM tiles (VITB200_LN_FOLD=0 keeps the separate LayerNorm kernel) */
+    e->ln_fold = bf && e->D % 256 == 0 && !(getenv("VITB200_LN_FOLD") && atoi(getenv("VITB200_LN_FOLD")) == 0);
     const size_t act = bf ? 2 : 4;
     const size_t rows = (size_t)e->B * e->T;
     const size_t img_elems = (size_t)3 * img * img;
@@ -245,6 +258,8 @@ int vitb200_create_model(vitb200_engine **out, int device, const vitb200_model *
     ENG_TRY(vitcu_malloc(&e->d_att, rows * e->D * (e->fp32_tc ? 6 : act)));
     ENG_TRY(vitcu_malloc(&e->d_hid, rows * e->HID * act));
     ENG_TRY(vitcu_malloc((void **)&e->d_cls, (size_t)e->B * e->D * sizeof(float)));
+    if (e->ln_fold)
+        ENG_TRY(vitcu_malloc(&e->d_lnstats, rows * (size_t)(e->D / 128) * 2 * sizeof(float)));
     ENG_TRY(vitcu_host_alloc((void **)&e->h_probs, (size_t)e->B * VITB200_CLASSES * sizeof(float) * 2));
     ENG_TRY(vitcu_host_alloc((void **)&e->h_logits, (size_t)e->B * VITB200_CLASSES * sizeof(float) * 2));
 #undef ENG_TRY
@@ -284,6 +299,7 @@ void vitb200_destroy(vitb200_engine *e)
     vitcu_free(e->d_att);
     vitcu_free(e->d_hid);
     vitcu_free(e->d_cls);
+    vitcu_free(e->d_lnstats);
     vitcu_host_free(e->h_probs);
     vitcu_host_free(e->h_logits);
     vitcu_free(e->d_topi);
@@ -328,10 +344,16 @@ int vitb200_load_weights(vitb200_engine *e, const vitb200_blob *net)
      * to the packed form: bf16 [N,K] on the BF16 path, three bf16 pieces [N,3K] on the FP32
      * tensor-core path.  Everything else (biases, LayerNorm, class token, position embedding, head,
      * and the conv filters of the TF32 patch embedding) stays fp32. */
-    size_t off32[VIT_MAX_BLOBS], off16[VIT_MAX_BLOBS], total = 0, scratch_elems = 0;
+    size_t off32[VIT_MAX_BLOBS], off16[VIT_MAX_BLOBS], offf[VIT_MAX_BLOBS], total = 0, scratch_elems = 0;
     for (int i = 0; i < e->nblobs; i++) {
         const size_t n = net[i].size;
         const int packed = is_gemm_weight(e, i) && (bf || e->fp32_tc);
+        offf[i] = (size_t)-1;
+        if (e->ln_fold && follows_layernorm(e, i)) { /* folded copy: bf16 [N,K] | colsum [N] | bias' [N] */
+            const size_t N = n / (size_t)e->D;
+            offf[i] = total;
+            total += ((n * sizeof(vitcu_bf16) + 255) & ~(size_t)255) + 2 * ((N * sizeof(float) + 255) & ~(size_t)255);
+        }
         const int keep32 = !packed || (bf && i == 1 && !e->pe_gather);
         const int need16 = packed && !(bf && i == 1 && !e->pe_gather);
         off32[i] = off16[i] = (size_t)-1;
@@ -354,7 +376,9 @@ int vitb200_load_weights(vitb200_engine *e, const vitb200_blob *net)
     float *scratch[2] = {NULL, NULL};
     float **w32 = (float **)calloc(VIT_MAX_BLOBS, sizeof(float *));
     vitcu_bf16 **w16 = (vitcu_bf16 **)calloc(VIT_MAX_BLOBS, sizeof(vitcu_bf16 *));
-    int rc = (w32 && w16) ? 0 : VITCU_E_ARG;
+    vitcu_bf16 **wf16 = (vitcu_bf16 **)calloc(VIT_MAX_BLOBS, sizeof(vitcu_bf16 *));
+    float **wf_cs = (float **)calloc(VIT_MAX_BLOBS, sizeof(float *)), **wf_b = (float **)calloc(VIT_MAX_BLOBS, sizeof(float *));
+    int rc = (w32 && w16 && wf16 && wf_cs && wf_b) ? 0 : VITCU_E_ARG;
     if (rc)
         vit_fail(__FILE__, __LINE__, rc, "out of host memory");
     if (!rc && (rc = vitcu_malloc(&arena, total)) != 0)
@@ -381,6 +405,19 @@ int vitb200_load_weights(vitb200_engine *e, const vitb200_blob *net)
                 const int K = gemm_weight_k(e, i);
                 rc = vitcu_split3(src, (size_t)K, w16[i], n / (size_t)K, K, e->stream);
             }
+            if (!rc && offf[i] != (size_t)-1) {
+                /* the LayerNorm in front of this GEMM folded into its weights (gamma / beta: blobs i-2, i-1;
+                 * bias: blob i+1, uploaded right here because the fold needs it before its own turn) */
+                const int N = (int)(n / (size_t)e->D);
+                char *base = (char *)arena + offf[i];
+                wf16[i] = (vitcu_bf16 *)base;
+                wf_cs[i] = (float *)(base + ((n * sizeof(vitcu_bf16) + 255) & ~(size_t)255));
+                wf_b[i] = (float *)((char *)wf_cs[i] + (((size_t)N * sizeof(float) + 255) & ~(size_t)255));
+                float *bias_dev = (float *)((char *)arena + off32[i + 1]);
+                rc = vitcu_memcpy_h2d(bias_dev, net[i + 1].data, (size_t)N * sizeof(float), e->stream);
+                if (!rc)
+                    rc = vitcu_ln_fold_weights(src, w32[i - 2], w32[i - 1], bias_dev, wf16[i], wf_cs[i], wf_b[i], N, e->D, e->stream);
+            }
         }
         if (rc)
             vit_fail(__FILE__, __LINE__, rc, NULL);
@@ -400,12 +437,18 @@ int vitb200_load_weights(vitb200_engine *e, const vitb200_blob *net)
         e->w_arena = arena;
         memcpy(e->w32, w32, sizeof(e->w32));
         memcpy(e->w16, w16, sizeof(e->w16));
+        memcpy(e->wf16, wf16, sizeof(e->wf16));
+        memcpy(e->wf_cs, wf_cs, sizeof(e->wf_cs));
+        memcpy(e->wf_b, wf_b, sizeof(e->wf_b));
         e->weights_loaded = 1;
     } else {
         vitcu_free(arena);
     }
     free(w32);
     free(w16);
+    free(wf16);
+    free(wf_cs);
+    free(wf_b);
     return rc;
 }
 
@@ -421,8 +464,10 @@ static int mark(vitb200_engine *e, int kind)
     return 0;
 }
 
+/* fold: 0 = plain; 1 = this GEMM follows a LayerNorm that is folded into it (A = bf16 residual rows, folded weights,
+ * statistics from d_lnstats); 2 = residual GEMM that also emits bf16(x) into d_ln and the row partial sums */
 static int gemm(vitb200_engine *e, const void *A, int a_split, int widx, int bidx, void *C, int M, int N, int K, int epi,
-                int out_bf16)
+                int out_bf16, int fold)
 {
     vitcu_gemm_desc d;
     memset(&d, 0, sizeof(d));
@@ -432,8 +477,16 @@ static int gemm(vitb200_engine *e, const void *A, int a_split, int widx, int bid
     d.lda = (size_t)K;
     d.ldc = (size_t)N;
     d.epilogue = epi;
-    d.bias = e->w32[bidx];
+    d.bias = fold == 1 ? e->wf_b[widx] : e->w32[bidx];
     d.out_bf16 = out_bf16;
+    if (fold == 1) {
+        d.ln_stats = e->d_lnstats;
+        d.ln_slots = e->D / 128;
+        d.ln_colsum = e->wf_cs[widx];
+    } else if (fold == 2) {
+        d.emit_bf16 = e->d_ln;
+        d.emit_stats = e->d_lnstats;
+    }
     if (epi == VITCU_EPI_BIAS_RESIDUAL)
         d.residual = (const float *)C;
     if (epi == VITCU_EPI_PATCH_EMBED) {
@@ -456,7 +509,7 @@ static int gemm(vitb200_engine *e, const void *A, int a_split, int widx, int bid
         VIT_TRY(vitcu_event_record(e->prof_ev[2 * e->prof_n], e->stream));
     int rc;
     if (e->precision == VITB200_BF16)
-        rc = vitcu_gemm_bf16((const vitcu_bf16 *)A, e->w16[widx], C, &d, e->stream);
+        rc = vitcu_gemm_bf16((const vitcu_bf16 *)A, fold == 1 ? e->wf16[widx] : e->w16[widx], C, &d, e->stream);
     else if (e->fp32_tc)
         rc = vitcu_gemm_bf16x3((const vitcu_bf16 *)A, e->w16[widx], C, &d, e->stream);
     else
@@ -486,31 +539,46 @@ static int enqueue_forward(vitb200_engine *e, int buf, int b)
     } else {
         VIT_TRY(vitcu_patch_gather_ex(e->d_images[buf], e->d_patches, b, e->img, e->patch, bf, s));
         e->launches++;
-        VIT_TRY(gemm(e, e->d_patches, 0, 1, 2, e->d_x, b * e->P, e->D, 3 * e->patch * e->patch, VITCU_EPI_PATCH_EMBED, 0));
+        VIT_TRY(gemm(e, e->d_patches, 0, 1, 2, e->d_x, b * e->P, e->D, 3 * e->patch * e->patch, VITCU_EPI_PATCH_EMBED, 0, 0));
     }
     MARK(VIT_K_OTHER);
     VIT_TRY(vitcu_cls_rows_ex(e->d_x, e->w32[0], e->w32[3], b, e->T, e->D, s));
     e->launches++;
 
     const int layers = e->stop_after < 0 ? e->depth : (e->stop_after < e->depth ? e->stop_after : e->depth);
+    /* LayerNorm folded into the GEMMs when the chunk is large enough for the CTA-pair kernel, whose residual
+     * epilogue can emit the bf16 rows and the row sums: 5 launches per layer instead of 7 and the fp32 stream is
+     * not re-read by a LayerNorm kernel.  Small chunks (batch-1 latency) keep the separate kernel. */
+    const int fold = e->ln_fold && vitcu_gemm_bf16_emit_supported(M, e->D);
+    if (fold && layers > 0) {
+        MARK(VIT_K_LAYERNORM);
+        VIT_TRY(vitcu_rowstats_cast(e->d_x, (vitcu_bf16 *)e->d_ln, e->d_lnstats, M, e->D, e->D / 128, s));
+        e->launches++;
+    }
     for (int l = 0; l < layers; l++) {
         const int w = 4 + 12 * l; /* blob base of the layer (R/ViT_seq.c:446-504) */
         /* x -> LN1 -> QKV -> attention -> out-proj (+x)  (R/ViT_opencl.c:710-730) */
-        MARK(VIT_K_LAYERNORM);
-        VIT_TRY(vitcu_layernorm_ex(e->d_x, e->D, e->d_ln, ln_mode, e->w32[w + 0], e->w32[w + 1], M, e->D, s));
-        e->launches++;
-        VIT_TRY(gemm(e, e->d_ln, 1, w + 2, w + 3, e->d_qkv, M, 3 * e->D, e->D, VITCU_EPI_BIAS, bf));
+        if (!fold) {
+            MARK(VIT_K_LAYERNORM);
+            VIT_TRY(vitcu_layernorm_ex(e->d_x, e->D, e->d_ln, ln_mode, e->w32[w + 0], e->w32[w + 1], M, e->D, s));
+            e->launches++;
+        }
+        VIT_TRY(gemm(e, e->d_ln, 1, w + 2, w + 3, e->d_qkv, M, 3 * e->D, e->D, VITCU_EPI_BIAS, bf, fold));
         MARK(VIT_K_ATTENTION);
         /* FP32 tensor-core path: the attention kernel writes its output already split into three bf16 pieces */
         VIT_TRY(vitcu_attention_ex(e->d_qkv, e->d_att, b, e->T, e->heads, e->fp32_tc ? 2 : bf, s));
         e->launches++;
-        VIT_TRY(gemm(e, e->d_att, e->fp32_tc, w + 4, w + 5, e->d_x, M, e->D, e->D, VITCU_EPI_BIAS_RESIDUAL, 0));
+        VIT_TRY(gemm(e, e->d_att, e->fp32_tc, w + 4, w + 5, e->d_x, M, e->D, e->D, VITCU_EPI_BIAS_RESIDUAL, 0, fold ? 2 : 0));
         /* -> LN2 -> fc1+GELU -> fc2 (+r1)  (R/ViT_opencl.c:732-746) */
-        MARK(VIT_K_LAYERNORM);
-        VIT_TRY(vitcu_layernorm_ex(e->d_x, e->D, e->d_ln, ln_mode, e->w32[w + 6], e->w32[w + 7], M, e->D, s));
-        e->launches++;
-        VIT_TRY(gemm(e, e->d_ln, 1, w + 8, w + 9, e->d_hid, M, e->HID, e->D, VITCU_EPI_BIAS_GELU, bf));
-        VIT_TRY(gemm(e, e->d_hid, 0, w + 10, w + 11, e->d_x, M, e->D, e->HID, VITCU_EPI_BIAS_RESIDUAL, 0));
+        if (!fold) {
+            MARK(VIT_K_LAYERNORM);
+            VIT_TRY(vitcu_layernorm_ex(e->d_x, e->D, e->d_ln, ln_mode, e->w32[w + 6], e->w32[w + 7], M, e->D, s));
+            e->launches++;
+        }
+        VIT_TRY(gemm(e, e->d_ln, 1, w + 8, w + 9, e->d_hid, M, e->HID, e->D, VITCU_EPI_BIAS_GELU, bf, fold));
+        /* the last layer's fc2 has no LayerNorm consumer over all rows (the final one visits the class rows only) */
+        VIT_TRY(gemm(e, e->d_hid, 0, w + 10, w + 11, e->d_x, M, e->D, e->HID, VITCU_EPI_BIAS_RESIDUAL, 0,
+                     fold && l + 1 < layers ? 2 : 0));
     }
     if (e->stop_after >= 0)
         return 0;

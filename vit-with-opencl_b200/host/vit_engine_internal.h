@@ -23,6 +23,13 @@ struct vitb200_engine {
     void *w_arena;                   /* one device allocation holding every weight below */
     float *w32[VIT_MAX_BLOBS];         /* fp32 blobs on the device (pointers into w_arena) */
     vitcu_bf16 *w16[VIT_MAX_BLOBS]; /* BF16 path: bf16 GEMM weights [N,K]; FP32 tensor-core path: three bf16 pieces [N,3K] */
+    /* LayerNorm folded into the GEMMs (BF16 path, big chunks): folded copies of the weights that follow a LayerNorm
+     * (in_proj: blob base + 2, fc1: base + 8): bf16(gamma * W), column sums, b + W beta; the bf16 copy of the residual
+     * rows lives in d_ln, the rows' partial sums in d_lnstats */
+    int ln_fold;
+    vitcu_bf16 *wf16[VIT_MAX_BLOBS];
+    float *wf_cs[VIT_MAX_BLOBS], *wf_b[VIT_MAX_BLOBS];
+    void *d_lnstats;                 /* float2 [D / 128][B*T] */
     vitcu_bf16 *d_a3;                /* FP32 tensor-core path: split form [rows,3K] of the current GEMM A operand */
     float *d_images[2];              /* double-buffered input chunk [B,3,img,img] */
     void *d_patches;                 /* [B*P,768] gathered patches */
