@@ -91,10 +91,64 @@ struct SmemLayout {
 // (4 per bf16 row).  Latency hiding: the tcgen05.ld of chunk c+1 and the residual / position rows
 // of chunk c+1 are in flight while chunk c is processed, and the first residual rows are requested
 // before the wait for the accumulator.
-template <int NCHUNK, int STAGE_BYTES_PER_WARP, bool PREFETCH>
+// Folded LayerNorm, consumer side: mean / rstd of one row from the producer's partial sums, slots in fixed order
+// (deterministic).  Single-pass variance like the reference (R/ViT_seq.c:126-135).
+struct LnRow {
+    float rstd, nrm; // y = rstd * acc + nrm * colsum[n] + bias'[n],  nrm = -rstd * mean
+};
+constexpr int kMaxLnSlots = 8;
+__device__ __forceinline__ void ln_row_fetch(const EpiParams &p, int row, float2 (&part)[kMaxLnSlots])
+{
+#pragma unroll
+    for (int sl = 0; sl < kMaxLnSlots; sl++) {
+        part[sl] = make_float2(0.f, 0.f);
+        if (sl < p.ln_slots && row < p.M)
+            part[sl] = __ldg(p.ln_stats + static_cast<size_t>(sl) * p.M + row);
+    }
+}
+__device__ __forceinline__ LnRow ln_row_finish(const EpiParams &p, const float2 (&part)[kMaxLnSlots])
+{
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int sl = 0; sl < kMaxLnSlots; sl++) {
+        s1 += part[sl].x;
+        s2 += part[sl].y;
+    }
+    const float mu = s1 * p.ln_inv_d;
+    const float var = fmaxf(s2 * p.ln_inv_d - mu * mu, 0.0f);
+    LnRow r;
+    r.rstd = 1.0f / sqrtf(var + 1e-6f);
+    r.nrm = -r.rstd * mu;
+    return r;
+}
+
+// Per-column epilogue coefficients in shared memory (upper 4 KB of a warp's staging area, two buffers of 256 floats:
+// bias at [0, 128), colsum at [128, 256)): available when the bf16 TMA-store path leaves that half free.
+template <bool LN, int STAGE_BYTES_PER_WARP, int NCHUNK>
+__device__ __forceinline__ bool coef_in_smem(const EpiParams &p)
+{
+    return LN || (STAGE_BYTES_PER_WARP >= 8192 && NCHUNK <= 4 && p.tma_out == 1);
+}
+// asynchronous copy (16 B per lane) of this warp's NCHUNK * 32 coefficients starting at column col_base
+template <bool LN, int NCHUNK>
+__device__ __forceinline__ void ln_coef_copy(const EpiParams &p, float *dst, int lane, int col_base)
+{
+    if (lane < NCHUNK * 8) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + 4 * lane)), "l"(p.bias + col_base + 4 * lane) : "memory");
+        if (LN)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + 128 + 4 * lane)), "l"(p.ln_colsum + col_base + 4 * lane) : "memory");
+    }
+}
+
+// ln: statistics of this thread's row for THIS tile (filled by the previous call, or by the caller before the first
+// tile); next_row0 >= 0: first row of this warp's share of the NEXT tile -- its partials are requested during the last
+// chunk of this tile (when the accumulator prefetch registers are free) and reduced after it, so that the L2 latency
+// of those loads never sits between two tiles of an epilogue-bound GEMM.
+template <int NCHUNK, int STAGE_BYTES_PER_WARP, bool PREFETCH, bool LN = false>
 __device__ __forceinline__ bool epilogue_tile(const EpiParams &p, void *C, const CUtensorMap *tmap_c, uint32_t &chunk_ctr,
                                               float *stage, int lane, int row0, int col_base, uint32_t taddr,
-                                              uint64_t *tfull, uint32_t parity, const Watchdog &wd, float bias_on = 1.0f)
+                                              uint64_t *tfull, uint32_t parity, const Watchdog &wd, LnRow &ln, int next_row0,
+                                              int next_col_base, uint32_t tile_it, float bias_on = 1.0f)
 {
     const bool fp32_add = !p.tma_out && !p.out_bf16 && p.epilogue != VITCU_EPI_BIAS; // residual or position rows to fetch
     const int rsub = lane >> 3, c4 = (lane & 7) * 4;
@@ -123,22 +177,23 @@ __device__ __forceinline__ bool epilogue_tile(const EpiParams &p, void *C, const
         }
     };
     fetch_add(0); // does not depend on the accumulator: in flight during the wait below
-    // LayerNorm folded into this GEMM: y = rstd * acc - rstd * mean * colsum[n] + bias'[n], with the statistics of
-    // this thread's row summed from the producer's partials in slot order (deterministic), R/ViT_seq.c:126-135
-    float rstd = 1.0f, nrm = 0.0f;
-    if (p.ln_stats) {
-        const int row = row0 + lane;
-        float s1 = 0.f, s2 = 0.f;
-        if (row < p.M)
-            for (int sl = 0; sl < p.ln_slots; sl++) {
-                const float2 v = __ldg(p.ln_stats + static_cast<size_t>(sl) * p.M + row);
-                s1 += v.x;
-                s2 += v.y;
-            }
-        const float mu = s1 * p.ln_inv_d;
-        const float var = fmaxf(s2 * p.ln_inv_d - mu * mu, 0.0f);
-        rstd = 1.0f / sqrtf(var + 1e-6f);
-        nrm = -rstd * mu;
+    const float rstd = ln.rstd, nrm = ln.nrm;
+    float2 part[kMaxLnSlots];
+    // Folded LayerNorm: the per-column coefficients of this warp's columns (bias' and colsum, NCHUNK * 32 floats each)
+    // sit in shared memory, double-buffered by tile: read through __ldg in the chunk loop they cost an L2 round trip
+    // per chunk on the epilogue's critical path (profiles/r02_layernorm_fold.md).  They are copied asynchronously
+    // (cp.async, 16 B per lane) one tile ahead into the upper half of the warp's staging area, which the bf16 TMA-store
+    // path does not use.
+    float *coef = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(stage) + 4096) + (tile_it & 1) * 256;
+    static_assert(!LN || (STAGE_BYTES_PER_WARP >= 8192 && NCHUNK <= 4), "coefficient buffers need the upper 4 KB of the staging area");
+    // the plain bias of the bf16-output GEMMs takes the same route (their FADDs waited on the same loads)
+    const bool coef_on = coef_in_smem<LN, STAGE_BYTES_PER_WARP, NCHUNK>(p);
+    if (coef_on) {
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncwarp();
+        if (next_col_base >= 0)
+            ln_coef_copy<LN, NCHUNK>(p, reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(stage) + 4096) + ((tile_it + 1) & 1) * 256,
+                                     lane, next_col_base);
     }
 
     bool ok = mbar_wait(tfull, parity, wd, 4);
@@ -160,17 +215,19 @@ __device__ __forceinline__ bool epilogue_tile(const EpiParams &p, void *C, const
         tmem_ld_wait();
         if (PREFETCH && c + 1 < NCHUNK)
             tmem_ld_32x32b_x32(taddr + (c + 1) * 32, acc[(c + 1) % NACC]);
+        if (LN && c + 1 == NCHUNK && next_row0 >= 0)
+            ln_row_fetch(p, next_row0 + lane, part); // in flight during the last chunk
         if (row0 >= p.M) // warp-uniform: nothing of this warp's rows exists
             continue;
         const int col0 = col_base + c * 32;
         // ---- row-per-thread part: bias (+ GELU), then into the staging tile ----
         float v[32];
-        if (p.ln_stats) {
+        if (LN) {
             const f32x2 r2 = pack2(rstd, rstd), n2 = pack2(nrm, nrm);
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-                const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + col0 + j));
-                const float4 cs = __ldg(reinterpret_cast<const float4 *>(p.ln_colsum + col0 + j));
+                const float4 b = *reinterpret_cast<const float4 *>(coef + c * 32 + j);
+                const float4 cs = *reinterpret_cast<const float4 *>(coef + 128 + c * 32 + j);
                 unpack2(fma2(pack2(__uint_as_float(acc[c % NACC][j + 0]), __uint_as_float(acc[c % NACC][j + 1])), r2,
                              fma2(pack2(cs.x, cs.y), n2, pack2(b.x, b.y))), v[j + 0], v[j + 1]);
                 unpack2(fma2(pack2(__uint_as_float(acc[c % NACC][j + 2]), __uint_as_float(acc[c % NACC][j + 3])), r2,
@@ -179,7 +236,8 @@ __device__ __forceinline__ bool epilogue_tile(const EpiParams &p, void *C, const
         } else {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-                const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + col0 + j));
+                const float4 b = coef_on ? *reinterpret_cast<const float4 *>(coef + c * 32 + j)
+                                         : __ldg(reinterpret_cast<const float4 *>(p.bias + col0 + j));
                 v[j + 0] = fmaf(b.x, bias_on, __uint_as_float(acc[c % NACC][j + 0]));
                 v[j + 1] = fmaf(b.y, bias_on, __uint_as_float(acc[c % NACC][j + 1]));
                 v[j + 2] = fmaf(b.z, bias_on, __uint_as_float(acc[c % NACC][j + 2]));
@@ -287,6 +345,8 @@ __device__ __forceinline__ bool epilogue_tile(const EpiParams &p, void *C, const
         }
         __syncwarp(); // the staging tile is reused by the next chunk
     }
+    if (LN && next_row0 >= 0)
+        ln = ln_row_finish(p, part);
     return true;
 }
 
@@ -299,6 +359,9 @@ __device__ __forceinline__ bool epilogue_tile(const EpiParams &p, void *C, const
 // x_new back IN PLACE and the TMA engine stores the tile; a second, bf16 tile goes out beside it.  The layernorm
 // kernel's launch and its re-read of the fp32 stream (4 of its 6 bytes per element) disappear.
 // Per-warp staging (12 KB): R[2] fp32 in/out tiles at 0 / 4096, B[2] bf16 tiles at 8192 / 10240; rbar[2] signal the loads.
+#ifndef VITCU_EMIT_VARIANT
+#define VITCU_EMIT_VARIANT 0 // diagnostics: 1 spin on the residual barrier, 2 no read-wait before the reload (racy), 3 no residual load (x_old = 0)
+#endif
 template <int NCHUNK>
 __device__ __forceinline__ bool epilogue_tile_emit(const EpiParams &p, const CUtensorMap *tmap_c, const CUtensorMap *tmap_d,
                                                    uint8_t *stage, uint64_t *rbar, uint32_t (&rphase)[2], int lane, int row0,
@@ -308,10 +371,12 @@ __device__ __forceinline__ bool epilogue_tile_emit(const EpiParams &p, const CUt
     const bool rows_exist = row0 < p.M; // warp-uniform
     if (rows_exist && lane == 0) {
         tma_wait_group_read<0>(); // this warp's stores of the previous tile have read the staging buffers
+#if VITCU_EMIT_VARIANT != 3
         for (int c = 0; c < 2 && c < NCHUNK; c++) {
             mbar_arrive_expect_tx(&rbar[c], 4096);
             tma_load_2d(stage + c * 4096, tmap_c, &rbar[c], col_base + c * 32, row0);
         }
+#endif
     }
     __syncwarp();
     bool ok = mbar_wait(tfull, parity, wd, 4);
@@ -341,7 +406,13 @@ __device__ __forceinline__ bool epilogue_tile_emit(const EpiParams &p, const CUt
             v[j + 3] = __uint_as_float(acc[c & 1][j + 3]) + bb.w;
         }
         // the residual tile of this chunk has landed
+#if VITCU_EMIT_VARIANT == 1
+        ok = mbar_wait_spin(&rbar[b], rphase[b], wd, 9);
+#elif VITCU_EMIT_VARIANT == 3
+        ok = true;
+#else
         ok = mbar_wait(&rbar[b], rphase[b], wd, 9);
+#endif
         ok = __all_sync(0xffffffffu, ok);
         if (!ok)
             return false;
@@ -371,9 +442,13 @@ __device__ __forceinline__ bool epilogue_tile_emit(const EpiParams &p, const CUt
             tma_store_2d(tmap_d, B, col0, row0);
             tma_commit_group();
             if (c + 2 < NCHUNK) { // the buffers are reloaded once the stores just issued have read them
+#if VITCU_EMIT_VARIANT != 2 && VITCU_EMIT_VARIANT != 3
                 tma_wait_group_read<0>();
+#endif
+#if VITCU_EMIT_VARIANT != 3
                 mbar_arrive_expect_tx(&rbar[b], 4096);
                 tma_load_2d(R, tmap_c, &rbar[b], col_base + (c + 2) * 32, row0);
+#endif
             }
         }
         __syncwarp();
@@ -383,7 +458,7 @@ __device__ __forceinline__ bool epilogue_tile_emit(const EpiParams &p, const CUt
     return true;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool LN = false>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_c, void *C, const EpiParams p, uint32_t *watchdog_flag)
@@ -509,14 +584,26 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         uint32_t it = 0, chunk_ctr = 0;
         if (warp == 2 && lane == 0)
             prefetch_tensormap(&tmap_c);
+        LnRow ln = {1.0f, 0.0f};
+        if (LN && (int)blockIdx.x < num_tiles) { // first tile: fetched here; later tiles one tile ahead
+            float2 part[kMaxLnSlots];
+            ln_row_fetch(p, ((int)blockIdx.x / p.splits / num_n) * BM + quad * 32 + lane, part);
+            ln = ln_row_finish(p, part);
+        }
+        if (coef_in_smem<LN, kStageFloats * 4, BN / 64>(p) && (int)blockIdx.x < num_tiles)
+            ln_coef_copy<LN, BN / 64>(p, reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(smem + L::EPI_OFFSET) + (warp - 2) * kStageFloats * 4 + 4096),
+                                      lane, (((int)blockIdx.x / p.splits) % num_n) * BN + half * (BN / 2));
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
             const int split = tile % p.splits, t2 = tile / p.splits;
             const int m_blk = t2 / num_n, n_blk = t2 - m_blk * num_n;
+            const int tile_n = tile + (int)gridDim.x;
+            const int next_row0 = tile_n < num_tiles ? (tile_n / p.splits / num_n) * BM + quad * 32 : -1;
+            const int next_col = tile_n < num_tiles ? ((tile_n / p.splits) % num_n) * BN + half * (BN / 2) : -1;
             const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
             float *stage_tile = reinterpret_cast<float *>(smem + L::EPI_OFFSET) + (warp - 2) * kStageFloats;
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + half * (BN / 2);
-            if (!epilogue_tile<BN / 64, kStageFloats * 4, true>(p, C, &tmap_c, chunk_ctr, stage_tile, lane, m_blk * BM + quad * 32,
-                                   n_blk * BN + half * (BN / 2), taddr, &tfull_bar[acc], acc_phase, wd,
+            if (!epilogue_tile<BN / 64, kStageFloats * 4, true, LN>(p, C, &tmap_c, chunk_ctr, stage_tile, lane, m_blk * BM + quad * 32,
+                                   n_blk * BN + half * (BN / 2), taddr, &tfull_bar[acc], acc_phase, wd, ln, next_row0, next_col, it,
                                    split == 0 ? 1.0f : 0.0f))
                 break;
             tcgen05_fence_before();
@@ -570,7 +657,7 @@ struct SmemLayout2 {
 // EPI_BYTES = epilogue staging per CTA: 64 KB with 5 operand stages, or 32 KB (4 KB per warp: two bf16 tiles
 // or one fp32 tile, TMA output path only) which makes room for a sixth stage
 // EMIT = residual epilogue that also emits bf16(x) and the row partial sums for the folded LayerNorm (epilogue_tile_emit)
-template <int STAGES, int EW, uint32_t EPI_BYTES = 65536, bool EMIT = false>
+template <int STAGES, int EW, uint32_t EPI_BYTES = 65536, bool EMIT = false, bool LN = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EW, 1)
 gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                      const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_d, void *C,
@@ -713,8 +800,19 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             if (EMIT)
                 prefetch_tensormap(&tmap_d);
         }
+        LnRow ln = {1.0f, 0.0f};
+        if (LN && pair < num_tiles) { // first tile: fetched here; later tiles one tile ahead
+            float2 part[kMaxLnSlots];
+            ln_row_fetch(p, (pair / num_n) * BM2 + (int)rank * BM + quad * 32 + lane, part);
+            ln = ln_row_finish(p, part);
+        }
+        if (!EMIT && coef_in_smem<LN, SBW, CW / 32>(p) && pair < num_tiles)
+            ln_coef_copy<LN, CW / 32>(p, reinterpret_cast<float *>(smem + L::EPI_OFFSET + (warp - 2) * SBW + 4096), lane,
+                                      (pair % num_n) * BN + cgrp * CW);
         for (int tile = pair; tile < num_tiles; tile += num_pairs, it++) {
             const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
+            const int next_row0 = tile + num_pairs < num_tiles ? ((tile + num_pairs) / num_n) * BM2 + (int)rank * BM + quad * 32 : -1;
+            const int next_col = tile + num_pairs < num_tiles ? ((tile + num_pairs) % num_n) * BN + cgrp * CW : -1;
             const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
             float *stage_tile = reinterpret_cast<float *>(smem + L::EPI_OFFSET + (warp - 2) * SBW);
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + cgrp * CW;
@@ -726,9 +824,9 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                                                       m_blk * BM2 + (int)rank * BM + quad * 32, n_blk * BN + cgrp * CW, taddr,
                                                       &tfull_bar[acc], acc_phase, wd);
             } else {
-                tile_ok = epilogue_tile<CW / 32, SBW, EW == 8>(p, C, &tmap_c, chunk_ctr, stage_tile, lane,
+                tile_ok = epilogue_tile<CW / 32, SBW, EW == 8, LN>(p, C, &tmap_c, chunk_ctr, stage_tile, lane,
                                                                m_blk * BM2 + (int)rank * BM + quad * 32, n_blk * BN + cgrp * CW,
-                                                               taddr, &tfull_bar[acc], acc_phase, wd);
+                                                               taddr, &tfull_bar[acc], acc_phase, wd, ln, next_row0, next_col, it);
             }
             if (!tile_ok)
                 break;
@@ -767,12 +865,12 @@ EncodeTiledFn encode_tiled_fn()
     return fn;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool LN = false>
 int launch(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &tc, void *C, const EpiParams &p, int sms,
            cudaStream_t st)
 {
     using L = SmemLayout<BN, STAGES>;
-    auto kernel = gemm_bf16_tc_kernel<BN, STAGES>;
+    auto kernel = gemm_bf16_tc_kernel<BN, STAGES, LN>;
     static bool configured[64] = {false};
     int dev = 0;
     VITCU_TRY(cudaGetDevice(&dev));
@@ -787,12 +885,12 @@ int launch(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &tc, 
     return 0;
 }
 
-template <int STAGES, int EW, uint32_t EPI_BYTES = 65536, bool EMIT = false>
+template <int STAGES, int EW, uint32_t EPI_BYTES = 65536, bool EMIT = false, bool LN = false>
 int launch_pair(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &tc, const CUtensorMap &td, void *C,
                 const EpiParams &p, int sms, cudaStream_t st)
 {
     using L = SmemLayout2<STAGES, EPI_BYTES>;
-    auto kernel = gemm_bf16_tc2_kernel<STAGES, EW, EPI_BYTES, EMIT>;
+    auto kernel = gemm_bf16_tc2_kernel<STAGES, EW, EPI_BYTES, EMIT, LN>;
     static bool configured[64] = {false};
     int dev = 0;
     VITCU_TRY(cudaGetDevice(&dev));
@@ -865,7 +963,7 @@ static int gemm_dispatch(const vitcu_bf16 *A, const vitcu_bf16 *W, void *C, cons
     VITCU_REQUIRE(d->M > 0 && d->N > 0 && d->K > 0, "empty GEMM");
     VITCU_REQUIRE(d->K % BK == 0, "bf16 GEMM needs K % 64 == 0");
     VITCU_REQUIRE(d->N % 128 == 0, "bf16 GEMM needs N % 128 == 0");
-    VITCU_REQUIRE(d->bias, "bias is required");
+    VITCU_REQUIRE(d->bias && ((uintptr_t)d->bias & 15) == 0, "bias is required (16-byte aligned)");
     VITCU_REQUIRE(d->epilogue != VITCU_EPI_BIAS_RESIDUAL || d->residual, "residual pointer missing");
     VITCU_REQUIRE(d->epilogue != VITCU_EPI_PATCH_EMBED || (d->pos && d->patches > 0 && d->tokens > d->patches),
                   "patch-embed epilogue needs pos, patches, tokens");
@@ -887,6 +985,8 @@ static int gemm_dispatch(const vitcu_bf16 *A, const vitcu_bf16 *W, void *C, cons
     if (d->ln_stats) {
         VITCU_REQUIRE(!split3 && d->ln_colsum && d->ln_slots > 0, "LayerNorm-folded GEMM needs bf16 operands, column sums and slots");
         VITCU_REQUIRE(d->epilogue == VITCU_EPI_BIAS || d->epilogue == VITCU_EPI_BIAS_GELU, "LayerNorm fold applies to bias / GELU epilogues");
+        VITCU_REQUIRE(d->out_bf16 && ((uintptr_t)C & 15) == 0 && ((uintptr_t)d->bias & 15) == 0 && ((uintptr_t)d->ln_colsum & 15) == 0,
+                      "LayerNorm-folded GEMM writes bf16 through the TMA store path and needs 16-byte aligned coefficient vectors");
         p.ln_stats = reinterpret_cast<const float2 *>(d->ln_stats);
         p.ln_colsum = d->ln_colsum;
         p.ln_slots = d->ln_slots;
@@ -967,13 +1067,15 @@ static int gemm_dispatch(const vitcu_bf16 *A, const vitcu_bf16 *W, void *C, cons
         // MUFU.TANH form 8 warps with double-buffered tcgen05.ld are as fast or faster (0.195 vs 0.198 ms)
         static const int force_ew = getenv("VITCU_GEMM_EW") ? atoi(getenv("VITCU_GEMM_EW")) : 0;
         const bool ew16 = p.tma_out != 0 && (force_ew ? force_ew == 16 : (VITCU_GELU_FORM == 0 && p.epilogue == VITCU_EPI_BIAS_GELU));
-        if (ew16)
+        if (ew16 && !p.ln_stats)
             return launch_pair<5, 16>(ta, tb, tc, td, C, p, sms, as_stream(s));
         // VITCU_GEMM_STAGES=6: a sixth operand stage in exchange for single-buffered epilogue staging (A/B)
         // measured (M=50432): bf16-output launches unchanged, fp32 reduce-add launches (out_proj, fc2) +1.5 %
         static const int stages = getenv("VITCU_GEMM_STAGES") ? atoi(getenv("VITCU_GEMM_STAGES")) : 0;
         if (p.tma_out != 0 && (stages == 6 || (stages == 0 && p.tma_out == 2)))
             return launch_pair<6, 8, 32768>(ta, tb, tc, td, C, p, sms, as_stream(s));
+        if (p.ln_stats)
+            return launch_pair<5, 8, 65536, false, true>(ta, tb, tc, td, C, p, sms, as_stream(s));
         return launch_pair<5, 8>(ta, tb, tc, td, C, p, sms, as_stream(s));
     }
     // 128x256 tiles when they divide N and still give every SM work; else 128x128
@@ -995,6 +1097,8 @@ static int gemm_dispatch(const vitcu_bf16 *A, const vitcu_bf16 *W, void *C, cons
     rc = make_tensor_map_2d(&tb, W, 2, (uint64_t)d->N, kphys, kphys * 2, wide ? 256 : 128, BK);
     if (rc)
         return rc;
+    if (p.ln_stats)
+        return wide ? launch<256, 3, true>(ta, tb, tc, C, p, sms, as_stream(s)) : launch<128, 5, true>(ta, tb, tc, C, p, sms, as_stream(s));
     if (wide)
         return launch<256, 3>(ta, tb, tc, C, p, sms, as_stream(s));
     return launch<128, 5>(ta, tb, tc, C, p, sms, as_stream(s));
