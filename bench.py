@@ -681,6 +681,30 @@ def run_engine_arm(args, dist: Dist):
                 line["config5"]["forward_breakdown_ms"] = {k: {"ms": round(v[0], 4), "launches": v[1]} for k, v in tl5.items()}
         except Exception as ex:
             line["config5"] = {"error": str(ex)}
+        # ---- FP8 variant: fc1 / fc2 on E4M3 operands; its own accuracy contract, NOT the headline ----
+        try:
+            with pkg.Engine(dev, IMG, pkg.FP8, max_batch=BATCH) as e8:
+                e8.load_weights(blobs)
+                pin8 = pkg.PinnedArray((BATCH, 3, IMG, IMG))
+                pin8.array[...] = pkg.synth.synthetic_images(BATCH, IMG, seed=1234 + dist.rank)
+                e8.stage(pin8.array)
+                for _ in range(max(args.warmup, 3)):
+                    e8.forward_resident(BATCH)
+                dist.barrier()
+                ms8 = e8.time_resident(BATCH, args.steps)
+                dist.barrier()
+                ms8 = dist.reduce(ms8, "max")
+                tl8 = e8.profile_timeline(BATCH, 2) if dist.rank == 0 else None
+                pin8.free()
+            v8 = dist.world * BATCH * args.steps / (ms8 / 1e3)
+            line["fp8"] = {"dtype": "fp8 (e4m3 fc1/fc2, bf16 elsewhere)", "value": v8, "unit": UNIT, "ms_per_step": ms8 / args.steps,
+                           "speedup_vs_bf16": v8 / value,
+                           "accuracy_contract": "max|dlogit| <= 2.5e-1 and identical top-1 on the 32-image parity set "
+                                                "(tests/test_gpu_bench_config_parity.py::test_fp8_batch256_vs_oracle)"}
+            if tl8:
+                line["fp8"]["forward_breakdown_ms"] = {k: {"ms": round(v[0], 4), "launches": v[1]} for k, v in tl8.items()}
+        except Exception as ex:
+            line["fp8"] = {"error": str(ex)}
         # ---- BASELINE config 4 through the product's own multi-GPU split (one ViT_opencl call) ----
         dist.cpu_barrier()          # every rank has released its engines; the GPUs are idle
         if dist.rank == 0:

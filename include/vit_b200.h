@@ -19,7 +19,7 @@
  *    implicit drain, R/ViT_opencl.c:978-983); there is no 100-image cap
  *    (R/ViT_opencl.c:107-111); image side is read from the struct so 384x384
  *    works; missing blobs are reported instead of dereferenced.
- *    Environment knobs: VITB200_PRECISION=fp32|bf16 (default fp32, the
+ *    Environment knobs: VITB200_PRECISION=fp32|bf16|fp8 (default fp32, the
  *    reference's arithmetic), VITB200_GPUS=<n> (default: 1 GPU per 256 images,
  *    capped by the visible devices), VITB200_BATCH=<images per chunk>,
  *    VITB200_PERSIST=1 (keep the engines and the packed weights across calls;
@@ -59,7 +59,11 @@ typedef Network vitb200_blob;
 #define VITB200_NBLOBS 152
 #define VITB200_CLASSES 1000
 
-enum { VITB200_FP32 = 0, VITB200_BF16 = 1 };
+/* VITB200_FP8: the BF16 path with the two MLP GEMMs (fc1, fc2: 63.5 % of the FLOPs) on E4M3 operands
+ * (tcgen05.mma kind::f8f6f4, per-tensor scales; activations calibrated on the engine's first chunk).  It applies to
+ * chunks large enough for the CTA-pair GEMM (>= 32 images at 224x224); smaller chunks run the BF16 kernels.
+ * Accuracy contract: INTEGRATION.md section "FP8". */
+enum { VITB200_FP32 = 0, VITB200_BF16 = 1, VITB200_FP8 = 2 };
 
 typedef struct vitb200_engine vitb200_engine;
 

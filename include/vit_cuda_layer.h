@@ -169,6 +169,15 @@ typedef struct {
      * over each block of 128 columns to emit_stats (float2, [N / 128][M]). */
     void *emit_bf16;
     void *emit_stats;
+    /* FP8 (E4M3) path, per-tensor scales (vitcu_gemm_e4m3 and the emit epilogue of vitcu_gemm_bf16):
+     *   acc_scale  = 1 / (scale_A * scale_W): multiplies the accumulator of an e4m3 x e4m3 product
+     *   out_fp8    : the output is e4m3(y * out_scale) [M,N] (the A operand of the next e4m3 GEMM)
+     *   emit_fp8   : the emit epilogue writes e4m3(x * emit_scale) to emit_bf16 instead of bf16(x) */
+    float acc_scale;
+    int out_fp8;
+    float out_scale;
+    int emit_fp8;
+    float emit_scale;
 } vitcu_gemm_desc;
 
 /* FP32 SIMT GEMM (replaces linear_layer, R/ll.cl:7-70 and QKV, R/multihead.cl:3-63
@@ -181,6 +190,24 @@ int vitcu_sgemm(const float *A, const float *W, void *C, const vitcu_gemm_desc *
  * A [M,K] bf16 (lda == K), W [N,K] bf16.  Requires K % 64 == 0, N % 16 == 0. */
 int vitcu_gemm_bf16(const vitcu_bf16 *A, const vitcu_bf16 *W, void *C,
                     const vitcu_gemm_desc *d, vitcu_stream s);
+
+/* FP8 tensor-core GEMM (tcgen05.mma kind::f8f6f4, E4M3 x E4M3 -> FP32): A [M,K] and W [N,K] are e4m3 bytes quantised
+ * with per-tensor scales, d->acc_scale = 1 / (scale_A * scale_W).  CTA-pair kernel only (vitcu_gemm_bf16_emit_supported
+ * (M, N) must hold, K % 128 == 0).  Two forms: (a) LayerNorm-folded consumer (ln_stats / ln_colsum, bias or GELU
+ * epilogue) writing e4m3 (out_fp8) or bf16; (b) in-place fp32 residual update that emits bf16(x) or e4m3(x) and the row
+ * sums (emit_bf16 / emit_stats), like the bf16 kernel's producer epilogue. */
+int vitcu_gemm_e4m3(const uint8_t *A, const uint8_t *W, void *C, const vitcu_gemm_desc *d, vitcu_stream s);
+
+/* Per-tensor absolute maximum into *out (device float, must be zeroed by the caller; the kernel max-combines):
+ * of an fp32 matrix [rows,K], optionally with column factors gamma[K] (the folded weight gamma * W), or of a bf16 buffer. */
+int vitcu_absmax_f32(const float *x, const float *gamma, size_t rows, int K, float *out, vitcu_stream s);
+int vitcu_absmax_bf16(const vitcu_bf16 *x, size_t n, float *out, vitcu_stream s);
+
+/* fp32 weights -> e4m3 with one scale: q[n,k] = e4m3(W[n,k] * gamma[k] * scale) (gamma NULL = 1).  When colsum is given:
+ * colsum[n] = sum_k deq(q[n,k]) / scale and bias_folded[n] = bias[n] + sum_k beta[k] W[n,k] (LayerNorm fold, see
+ * vitcu_ln_fold_weights). */
+int vitcu_fp8_quant_weights(const float *W, const float *gamma, const float *beta, const float *bias, float scale, uint8_t *q,
+                            float *colsum, float *bias_folded, int N, int K, vitcu_stream s);
 
 /* 1 when vitcu_gemm_bf16 can run the LayerNorm-producer epilogue (emit_bf16 / emit_stats) for an [M,N] output */
 int vitcu_gemm_bf16_emit_supported(int M, int N);

@@ -551,3 +551,120 @@ def test_gemm_layernorm_fold_producer(pkg, lib, M, K):
     blocks = x_emit.astype(np.float64).reshape(M, slots, 128)
     np.testing.assert_allclose(st[:, :, 0].T, blocks.sum(2), rtol=1e-5, atol=1e-3)
     np.testing.assert_allclose(st[:, :, 1].T, (blocks ** 2).sum(2), rtol=1e-5, atol=1e-3)
+
+
+# ---------------------------------------------------------------- FP8 (E4M3) GEMMs
+def _e4m3(x):
+    """float -> (e4m3 bytes, de-quantised float32), round to nearest even (values must stay below 448)"""
+    torch = pytest.importorskip("torch")
+    q = torch.from_numpy(np.ascontiguousarray(x, np.float32)).to(torch.float8_e4m3fn)
+    return q.view(torch.uint8).numpy().copy(), q.to(torch.float32).numpy()
+
+
+def _e4m3_decode(bytes_):
+    torch = pytest.importorskip("torch")
+    return torch.from_numpy(np.ascontiguousarray(bytes_)).view(torch.float8_e4m3fn).to(torch.float32).numpy()
+
+
+@pytest.mark.parametrize("M,N,gelu,out_fp8", [(6304, 3072, 1, 1), (12611, 3072, 1, 0), (6500, 2304, 0, 1)])
+def test_gemm_e4m3_layernorm_fold_consumer(pkg, lib, M, N, gelu, out_fp8):
+    """fc1 on the FP8 tensor cores (tcgen05 kind::f8f6f4): e4m3 residual rows x e4m3 folded weights, LayerNorm and
+    de-quantisation in the epilogue, e4m3 (or bf16) output -- against an exact float64 product of the same
+    quantised operands, so only the output rounding is left"""
+    from scipy.special import erf
+    K = 768
+    rng = np.random.default_rng(M + N)
+    x = (rng.standard_normal((M, K), dtype=np.float32) * 1.7 + 0.3).astype(np.float32)
+    w = (rng.standard_normal((N, K), dtype=np.float32) * 0.03).astype(np.float32)
+    g = (1.0 + 0.2 * rng.standard_normal(K, dtype=np.float32)).astype(np.float32)
+    be = (0.1 * rng.standard_normal(K, dtype=np.float32)).astype(np.float32)
+    b = rng.standard_normal(N, dtype=np.float32)
+    sx = np.float32(224.0 / np.abs(x).max())
+    xq_bytes, xq = _e4m3(x * sx)
+    dx, dw, dg, dbe, db = (_dev(pkg, a) for a in (x, w, g, be, b))
+    amax = _dev(pkg, np.zeros(1, np.float32))
+    pkg.layer_check(lib.vitcu_absmax_f32(dw.ptr, dg.ptr, N, K, amax.ptr, None))
+    wmax = float(amax.to_numpy(np.float32, (1,))[0])
+    assert abs(wmax - np.abs(w * g[None, :]).max()) <= 1e-6 * wmax
+    sw = np.float32(448.0 / wmax)
+    dq, dcs, dbf = pkg.DeviceBuffer(N * K), pkg.DeviceBuffer(N * 4), pkg.DeviceBuffer(N * 4)
+    pkg.layer_check(lib.vitcu_fp8_quant_weights(dw.ptr, dg.ptr, dbe.ptr, db.ptr, sw, dq.ptr, dcs.ptr, dbf.ptr, N, K, None))
+    wq = _e4m3_decode(dq.to_numpy(np.uint8, (N, K)))
+    want_bytes, want_wq = _e4m3(w * g[None, :] * sw)
+    assert np.array_equal(wq, want_wq)
+    cs = dcs.to_numpy(np.float32, (N,))
+    np.testing.assert_allclose(cs, wq.astype(np.float64).sum(1) / sw, rtol=1e-5, atol=1e-5)
+    bf = dbf.to_numpy(np.float32, (N,))
+    slots = K // 128
+    dxb, dst = pkg.DeviceBuffer(M * K * 2), pkg.DeviceBuffer(slots * M * 8)
+    pkg.layer_check(lib.vitcu_rowstats_cast(dx.ptr, dxb.ptr, dst.ptr, M, K, slots, None))
+    dxq = _dev(pkg, xq_bytes)
+    sh = np.float32(32.0)
+    dy = pkg.DeviceBuffer(M * N * (1 if out_fp8 else 2))
+    d = _gemm_desc(pkg, M, N, K, pkg.EPI_BIAS_GELU if gelu else pkg.EPI_BIAS, dbf, out_bf16=0 if out_fp8 else 1)
+    d.ln_stats, d.ln_slots, d.ln_colsum = dst.ptr.value, slots, dcs.ptr.value
+    d.acc_scale, d.out_fp8, d.out_scale = float(1.0 / (sx * sw)), out_fp8, float(sh)
+    pkg.layer_check(lib.vitcu_gemm_e4m3(dxq.ptr, dq.ptr, dy.ptr, C.byref(d), None))
+    assert lib.vitcu_watchdog_check() == 0
+    rows = np.r_[0:96, M - 96:M]
+    xr = x[rows].astype(np.float64)
+    mu = xr.mean(1, keepdims=True)
+    rstd = 1.0 / np.sqrt((xr * xr).mean(1, keepdims=True) - mu * mu + 1e-6)
+    acc = xq[rows].astype(np.float64) @ wq.astype(np.float64).T
+    ref = rstd * acc / (float(sx) * float(sw)) - rstd * mu * cs[None, :] + bf[None, :]
+    if gelu:
+        ref = 0.5 * ref * (1.0 + erf(ref / np.sqrt(2.0)))
+    if out_fp8:
+        y = _e4m3_decode(dy.to_numpy(np.uint8, (M, N)))[rows] / sh
+        tol = 2.0 ** -4 * np.abs(ref) + 2.0 ** -9 / sh + 1e-3     # one e4m3 rounding (3 mantissa bits), subnormal floor
+    else:
+        y = pkg.bf16_bits_to_f32(dy.to_numpy(np.uint16, (M, N)))[rows]
+        tol = 2.0 ** -8 * np.abs(ref) + 1e-3
+    err = np.abs(y - ref)
+    assert (err <= tol).all(), f"max excess {(err - tol).max()} at {np.unravel_index((err - tol).argmax(), err.shape)}"
+
+
+@pytest.mark.parametrize("fp8_in,emit_fp8,M,K", [(1, 0, 6304, 3072), (1, 0, 12611, 3072), (0, 1, 6400, 768), (1, 1, 6304, 3072)])
+def test_gemm_e4m3_residual_emit(pkg, lib, fp8_in, emit_fp8, M, K):
+    """fc2 with e4m3 operands (residual update + bf16 copy + row sums for the next qkv) and the bf16 out-proj that
+    emits the e4m3 copy fc1 reads: against the exact product of the quantised operands"""
+    N = 768
+    rng = np.random.default_rng(M + K + fp8_in + 2 * emit_fp8)
+    a = rng.standard_normal((M, K), dtype=np.float32)
+    w = (rng.standard_normal((N, K), dtype=np.float32) * 0.03).astype(np.float32)
+    b = rng.standard_normal(N, dtype=np.float32)
+    r = rng.standard_normal((M, N), dtype=np.float32)
+    db, dr = _dev(pkg, b), _dev(pkg, r)
+    slots = N // 128
+    dsec, dst = pkg.DeviceBuffer(M * N * 2), pkg.DeviceBuffer(slots * M * 8)
+    d = _gemm_desc(pkg, M, N, K, pkg.EPI_BIAS_RESIDUAL, db, residual=dr)
+    d.emit_bf16, d.emit_stats = dsec.ptr.value, dst.ptr.value
+    es = np.float32(24.0)
+    d.emit_fp8, d.emit_scale = emit_fp8, float(es)
+    if fp8_in:
+        sa, sw = np.float32(64.0), np.float32(448.0 / np.abs(w).max())
+        a_bytes, aq = _e4m3(a * sa)
+        w_bytes, wq = _e4m3(w * sw)
+        d.acc_scale = float(1.0 / (sa * sw))
+        da, dw = _dev(pkg, a_bytes), _dev(pkg, w_bytes)
+        pkg.layer_check(lib.vitcu_gemm_e4m3(da.ptr, dw.ptr, dr.ptr, C.byref(d), None))
+        exact = aq.astype(np.float64) @ wq.astype(np.float64).T / (float(sa) * float(sw))
+    else:
+        a_bits, w_bits = pkg.f32_to_bf16_bits(a), pkg.f32_to_bf16_bits(w)
+        da, dw = _dev(pkg, a_bits), _dev(pkg, w_bits)
+        pkg.layer_check(lib.vitcu_gemm_bf16(da.ptr, dw.ptr, dr.ptr, C.byref(d), None))
+        exact = pkg.bf16_bits_to_f32(a_bits).astype(np.float64) @ pkg.bf16_bits_to_f32(w_bits).astype(np.float64).T
+    assert lib.vitcu_watchdog_check() == 0
+    ref = r + exact + b
+    x = dr.to_numpy(np.float32, (M, N))
+    assert np.abs(x - ref).max() <= 1e-4 * np.abs(ref).max()
+    if emit_fp8:
+        got = _e4m3_decode(dsec.to_numpy(np.uint8, (M, N)))
+        _, want = _e4m3(x * es)
+        assert np.array_equal(got, want)
+    else:
+        assert np.array_equal(dsec.to_numpy(np.uint16, (M, N)), pkg.f32_to_bf16_bits(x))
+    st = dst.to_numpy(np.float32, (slots, M, 2)).astype(np.float64)
+    blocks = x.astype(np.float64).reshape(M, slots, 128)
+    np.testing.assert_allclose(st[:, :, 0].T, blocks.sum(2), rtol=1e-5, atol=1e-3)
+    np.testing.assert_allclose(st[:, :, 1].T, (blocks ** 2).sum(2), rtol=1e-5, atol=1e-3)

@@ -127,3 +127,34 @@ def test_edge_cases(oracle, pkg, synth_blobs224):
     holed[6] = None
     with pytest.raises(ValueError):
         oracle.forward(np.zeros((1, 3, 224, 224), np.float32), holed)
+
+
+def test_l16_oracle_pinned_to_torchvision():
+    """ViT-L/16 (depth 24) cannot be expressed by the reference's unrolled encoder calls (R/ViT_seq.c:446-504), so its
+    -D build of the restatement has no compiled-reference pin; it is pinned here against the secondary oracle SURVEY.md
+    section 8c names: torchvision's vit_l_16 loaded with the same 296 blobs (file index == state_dict() position), on CPU
+    in fp64.  The same check for ViT-B/16 ties the two oracles together (label and probabilities to 1e-6)."""
+    torch = pytest.importorskip("torch")
+    tv = pytest.importorskip("torchvision")
+    import __graft_entry__ as g
+    pkg = g.load_package()
+    from oracle import binding
+    for variant, ctor in (("l16", tv.models.vit_l_16), ("b16", tv.models.vit_b_16)):
+        blobs = pkg.synth.variant_blobs(variant, 224, seed=7)
+        img = pkg.synth.synthetic_images(1, 224, seed=1234)
+        ref = binding.Oracle(variant).forward(img, blobs)
+        m = ctor(weights=None).double().eval()
+        sd = m.state_dict()
+        assert len(sd) == len(blobs)
+        m.load_state_dict({k: torch.from_numpy(np.asarray(b, np.float64)).reshape(v.shape) for (k, v), b in zip(sd.items(), blobs)})
+        for mod in m.modules():  # the reference's eps is 1e-6 (R/ViT_seq.c:21), which is torchvision's too
+            if isinstance(mod, torch.nn.LayerNorm):
+                assert mod.eps == 1e-6
+        with torch.no_grad():
+            logits = m(torch.from_numpy(img).double()).numpy()[0]
+        probs = np.exp(logits - logits.max())
+        probs /= probs.sum()
+        scale = np.abs(logits).max()
+        assert np.abs(ref["logits"][0] - logits).max() <= 2e-5 * scale, variant
+        assert int(ref["probs"][0].argmax()) == int(probs.argmax())
+        assert np.abs(ref["probs"][0] - probs).max() <= 1e-6

@@ -25,7 +25,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libvit_b200.so")
 INCLUDE_DIR = os.path.join(os.path.dirname(HERE), "include")
 
-FP32, BF16 = 0, 1
+FP32, BF16, FP8 = 0, 1, 2
 NBLOBS, CLASSES = 152, 1000
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_PATCH_EMBED = 0, 1, 2, 3
 
@@ -52,7 +52,9 @@ class GemmDesc(C.Structure):
                 ("bias", C.c_void_p), ("residual", C.c_void_p), ("pos", C.c_void_p), ("patches", C.c_int),
                 ("tokens", C.c_int), ("out_bf16", C.c_int), ("ldc", C.c_size_t),
                 ("ln_stats", C.c_void_p), ("ln_slots", C.c_int), ("ln_colsum", C.c_void_p),
-                ("emit_bf16", C.c_void_p), ("emit_stats", C.c_void_p)]
+                ("emit_bf16", C.c_void_p), ("emit_stats", C.c_void_p),
+                ("acc_scale", C.c_float), ("out_fp8", C.c_int), ("out_scale", C.c_float), ("emit_fp8", C.c_int),
+                ("emit_scale", C.c_float)]
 
 
 def build(verbose: bool = False) -> str:
@@ -141,6 +143,11 @@ def lib() -> C.CDLL:
         L.vitcu_ln_fold_weights.argtypes = [C.c_void_p] * 7 + [C.c_int, C.c_int, C.c_void_p]
         L.vitcu_rowstats_cast.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.vitcu_gemm_bf16_emit_supported.argtypes = [C.c_int, C.c_int]
+        L.vitcu_gemm_e4m3.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(GemmDesc), C.c_void_p]
+        L.vitcu_absmax_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p]
+        L.vitcu_absmax_bf16.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+        L.vitcu_fp8_quant_weights.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.vitcu_split3.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
         L.vitcu_attention.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.vitcu_softmax_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]

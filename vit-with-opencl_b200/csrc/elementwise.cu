@@ -3,6 +3,8 @@
 // All are vectorised (128-bit) and coalesced; none has data reuse, so none
 // stages through shared memory.  R/ = /root/reference/MulticoreMainProject/.
 #include "common.cuh"
+#include <cuda_fp8.h>
+#include <cuda_fp16.h>
 
 using namespace vitcu;
 
@@ -217,6 +219,95 @@ __global__ void __launch_bounds__(256) rowstats_cast_kernel(const float *__restr
     s2 = warp_sum(s2);
     if (lane < slots)
         stats[(size_t)lane * rows + row] = lane == 0 ? make_float2(s1, s2) : make_float2(0.f, 0.f);
+}
+
+// ---------------------------------------------------------------------------
+// FP8 (E4M3) path: per-tensor absolute maxima (scales are 448 / amax with head room) and weight quantisation
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void absmax_commit(float m, float *out)
+{
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0 && m > 0.f)
+        atomicMax(reinterpret_cast<int *>(out), __float_as_int(m)); // non-negative floats order like their bit patterns
+}
+__global__ void __launch_bounds__(256) absmax_f32_kernel(const float *__restrict__ x, const float *__restrict__ gamma, size_t rows,
+                                                         int K, float *__restrict__ out)
+{
+    pdl_trigger();
+    pdl_wait();
+    float m = 0.f;
+    const size_t n4 = rows * (size_t)(K / 4);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        float4 v = reinterpret_cast<const float4 *>(x)[i];
+        if (gamma) {
+            const float4 g = reinterpret_cast<const float4 *>(gamma)[i % (size_t)(K / 4)];
+            v = make_float4(v.x * g.x, v.y * g.y, v.z * g.z, v.w * g.w);
+        }
+        m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+    }
+    absmax_commit(m, out);
+}
+__global__ void __launch_bounds__(256) absmax_bf16_kernel(const uint4 *__restrict__ x, size_t n8, float *__restrict__ out)
+{
+    pdl_trigger();
+    pdl_wait();
+    float m = 0.f;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 v = x[i];
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            m = fmaxf(m, fmaxf(fabsf(__uint_as_float(w[k] << 16)), fabsf(__uint_as_float(w[k] & 0xffff0000u))));
+    }
+    absmax_commit(m, out);
+}
+__device__ __forceinline__ uint32_t tc_pack_e4m3x4(float a, float b, float c, float d)
+{
+    uint16_t lo, hi;
+    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(lo) : "f"(b), "f"(a));
+    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(hi) : "f"(d), "f"(c));
+    return static_cast<uint32_t>(lo) | (static_cast<uint32_t>(hi) << 16);
+}
+__device__ __forceinline__ float e4m3_to_float(uint32_t byte)
+{
+    __half_raw h = __nv_cvt_fp8_to_halfraw(static_cast<__nv_fp8_storage_t>(byte), __NV_E4M3);
+    return __half2float(*reinterpret_cast<__half *>(&h));
+}
+// one warp per output feature n (see ln_fold_weights_kernel); q = e4m3(gamma W scale), colsum of the de-quantised row
+__global__ void __launch_bounds__(256) fp8_quant_weights_kernel(const float *__restrict__ W, const float *__restrict__ gamma,
+                                                                const float *__restrict__ beta, const float *__restrict__ bias,
+                                                                float scale, uint8_t *__restrict__ q, float *__restrict__ colsum,
+                                                                float *__restrict__ bias_f, int N, int K)
+{
+    pdl_trigger();
+    pdl_wait();
+    const int lane = threadIdx.x & 31;
+    const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (n >= N)
+        return;
+    const float4 *w4 = reinterpret_cast<const float4 *>(W + (size_t)n * K);
+    uint32_t *o = reinterpret_cast<uint32_t *>(q + (size_t)n * K);
+    float cs = 0.f, bs = 0.f;
+    for (int i = lane; i < K / 4; i += 32) {
+        const float4 w = w4[i];
+        float4 g = make_float4(1.f, 1.f, 1.f, 1.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gamma)
+            g = reinterpret_cast<const float4 *>(gamma)[i];
+        if (beta)
+            b = reinterpret_cast<const float4 *>(beta)[i];
+        const uint32_t pk = tc_pack_e4m3x4(w.x * g.x * scale, w.y * g.y * scale, w.z * g.z * scale, w.w * g.w * scale);
+        o[i] = pk;
+        cs += (e4m3_to_float(pk & 0xff) + e4m3_to_float((pk >> 8) & 0xff)) + (e4m3_to_float((pk >> 16) & 0xff) + e4m3_to_float(pk >> 24));
+        bs += (w.x * b.x + w.y * b.y) + (w.z * b.z + w.w * b.w);
+    }
+    cs = warp_sum(cs);
+    bs = warp_sum(bs);
+    if (lane == 0) {
+        if (colsum)
+            colsum[n] = cs / scale;
+        if (bias_f)
+            bias_f[n] = bias[n] + bs;
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -444,6 +535,31 @@ int vitcu_rowstats_cast(const float *x, vitcu_bf16 *xb, void *stats, int rows, i
     default:
         return set_error(VITCU_E_ARG, __FILE__, __LINE__, "row width must be 256, 512, 768 or 1024");
     }
+    VITCU_LAUNCHED();
+    return 0;
+}
+
+int vitcu_absmax_f32(const float *x, const float *gamma, size_t rows, int K, float *out, vitcu_stream s)
+{
+    VITCU_REQUIRE(x && out && rows > 0 && K > 0 && K % 4 == 0, "bad argument");
+    VITCU_TRY(launch_kernel(absmax_f32_kernel, grid_for(rows * (size_t)(K / 4), 256, 148 * 8), 256, 0, as_stream(s), x, gamma, rows, K, out));
+    VITCU_LAUNCHED();
+    return 0;
+}
+int vitcu_absmax_bf16(const vitcu_bf16 *x, size_t n, float *out, vitcu_stream s)
+{
+    VITCU_REQUIRE(x && out && n > 0 && n % 8 == 0 && ((uintptr_t)x & 15) == 0, "bad argument");
+    VITCU_TRY(launch_kernel(absmax_bf16_kernel, grid_for(n / 8, 256, 148 * 8), 256, 0, as_stream(s), reinterpret_cast<const uint4 *>(x), n / 8, out));
+    VITCU_LAUNCHED();
+    return 0;
+}
+int vitcu_fp8_quant_weights(const float *W, const float *gamma, const float *beta, const float *bias, float scale, uint8_t *q,
+                            float *colsum, float *bias_folded, int N, int K, vitcu_stream s)
+{
+    VITCU_REQUIRE(W && q && N > 0 && K > 0 && K % 4 == 0 && scale > 0.f, "bad argument");
+    VITCU_REQUIRE(!bias_folded || bias, "bias_folded needs bias");
+    VITCU_TRY(launch_kernel(fp8_quant_weights_kernel, (N + 7) / 8, 256, 0, as_stream(s), W, gamma, beta, bias, scale, q, colsum,
+                            bias_folded, N, K));
     VITCU_LAUNCHED();
     return 0;
 }

@@ -58,6 +58,13 @@ struct EpiParams {
     float ln_inv_d;          // 1 / row length
     // ... and producer side (tma_out == 4): the residual epilogue also emits bf16(x_new) and the row partials
     float2 *emit_stats;      // [N / 128][M]
+    // FP8 (E4M3) path: operands are quantised with per-tensor scales, acc_scale = 1 / (scale_A * scale_W) brings the
+    // accumulator back; out_scale / emit_scale quantise what this GEMM hands to the next FP8 GEMM
+    int kb_elems;            // operand elements per 128-byte k-block row: 64 (bf16) or 128 (e4m3)
+    float acc_scale;         // multiplies the accumulator (1 for bf16 operands)
+    float out_scale;         // tma_out == 5: y * out_scale -> e4m3
+    int emit_fp8;            // emit mode: the second output is e4m3(x * emit_scale) instead of bf16(x)
+    float emit_scale;
 };
 
 constexpr int BM = 128;
@@ -127,7 +134,7 @@ __device__ __forceinline__ LnRow ln_row_finish(const EpiParams &p, const float2 
 template <bool LN, int STAGE_BYTES_PER_WARP, int NCHUNK>
 __device__ __forceinline__ bool coef_in_smem(const EpiParams &p)
 {
-    return LN || (STAGE_BYTES_PER_WARP >= 8192 && NCHUNK <= 4 && p.tma_out == 1);
+    return LN || (STAGE_BYTES_PER_WARP >= 8192 && NCHUNK <= 4 && (p.tma_out == 1 || p.tma_out == 5));
 }
 // asynchronous copy (16 B per lane) of this warp's NCHUNK * 32 coefficients starting at column col_base
 template <bool LN, int NCHUNK>
@@ -177,7 +184,7 @@ __device__ __forceinline__ bool epilogue_tile(const EpiParams &p, void *C, const
         }
     };
     fetch_add(0); // does not depend on the accumulator: in flight during the wait below
-    const float rstd = ln.rstd, nrm = ln.nrm;
+    const float rstd = ln.rstd * p.acc_scale, nrm = ln.nrm; // FP8 operands: the de-quantisation rides on the row factor
     float2 part[kMaxLnSlots];
     // Folded LayerNorm: the per-column coefficients of this warp's columns (bias' and colsum, NCHUNK * 32 floats each)
     // sit in shared memory, double-buffered by tile: read through __ldg in the chunk loop they cost an L2 round trip
@@ -278,8 +285,8 @@ __device__ __forceinline__ bool epilogue_tile(const EpiParams &p, void *C, const
             // tile and the TMA engine writes (bf16) or reduce-adds (fp32 residual stream) it to global
             // memory, clipped at M.  No global-memory latency is left on this warp's critical path.
             // staging tiles: 2 KB (bf16) or 4 KB (fp32) each, double-buffered when the warp's share allows
-            const uint32_t tile_bytes = p.tma_out == 1 ? 2048u : 4096u;
-            const bool two = STAGE_BYTES_PER_WARP >= 8192 || (STAGE_BYTES_PER_WARP >= 4096 && p.tma_out == 1);
+            const uint32_t tile_bytes = p.tma_out == 5 ? 1024u : (p.tma_out == 1 ? 2048u : 4096u);
+            const bool two = STAGE_BYTES_PER_WARP >= 8192 || (STAGE_BYTES_PER_WARP >= 4096 && (p.tma_out == 1 || p.tma_out == 5));
             uint8_t *buf = reinterpret_cast<uint8_t *>(stage) + (two ? (chunk_ctr & 1) * tile_bytes : 0u);
             if (lane == 0) { // the store that used this buffer before has finished reading it
                 if (two)
@@ -288,7 +295,16 @@ __device__ __forceinline__ bool epilogue_tile(const EpiParams &p, void *C, const
                     tma_wait_group_read<0>();
             }
             __syncwarp();
-            if (p.tma_out == 1) { // 32 x 64 B rows, 64-byte swizzle: 16-byte chunk ^= (row / 2) % 4
+            if (p.tma_out == 5) { // 32 x 32 B rows of e4m3, no swizzle
+                const float os = p.out_scale;
+#pragma unroll
+                for (int q = 0; q < 2; q++)
+                    *reinterpret_cast<uint4 *>(buf + lane * 32 + (q << 4)) =
+                        make_uint4(pack_e4m3x4(v[16 * q + 0] * os, v[16 * q + 1] * os, v[16 * q + 2] * os, v[16 * q + 3] * os),
+                                   pack_e4m3x4(v[16 * q + 4] * os, v[16 * q + 5] * os, v[16 * q + 6] * os, v[16 * q + 7] * os),
+                                   pack_e4m3x4(v[16 * q + 8] * os, v[16 * q + 9] * os, v[16 * q + 10] * os, v[16 * q + 11] * os),
+                                   pack_e4m3x4(v[16 * q + 12] * os, v[16 * q + 13] * os, v[16 * q + 14] * os, v[16 * q + 15] * os));
+            } else if (p.tma_out == 1) { // 32 x 64 B rows, 64-byte swizzle: 16-byte chunk ^= (row / 2) % 4
 #pragma unroll
                 for (int q = 0; q < 4; q++)
                     *reinterpret_cast<uint4 *>(buf + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) =
@@ -400,10 +416,10 @@ __device__ __forceinline__ bool epilogue_tile_emit(const EpiParams &p, const CUt
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
             const float4 bb = __ldg(reinterpret_cast<const float4 *>(p.bias + col0 + j));
-            v[j + 0] = __uint_as_float(acc[c & 1][j + 0]) + bb.x;
-            v[j + 1] = __uint_as_float(acc[c & 1][j + 1]) + bb.y;
-            v[j + 2] = __uint_as_float(acc[c & 1][j + 2]) + bb.z;
-            v[j + 3] = __uint_as_float(acc[c & 1][j + 3]) + bb.w;
+            v[j + 0] = fmaf(__uint_as_float(acc[c & 1][j + 0]), p.acc_scale, bb.x);
+            v[j + 1] = fmaf(__uint_as_float(acc[c & 1][j + 1]), p.acc_scale, bb.y);
+            v[j + 2] = fmaf(__uint_as_float(acc[c & 1][j + 2]), p.acc_scale, bb.z);
+            v[j + 3] = fmaf(__uint_as_float(acc[c & 1][j + 3]), p.acc_scale, bb.w);
         }
         // the residual tile of this chunk has landed
 #if VITCU_EMIT_VARIANT == 1
@@ -430,11 +446,22 @@ __device__ __forceinline__ bool epilogue_tile_emit(const EpiParams &p, const CUt
             s1 += (a0 + a1) + (a2 + a3);
             s2 = fmaf(a0, a0, fmaf(a1, a1, fmaf(a2, a2, fmaf(a3, a3, s2))));
         }
+        if (p.emit_fp8) { // 32 x 32 B rows of e4m3(x * emit_scale), no swizzle: the A operand of an FP8 GEMM
+            const float es = p.emit_scale;
 #pragma unroll
-        for (int q = 0; q < 4; q++) // 32 x 64 B rows, 64-byte swizzle: 16-byte chunk ^= (row / 2) % 4
-            *reinterpret_cast<uint4 *>(B + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) =
-                make_uint4(pack_bf16x2(v[8 * q + 0], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
-                           pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
+            for (int q = 0; q < 2; q++)
+                *reinterpret_cast<uint4 *>(B + lane * 32 + (q << 4)) =
+                    make_uint4(pack_e4m3x4(v[16 * q + 0] * es, v[16 * q + 1] * es, v[16 * q + 2] * es, v[16 * q + 3] * es),
+                               pack_e4m3x4(v[16 * q + 4] * es, v[16 * q + 5] * es, v[16 * q + 6] * es, v[16 * q + 7] * es),
+                               pack_e4m3x4(v[16 * q + 8] * es, v[16 * q + 9] * es, v[16 * q + 10] * es, v[16 * q + 11] * es),
+                               pack_e4m3x4(v[16 * q + 12] * es, v[16 * q + 13] * es, v[16 * q + 14] * es, v[16 * q + 15] * es));
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; q++) // 32 x 64 B rows, 64-byte swizzle: 16-byte chunk ^= (row / 2) % 4
+                *reinterpret_cast<uint4 *>(B + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) =
+                    make_uint4(pack_bf16x2(v[8 * q + 0], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
+                               pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
+        }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
@@ -657,7 +684,8 @@ struct SmemLayout2 {
 // EPI_BYTES = epilogue staging per CTA: 64 KB with 5 operand stages, or 32 KB (4 KB per warp: two bf16 tiles
 // or one fp32 tile, TMA output path only) which makes room for a sixth stage
 // EMIT = residual epilogue that also emits bf16(x) and the row partial sums for the folded LayerNorm (epilogue_tile_emit)
-template <int STAGES, int EW, uint32_t EPI_BYTES = 65536, bool EMIT = false, bool LN = false>
+// FP8 = E4M3 operands (tcgen05.mma kind::f8f6f4): the same byte layout in shared memory, 128 elements per k-block row
+template <int STAGES, int EW, uint32_t EPI_BYTES = 65536, bool EMIT = false, bool LN = false, bool FP8 = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EW, 1)
 gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                      const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_d, void *C,
@@ -666,7 +694,7 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     using L = SmemLayout2<STAGES, EPI_BYTES>;
     constexpr int BN = 256, BM2 = 256;
     constexpr uint32_t TMEM_COLS = 512;
-    constexpr uint32_t IDESC = umma_idesc_bf16(BM2, BN, false, false);
+    constexpr uint32_t IDESC = FP8 ? umma_idesc_e4m3(BM2, BN) : umma_idesc_bf16(BM2, BN, false, false);
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -739,8 +767,8 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                     tma_load_2d_2sm(sa + L::A_BYTES, &tmap_b, full_leader, bcol, brow);
                 }
                 __syncwarp();
-                acol += BK;
-                bcol += BK;
+                acol += p.kb_elems;
+                bcol += p.kb_elems;
                 if (++kin == p.seg_kb && kb + 1 < num_kb) {
                     kin = 0;
                     seg++;
@@ -773,8 +801,12 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                         const uint64_t a_desc = umma_desc_k_sw128(sa);
                         const uint64_t b_desc = umma_desc_k_sw128(sa + L::A_BYTES);
 #pragma unroll
-                        for (int k = 0; k < BK / 16; k++)
-                            umma_bf16_ss_2sm(d_tmem, a_desc + 2 * k, b_desc + 2 * k, IDESC, (kb | k) != 0);
+                        for (int k = 0; k < BK / 16; k++) { // four instructions per k-block, 32 bytes of K each
+                            if (FP8)
+                                umma_e4m3_ss_2sm(d_tmem, a_desc + 2 * k, b_desc + 2 * k, IDESC, (kb | k) != 0);
+                            else
+                                umma_bf16_ss_2sm(d_tmem, a_desc + 2 * k, b_desc + 2 * k, IDESC, (kb | k) != 0);
+                        }
                         umma_commit_2sm(&empty_bar[stage], 0x3); // frees the slot in both CTAs
                         if (kb == num_kb - 1)
                             umma_commit_2sm(&tfull_bar[acc], 0x3); // accumulator complete in both CTAs
@@ -885,12 +917,12 @@ int launch(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &tc, 
     return 0;
 }
 
-template <int STAGES, int EW, uint32_t EPI_BYTES = 65536, bool EMIT = false, bool LN = false>
+template <int STAGES, int EW, uint32_t EPI_BYTES = 65536, bool EMIT = false, bool LN = false, bool FP8 = false>
 int launch_pair(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &tc, const CUtensorMap &td, void *C,
                 const EpiParams &p, int sms, cudaStream_t st)
 {
     using L = SmemLayout2<STAGES, EPI_BYTES>;
-    auto kernel = gemm_bf16_tc2_kernel<STAGES, EW, EPI_BYTES, EMIT, LN>;
+    auto kernel = gemm_bf16_tc2_kernel<STAGES, EW, EPI_BYTES, EMIT, LN, FP8>;
     static bool configured[64] = {false};
     int dev = 0;
     VITCU_TRY(cudaGetDevice(&dev));
@@ -915,7 +947,8 @@ int make_tensor_map_2d(CUtensorMap *map, const void *base, int elem_bytes, uint6
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn)
         return set_error(VITCU_E_NODEVICE, __FILE__, __LINE__, "cuTensorMapEncodeTiled is unavailable");
-    const CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    const CUtensorMapDataType dt = elem_bytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8
+                                   : elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
     cuuint64_t dims[2] = {cols, rows};
     cuuint64_t strides[1] = {ld_bytes};
     cuuint32_t box[2] = {box_cols, box_rows};
@@ -981,6 +1014,8 @@ static int gemm_dispatch(const vitcu_bf16 *A, const vitcu_bf16 *W, void *C, cons
     p.tokens = d->tokens;
     p.out_bf16 = d->out_bf16;
     p.exact_gelu = split3 && !d->out_bf16;
+    p.kb_elems = BK;
+    p.acc_scale = 1.0f;
     // LayerNorm folded into the GEMM (see vitcu_gemm_desc)
     if (d->ln_stats) {
         VITCU_REQUIRE(!split3 && d->ln_colsum && d->ln_slots > 0, "LayerNorm-folded GEMM needs bf16 operands, column sums and slots");
@@ -999,6 +1034,9 @@ static int gemm_dispatch(const vitcu_bf16 *A, const vitcu_bf16 *W, void *C, cons
                       "emit mode needs the in-place fp32 residual epilogue");
         VITCU_REQUIRE(vitcu_gemm_bf16_emit_supported(d->M, d->N), "emit mode needs the CTA-pair kernel (N % 256 == 0, enough tiles)");
         p.emit_stats = reinterpret_cast<float2 *>(d->emit_stats);
+        p.emit_fp8 = d->emit_fp8;
+        p.emit_scale = d->emit_scale;
+        VITCU_REQUIRE(!d->emit_fp8 || d->emit_scale > 0.f, "emit_fp8 needs a positive emit_scale");
     }
     VITCU_REQUIRE(p.ldc % 8 == 0, "ldc must be a multiple of 8");
     const uint64_t kphys = split3 ? 3 * (uint64_t)d->K : (uint64_t)d->K; // physical operand width
@@ -1039,7 +1077,8 @@ static int gemm_dispatch(const vitcu_bf16 *A, const vitcu_bf16 *W, void *C, cons
     int rc = 0;
     if (emit) {
         p.tma_out = 4;
-        rc = make_tensor_map_2d(&td, d->emit_bf16, 2, (uint64_t)d->M, (uint64_t)d->N, (size_t)d->N * 2, 32, 32, 64);
+        rc = d->emit_fp8 ? make_tensor_map_2d(&td, d->emit_bf16, 1, (uint64_t)d->M, (uint64_t)d->N, (size_t)d->N, 32, 32, 0)
+                         : make_tensor_map_2d(&td, d->emit_bf16, 2, (uint64_t)d->M, (uint64_t)d->N, (size_t)d->N * 2, 32, 32, 64);
         if (rc)
             return rc;
     }
@@ -1102,6 +1141,76 @@ static int gemm_dispatch(const vitcu_bf16 *A, const vitcu_bf16 *W, void *C, cons
     if (wide)
         return launch<256, 3>(ta, tb, tc, C, p, sms, as_stream(s));
     return launch<128, 5>(ta, tb, tc, C, p, sms, as_stream(s));
+}
+
+// E4M3 operands (per-tensor scales), CTA-pair kernel only.  Two uses: the LayerNorm-folded fc1 (GELU, e4m3 or bf16 out)
+// and the residual fc2 that emits bf16(x) / e4m3(x) + row sums.
+extern "C" int vitcu_gemm_e4m3(const uint8_t *A, const uint8_t *W, void *C, const vitcu_gemm_desc *d, vitcu_stream s)
+{
+    VITCU_REQUIRE(A && W && C && d, "NULL argument");
+    VITCU_REQUIRE(d->M > 0 && d->N > 0 && d->K > 0 && d->K % 128 == 0 && d->N % 256 == 0, "e4m3 GEMM needs K % 128 == 0, N % 256 == 0");
+    VITCU_REQUIRE(pair_eligible(d->M, d->N), "e4m3 GEMM runs on the CTA-pair kernel only (M too small)");
+    VITCU_REQUIRE(d->bias && ((uintptr_t)d->bias & 15) == 0 && ((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0 && ((uintptr_t)C & 15) == 0,
+                  "16-byte aligned operands, output and bias are required");
+    VITCU_REQUIRE(d->acc_scale > 0.f, "acc_scale = 1 / (scale_A * scale_W) must be positive");
+    EpiParams p;
+    memset(&p, 0, sizeof(p));
+    p.M = d->M;
+    p.N = d->N;
+    p.K = d->K;
+    p.ldc = (size_t)d->N;
+    p.epilogue = d->epilogue;
+    p.bias = d->bias;
+    p.residual = d->residual;
+    p.out_bf16 = d->out_bf16;
+    p.kb_elems = 128;
+    p.acc_scale = d->acc_scale;
+    p.nseg = 1;
+    p.seg_kb = d->K / 128;
+    p.splits = 1;
+    const int sms = device_sm_count();
+    CUtensorMap ta, tb, tc, td;
+    memset(&td, 0, sizeof(td));
+    int rc = make_tensor_map_2d(&ta, A, 1, (uint64_t)d->M, (uint64_t)d->K, (size_t)d->K, BM, 128);
+    if (!rc)
+        rc = make_tensor_map_2d(&tb, W, 1, (uint64_t)d->N, (uint64_t)d->K, (size_t)d->K, 128, 128);
+    if (rc)
+        return rc;
+    if (d->emit_bf16) { // residual update in place + bf16 / e4m3 copy + row sums
+        VITCU_REQUIRE(d->emit_stats && d->epilogue == VITCU_EPI_BIAS_RESIDUAL && d->residual == (const float *)C && !d->out_bf16 &&
+                          ((uintptr_t)d->emit_bf16 & 15) == 0, "emit mode needs the in-place fp32 residual epilogue");
+        VITCU_REQUIRE(!d->emit_fp8 || d->emit_scale > 0.f, "emit_fp8 needs a positive emit_scale");
+        p.emit_stats = reinterpret_cast<float2 *>(d->emit_stats);
+        p.emit_fp8 = d->emit_fp8;
+        p.emit_scale = d->emit_scale;
+        p.tma_out = 4;
+        rc = make_tensor_map_2d(&tc, C, 4, (uint64_t)d->M, (uint64_t)d->N, (size_t)d->N * 4, 32, 32, 128);
+        if (!rc)
+            rc = d->emit_fp8 ? make_tensor_map_2d(&td, d->emit_bf16, 1, (uint64_t)d->M, (uint64_t)d->N, (size_t)d->N, 32, 32, 0)
+                             : make_tensor_map_2d(&td, d->emit_bf16, 2, (uint64_t)d->M, (uint64_t)d->N, (size_t)d->N * 2, 32, 32, 64);
+        if (rc)
+            return rc;
+        return launch_pair<4, 8, 98304, true, false, true>(ta, tb, tc, td, C, p, sms, as_stream(s));
+    }
+    VITCU_REQUIRE(d->ln_stats && d->ln_colsum && d->ln_slots > 0 && ((uintptr_t)d->ln_colsum & 15) == 0,
+                  "the non-residual e4m3 GEMM is the LayerNorm-folded one: ln_stats / ln_colsum / ln_slots are required");
+    VITCU_REQUIRE(d->epilogue == VITCU_EPI_BIAS || d->epilogue == VITCU_EPI_BIAS_GELU, "LayerNorm fold applies to bias / GELU epilogues");
+    VITCU_REQUIRE(d->out_fp8 ? d->out_scale > 0.f : d->out_bf16, "output must be e4m3 (out_fp8 + out_scale) or bf16");
+    p.ln_stats = reinterpret_cast<const float2 *>(d->ln_stats);
+    p.ln_colsum = d->ln_colsum;
+    p.ln_slots = d->ln_slots;
+    p.ln_inv_d = 1.0f / (float)d->K;
+    if (d->out_fp8) {
+        p.tma_out = 5;
+        p.out_scale = d->out_scale;
+        rc = make_tensor_map_2d(&tc, C, 1, (uint64_t)d->M, (uint64_t)d->N, (size_t)d->N, 32, 32, 0);
+    } else {
+        p.tma_out = 1;
+        rc = make_tensor_map_2d(&tc, C, 2, (uint64_t)d->M, (uint64_t)d->N, (size_t)d->N * 2, 32, 32, 64);
+    }
+    if (rc)
+        return rc;
+    return launch_pair<5, 8, 65536, false, true, true>(ta, tb, tc, td, C, p, sms, as_stream(s));
 }
 
 extern "C" int vitcu_gemm_bf16(const vitcu_bf16 *A, const vitcu_bf16 *W, void *C, const vitcu_gemm_desc *d,

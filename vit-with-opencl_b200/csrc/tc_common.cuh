@@ -331,6 +331,32 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, bool a_mn_m
            | (static_cast<uint32_t>(M >> 4) << 24); // m_dim          [24,29)
 }
 
+// instruction descriptor, kind::f8f6f4, E4M3 x E4M3 -> FP32 (a_format = b_format = 0; K = 32 per instruction)
+__host__ __device__ constexpr uint32_t umma_idesc_e4m3(int M, int N)
+{
+    return (1u << 4)                                  // c_format = F32
+           | (static_cast<uint32_t>(N >> 3) << 17)    // n_dim
+           | (static_cast<uint32_t>(M >> 4) << 24);   // m_dim
+}
+// FP8 (E4M3) operands over a CTA pair: same shared-memory layout as the bf16 kernel -- 128-byte swizzled rows hold
+// 128 elements, one instruction consumes 32 bytes of K like the bf16 one -- at twice the FLOPs per instruction
+__device__ __forceinline__ void umma_e4m3_ss_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                 uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+                 : "memory");
+}
+// four floats -> four E4M3 bytes (round to nearest even, saturating at +-448), element 0 in the lowest byte
+__device__ __forceinline__ uint32_t pack_e4m3x4(float a, float b, float c, float d)
+{
+    uint16_t lo, hi;
+    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(lo) : "f"(b), "f"(a));
+    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(hi) : "f"(d), "f"(c));
+    return static_cast<uint32_t>(lo) | (static_cast<uint32_t>(hi) << 16);
+}
+
 // D[tmem] (+)= A[smem] * B[smem]; one thread issues for the CTA
 __device__ __forceinline__ void umma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                              uint32_t accumulate)

@@ -108,6 +108,16 @@ static int follows_layernorm(const vitb200_engine *e, int idx)
     return 0;
 }
 
+/* the two MLP matrices of a layer (fc1: base + 8, fc2: base + 10): 63.5 % of the FLOPs, the FP8 candidates */
+static int is_mlp_weight(const vitb200_engine *e, int idx)
+{
+    if (idx >= 4 && idx < e->nblobs - 4) {
+        int k = (idx - 4) % 12;
+        return k == 8 || k == 10;
+    }
+    return 0;
+}
+
 /* K (row length) of GEMM weight idx */
 static int gemm_weight_k(const vitb200_engine *e, int idx)
 {
@@ -181,8 +191,10 @@ int vitb200_create_model(vitb200_engine **out, int device, const vitb200_model *
         return vit_fail(__FILE__, __LINE__, VITCU_E_ARG, "depth must be 1..32");
     if (m->hidden <= 0 || m->hidden % 128 != 0)
         return vit_fail(__FILE__, __LINE__, VITCU_E_ARG, "MLP width must be a positive multiple of 128");
-    if (precision != VITB200_FP32 && precision != VITB200_BF16)
-        return vit_fail(__FILE__, __LINE__, VITCU_E_ARG, "precision must be VITB200_FP32 or VITB200_BF16");
+    if (precision != VITB200_FP32 && precision != VITB200_BF16 && precision != VITB200_FP8)
+        return vit_fail(__FILE__, __LINE__, VITCU_E_ARG, "precision must be VITB200_FP32, VITB200_BF16 or VITB200_FP8");
+    if (precision == VITB200_FP8 && (m->embed % 256 != 0 || m->hidden % 256 != 0))
+        return vit_fail(__FILE__, __LINE__, VITCU_E_ARG, "FP8 precision needs embed and MLP widths that are multiples of 256");
     if (max_batch <= 0)
         return vit_fail(__FILE__, __LINE__, VITCU_E_ARG, "max_batch must be positive");
     int ndev = 0;
@@ -219,10 +231,11 @@ int vitb200_create_model(vitb200_engine **out, int device, const vitb200_model *
     e->fp32_tc = precision == VITB200_FP32 && getenv("VITB200_FP32_SIMT") == NULL;
     /* VITB200_PE_GATHER=1: separate gather kernel + BF16 GEMM instead of the TMA-gather TF32 GEMM */
     e->pe_gather = getenv("VITB200_PE_GATHER") != NULL || e->patch != 16 || e->D % 256 != 0;
-    const int bf = precision == VITB200_BF16;
+    const int bf = precision != VITB200_FP32; /* FP8 = the BF16 path with fc1 / fc2 on e4m3 operands */
+    e->fp8 = precision == VITB200_FP8;
     /* LayerNorm folded into the qkv / fc1 GEMMs and produced by the out-proj / fc2 epilogues: BF16 path, widths the
      * CTA-pair GEMM tiles (VITB200_LN_FOLD=0 keeps the separate LayerNorm kernel) */
-    e->ln_fold = bf && e->D % 256 == 0 && !(getenv("VITB200_LN_FOLD") && atoi(getenv("VITB200_LN_FOLD")) == 0);
+    e->ln_fold = bf && e->D % 256 == 0 && (e->fp8 || !(getenv("VITB200_LN_FOLD") && atoi(getenv("VITB200_LN_FOLD")) == 0));
     const size_t act = bf ? 2 : 4;
     const size_t rows = (size_t)e->B * e->T;
     const size_t img_elems = (size_t)3 * img * img;
@@ -260,6 +273,8 @@ int vitb200_create_model(vitb200_engine **out, int device, const vitb200_model *
     ENG_TRY(vitcu_malloc((void **)&e->d_cls, (size_t)e->B * e->D * sizeof(float)));
     if (e->ln_fold)
         ENG_TRY(vitcu_malloc(&e->d_lnstats, rows * (size_t)(e->D / 128) * 2 * sizeof(float)));
+    if (e->fp8)
+        ENG_TRY(vitcu_malloc((void **)&e->d_amax, (size_t)2 * VIT_MAX_DEPTH * sizeof(float)));
     ENG_TRY(vitcu_host_alloc((void **)&e->h_probs, (size_t)e->B * VITB200_CLASSES * sizeof(float) * 2));
     ENG_TRY(vitcu_host_alloc((void **)&e->h_logits, (size_t)e->B * VITB200_CLASSES * sizeof(float) * 2));
 #undef ENG_TRY
@@ -300,6 +315,7 @@ void vitb200_destroy(vitb200_engine *e)
     vitcu_free(e->d_hid);
     vitcu_free(e->d_cls);
     vitcu_free(e->d_lnstats);
+    vitcu_free(e->d_amax);
     vitcu_host_free(e->h_probs);
     vitcu_host_free(e->h_logits);
     vitcu_free(e->d_topi);
@@ -338,17 +354,22 @@ int vitb200_load_weights(vitb200_engine *e, const vitb200_blob *net)
             return vit_fail(__FILE__, __LINE__, VITCU_E_ARG, what);
         }
     }
-    const int bf = e->precision == VITB200_BF16;
+    const int bf = e->precision != VITB200_FP32;
     /* One device allocation for all weights (152 cudaMalloc + 49 cudaFree calls cost more than the
      * upload itself) and two fp32 scratch buffers through which the GEMM weights pass on their way
      * to the packed form: bf16 [N,K] on the BF16 path, three bf16 pieces [N,3K] on the FP32
      * tensor-core path.  Everything else (biases, LayerNorm, class token, position embedding, head,
      * and the conv filters of the TF32 patch embedding) stays fp32. */
-    size_t off32[VIT_MAX_BLOBS], off16[VIT_MAX_BLOBS], offf[VIT_MAX_BLOBS], total = 0, scratch_elems = 0;
+    size_t off32[VIT_MAX_BLOBS], off16[VIT_MAX_BLOBS], offf[VIT_MAX_BLOBS], off8[VIT_MAX_BLOBS], total = 0, scratch_elems = 0;
     for (int i = 0; i < e->nblobs; i++) {
         const size_t n = net[i].size;
         const int packed = is_gemm_weight(e, i) && (bf || e->fp32_tc);
-        offf[i] = (size_t)-1;
+        offf[i] = off8[i] = (size_t)-1;
+        if (e->fp8 && is_mlp_weight(e, i)) { /* e4m3 copy [N,K] (+ colsum [N] | bias' [N] for the folded fc1) */
+            const size_t N = n / (size_t)gemm_weight_k(e, i);
+            off8[i] = total;
+            total += ((n + 255) & ~(size_t)255) + 2 * ((N * sizeof(float) + 255) & ~(size_t)255);
+        }
         if (e->ln_fold && follows_layernorm(e, i)) { /* folded copy: bf16 [N,K] | colsum [N] | bias' [N] */
             const size_t N = n / (size_t)e->D;
             offf[i] = total;
@@ -378,7 +399,10 @@ int vitb200_load_weights(vitb200_engine *e, const vitb200_blob *net)
     vitcu_bf16 **w16 = (vitcu_bf16 **)calloc(VIT_MAX_BLOBS, sizeof(vitcu_bf16 *));
     vitcu_bf16 **wf16 = (vitcu_bf16 **)calloc(VIT_MAX_BLOBS, sizeof(vitcu_bf16 *));
     float **wf_cs = (float **)calloc(VIT_MAX_BLOBS, sizeof(float *)), **wf_b = (float **)calloc(VIT_MAX_BLOBS, sizeof(float *));
-    int rc = (w32 && w16 && wf16 && wf_cs && wf_b) ? 0 : VITCU_E_ARG;
+    unsigned char **wq8 = (unsigned char **)calloc(VIT_MAX_BLOBS, sizeof(unsigned char *));
+    float **wq8_cs = (float **)calloc(VIT_MAX_BLOBS, sizeof(float *)), **wq8_b = (float **)calloc(VIT_MAX_BLOBS, sizeof(float *));
+    float *wq8_scale = (float *)calloc(VIT_MAX_BLOBS, sizeof(float));
+    int rc = (w32 && w16 && wf16 && wf_cs && wf_b && wq8 && wq8_cs && wq8_b && wq8_scale) ? 0 : VITCU_E_ARG;
     if (rc)
         vit_fail(__FILE__, __LINE__, rc, "out of host memory");
     if (!rc && (rc = vitcu_malloc(&arena, total)) != 0)
@@ -418,6 +442,33 @@ int vitb200_load_weights(vitb200_engine *e, const vitb200_blob *net)
                 if (!rc)
                     rc = vitcu_ln_fold_weights(src, w32[i - 2], w32[i - 1], bias_dev, wf16[i], wf_cs[i], wf_b[i], N, e->D, e->stream);
             }
+            if (!rc && off8[i] != (size_t)-1) {
+                /* FP8: one scale per weight matrix, 448 / max|gamma W| (e4m3 is a floating-point format: 3 mantissa bits
+                 * over 2^15 of range, so a per-tensor scale loses nothing a per-channel one would keep) */
+                const int K = gemm_weight_k(e, i), N = (int)(n / (size_t)K);
+                const int folded = follows_layernorm(e, i);
+                char *base = (char *)arena + off8[i];
+                wq8[i] = (unsigned char *)base;
+                wq8_cs[i] = (float *)(base + ((n + 255) & ~(size_t)255));
+                wq8_b[i] = (float *)((char *)wq8_cs[i] + (((size_t)N * sizeof(float) + 255) & ~(size_t)255));
+                float amax = 0.f;
+                rc = vitcu_memset(e->d_amax, 0, sizeof(float), e->stream);
+                if (!rc)
+                    rc = vitcu_absmax_f32(src, folded ? w32[i - 2] : NULL, (size_t)N, K, e->d_amax, e->stream);
+                if (!rc)
+                    rc = vitcu_memcpy_d2h(&amax, e->d_amax, sizeof(float), e->stream);
+                if (!rc)
+                    rc = vitcu_stream_sync(e->stream);
+                if (!rc) {
+                    wq8_scale[i] = amax > 0.f ? 448.0f / amax : 1.0f;
+                    float *bias_dev = (float *)((char *)arena + off32[i + 1]);
+                    if (folded)
+                        rc = vitcu_fp8_quant_weights(src, w32[i - 2], w32[i - 1], bias_dev, wq8_scale[i], wq8[i], wq8_cs[i], wq8_b[i], N, K,
+                                                     e->stream);
+                    else
+                        rc = vitcu_fp8_quant_weights(src, NULL, NULL, NULL, wq8_scale[i], wq8[i], NULL, NULL, N, K, e->stream);
+                }
+            }
         }
         if (rc)
             vit_fail(__FILE__, __LINE__, rc, NULL);
@@ -440,6 +491,11 @@ int vitb200_load_weights(vitb200_engine *e, const vitb200_blob *net)
         memcpy(e->wf16, wf16, sizeof(e->wf16));
         memcpy(e->wf_cs, wf_cs, sizeof(e->wf_cs));
         memcpy(e->wf_b, wf_b, sizeof(e->wf_b));
+        memcpy(e->wq8, wq8, sizeof(e->wq8));
+        memcpy(e->wq8_cs, wq8_cs, sizeof(e->wq8_cs));
+        memcpy(e->wq8_b, wq8_b, sizeof(e->wq8_b));
+        memcpy(e->wq8_scale, wq8_scale, sizeof(e->wq8_scale));
+        e->fp8_calibrated = 0; /* activation scales belong to the weights: recalibrate on the next chunk */
         e->weights_loaded = 1;
     } else {
         vitcu_free(arena);
@@ -449,6 +505,10 @@ int vitb200_load_weights(vitb200_engine *e, const vitb200_blob *net)
     free(wf16);
     free(wf_cs);
     free(wf_b);
+    free(wq8);
+    free(wq8_cs);
+    free(wq8_b);
+    free(wq8_scale);
     return rc;
 }
 
@@ -465,7 +525,8 @@ static int mark(vitb200_engine *e, int kind)
 }
 
 /* fold: 0 = plain; 1 = this GEMM follows a LayerNorm that is folded into it (A = bf16 residual rows, folded weights,
- * statistics from d_lnstats); 2 = residual GEMM that also emits bf16(x) into d_ln and the row partial sums */
+ * statistics from d_lnstats); 2 = residual GEMM that also emits bf16(x) into d_ln and the row partial sums;
+ * 3 + layer = the same with an e4m3 copy for that layer's FP8 fc1 */
 static int gemm(vitb200_engine *e, const void *A, int a_split, int widx, int bidx, void *C, int M, int N, int K, int epi,
                 int out_bf16, int fold)
 {
@@ -483,9 +544,13 @@ static int gemm(vitb200_engine *e, const void *A, int a_split, int widx, int bid
         d.ln_stats = e->d_lnstats;
         d.ln_slots = e->D / 128;
         d.ln_colsum = e->wf_cs[widx];
-    } else if (fold == 2) {
+    } else if (fold >= 2) {
         d.emit_bf16 = e->d_ln;
         d.emit_stats = e->d_lnstats;
+        if (fold > 2) { /* 3 + layer: the copy is e4m3(x * scale), the A operand of that layer's FP8 fc1 */
+            d.emit_fp8 = 1;
+            d.emit_scale = e->act_scale_x[fold - 3];
+        }
     }
     if (epi == VITCU_EPI_BIAS_RESIDUAL)
         d.residual = (const float *)C;
@@ -508,7 +573,7 @@ static int gemm(vitb200_engine *e, const void *A, int a_split, int widx, int bid
     if (prof)
         VIT_TRY(vitcu_event_record(e->prof_ev[2 * e->prof_n], e->stream));
     int rc;
-    if (e->precision == VITB200_BF16)
+    if (e->precision != VITB200_FP32)
         rc = vitcu_gemm_bf16((const vitcu_bf16 *)A, fold == 1 ? e->wf16[widx] : e->w16[widx], C, &d, e->stream);
     else if (e->fp32_tc)
         rc = vitcu_gemm_bf16x3((const vitcu_bf16 *)A, e->w16[widx], C, &d, e->stream);
@@ -519,11 +584,62 @@ static int gemm(vitb200_engine *e, const void *A, int a_split, int widx, int bid
     return rc;
 }
 
+/* FP8 GEMMs of the MLP (vitcu_gemm_e4m3): fc1 = LayerNorm-folded consumer with GELU writing e4m3, fc2 = residual
+ * update emitting the bf16 rows + row sums the next layer's qkv reads */
+static int gemm_fp8(vitb200_engine *e, int layer, int is_fc2, int M)
+{
+    const int w = 4 + 12 * layer;
+    vitcu_gemm_desc d;
+    memset(&d, 0, sizeof(d));
+    d.M = M;
+    e->launches++;
+    VIT_TRY_RC(mark(e, VIT_K_GEMM));
+    const int prof = e->prof_ev && e->prof_n < e->prof_cap;
+    if (prof)
+        VIT_TRY(vitcu_event_record(e->prof_ev[2 * e->prof_n], e->stream));
+    int rc;
+    if (!is_fc2) {
+        d.N = e->HID;
+        d.K = e->D;
+        d.epilogue = VITCU_EPI_BIAS_GELU;
+        d.bias = e->wq8_b[w + 8];
+        d.ln_stats = e->d_lnstats;
+        d.ln_slots = e->D / 128;
+        d.ln_colsum = e->wq8_cs[w + 8];
+        d.acc_scale = 1.0f / (e->act_scale_x[layer] * e->wq8_scale[w + 8]);
+        d.out_fp8 = 1;
+        d.out_scale = e->act_scale_h[layer];
+        rc = vitcu_gemm_e4m3((const uint8_t *)e->d_ln, e->wq8[w + 8], e->d_hid, &d, e->stream);
+    } else {
+        d.N = e->D;
+        d.K = e->HID;
+        d.epilogue = VITCU_EPI_BIAS_RESIDUAL;
+        d.bias = e->w32[w + 11];
+        d.residual = e->d_x;
+        d.emit_bf16 = e->d_ln;
+        d.emit_stats = e->d_lnstats;
+        d.acc_scale = 1.0f / (e->act_scale_h[layer] * e->wq8_scale[w + 10]);
+        rc = vitcu_gemm_e4m3((const uint8_t *)e->d_hid, e->wq8[w + 10], e->d_x, &d, e->stream);
+    }
+    d.lda = (size_t)d.K;
+    d.ldc = (size_t)d.N;
+    if (!rc && prof)
+        VIT_TRY(vitcu_event_record(e->prof_ev[2 * e->prof_n++ + 1], e->stream));
+    if (rc)
+        return vit_fail(__FILE__, __LINE__, rc, NULL);
+    return 0;
+}
+
 /* Enqueue the forward of b images resident in d_images[buf] on e->stream. */
 #define MARK(kind) VIT_TRY_RC(mark(e, kind))
-static int enqueue_forward(vitb200_engine *e, int buf, int b)
+static int enqueue_forward_mode(vitb200_engine *e, int buf, int b, int calibrate);
+static int enqueue_forward(vitb200_engine *e, int buf, int b) { return enqueue_forward_mode(e, buf, b, 0); }
+
+/* calibrate = 1 (FP8 engines, once): run the BF16 chain and record the per-layer maxima of the two tensors the FP8
+ * GEMMs will read -- the residual rows in front of LN2 and the GELU output -- into d_amax */
+static int enqueue_forward_mode(vitb200_engine *e, int buf, int b, int calibrate)
 {
-    const int bf = e->precision == VITB200_BF16;
+    const int bf = e->precision != VITB200_FP32;
     const int M = b * e->T;
     const int ln_mode = bf ? 1 : (e->fp32_tc ? 2 : 0); /* LayerNorm output: bf16 / three bf16 pieces / fp32 */
     vitcu_stream s = e->stream;
@@ -550,6 +666,11 @@ static int enqueue_forward(vitb200_engine *e, int buf, int b)
      * epilogue can emit the bf16 rows and the row sums: 5 launches per layer instead of 7 and the fp32 stream is
      * not re-read by a LayerNorm kernel.  Small chunks (batch-1 latency) keep the separate kernel. */
     const int fold = e->ln_fold && vitcu_gemm_bf16_emit_supported(M, e->D);
+    const int fp8 = e->fp8 && fold && e->fp8_calibrated && !calibrate;
+    if (calibrate && !fold)
+        return vit_fail(__FILE__, __LINE__, VITCU_E_ARG, "FP8 calibration needs a chunk that runs the CTA-pair GEMM");
+    if (calibrate)
+        VIT_TRY(vitcu_memset(e->d_amax, 0, (size_t)2 * VIT_MAX_DEPTH * sizeof(float), s));
     if (fold && layers > 0) {
         MARK(VIT_K_LAYERNORM);
         VIT_TRY(vitcu_rowstats_cast(e->d_x, (vitcu_bf16 *)e->d_ln, e->d_lnstats, M, e->D, e->D / 128, s));
@@ -568,14 +689,28 @@ static int enqueue_forward(vitb200_engine *e, int buf, int b)
         /* FP32 tensor-core path: the attention kernel writes its output already split into three bf16 pieces */
         VIT_TRY(vitcu_attention_ex(e->d_qkv, e->d_att, b, e->T, e->heads, e->fp32_tc ? 2 : bf, s));
         e->launches++;
-        VIT_TRY(gemm(e, e->d_att, e->fp32_tc, w + 4, w + 5, e->d_x, M, e->D, e->D, VITCU_EPI_BIAS_RESIDUAL, 0, fold ? 2 : 0));
+        VIT_TRY(gemm(e, e->d_att, e->fp32_tc, w + 4, w + 5, e->d_x, M, e->D, e->D, VITCU_EPI_BIAS_RESIDUAL, 0,
+                     fp8 ? 3 + l : (fold ? 2 : 0)));
+        if (calibrate) {
+            VIT_TRY(vitcu_absmax_bf16((const vitcu_bf16 *)e->d_ln, (size_t)M * e->D, e->d_amax + 2 * l, s));
+            e->launches++;
+        }
         /* -> LN2 -> fc1+GELU -> fc2 (+r1)  (R/ViT_opencl.c:732-746) */
         if (!fold) {
             MARK(VIT_K_LAYERNORM);
             VIT_TRY(vitcu_layernorm_ex(e->d_x, e->D, e->d_ln, ln_mode, e->w32[w + 6], e->w32[w + 7], M, e->D, s));
             e->launches++;
         }
+        if (fp8) {
+            VIT_TRY_RC(gemm_fp8(e, l, 0, M));
+            VIT_TRY_RC(gemm_fp8(e, l, 1, M));
+            continue;
+        }
         VIT_TRY(gemm(e, e->d_ln, 1, w + 8, w + 9, e->d_hid, M, e->HID, e->D, VITCU_EPI_BIAS_GELU, bf, fold));
+        if (calibrate) {
+            VIT_TRY(vitcu_absmax_bf16((const vitcu_bf16 *)e->d_hid, (size_t)M * e->HID, e->d_amax + 2 * l + 1, s));
+            e->launches++;
+        }
         /* the last layer's fc2 has no LayerNorm consumer over all rows (the final one visits the class rows only) */
         VIT_TRY(gemm(e, e->d_hid, 0, w + 10, w + 11, e->d_x, M, e->D, e->HID, VITCU_EPI_BIAS_RESIDUAL, 0,
                      fold && l + 1 < layers ? 2 : 0));
@@ -607,8 +742,26 @@ static int enqueue_forward(vitb200_engine *e, int buf, int b)
 }
 
 /* forward of a chunk, through the captured graph when the chunk is full-size */
+/* FP8 engines: activation scales from the maxima of the first eligible chunk, with a factor 2 of head room (the
+ * conversion saturates at +-448).  One extra BF16 forward per weight load. */
+static int fp8_calibrate(vitb200_engine *e, int buf, int b)
+{
+    float amax[2 * VIT_MAX_DEPTH];
+    VIT_TRY_RC(enqueue_forward_mode(e, buf, b, 1));
+    VIT_TRY(vitcu_memcpy_d2h(amax, e->d_amax, sizeof(amax), e->stream));
+    VIT_TRY(vitcu_stream_sync(e->stream));
+    for (int l = 0; l < e->depth; l++) {
+        e->act_scale_x[l] = amax[2 * l] > 0.f ? 224.0f / amax[2 * l] : 1.0f;
+        e->act_scale_h[l] = amax[2 * l + 1] > 0.f ? 224.0f / amax[2 * l + 1] : 1.0f;
+    }
+    e->fp8_calibrated = 1;
+    return 0;
+}
+
 static int run_chunk(vitb200_engine *e, int buf, int b)
 {
+    if (e->fp8 && !e->fp8_calibrated && e->stop_after < 0 && vitcu_gemm_bf16_emit_supported(b * e->T, e->D))
+        VIT_TRY_RC(fp8_calibrate(e, buf, b));
     /* the first full-size chunk runs eagerly (module load, attribute set-up);
      * later ones are captured once per input buffer and replayed */
     if (b == e->B && e->stop_after < 0 && !e->no_graph && e->warmed) {

@@ -30,6 +30,14 @@ struct vitb200_engine {
     vitcu_bf16 *wf16[VIT_MAX_BLOBS];
     float *wf_cs[VIT_MAX_BLOBS], *wf_b[VIT_MAX_BLOBS];
     void *d_lnstats;                 /* float2 [D / 128][B*T] */
+    /* FP8 precision: fc1 (folded) and fc2 weights as e4m3 with one scale each; activation scales (the e4m3 copy of the
+     * residual rows that fc1 reads, the GELU output that fc2 reads) from a calibration pass over the first chunk */
+    int fp8, fp8_calibrated;
+    unsigned char *wq8[VIT_MAX_BLOBS];
+    float *wq8_cs[VIT_MAX_BLOBS], *wq8_b[VIT_MAX_BLOBS];
+    float wq8_scale[VIT_MAX_BLOBS];
+    float act_scale_x[VIT_MAX_DEPTH], act_scale_h[VIT_MAX_DEPTH];
+    float *d_amax;                   /* [2 * depth] calibration maxima */
     vitcu_bf16 *d_a3;                /* FP32 tensor-core path: split form [rows,3K] of the current GEMM A operand */
     float *d_images[2];              /* double-buffered input chunk [B,3,img,img] */
     void *d_patches;                 /* [B*P,768] gathered patches */

@@ -297,7 +297,9 @@ void ViT_opencl(vitb200_image *image, vitb200_blob *networks, float **prb)
     clock_gettime(CLOCK_MONOTONIC, &t0);
 
     const char *prec = getenv("VITB200_PRECISION");
-    const int precision = (prec && (!strcmp(prec, "bf16") || !strcmp(prec, "BF16"))) ? VITB200_BF16 : VITB200_FP32;
+    const int precision = (prec && (!strcmp(prec, "bf16") || !strcmp(prec, "BF16")))  ? VITB200_BF16
+                          : (prec && (!strcmp(prec, "fp8") || !strcmp(prec, "FP8"))) ? VITB200_FP8
+                                                                                     : VITB200_FP32;
     const int ndev = vitb200_device_count();
     if (ndev <= 0)
         die("[vit_opencl.c] CUDA error 90002 (ViT_opencl: no CUDA device; there is no CPU fallback)");
@@ -312,7 +314,7 @@ void ViT_opencl(vitb200_image *image, vitb200_blob *networks, float **prb)
     if (gpus > 64)
         gpus = 64;
     const int used = vitb200_shard_plan(n, gpus, first_of, count_of);
-    int batch = env_int("VITB200_BATCH", precision == VITB200_BF16 ? 256 : 64);
+    int batch = env_int("VITB200_BATCH", precision != VITB200_FP32 ? 256 : 64);
     if (batch > count_of[0])
         batch = count_of[0];
 
@@ -361,7 +363,7 @@ void ViT_opencl(vitb200_image *image, vitb200_blob *networks, float **prb)
         mf = jobs[g].t_forward > mf ? jobs[g].t_forward : mf;
     }
     printf("ViT_b200: %d images, %d GPU(s), %s%s, %.3f s wall (device bring-up %.3f + weight upload %.3f + forward %.3f, "
-           "slowest shard each)\n", n, used, precision == VITB200_BF16 ? "bf16" : "fp32",
+           "slowest shard each)\n", n, used, precision == VITB200_BF16 ? "bf16" : (precision == VITB200_FP8 ? "fp8" : "fp32"),
            persist ? ", persistent context" : "",
            (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec), mc, mw, mf);
     g_last_call.images = n;
