@@ -1,0 +1,9 @@
+set -x
+cd $GRAFT_REPO_ROOT
+python tools/fold_bench.py 256 20 > gpurun_out/r02p_fold.log 2>&1
+python tools/attn_ab.py > gpurun_out/r02p_attn.log 2>&1
+timeout 900 python -m pytest tests/test_gpu_kernels.py -m gpu -x -q > gpurun_out/r02p_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r02p_pytest.log
+for r in 1 2; do
+  VITB200_LN_FOLD=0 timeout 300 python bench.py --steps 20 --warmup 5 --no-extras >> gpurun_out/r02p_bench_nofold.json 2>>gpurun_out/r02p_bench.err
+  timeout 300 python bench.py --steps 20 --warmup 5 --no-extras >> gpurun_out/r02p_bench_fold.json 2>>gpurun_out/r02p_bench.err
+done

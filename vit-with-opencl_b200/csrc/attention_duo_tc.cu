@@ -367,7 +367,7 @@ attention_duo_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
                         const uint32_t lo = e < 32 ? vlo[e & 31] : vhi[e & 31], hi = e < 32 ? vlo[(e + 1) & 31] : vhi[(e + 1) & 31];
                         w[q] = pack_bf16x2(__uint_as_float(lo) * inv, __uint_as_float(hi) * inv);
                     }
-                    *reinterpret_cast<uint4 *>(tile + lane * 128 + ((i ^ (lane & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+                    sts128(tile + lane * 128 + ((i ^ (lane & 7)) << 4), make_uint4(w[0], w[1], w[2], w[3]));
                 }
                 fence_proxy_async_smem();
                 __syncwarp();

@@ -233,8 +233,8 @@ __device__ __forceinline__ bool epilogue_tile(const EpiParams &p, void *C, const
             const f32x2 r2 = pack2(rstd, rstd), n2 = pack2(nrm, nrm);
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-                const float4 b = *reinterpret_cast<const float4 *>(coef + c * 32 + j);
-                const float4 cs = *reinterpret_cast<const float4 *>(coef + 128 + c * 32 + j);
+                const float4 b = lds128(coef + c * 32 + j);
+                const float4 cs = lds128(coef + 128 + c * 32 + j);
                 unpack2(fma2(pack2(__uint_as_float(acc[c % NACC][j + 0]), __uint_as_float(acc[c % NACC][j + 1])), r2,
                              fma2(pack2(cs.x, cs.y), n2, pack2(b.x, b.y))), v[j + 0], v[j + 1]);
                 unpack2(fma2(pack2(__uint_as_float(acc[c % NACC][j + 2]), __uint_as_float(acc[c % NACC][j + 3])), r2,
@@ -243,7 +243,7 @@ __device__ __forceinline__ bool epilogue_tile(const EpiParams &p, void *C, const
         } else {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-                const float4 b = coef_on ? *reinterpret_cast<const float4 *>(coef + c * 32 + j)
+                const float4 b = coef_on ? lds128(coef + c * 32 + j)
                                          : __ldg(reinterpret_cast<const float4 *>(p.bias + col0 + j));
                 v[j + 0] = fmaf(b.x, bias_on, __uint_as_float(acc[c % NACC][j + 0]));
                 v[j + 1] = fmaf(b.y, bias_on, __uint_as_float(acc[c % NACC][j + 1]));
@@ -299,22 +299,21 @@ __device__ __forceinline__ bool epilogue_tile(const EpiParams &p, void *C, const
                 const float os = p.out_scale;
 #pragma unroll
                 for (int q = 0; q < 2; q++)
-                    *reinterpret_cast<uint4 *>(buf + lane * 32 + (q << 4)) =
+                    sts128(buf + lane * 32 + (q << 4),
                         make_uint4(pack_e4m3x4(v[16 * q + 0] * os, v[16 * q + 1] * os, v[16 * q + 2] * os, v[16 * q + 3] * os),
                                    pack_e4m3x4(v[16 * q + 4] * os, v[16 * q + 5] * os, v[16 * q + 6] * os, v[16 * q + 7] * os),
                                    pack_e4m3x4(v[16 * q + 8] * os, v[16 * q + 9] * os, v[16 * q + 10] * os, v[16 * q + 11] * os),
-                                   pack_e4m3x4(v[16 * q + 12] * os, v[16 * q + 13] * os, v[16 * q + 14] * os, v[16 * q + 15] * os));
+                                   pack_e4m3x4(v[16 * q + 12] * os, v[16 * q + 13] * os, v[16 * q + 14] * os, v[16 * q + 15] * os)));
             } else if (p.tma_out == 1) { // 32 x 64 B rows, 64-byte swizzle: 16-byte chunk ^= (row / 2) % 4
 #pragma unroll
                 for (int q = 0; q < 4; q++)
-                    *reinterpret_cast<uint4 *>(buf + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) =
-                        make_uint4(pack_bf16x2(v[8 * q + 0], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
-                                   pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
+                    sts128(buf + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4),
+                           make_uint4(pack_bf16x2(v[8 * q + 0], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
+                                      pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7])));
             } else { // 32 x 128 B rows, 128-byte swizzle: 16-byte chunk ^= row % 8
 #pragma unroll
                 for (int q = 0; q < 8; q++)
-                    *reinterpret_cast<float4 *>(buf + lane * 128 + ((q ^ (lane & 7)) << 4)) =
-                        make_float4(v[4 * q + 0], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    sts128(buf + lane * 128 + ((q ^ (lane & 7)) << 4), make_float4(v[4 * q + 0], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
             }
             fence_proxy_async_smem();
             __syncwarp();
@@ -328,10 +327,9 @@ __device__ __forceinline__ bool epilogue_tile(const EpiParams &p, void *C, const
             chunk_ctr++;
             continue;
         }
-        float4 *srow = reinterpret_cast<float4 *>(stage + lane * kStageLd);
 #pragma unroll
         for (int j = 0; j < 8; j++)
-            srow[j] = make_float4(v[4 * j + 0], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            sts128(stage + lane * kStageLd + 4 * j, make_float4(v[4 * j + 0], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
         __syncwarp();
         // ---- coalesced part ----
         if (p.out_bf16) {
@@ -340,8 +338,8 @@ __device__ __forceinline__ bool epilogue_tile(const EpiParams &p, void *C, const
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 const int r = i * 8 + rs, row = row0 + r;
-                const float4 x = *reinterpret_cast<const float4 *>(stage + r * kStageLd + c8);
-                const float4 y = *reinterpret_cast<const float4 *>(stage + r * kStageLd + c8 + 4);
+                const float4 x = lds128(stage + r * kStageLd + c8);
+                const float4 y = lds128(stage + r * kStageLd + c8 + 4);
                 if (row < p.M)
                     *reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(C) + static_cast<size_t>(row) * p.ldc + col0 + c8) =
                         make_uint4(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w), pack_bf16x2(y.x, y.y), pack_bf16x2(y.z, y.w));
@@ -351,7 +349,7 @@ __device__ __forceinline__ bool epilogue_tile(const EpiParams &p, void *C, const
 #pragma unroll
             for (int i = 0; i < 8; i++) {
                 const int r = i * 4 + rsub, row = row0 + r;
-                const float4 x = *reinterpret_cast<const float4 *>(stage + r * kStageLd + c4);
+                const float4 x = lds128(stage + r * kStageLd + c4);
                 if (row < p.M)
                     *reinterpret_cast<float4 *>(reinterpret_cast<float *>(C) + out_off(row) + c * 32) =
                         make_float4(x.x + add[i].x, x.y + add[i].y, x.z + add[i].z, x.w + add[i].w);
@@ -435,14 +433,14 @@ __device__ __forceinline__ bool epilogue_tile_emit(const EpiParams &p, const CUt
         rphase[b] ^= 1;
 #pragma unroll
         for (int q = 0; q < 8; q++) { // 32 x 128 B rows, 128-byte swizzle: 16-byte chunk ^= row % 8
-            float4 *slot = reinterpret_cast<float4 *>(R + lane * 128 + ((q ^ (lane & 7)) << 4));
-            const float4 xo = *slot;
+            uint8_t *slot = R + lane * 128 + ((q ^ (lane & 7)) << 4);
+            const float4 xo = lds128(slot);
             const float a0 = xo.x + v[4 * q + 0], a1 = xo.y + v[4 * q + 1], a2 = xo.z + v[4 * q + 2], a3 = xo.w + v[4 * q + 3];
             v[4 * q + 0] = a0;
             v[4 * q + 1] = a1;
             v[4 * q + 2] = a2;
             v[4 * q + 3] = a3;
-            *slot = make_float4(a0, a1, a2, a3);
+            sts128(slot, make_float4(a0, a1, a2, a3));
             s1 += (a0 + a1) + (a2 + a3);
             s2 = fmaf(a0, a0, fmaf(a1, a1, fmaf(a2, a2, fmaf(a3, a3, s2))));
         }
@@ -450,17 +448,17 @@ __device__ __forceinline__ bool epilogue_tile_emit(const EpiParams &p, const CUt
             const float es = p.emit_scale;
 #pragma unroll
             for (int q = 0; q < 2; q++)
-                *reinterpret_cast<uint4 *>(B + lane * 32 + (q << 4)) =
-                    make_uint4(pack_e4m3x4(v[16 * q + 0] * es, v[16 * q + 1] * es, v[16 * q + 2] * es, v[16 * q + 3] * es),
-                               pack_e4m3x4(v[16 * q + 4] * es, v[16 * q + 5] * es, v[16 * q + 6] * es, v[16 * q + 7] * es),
-                               pack_e4m3x4(v[16 * q + 8] * es, v[16 * q + 9] * es, v[16 * q + 10] * es, v[16 * q + 11] * es),
-                               pack_e4m3x4(v[16 * q + 12] * es, v[16 * q + 13] * es, v[16 * q + 14] * es, v[16 * q + 15] * es));
+                sts128(B + lane * 32 + (q << 4),
+                       make_uint4(pack_e4m3x4(v[16 * q + 0] * es, v[16 * q + 1] * es, v[16 * q + 2] * es, v[16 * q + 3] * es),
+                                  pack_e4m3x4(v[16 * q + 4] * es, v[16 * q + 5] * es, v[16 * q + 6] * es, v[16 * q + 7] * es),
+                                  pack_e4m3x4(v[16 * q + 8] * es, v[16 * q + 9] * es, v[16 * q + 10] * es, v[16 * q + 11] * es),
+                                  pack_e4m3x4(v[16 * q + 12] * es, v[16 * q + 13] * es, v[16 * q + 14] * es, v[16 * q + 15] * es)));
         } else {
 #pragma unroll
             for (int q = 0; q < 4; q++) // 32 x 64 B rows, 64-byte swizzle: 16-byte chunk ^= (row / 2) % 4
-                *reinterpret_cast<uint4 *>(B + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) =
-                    make_uint4(pack_bf16x2(v[8 * q + 0], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
-                               pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
+                sts128(B + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4),
+                       make_uint4(pack_bf16x2(v[8 * q + 0], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
+                                  pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7])));
         }
         fence_proxy_async_smem();
         __syncwarp();

@@ -29,6 +29,24 @@ __device__ __forceinline__ bool elect_one()
     return pred != 0;
 }
 
+// Explicit shared-space 128-bit accesses.  A pointer derived from the dynamic shared-memory base through several casts
+// is a GENERIC pointer to ptxas, which then emits LD.E / ST.E (generic-address path, long scoreboard) instead of
+// LDS / STS -- visible as FFMA2s stalled on "long_sb" in the epilogues (profiles/r02_layernorm_fold.md).
+__device__ __forceinline__ float4 lds128(const void *p)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
+    return v;
+}
+__device__ __forceinline__ void sts128(void *p, float4 v)
+{
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(p)), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts128(void *p, uint4 v)
+{
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(p)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 // ---- mbarrier -------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 {
