@@ -42,19 +42,28 @@ def test_bf16_batch256_pair_gemm_graph_vs_oracle(pkg, lib, blobs224, bench_case)
     imgs, ref = bench_case
     with pkg.Engine(0, 224, pkg.BF16, max_batch=256) as eng:
         eng.load_weights(blobs224)
+        # exactly what bench.py times: the 256-image chunk resident in HBM, one forward per step
+        eng.stage(imgs)
         lib.vitcu_launch_count_reset()
-        p_eager, l_eager = eng.forward(imgs, want_logits=True)     # first full chunk: eager launches
+        eng.forward_resident(256)                                   # first full chunk: eager launches
         counts = pkg.launch_counts()
-        p_graph, l_graph = eng.forward(imgs, want_logits=True)     # second: captured CUDA graph, replayed
-        p_again, l_again = eng.forward(imgs, want_logits=True)     # third: replay of the same graph
+        p_eager, l_eager = eng.read_probs(256)
+        eng.forward_resident(256)                                   # second: captured into a CUDA graph, replayed
+        p_graph, l_graph = eng.read_probs(256)
+        eng.forward_resident(256)                                   # third: replay of the same graph
+        p_again, l_again = eng.read_probs(256)
+        # the public call over host images (upload, chunk pipeline, read-back) must give the same bits
+        p_call, l_call = eng.forward(imgs, want_logits=True)
         assert lib.vitcu_watchdog_check() == 0
     # the kernels the bench times are the ones checked here
     assert counts["gemm_bf16_tc2_kernel"] == 48, counts           # qkv, out_proj, fc1, fc2 x 12 as CTA pairs
     assert counts["gemm_bf16_tc_kernel"] == 0, counts
     assert counts["attention_duo_tc_kernel"] + counts["attention_tc_kernel"] == 12, counts
     assert counts["patch_embed_tc_kernel"] == 1, counts
+    assert counts["layernorm_kernel"] == 1, counts                # the final one; the 24 others are folded into the GEMMs
     assert np.array_equal(l_eager, l_graph) and np.array_equal(l_graph, l_again)
     assert np.array_equal(p_eager, p_graph)
+    assert np.array_equal(l_call, l_graph) and np.array_equal(p_call, p_graph)
     err = np.abs(l_graph[:N_CHECK] - ref["logits"]).max(1)         # per image
     margin = np.sort(ref["logits"], 1)
     margin = margin[:, -1] - margin[:, -2]
@@ -120,11 +129,15 @@ def test_fp8_batch256_vs_oracle(pkg, lib, blobs224, bench_case):
     imgs, ref = bench_case
     with pkg.Engine(0, 224, pkg.FP8, max_batch=256) as eng:
         eng.load_weights(blobs224)
+        eng.stage(imgs)
         lib.vitcu_launch_count_reset()
-        p1, l1 = eng.forward(imgs, want_logits=True)      # calibration pass + eager FP8 forward
+        eng.forward_resident(256)                         # calibration pass (bf16 chain) + eager FP8 forward
         counts = pkg.launch_counts()
-        p2, l2 = eng.forward(imgs, want_logits=True)      # captured graph
-        p3, l3 = eng.forward(imgs, want_logits=True)      # replay
+        p1, l1 = eng.read_probs(256)
+        eng.forward_resident(256)                         # captured graph
+        p2, l2 = eng.read_probs(256)
+        eng.forward_resident(256)                         # replay
+        p3, l3 = eng.read_probs(256)
         assert lib.vitcu_watchdog_check() == 0
     assert counts["gemm_bf16_tc2_kernel"] == 2 * 48, counts       # calibration (bf16) + fp8 forward, all CTA pairs
     assert np.array_equal(l1, l2) and np.array_equal(l2, l3)

@@ -69,7 +69,7 @@ static pthread_mutex_t g_cache_mu = PTHREAD_MUTEX_INITIALIZER;
  * core): a few ms against the ~40 ms a re-upload costs.  Piece hashes are combined in blob order,
  * so the value does not depend on the thread count. */
 #define SIG_PIECE ((size_t)1 << 20)
-#define SIG_MAX_THREADS 8
+#define SIG_MAX_THREADS 16
 typedef struct {
     const vitb200_blob *net;
     int nblobs;
@@ -320,7 +320,9 @@ void ViT_opencl(vitb200_image *image, vitb200_blob *networks, float **prb)
 
     const char *pe = getenv("VITB200_PERSIST");
     const int persist = pe && *pe && strcmp(pe, "0") != 0;
+    const double ts0 = now_s();
     const unsigned long long wsig = persist ? weights_signature(networks, 8 + 12 * model.depth) : 0;
+    const double sig_s = now_s() - ts0;
 
     shard_job *jobs = (shard_job *)calloc((size_t)gpus, sizeof(shard_job));
     pthread_t *threads = (pthread_t *)calloc((size_t)gpus, sizeof(pthread_t));
@@ -362,6 +364,8 @@ void ViT_opencl(vitb200_image *image, vitb200_blob *networks, float **prb)
         mw = jobs[g].t_weights > mw ? jobs[g].t_weights : mw;
         mf = jobs[g].t_forward > mf ? jobs[g].t_forward : mf;
     }
+    if (persist)
+        printf("ViT_b200: weight signature (every byte of %d blobs hashed) %.4f s\n", 8 + 12 * model.depth, sig_s);
     printf("ViT_b200: %d images, %d GPU(s), %s%s, %.3f s wall (device bring-up %.3f + weight upload %.3f + forward %.3f, "
            "slowest shard each)\n", n, used, precision == VITB200_BF16 ? "bf16" : (precision == VITB200_FP8 ? "fp8" : "fp32"),
            persist ? ", persistent context" : "",
