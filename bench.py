@@ -631,11 +631,17 @@ def run_engine_arm(args, dist: Dist):
             timed_s = total_ms / 1e3
             use_burst = timed_s < 2.0
             peak = peaks["bf16_burst"] if use_burst else peaks["bf16_sustained"]
+            fold_on = tl["layernorm"][1] <= 1
             line["roofline"] = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                                 "frac": achieved / peak, "traffic": traffic,
                                 "kernel": f"gemm_bf16_tc2_kernel: the {insitu_launches} dense-layer launches of a forward (M={M}), "
                                           f"{gemm_flops_fwd / insitu_launches / 1e9:.1f} GFLOP and {insitu_ms / insitu_launches * 1e3:.1f} us per launch on average; "
-                                          "traffic = DRAM bytes of the four launches of one layer (committed ncu capture)",
+                                          "traffic = DRAM bytes of the four launches of one layer (committed ncu capture)"
+                                          + ("; these launches also do the work of the 24 LayerNorm launches of round 1 (statistics, "
+                                             "normalisation, the bf16 copy of the residual rows: 464 MB of DRAM traffic per layer that no "
+                                             "longer exists), which the FLOP count does not credit -- VITB200_LN_FOLD=0 gives the unfused "
+                                             "kernels back" if fold_on else ""),
+                                "layernorm_folded_into_gemm": fold_on,
                                 "launches": insitu_launches, "ms_per_forward": insitu_ms,
                                 "peak_source": peaks["source"] + (", burst figure: the timed region lasts "
                                                                   f"{timed_s:.2f} s" if use_burst else ", sustained figure"),
