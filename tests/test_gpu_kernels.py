@@ -161,7 +161,8 @@ def test_patch_embed_tma_gather_tf32(pkg, lib, oracle, img, batch):
 
 # ---------------------------------------------------------------- attention
 @pytest.mark.parametrize("T,batch,bf16", [(197, 2, False), (577, 1, False), (197, 2, True), (577, 1, True), (50, 1, False),
-                                           (197, 4, False), (577, 2, False), (33, 13, False)])  # 64-query tiles from 148 CTAs up
+                                           (197, 4, False), (577, 2, False), (33, 13, False),  # 64-query tiles from 148 CTAs up
+                                           (785, 2, False)])  # 448 x 448: the 64-query score tile no longer fits shared memory
 def test_attention_simt(pkg, lib, oracle, T, batch, bf16):
     rng = np.random.default_rng(T + batch)
     qkv = (rng.standard_normal((batch, T, 2304), dtype=np.float32) * 1.5).astype(np.float32)
