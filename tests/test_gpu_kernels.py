@@ -249,9 +249,12 @@ def test_attention_tensor_core_score_ranges(pkg, lib, oracle, scale, kernel, mon
         assert np.abs(out[i] - ref).max() <= tol
 
 
-@pytest.mark.parametrize("T,batch", [(577, 2), (300, 1), (257, 1), (640, 1), (1025, 1), (577, 20)])
-def test_attention_flash_tensor_core(pkg, lib, oracle, T, batch):
-    """key-blocked tcgen05 attention (tokens > 256): odd tile counts, ragged last key block, 577 tokens"""
+@pytest.mark.parametrize("kernel", ["duo", "solo"])
+@pytest.mark.parametrize("T,batch", [(577, 2), (300, 1), (257, 1), (640, 1), (1025, 1), (577, 20), (785, 9), (225, 30)])
+def test_attention_flash_tensor_core(pkg, lib, oracle, T, batch, kernel, monkeypatch):
+    """key-blocked tcgen05 attention (tokens > 224): odd tile counts, ragged last key block, 577 tokens, more items than
+    CTAs; both kernels: "duo" (one query tile per CTA, two CTAs per SM, default) and "solo" (round 1: tile pairs)"""
+    monkeypatch.setenv("VITCU_ATTN_KERNEL", kernel)
     rng = np.random.default_rng(2000 + T + batch)
     bits = pkg.f32_to_bf16_bits((rng.standard_normal((batch, T, 2304), dtype=np.float32) * 1.5).astype(np.float32))
     qkv = pkg.bf16_bits_to_f32(bits).reshape(batch, T, 2304)
@@ -669,3 +672,32 @@ def test_gemm_e4m3_residual_emit(pkg, lib, fp8_in, emit_fp8, M, K):
     blocks = x.astype(np.float64).reshape(M, slots, 128)
     np.testing.assert_allclose(st[:, :, 0].T, blocks.sum(2), rtol=1e-5, atol=1e-3)
     np.testing.assert_allclose(st[:, :, 1].T, (blocks ** 2).sum(2), rtol=1e-5, atol=1e-3)
+
+
+@pytest.mark.parametrize("kernel", ["duo", "solo"])
+@pytest.mark.parametrize("scale", [0.05, 3.0, 12.0])
+def test_attention_flash_score_ranges(pkg, lib, oracle, scale, kernel, monkeypatch):
+    """key-blocked kernels over score magnitudes from nearly uniform rows to one-hot rows.  The duo kernel keeps O in
+    tensor memory over the key blocks and moves a row's reference maximum (rescaling O and the row sum in place) only when a
+    later block exceeds it by more than 2^8 in the exp2 domain: scale 0.05 never takes that path, scale 12 takes it on
+    most rows, and the keys are ordered so that the largest scores come LAST (the worst case for a stale maximum)"""
+    monkeypatch.setenv("VITCU_ATTN_KERNEL", kernel)
+    T, batch = 577, 2
+    rng = np.random.default_rng(91)
+    x = rng.standard_normal((batch, T, 2304), dtype=np.float32) * scale
+    # key norms grow with the key index: later key blocks dominate every row
+    x[:, :, 768:1536] *= np.linspace(0.2, 1.8, T, dtype=np.float32)[None, :, None]
+    bits = pkg.f32_to_bf16_bits(x.astype(np.float32))
+    qkv = pkg.bf16_bits_to_f32(bits).reshape(batch, T, 2304)
+    dq = _dev(pkg, bits)
+    do = pkg.DeviceBuffer(batch * T * 768 * 2)
+    pkg.layer_check(lib.vitcu_memset(do.ptr, 0xFF, batch * T * 768 * 2, None))
+    pkg.layer_check(lib.vitcu_attention(dq.ptr, do.ptr, batch, T, 1, None))
+    assert lib.vitcu_watchdog_check() == 0
+    out = pkg.bf16_bits_to_f32(do.to_numpy(np.uint16, (batch, T, 768)))
+    assert np.isfinite(out).all()
+    for i in range(batch):
+        ref = oracle.attention_core(qkv[i, :, :768], qkv[i, :, 768:1536], qkv[i, :, 1536:])
+        tol = 3 * 2.0 ** -8 * np.abs(ref).max() + 1e-3
+        err = np.abs(out[i] - ref)
+        assert err.max() <= tol, f"image {i}: max err {err.max()} at {np.unravel_index(err.argmax(), err.shape)} tol {tol}"

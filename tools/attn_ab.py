@@ -12,7 +12,8 @@ import __graft_entry__ as g  # noqa: E402
 
 pkg = g.load_package()
 L = pkg.lib()
-B, T = 256, int(sys.argv[1]) if len(sys.argv) > 1 else 197
+T = int(sys.argv[1]) if len(sys.argv) > 1 else 197
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 256
 rng = np.random.default_rng(0)
 qkv = pkg.DeviceBuffer.from_numpy(pkg.f32_to_bf16_bits(rng.standard_normal((B * T, 2304), dtype=np.float32)))
 out = pkg.DeviceBuffer(B * T * 768 * 2)

@@ -45,6 +45,15 @@ using namespace vitcu::tc;
 
 namespace {
 
+#ifndef VITCU_CTL_SPIN
+#define VITCU_CTL_SPIN 0 // measured: spinning costs 10 % (flash) / 1.5 % (single-block) -- control warp: 1 = spin on its mbarriers (a parked warp wakes up late and everything it issues is on the CTA's chain)
+#endif
+#if VITCU_CTL_SPIN
+#define ctl_wait mbar_wait_spin_warp
+#else
+#define ctl_wait mbar_wait_warp
+#endif
+
 constexpr int kThreadsDuo = 160;
 constexpr int QT = 128;                   // queries per tile
 constexpr uint32_t Q_BYTES = QT * 128;    // [128 x 64] bf16
@@ -231,9 +240,9 @@ attention_duo_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         };
         auto issue_s = [&](int k) {
             const int il = k / ntiles, t = k - il * ntiles;
-            bool ok = mbar_wait_warp(&bars[Q_FULL], k & 1, wd, 3);
+            bool ok = ctl_wait(&bars[Q_FULL], k & 1, wd, 3);
             if (ok && t == 0)
-                ok = mbar_wait_warp(&bars[K_FULL], il & 1, wd, 4);
+                ok = ctl_wait(&bars[K_FULL], il & 1, wd, 4);
             if (!ok)
                 return;
             tcgen05_fence_after();
@@ -250,7 +259,7 @@ attention_duo_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         // P V over key chunks [c0, c1): 16 keys per step = 8 packed P columns and 16 V rows of 128 B
         auto issue_pv = [&](int k, int c0, int c1, bool last) {
             const int il = k / ntiles, t = k - il * ntiles;
-            if (c0 == 0 && t == 0 && !mbar_wait_warp(&bars[V_FULL + (il & 1)], (il >> 1) & 1, wd, 5))
+            if (c0 == 0 && t == 0 && !ctl_wait(&bars[V_FULL + (il & 1)], (il >> 1) & 1, wd, 5))
                 return;
             tcgen05_fence_after();
             if (elect_one()) {
@@ -271,7 +280,7 @@ attention_duo_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         }
         for (int k = 0; k < n_units; k++) {
             // S(k) retired: the Q buffer (and K, after the item's last tile) can take the next unit's operands
-            if (!mbar_wait_warp(&bars[S_FULL], k & 1, wd, 6))
+            if (!ctl_wait(&bars[S_FULL], k & 1, wd, 6))
                 break; // the softmax warps wait on the same barrier and leave with us
             if (k + 1 < n_units)
                 load_unit(k + 1);

@@ -247,6 +247,7 @@ namespace vitcu {
 int attention_bf16_tc(const void *qkv, void *out, int batch, int tokens, int heads, cudaStream_t st);       // attention_tc.cu
 int attention_bf16_flash_tc(const void *qkv, void *out, int batch, int tokens, int heads, cudaStream_t st); // attention_flash_tc.cu
 int attention_bf16_duo_tc(const void *qkv, void *out, int batch, int tokens, int heads, cudaStream_t st);   // attention_duo_tc.cu
+int attention_bf16_flash_duo_tc(const void *qkv, void *out, int batch, int tokens, int heads, cudaStream_t st); // attention_flash_duo_tc.cu
 }
 
 extern "C" int vitcu_attention_ex(const void *qkv, void *out, int batch, int tokens, int heads, int is_bf16, vitcu_stream s)
@@ -263,10 +264,13 @@ extern "C" int vitcu_attention_ex(const void *qkv, void *out, int batch, int tok
     const char *which = getenv("VITCU_ATTN_KERNEL"); // read per call: the tests exercise both kernels in one process
     const bool solo = which && !strcmp(which, "solo");
     if (is_bf16 == 1 && !force_simt) {
+        if (tokens <= 208 && !force_flash)
+            return solo ? attention_bf16_tc(qkv, out, batch, tokens, heads, as_stream(s))
+                        : attention_bf16_duo_tc(qkv, out, batch, tokens, heads, as_stream(s));
         if (tokens <= 224 && !force_flash)
-            return solo || tokens > 208 ? attention_bf16_tc(qkv, out, batch, tokens, heads, as_stream(s))
-                                        : attention_bf16_duo_tc(qkv, out, batch, tokens, heads, as_stream(s));
-        return attention_bf16_flash_tc(qkv, out, batch, tokens, heads, as_stream(s));
+            return attention_bf16_tc(qkv, out, batch, tokens, heads, as_stream(s));
+        return solo ? attention_bf16_flash_tc(qkv, out, batch, tokens, heads, as_stream(s))
+                    : attention_bf16_flash_duo_tc(qkv, out, batch, tokens, heads, as_stream(s));
     }
     // 16-query tiles when 64-query tiles would leave most of the 148 SMs idle (small batches)
     // ... or when the 64-query score tile does not fit shared memory (more than ~620 tokens: 448x448 images)
