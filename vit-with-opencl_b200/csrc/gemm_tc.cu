@@ -58,6 +58,7 @@ struct EpiParams {
     float ln_inv_d;          // 1 / row length
     // ... and producer side (tma_out == 4): the residual epilogue also emits bf16(x_new) and the row partials
     float2 *emit_stats;      // [N / 128][M]
+    void *emit_ptr;          // bf16 [M,N] (or e4m3 [M,N]) copy of the updated rows
     // FP8 (E4M3) path: operands are quantised with per-tensor scales, acc_scale = 1 / (scale_A * scale_W) brings the
     // accumulator back; out_scale / emit_scale quantise what this GEMM hands to the next FP8 GEMM
     int kb_elems;            // operand elements per 128-byte k-block row: 64 (bf16) or 128 (e4m3)
@@ -483,6 +484,142 @@ __device__ __forceinline__ bool epilogue_tile_emit(const EpiParams &p, const CUt
     return true;
 }
 
+// The same producer epilogue without the TMA engine (VITCU_EMIT_VARIANT 4): the epilogue's TMA loads and the read-waits
+// of its TMA stores queue behind the main loop's operand loads (profiles/r02_layernorm_fold.md), so here the residual tile
+// arrives by cp.async (16 B per lane, 8 lanes per 128-byte row, written into the same swizzled layout) two chunks ahead
+// into a ring of three 4 KB buffers, and both outputs leave through coalesced 128-bit stores of the warp itself: x_new goes
+// back into its buffer, is read out with the 8-lanes-per-row mapping and stored; the bf16 / e4m3 rows take the same route
+// through the same buffer.  Every read of a buffer is synchronous, so it can be refilled after a __syncwarp.
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+template <int NCHUNK>
+__device__ __forceinline__ bool epilogue_tile_emit_lsu(const EpiParams &p, uint8_t *stage, int lane, int row0, int col_base,
+                                                       uint32_t taddr, uint64_t *tfull, uint32_t parity, const Watchdog &wd)
+{
+    const bool rows_exist = row0 < p.M; // warp-uniform
+    const int rs = lane >> 3, q8 = lane & 7; // fp32 tiles: 8 lanes per 128-byte row, 4 rows per instruction
+    float *xg = const_cast<float *>(p.residual);
+    auto load_chunk = [&](int c) {
+        uint8_t *R = stage + (c % 3) * 4096;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int r = 4 * i + rs;
+            if (row0 + r < p.M)
+                cp_async16(R + r * 128 + ((q8 ^ (r & 7)) << 4), xg + static_cast<size_t>(row0 + r) * p.ldc + col_base + c * 32 + 4 * q8);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (rows_exist) {
+        load_chunk(0);
+        if (NCHUNK > 1)
+            load_chunk(1);
+    }
+    bool ok = mbar_wait(tfull, parity, wd, 4);
+    ok = __all_sync(0xffffffffu, ok);
+    if (!ok)
+        return false;
+    tcgen05_fence_after();
+    uint32_t acc[2][32];
+    tmem_ld_32x32b_x32(taddr, acc[0]);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCHUNK; c++) {
+        tmem_ld_wait();
+        if (c + 1 < NCHUNK)
+            tmem_ld_32x32b_x32(taddr + (c + 1) * 32, acc[(c + 1) & 1]);
+        if (!rows_exist)
+            continue;
+        const int col0 = col_base + c * 32;
+        uint8_t *R = stage + (c % 3) * 4096;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            const float4 bb = __ldg(reinterpret_cast<const float4 *>(p.bias + col0 + j));
+            v[j + 0] = fmaf(__uint_as_float(acc[c & 1][j + 0]), p.acc_scale, bb.x);
+            v[j + 1] = fmaf(__uint_as_float(acc[c & 1][j + 1]), p.acc_scale, bb.y);
+            v[j + 2] = fmaf(__uint_as_float(acc[c & 1][j + 2]), p.acc_scale, bb.z);
+            v[j + 3] = fmaf(__uint_as_float(acc[c & 1][j + 3]), p.acc_scale, bb.w);
+        }
+        if (c + 2 < NCHUNK)
+            load_chunk(c + 2); // its buffer was last used by chunk c - 1, read out synchronously
+        // chunk c has landed: at most the groups of chunks c + 1, c + 2 may still be in flight
+        if (c + 2 < NCHUNK)
+            cp_async_wait<2>();
+        else if (c + 1 < NCHUNK)
+            cp_async_wait<1>();
+        else
+            cp_async_wait<0>();
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 8; q++) { // thread = row: 32 x 128 B rows, 128-byte swizzle: 16-byte chunk ^= row % 8
+            uint8_t *slot = R + lane * 128 + ((q ^ (lane & 7)) << 4);
+            const float4 xo = lds128(slot);
+            const float a0 = xo.x + v[4 * q + 0], a1 = xo.y + v[4 * q + 1], a2 = xo.z + v[4 * q + 2], a3 = xo.w + v[4 * q + 3];
+            v[4 * q + 0] = a0;
+            v[4 * q + 1] = a1;
+            v[4 * q + 2] = a2;
+            v[4 * q + 3] = a3;
+            sts128(slot, make_float4(a0, a1, a2, a3));
+            s1 += (a0 + a1) + (a2 + a3);
+            s2 = fmaf(a0, a0, fmaf(a1, a1, fmaf(a2, a2, fmaf(a3, a3, s2))));
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; i++) { // x_new out: 8 lanes per row, 4 rows (4 x 128 contiguous bytes) per instruction
+            const int r = 4 * i + rs;
+            const float4 xn = lds128(R + r * 128 + ((q8 ^ (r & 7)) << 4));
+            if (row0 + r < p.M)
+                *reinterpret_cast<float4 *>(xg + static_cast<size_t>(row0 + r) * p.ldc + col0 + 4 * q8) = xn;
+        }
+        __syncwarp(); // the fp32 tile has been read: its buffer takes the 16-bit / 8-bit copy
+        if (p.emit_fp8) { // 32 x 32 B rows of e4m3(x * emit_scale)
+            const float es = p.emit_scale;
+#pragma unroll
+            for (int q = 0; q < 2; q++)
+                sts128(R + lane * 32 + (q << 4),
+                       make_uint4(pack_e4m3x4(v[16 * q + 0] * es, v[16 * q + 1] * es, v[16 * q + 2] * es, v[16 * q + 3] * es),
+                                  pack_e4m3x4(v[16 * q + 4] * es, v[16 * q + 5] * es, v[16 * q + 6] * es, v[16 * q + 7] * es),
+                                  pack_e4m3x4(v[16 * q + 8] * es, v[16 * q + 9] * es, v[16 * q + 10] * es, v[16 * q + 11] * es),
+                                  pack_e4m3x4(v[16 * q + 12] * es, v[16 * q + 13] * es, v[16 * q + 14] * es, v[16 * q + 15] * es)));
+            __syncwarp();
+            uint8_t *og = reinterpret_cast<uint8_t *>(p.emit_ptr);
+#pragma unroll
+            for (int i = 0; i < 2; i++) { // 2 lanes per 32-byte row, 16 rows per instruction
+                const int r = 16 * i + (lane >> 1);
+                const float4 t = lds128(R + r * 32 + ((lane & 1) << 4));
+                if (row0 + r < p.M)
+                    *reinterpret_cast<float4 *>(og + static_cast<size_t>(row0 + r) * p.N + col0 + 16 * (lane & 1)) = t;
+            }
+        } else { // 32 x 64 B rows of bf16, 64-byte swizzle: 16-byte chunk ^= (row / 2) % 4
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                sts128(R + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4),
+                       make_uint4(pack_bf16x2(v[8 * q + 0], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
+                                  pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7])));
+            __syncwarp();
+            __nv_bfloat16 *og = reinterpret_cast<__nv_bfloat16 *>(p.emit_ptr);
+#pragma unroll
+            for (int i = 0; i < 4; i++) { // 4 lanes per 64-byte row, 8 rows per instruction
+                const int r = 8 * i + (lane >> 2), q4 = lane & 3;
+                const float4 t = lds128(R + r * 64 + ((q4 ^ ((r >> 1) & 3)) << 4));
+                if (row0 + r < p.M)
+                    *reinterpret_cast<float4 *>(og + static_cast<size_t>(row0 + r) * p.N + col0 + 8 * q4) = t;
+            }
+        }
+        __syncwarp(); // the buffer may be refilled (by the cp.async of chunk c + 3, issued one iteration later)
+    }
+    if (rows_exist && row0 + lane < p.M)
+        p.emit_stats[static_cast<size_t>(col_base / (32 * NCHUNK)) * p.M + row0 + lane] = make_float2(s1, s2);
+    return true;
+}
+
 template <int BN, int STAGES, bool LN = false>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -849,10 +986,16 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             bool tile_ok;
             if (EMIT) {
                 static_assert(!EMIT || SBW >= 12288, "emit mode needs 12 KB of staging per epilogue warp");
+#if VITCU_EMIT_VARIANT == 4
+                tile_ok = epilogue_tile_emit_lsu<CW / 32>(p, reinterpret_cast<uint8_t *>(stage_tile), lane,
+                                                          m_blk * BM2 + (int)rank * BM + quad * 32, n_blk * BN + cgrp * CW, taddr,
+                                                          &tfull_bar[acc], acc_phase, wd);
+#else
                 tile_ok = epilogue_tile_emit<CW / 32>(p, &tmap_c, &tmap_d, reinterpret_cast<uint8_t *>(stage_tile),
                                                       &res_bar[2 * (warp - 2)], rphase, lane,
                                                       m_blk * BM2 + (int)rank * BM + quad * 32, n_blk * BN + cgrp * CW, taddr,
                                                       &tfull_bar[acc], acc_phase, wd);
+#endif
             } else {
                 tile_ok = epilogue_tile<CW / 32, SBW, EW == 8, LN>(p, C, &tmap_c, chunk_ctr, stage_tile, lane,
                                                                m_blk * BM2 + (int)rank * BM + quad * 32, n_blk * BN + cgrp * CW,
@@ -1032,6 +1175,7 @@ static int gemm_dispatch(const vitcu_bf16 *A, const vitcu_bf16 *W, void *C, cons
                       "emit mode needs the in-place fp32 residual epilogue");
         VITCU_REQUIRE(vitcu_gemm_bf16_emit_supported(d->M, d->N), "emit mode needs the CTA-pair kernel (N % 256 == 0, enough tiles)");
         p.emit_stats = reinterpret_cast<float2 *>(d->emit_stats);
+        p.emit_ptr = d->emit_bf16;
         p.emit_fp8 = d->emit_fp8;
         p.emit_scale = d->emit_scale;
         VITCU_REQUIRE(!d->emit_fp8 || d->emit_scale > 0.f, "emit_fp8 needs a positive emit_scale");
@@ -1179,6 +1323,7 @@ extern "C" int vitcu_gemm_e4m3(const uint8_t *A, const uint8_t *W, void *C, cons
                           ((uintptr_t)d->emit_bf16 & 15) == 0, "emit mode needs the in-place fp32 residual epilogue");
         VITCU_REQUIRE(!d->emit_fp8 || d->emit_scale > 0.f, "emit_fp8 needs a positive emit_scale");
         p.emit_stats = reinterpret_cast<float2 *>(d->emit_stats);
+        p.emit_ptr = d->emit_bf16;
         p.emit_fp8 = d->emit_fp8;
         p.emit_scale = d->emit_scale;
         p.tma_out = 4;
