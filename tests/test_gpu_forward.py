@@ -454,3 +454,34 @@ def test_vit_opencl_multi_gpu_split(pkg, lib, blobs224, monkeypatch):
     assert np.array_equal(ragged.argmax(1), one[:n - 37].argmax(1))
     np.testing.assert_allclose(ragged, one[:n - 37], rtol=3e-2, atol=1e-7)
     assert lib.vitcu_watchdog_check() == 0
+
+
+@pytest.mark.parametrize("variant,img,batch", [("l16", 224, 64), ("b32", 224, 256)])
+def test_model_variants_large_chunks_match_small_chunks(pkg, lib, variant, img, batch):
+    """the other model widths at chunk sizes that take the CTA-pair GEMMs, the folded LayerNorm (6 or 8 partial-sum slots)
+    and the duo attention kernel, against the same images through 4-image chunks (separate LayerNorm kernel, single-CTA
+    GEMM tiles), which test_model_variants_match_oracle ties to the oracle; FP8 on the same chunk within its own contract"""
+    blobs = pkg.synth.variant_blobs(variant, img, seed=7)
+    imgs = pkg.synth.synthetic_images(batch, img, seed=99)
+    with pkg.Engine(0, img, pkg.BF16, max_batch=4, model=variant) as eng:
+        eng.load_weights(blobs)
+        small, small_logits = eng.forward(imgs[:16], want_logits=True)
+    with pkg.Engine(0, img, pkg.BF16, max_batch=batch, model=variant) as eng:
+        eng.load_weights(blobs)
+        lib.vitcu_launch_count_reset()
+        big, big_logits = eng.forward(imgs, want_logits=True)
+        counts = pkg.launch_counts()
+        again = eng.forward(imgs)
+        assert lib.vitcu_watchdog_check() == 0
+    depth = pkg.synth.VARIANTS[variant][2]
+    assert counts["gemm_bf16_tc2_kernel"] == 4 * depth, counts
+    assert counts["layernorm_kernel"] == 1, counts              # only the final one: the others are folded
+    assert np.array_equal(big, again)
+    assert np.abs(big_logits[:16] - small_logits).max() <= 2e-2
+    assert np.array_equal(big[:16].argmax(1), small.argmax(1))
+    with pkg.Engine(0, img, pkg.FP8, max_batch=batch, model=variant) as eng:
+        eng.load_weights(blobs)
+        p8, l8 = eng.forward(imgs, want_logits=True)
+        assert lib.vitcu_watchdog_check() == 0
+    assert np.isfinite(l8).all()
+    assert np.abs(l8[:16] - small_logits).max() <= 2.5e-1

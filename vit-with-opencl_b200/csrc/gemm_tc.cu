@@ -375,7 +375,7 @@ __device__ __forceinline__ bool epilogue_tile(const EpiParams &p, void *C, const
 // kernel's launch and its re-read of the fp32 stream (4 of its 6 bytes per element) disappear.
 // Per-warp staging (12 KB): R[2] fp32 in/out tiles at 0 / 4096, B[2] bf16 tiles at 8192 / 10240; rbar[2] signal the loads.
 #ifndef VITCU_EMIT_VARIANT
-#define VITCU_EMIT_VARIANT 0 // diagnostics: 1 spin on the residual barrier, 2 no read-wait before the reload (racy), 3 no residual load (x_old = 0)
+#define VITCU_EMIT_VARIANT 0 // 0: residual tiles and outputs through the TMA engine (default); 4: cp.async + coalesced stores (A/B, not faster)
 #endif
 template <int NCHUNK>
 __device__ __forceinline__ bool epilogue_tile_emit(const EpiParams &p, const CUtensorMap *tmap_c, const CUtensorMap *tmap_d,
@@ -386,12 +386,10 @@ __device__ __forceinline__ bool epilogue_tile_emit(const EpiParams &p, const CUt
     const bool rows_exist = row0 < p.M; // warp-uniform
     if (rows_exist && lane == 0) {
         tma_wait_group_read<0>(); // this warp's stores of the previous tile have read the staging buffers
-#if VITCU_EMIT_VARIANT != 3
         for (int c = 0; c < 2 && c < NCHUNK; c++) {
             mbar_arrive_expect_tx(&rbar[c], 4096);
             tma_load_2d(stage + c * 4096, tmap_c, &rbar[c], col_base + c * 32, row0);
         }
-#endif
     }
     __syncwarp();
     bool ok = mbar_wait(tfull, parity, wd, 4);
@@ -421,13 +419,7 @@ __device__ __forceinline__ bool epilogue_tile_emit(const EpiParams &p, const CUt
             v[j + 3] = fmaf(__uint_as_float(acc[c & 1][j + 3]), p.acc_scale, bb.w);
         }
         // the residual tile of this chunk has landed
-#if VITCU_EMIT_VARIANT == 1
-        ok = mbar_wait_spin(&rbar[b], rphase[b], wd, 9);
-#elif VITCU_EMIT_VARIANT == 3
-        ok = true;
-#else
         ok = mbar_wait(&rbar[b], rphase[b], wd, 9);
-#endif
         ok = __all_sync(0xffffffffu, ok);
         if (!ok)
             return false;
@@ -468,13 +460,9 @@ __device__ __forceinline__ bool epilogue_tile_emit(const EpiParams &p, const CUt
             tma_store_2d(tmap_d, B, col0, row0);
             tma_commit_group();
             if (c + 2 < NCHUNK) { // the buffers are reloaded once the stores just issued have read them
-#if VITCU_EMIT_VARIANT != 2 && VITCU_EMIT_VARIANT != 3
                 tma_wait_group_read<0>();
-#endif
-#if VITCU_EMIT_VARIANT != 3
                 mbar_arrive_expect_tx(&rbar[b], 4096);
                 tma_load_2d(R, tmap_c, &rbar[b], col_base + (c + 2) * 32, row0);
-#endif
             }
         }
         __syncwarp();
