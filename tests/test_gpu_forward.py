@@ -474,14 +474,24 @@ def test_model_variants_large_chunks_match_small_chunks(pkg, lib, variant, img, 
         again = eng.forward(imgs)
         assert lib.vitcu_watchdog_check() == 0
     depth = pkg.synth.VARIANTS[variant][2]
-    assert counts["gemm_bf16_tc2_kernel"] == 4 * depth, counts
+    # (+ 1 for /32 patches: their patch embedding is a gather + the same GEMM)
+    assert counts["gemm_bf16_tc2_kernel"] == 4 * depth + (1 if variant == "b32" else 0), counts
     assert counts["layernorm_kernel"] == 1, counts              # only the final one: the others are folded
     assert np.array_equal(big, again)
-    assert np.abs(big_logits[:16] - small_logits).max() <= 2e-2
-    assert np.array_equal(big[:16].argmax(1), small.argmax(1))
+    # two BF16 paths with different rounding points (each within 2e-2 of the oracle): up to twice that apart
+    # (no top-1 comparison between the two: with random-init weights some images have top-1 margins below the rounding)
+    assert np.abs(big_logits[:16] - small_logits).max() <= 4e-2
+    from oracle import binding
+    ref = binding.Oracle(variant).forward(imgs[:3], blobs)
+    err = np.abs(big_logits[:3] - ref["logits"]).max()
+    print(f"\n{variant} batch {batch}: folded BF16 path vs oracle max|dlogit| = {err:.3e}")
+    assert err <= BF16_ABS
+    srt = np.sort(ref["logits"], 1)
+    clear = (srt[:, -1] - srt[:, -2]) > 2 * BF16_ABS             # top-1 must agree wherever the oracle's margin allows it
+    assert np.array_equal(big[:3].argmax(1)[clear], ref["probs"].argmax(1)[clear])
     with pkg.Engine(0, img, pkg.FP8, max_batch=batch, model=variant) as eng:
         eng.load_weights(blobs)
         p8, l8 = eng.forward(imgs, want_logits=True)
         assert lib.vitcu_watchdog_check() == 0
     assert np.isfinite(l8).all()
-    assert np.abs(l8[:16] - small_logits).max() <= 2.5e-1
+    assert np.abs(l8[:3] - ref["logits"]).max() <= 2.5e-1
