@@ -674,6 +674,36 @@ def run_engine_arm(args, dist: Dist):
             line["roofline"] = {"error": str(ex)}
     eng.close()
 
+    if dist.rank == 0 and isinstance(line.get("roofline"), dict) and line["roofline"].get("layernorm_folded_into_gemm"):
+        # The same forward with the LayerNorm kernels separate (VITB200_LN_FOLD=0), in the same process and on the same
+        # staged batch: what the plain GEMM launches reach without the LayerNorm work, and what the step costs that way.
+        prev_fold = os.environ.get("VITB200_LN_FOLD")
+        try:
+            os.environ["VITB200_LN_FOLD"] = "0"
+            with pkg.Engine(dev, IMG, pkg.BF16, max_batch=BATCH) as e0:
+                e0.load_weights(blobs)
+                e0.stage(pinned.array)
+                for _ in range(max(args.warmup, 3)):
+                    e0.forward_resident(BATCH)
+                ms0 = e0.time_resident(BATCH, args.steps) / args.steps
+                g_ms, g_n = e0.profile_gemms(BATCH, 5)
+                tl0 = e0.profile_timeline(BATCH, 3)
+            T = (IMG // 16) ** 2 + 1
+            fl = 12 * 2.0 * BATCH * T * 768 * (2304 + 768 + 3072 + 3072)
+            line["roofline"]["unfused_reference"] = {
+                "what": "VITB200_LN_FOLD=0: plain GEMM epilogues + 24 LayerNorm launches, same box, same batch",
+                "gemm_ms_per_forward": g_ms, "gemm_tflops": fl / g_ms / 1e9, "gemm_frac_of_burst_peak": fl / g_ms / 1e9 / peaks["bf16_burst"],
+                "layernorm_ms_per_forward": round(tl0["layernorm"][0], 4), "ms_per_step": ms0,
+                "gemm_plus_layernorm_ms": round(g_ms + tl0["layernorm"][0], 4),
+                "folded_gemm_ms": line["roofline"]["ms_per_forward"]}
+        except Exception as ex:
+            line["roofline"]["unfused_reference"] = {"error": str(ex)}
+        finally:
+            if prev_fold is None:
+                os.environ.pop("VITB200_LN_FOLD", None)
+            else:
+                os.environ["VITB200_LN_FOLD"] = prev_fold
+
     if (IMG, BATCH) == (224, 256) and not args.no_extras:
         # ---- BASELINE config 5 shape (384x384, 577 tokens, 64 images per GPU; 512 over 8 GPUs) ----
         try:
