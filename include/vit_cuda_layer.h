@@ -98,6 +98,10 @@ int vitcu_f32_to_bf16(const float *src, vitcu_bf16 *dst, size_t n, vitcu_stream 
 /* fp32 [rows,K] (row stride ld) -> bf16 [rows, 3K] = [x1 | x2 | x3] with x = x1 + x2 + x3 to 24
  * mantissa bits: the operand format of vitcu_gemm_bf16x3 (FP32 path on the tensor cores). */
 int vitcu_split3(const float *x, size_t ld, vitcu_bf16 *out, size_t rows, int K, vitcu_stream s);
+/* same with the exact-erf GELU (R/ViT_seq.c:283-286) applied first: out = split3(gelu(x)).  The fc1 output of the
+ * accumulate-mode chain (vitcu_gemm_desc.accumulate) is complete only when every K slice has landed, so its GELU moves
+ * from the GEMM epilogue into the split pass in front of fc2. */
+int vitcu_split3_gelu(const float *x, size_t ld, vitcu_bf16 *out, size_t rows, int K, vitcu_stream s);
 
 /* Patch gather (replaces the data movement of conv2d_kernel, R/conv2d.cl:1-36):
  * images [B,3,img,img] fp32 -> patches [B*P, 768] with column order (c,kh,kw),
@@ -137,6 +141,10 @@ int vitcu_layernorm(const float *x, size_t x_row_stride, void *y, int y_bf16,
 /* same over `cols` features: 384, 768 or 1024 (embed_dim of the model variants, R/ViT_seq.c:14) */
 int vitcu_layernorm_ex(const float *x, size_t x_row_stride, void *y, int y_bf16, const float *gamma,
                        const float *beta, int rows, int cols, vitcu_stream s);
+/* same, and the launch also zero-fills zero_bytes (a multiple of 16) at zero_ptr (16-byte aligned): the output buffer
+ * of the accumulate-mode GEMM that consumes y (vitcu_gemm_desc.accumulate) without a launch of its own */
+int vitcu_layernorm_zero(const float *x, size_t x_row_stride, void *y, int y_bf16, const float *gamma,
+                         const float *beta, int rows, int cols, void *zero_ptr, size_t zero_bytes, vitcu_stream s);
 
 /* Epilogue selector for both GEMM families */
 enum {
@@ -178,6 +186,11 @@ typedef struct {
     float out_scale;
     int emit_fp8;
     float emit_scale;
+    /* accumulate (FP32 path at small M, the batch-1 latency shape): C [M,N] fp32 has been ZEROED by the caller and the
+     * GEMM adds acc + bias into it through TMA reduce-add (EPI_BIAS only).  With no value to finish per element the K
+     * range can be cut into slices that run on different SMs (split-K, chosen so that the work items fill the device):
+     * a [197 x 768] x [768 x 2304] product is 36 tiles, 36 of 148 SMs busy, unless sliced. */
+    int accumulate;
 } vitcu_gemm_desc;
 
 /* FP32 SIMT GEMM (replaces linear_layer, R/ll.cl:7-70 and QKV, R/multihead.cl:3-63
@@ -208,6 +221,10 @@ int vitcu_absmax_bf16(const vitcu_bf16 *x, size_t n, float *out, vitcu_stream s)
  * vitcu_ln_fold_weights). */
 int vitcu_fp8_quant_weights(const float *W, const float *gamma, const float *beta, const float *bias, float scale, uint8_t *q,
                             float *colsum, float *bias_folded, int N, int K, vitcu_stream s);
+
+/* 1 when an [M,N] product would leave SMs idle without split-K (fewer 128 x 128 tiles than half the SMs): the shapes
+ * for which the engine's FP32 chain uses accumulate mode */
+int vitcu_gemm_split_k_pays(int M, int N);
 
 /* 1 when vitcu_gemm_bf16 can run the LayerNorm-producer epilogue (emit_bf16 / emit_stats) for an [M,N] output */
 int vitcu_gemm_bf16_emit_supported(int M, int N);

@@ -471,6 +471,50 @@ def test_gemm_bf16x3_is_fp32_accurate(pkg, lib, oracle, M, N, K, epi):
         assert _rel_err(y, oracle.linear(x, w, b)) <= 2e-5
 
 
+@pytest.mark.parametrize("M,N,gelu", [(197, 2304, False), (197, 3072, True), (394, 1536, False), (12608, 768, False)])
+def test_gemm_bf16x3_accumulate_chain(pkg, lib, oracle, M, N, gelu):
+    """the FP32 chain at small M (batch-1 latency): the LayerNorm launch zeroes the GEMM's output, the GEMM runs in
+    accumulate mode (K slices on different SMs meeting through TMA reduce-add) and, for fc1, the GELU is applied by the
+    split pass in front of fc2 -- against layer_norm_seq + linear_layer_seq (+ gelu) of the oracle
+    (R/ViT_seq.c:120-142, 283-309)"""
+    K = 768
+    rng = np.random.default_rng(M * 3 + N)
+    x = (rng.standard_normal((M, K), dtype=np.float32) * 1.3 + 0.2).astype(np.float32)
+    w = (rng.standard_normal((N, K), dtype=np.float32) * 0.03).astype(np.float32)
+    g = (1.0 + 0.2 * rng.standard_normal(K, dtype=np.float32)).astype(np.float32)
+    be = (0.1 * rng.standard_normal(K, dtype=np.float32)).astype(np.float32)
+    b = rng.standard_normal(N, dtype=np.float32)
+    dx, dw, dg, dbe, db = (_dev(pkg, a) for a in (x, w, g, be, b))
+    dw3, dln3 = pkg.DeviceBuffer(N * 3 * K * 2), pkg.DeviceBuffer(M * 3 * K * 2)
+    pkg.layer_check(lib.vitcu_split3(dw.ptr, K, dw3.ptr, N, K, None))
+    dc = _dev(pkg, np.full((M, N), 7.0, np.float32))  # stale contents: the LayerNorm launch has to clear them
+    assert lib.vitcu_gemm_split_k_pays(M, N) == (1 if M < 1000 else 0)
+    pkg.layer_check(lib.vitcu_layernorm_zero(dx.ptr, K, dln3.ptr, 2, dg.ptr, dbe.ptr, M, K, dc.ptr, M * N * 4, None))
+    d = _gemm_desc(pkg, M, N, K, pkg.EPI_BIAS, db)
+    d.accumulate = 1
+    pkg.layer_check(lib.vitcu_gemm_bf16x3(dln3.ptr, dw3.ptr, dc.ptr, C.byref(d), None))
+    assert lib.vitcu_watchdog_check() == 0
+    y = dc.to_numpy(np.float32, (M, N))
+    ln64 = x.astype(np.float64)
+    ln64 = (ln64 - ln64.mean(1, keepdims=True)) / np.sqrt(ln64.var(1, keepdims=True) + 1e-6) * g + be
+    exact = ln64 @ w.astype(np.float64).T + b
+    assert np.abs(y - exact).max() <= 1e-5 * np.abs(exact).max()
+    if M <= 400:
+        ref = oracle.linear(oracle.layer_norm(x, g, be), w, b)
+        assert _rel_err(y, ref) <= 3e-5
+    if gelu:  # the split pass applies the exact-erf GELU: pieces sum to gelu(y) to 24 bits
+        from scipy.special import erf
+        d3 = pkg.DeviceBuffer(M * 3 * N * 2)
+        pkg.layer_check(lib.vitcu_split3_gelu(dc.ptr, N, d3.ptr, M, N, None))
+        pieces = pkg.bf16_bits_to_f32(d3.to_numpy(np.uint16, (M, 3, N)))
+        got = pieces[:, 0].astype(np.float64) + pieces[:, 1] + pieces[:, 2]
+        y64 = y.astype(np.float64)
+        want = 0.5 * y64 * (1.0 + erf(y64 / np.sqrt(2.0)))
+        assert np.abs(got - want).max() <= 1e-6 * max(1.0, np.abs(want).max())
+        if M <= 400:
+            assert _rel_err(got.astype(np.float32), oracle.linear(oracle.layer_norm(x, g, be), w, b, gelu=True)) <= 3e-5
+
+
 # ---------------------------------------------------------------- LayerNorm folded into the GEMMs
 @pytest.mark.parametrize("M,N,gelu", [(300, 2304, 0), (6500, 2304, 0), (6304, 3072, 1), (12611, 3072, 1)])
 def test_gemm_layernorm_fold_consumer(pkg, lib, oracle, M, N, gelu):

@@ -54,7 +54,7 @@ class GemmDesc(C.Structure):
                 ("ln_stats", C.c_void_p), ("ln_slots", C.c_int), ("ln_colsum", C.c_void_p),
                 ("emit_bf16", C.c_void_p), ("emit_stats", C.c_void_p),
                 ("acc_scale", C.c_float), ("out_fp8", C.c_int), ("out_scale", C.c_float), ("emit_fp8", C.c_int),
-                ("emit_scale", C.c_float)]
+                ("emit_scale", C.c_float), ("accumulate", C.c_int)]
 
 
 def build(verbose: bool = False) -> str:
@@ -149,6 +149,9 @@ def lib() -> C.CDLL:
         L.vitcu_fp8_quant_weights.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p,
                                               C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.vitcu_split3.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
+        L.vitcu_split3_gelu.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
+        L.vitcu_layernorm_zero.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                           C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
         L.vitcu_attention.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.vitcu_softmax_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.vitcu_topk_rows.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]

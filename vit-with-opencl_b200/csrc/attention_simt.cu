@@ -219,6 +219,187 @@ __global__ void __launch_bounds__(256) attention_simt_kernel(const T *__restrict
     }
 }
 
+// ---------------------------------------------------------------------------
+// Small-batch variant (batch-1 latency, FP32 storage, tokens <= 256).  The kernel above loads K and V in
+// dependent load -> transposing-store loops, block after block; with a handful of images that chain of L2 round
+// trips IS the kernel (24 us at batch 1 for 1.7 us of arithmetic).  Here one CTA owns QT queries of one
+// (image, head) and requests everything it will ever read in its first instructions: Q + K rows as one cp.async
+// group, V rows as a second that lands under the score phase.  All tiles stay row-major ([row][64 + 4]: eight
+// consecutive rows start four banks apart, so a quarter-warp of float4 reads is conflict-free), scores are kept as
+// Ss[query][key] (row pitch 264 = 8 mod 32: the 4-query x 8-key store pattern of a warp hits 32 distinct banks):
+//   S    thread (tx, ty): queries tx + 4i, keys ty + 64j -> QT/4 x 4 register tile over d
+//   softmax  a warp per query row (R/ViT_seq.c:216-234: max, expf, sum, divide)
+//   P V  thread (px, py): head dims 4px..4px+3 of queries py + 16i, four keys per step
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16_zfill(void *smem_dst, const void *gmem_src, bool valid)
+{
+    const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+    const int bytes = valid ? 16 : 0; // src-size 0: the 16 destination bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gmem_src), "r"(bytes) : "memory");
+}
+
+constexpr int kSmallLdr = kHeadDim + 4; // Q / K row pitch (floats)
+constexpr int kSmallLds = 256 + 8;      // score row pitch (floats), keys padded to 256
+
+template <int QT, bool kSplit>
+__global__ void __launch_bounds__(256) attention_simt_small_kernel(const float *__restrict__ qkv, void *__restrict__ out_, int tokens,
+                                                                   int embed)
+{
+    constexpr int NI = QT / 4;  // queries per thread in the score phase
+    constexpr int NQ = QT / 16; // queries per thread in the P V phase
+    pdl_trigger();
+    pdl_wait();
+    extern __shared__ __align__(16) float smem[];
+    const int tok4 = (tokens + 3) & ~3;
+    float *Qs = smem;                          // [QT][68]
+    float *Ks = Qs + QT * kSmallLdr;           // [tok4][68]
+    float *Vs = Ks + (size_t)tok4 * kSmallLdr; // [tok4][64]
+    float *Ss = Vs + (size_t)tok4 * kHeadDim;  // [QT][264]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int q0 = blockIdx.x * QT, head = blockIdx.y, img = blockIdx.z;
+    const size_t ld = 3 * (size_t)embed;
+    const float *base = qkv + (size_t)img * tokens * ld + head * kHeadDim;
+
+    // ---- every global read of the kernel, up front ----
+    for (int f = tid; f < QT * 16; f += 256) {
+        const int r = f >> 4, c = (f & 15) * 4;
+        const bool ok = q0 + r < tokens;
+        cp_async16_zfill(Qs + r * kSmallLdr + c, base + (size_t)(ok ? q0 + r : 0) * ld + c, ok);
+    }
+    for (int f = tid; f < tok4 * 16; f += 256) {
+        const int r = f >> 4, c = (f & 15) * 4;
+        const bool ok = r < tokens;
+        cp_async16_zfill(Ks + r * kSmallLdr + c, base + embed + (size_t)(ok ? r : 0) * ld + c, ok);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    for (int f = tid; f < tok4 * 16; f += 256) {
+        const int r = f >> 4, c = (f & 15) * 4;
+        const bool ok = r < tokens;
+        cp_async16_zfill(Vs + r * kHeadDim + c, base + 2 * embed + (size_t)(ok ? r : 0) * ld + c, ok);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncthreads();
+
+    // ---- S = Q K^T / 8 (scaled after the dot product, R/ViT_seq.c:211) ----
+    {
+        const int tx = tid & 3, ty = tid >> 2;
+        int kr[4]; // key rows read (clamped into the staged range; results past `tokens` are not stored)
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            kr[j] = min(ty + 64 * j, tok4 - 1);
+        float acc[NI][4];
+#pragma unroll
+        for (int i = 0; i < NI; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                acc[i][j] = 0.f;
+#pragma unroll 4
+        for (int d = 0; d < kHeadDim; d += 4) {
+            float4 kv[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                kv[j] = *reinterpret_cast<const float4 *>(Ks + kr[j] * kSmallLdr + d);
+#pragma unroll
+            for (int i = 0; i < NI; i++) {
+                const float4 qv = *reinterpret_cast<const float4 *>(Qs + (tx + 4 * i) * kSmallLdr + d);
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    acc[i][j] = fmaf(qv.w, kv[j].w, fmaf(qv.z, kv[j].z, fmaf(qv.y, kv[j].y, fmaf(qv.x, kv[j].x, acc[i][j]))));
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int k = ty + 64 * j;
+            if (k < tokens) {
+#pragma unroll
+                for (int i = 0; i < NI; i++)
+                    Ss[(tx + 4 * i) * kSmallLds + k] = acc[i][j] * 0.125f;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- row softmax, one warp per query ----
+    for (int q = warp; q < QT; q += 8) {
+        float *row = Ss + q * kSmallLds;
+        float m = -INFINITY;
+        for (int k = lane; k < tokens; k += 32)
+            m = fmaxf(m, row[k]);
+        m = warp_max(m);
+        float s = 0.f;
+        for (int k = lane; k < tokens; k += 32) {
+            const float e = expf(row[k] - m);
+            row[k] = e;
+            s += e;
+        }
+        s = warp_sum(s);
+        for (int k = lane; k < tok4; k += 32)
+            row[k] = k < tokens ? row[k] / s : 0.f; // the pad keys of the last step of four contribute nothing
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+
+    // ---- O = P V ----
+    const int px = tid & 15, py = tid >> 4;
+    float o[NQ][4];
+#pragma unroll
+    for (int i = 0; i < NQ; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            o[i][j] = 0.f;
+#pragma unroll 2
+    for (int k = 0; k < tok4; k += 4) {
+        float4 v[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            v[j] = *reinterpret_cast<const float4 *>(Vs + (k + j) * kHeadDim + px * 4);
+#pragma unroll
+        for (int i = 0; i < NQ; i++) {
+            const float4 p = *reinterpret_cast<const float4 *>(Ss + (py + 16 * i) * kSmallLds + k);
+            const float pv[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                o[i][0] = fmaf(pv[j], v[j].x, o[i][0]);
+                o[i][1] = fmaf(pv[j], v[j].y, o[i][1]);
+                o[i][2] = fmaf(pv[j], v[j].z, o[i][2]);
+                o[i][3] = fmaf(pv[j], v[j].w, o[i][3]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NQ; i++) {
+        const int q = q0 + py + 16 * i;
+        if (q < tokens) {
+            const float4 r = make_float4(o[i][0], o[i][1], o[i][2], o[i][3]);
+            if (kSplit)
+                split3_store4(reinterpret_cast<__nv_bfloat16 *>(out_) + ((size_t)img * tokens + q) * 3 * embed, embed,
+                              head * kHeadDim + px * 4, r);
+            else
+                *reinterpret_cast<float4 *>(reinterpret_cast<float *>(out_) + ((size_t)img * tokens + q) * embed + head * kHeadDim + px * 4) = r;
+        }
+    }
+}
+
+template <int QT>
+size_t attention_simt_small_smem(int tokens)
+{
+    const size_t tok4 = (size_t)(tokens + 3) & ~(size_t)3;
+    return sizeof(float) * ((size_t)QT * kSmallLdr + tok4 * kSmallLdr + tok4 * kHeadDim + (size_t)QT * kSmallLds);
+}
+
+template <int QT, bool kSplit>
+int launch_attention_simt_small(const void *qkv, void *out, int batch, int tokens, int heads, cudaStream_t st)
+{
+    const size_t smem = attention_simt_small_smem<QT>(tokens);
+    auto k = attention_simt_small_kernel<QT, kSplit>;
+    VITCU_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((tokens + QT - 1) / QT, heads, batch);
+    VITCU_TRY(launch_kernel(k, grid, 256, smem, st, reinterpret_cast<const float *>(qkv), out, tokens, heads * kHeadDim));
+    return 0;
+}
+
 template <int QT>
 size_t attention_simt_smem(int tokens)
 {
@@ -248,6 +429,7 @@ int attention_bf16_tc(const void *qkv, void *out, int batch, int tokens, int hea
 int attention_bf16_flash_tc(const void *qkv, void *out, int batch, int tokens, int heads, cudaStream_t st); // attention_flash_tc.cu
 int attention_bf16_duo_tc(const void *qkv, void *out, int batch, int tokens, int heads, cudaStream_t st);   // attention_duo_tc.cu
 int attention_bf16_flash_duo_tc(const void *qkv, void *out, int batch, int tokens, int heads, cudaStream_t st); // attention_flash_duo_tc.cu
+int device_sm_count(); // gemm_tc.cu
 }
 
 extern "C" int vitcu_attention_ex(const void *qkv, void *out, int batch, int tokens, int heads, int is_bf16, vitcu_stream s)
@@ -277,6 +459,22 @@ extern "C" int vitcu_attention_ex(const void *qkv, void *out, int batch, int tok
     const bool small = ((long)batch * heads * ((tokens + 63) / 64) < 148 || attention_simt_smem<64>(tokens) > 227 * 1024) &&
                        attention_simt_smem<16>(tokens) <= 227 * 1024;
     int rc;
+    // fp32 storage, a few images, all keys in one staged block: the cp.async kernel (16-query tiles while they give
+    // every CTA its own SM, else 32-query tiles); VITCU_ATTN_SMALL=0 keeps the block-by-block kernel (A/B)
+    static const bool no_small = getenv("VITCU_ATTN_SMALL") && !strcmp(getenv("VITCU_ATTN_SMALL"), "0");
+    if (small && !no_small && is_bf16 != 1 && tokens <= 256) {
+        const bool q16 = (long)batch * heads * ((tokens + 15) / 16) <= device_sm_count();
+        if (is_bf16 == 2)
+            rc = q16 ? launch_attention_simt_small<16, true>(qkv, out, batch, tokens, heads, as_stream(s))
+                     : launch_attention_simt_small<32, true>(qkv, out, batch, tokens, heads, as_stream(s));
+        else
+            rc = q16 ? launch_attention_simt_small<16, false>(qkv, out, batch, tokens, heads, as_stream(s))
+                     : launch_attention_simt_small<32, false>(qkv, out, batch, tokens, heads, as_stream(s));
+        if (rc)
+            return rc;
+        VITCU_LAUNCHED_KIND(LK_ATTN_SIMT);
+        return 0;
+    }
     if (is_bf16 == 2)
         rc = small ? launch_attention_simt<float, 16, true>(qkv, out, batch, tokens, heads, as_stream(s))
                    : launch_attention_simt<float, 64, true>(qkv, out, batch, tokens, heads, as_stream(s));

@@ -34,6 +34,7 @@ __global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float4 *__restri
 // (a3 w1 + a2 w2 + a1 w3 + a2 w1 + a1 w2 + a1 w1: relative error ~1e-7, below a plain fp32 GEMM's
 // summation error), see vitcu_gemm_bf16x3.  Output row r = [x1 | x2 | x3], each K wide.
 // ---------------------------------------------------------------------------
+template <bool kGelu>
 __global__ void __launch_bounds__(256) split3_kernel(const float *__restrict__ x, size_t ld, __nv_bfloat16 *__restrict__ out,
                                                      size_t rows, int K)
 {
@@ -45,7 +46,10 @@ __global__ void __launch_bounds__(256) split3_kernel(const float *__restrict__ x
     for (; i < total; i += stride) {
         const size_t r = i / k4;
         const int c = (int)(i - r * k4) * 4;
-        split3_store4(out + r * 3 * (size_t)K, K, c, *reinterpret_cast<const float4 *>(x + r * ld + c));
+        float4 v = *reinterpret_cast<const float4 *>(x + r * ld + c);
+        if (kGelu) // exact-erf form (R/ViT_seq.c:283-286): the GELU of an fc1 whose K slices met in global memory
+            v = make_float4(gelu_erf(v.x), gelu_erf(v.y), gelu_erf(v.z), gelu_erf(v.w));
+        split3_store4(out + r * 3 * (size_t)K, K, c, v);
     }
 }
 
@@ -107,10 +111,14 @@ __global__ void __launch_bounds__(256) cls_rows_kernel(float *__restrict__ x, co
 template <int kOut, int NV> // kOut 0: fp32, 1: bf16, 2: three bf16 pieces [rows, 3*cols]
 __global__ void __launch_bounds__(256) layernorm_kernel(const float *__restrict__ x, size_t x_row_stride,
                                                         void *__restrict__ y, const float *__restrict__ gamma,
-                                                        const float *__restrict__ beta, int rows, int rev)
+                                                        const float *__restrict__ beta, int rows, int rev,
+                                                        uint4 *__restrict__ zero_ptr, size_t zero_n16)
 {
     pdl_trigger();
     pdl_wait();
+    // vitcu_layernorm_zero: the launch also clears the output buffer of the accumulate-mode GEMM that follows
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < zero_n16; i += (size_t)gridDim.x * blockDim.x)
+        zero_ptr[i] = make_uint4(0u, 0u, 0u, 0u);
     const int lane = threadIdx.x & 31;
     int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows)
@@ -424,7 +432,15 @@ int vitcu_f32_to_bf16(const float *src, vitcu_bf16 *dst, size_t n, vitcu_stream 
 int vitcu_split3(const float *x, size_t ld, vitcu_bf16 *out, size_t rows, int K, vitcu_stream s)
 {
     VITCU_REQUIRE(x && out && rows > 0 && K > 0 && K % 4 == 0 && ld % 4 == 0 && ld >= (size_t)K, "bad argument");
-    VITCU_TRY(launch_kernel(split3_kernel, grid_for(rows * (size_t)(K / 4), 256, 148 * 32), 256, 0, as_stream(s), x, ld, reinterpret_cast<__nv_bfloat16 *>(out), rows, K));
+    VITCU_TRY(launch_kernel(split3_kernel<false>, grid_for(rows * (size_t)(K / 4), 256, 148 * 32), 256, 0, as_stream(s), x, ld, reinterpret_cast<__nv_bfloat16 *>(out), rows, K));
+    VITCU_LAUNCHED();
+    return 0;
+}
+
+int vitcu_split3_gelu(const float *x, size_t ld, vitcu_bf16 *out, size_t rows, int K, vitcu_stream s)
+{
+    VITCU_REQUIRE(x && out && rows > 0 && K > 0 && K % 4 == 0 && ld % 4 == 0 && ld >= (size_t)K, "bad argument");
+    VITCU_TRY(launch_kernel(split3_kernel<true>, grid_for(rows * (size_t)(K / 4), 256, 148 * 32), 256, 0, as_stream(s), x, ld, reinterpret_cast<__nv_bfloat16 *>(out), rows, K));
     VITCU_LAUNCHED();
     return 0;
 }
@@ -466,36 +482,49 @@ int vitcu_cls_rows(float *x, const float *cls, const float *pos, int batch, int 
 extern "C++" {
 template <int NV>
 static int launch_layernorm(const float *x, size_t x_row_stride, void *y, int y_bf16, const float *gamma, const float *beta,
-                            int rows, vitcu_stream s)
+                            int rows, vitcu_stream s, void *zero_ptr = nullptr, size_t zero_bytes = 0)
 {
-    const int grid = (rows + 7) / 8;
+    int grid = (rows + 7) / 8;
+    // extra CTAs (no rows of their own) when there is a buffer to clear: 16 stores of 16 bytes per thread, at most one wave
+    const size_t zero_n16 = zero_bytes / 16;
+    const int zgrid = (int)((zero_n16 + 256 * 16 - 1) / (256 * 16));
+    if (zgrid > grid)
+        grid = zgrid < 148 ? zgrid : (grid > 148 ? grid : 148);
+    uint4 *zp = reinterpret_cast<uint4 *>(zero_ptr);
     static const int rev = !(getenv("VITCU_SERPENTINE") && atoi(getenv("VITCU_SERPENTINE")) == 0);
     if (y_bf16 == 1)
-        VITCU_TRY(launch_kernel(layernorm_kernel<1, NV>, grid, 256, 0, as_stream(s), x, x_row_stride, y, gamma, beta, rows, rev));
+        VITCU_TRY(launch_kernel(layernorm_kernel<1, NV>, grid, 256, 0, as_stream(s), x, x_row_stride, y, gamma, beta, rows, rev, zp, zero_n16));
     else if (y_bf16 == 2)
-        VITCU_TRY(launch_kernel(layernorm_kernel<2, NV>, grid, 256, 0, as_stream(s), x, x_row_stride, y, gamma, beta, rows, rev));
+        VITCU_TRY(launch_kernel(layernorm_kernel<2, NV>, grid, 256, 0, as_stream(s), x, x_row_stride, y, gamma, beta, rows, rev, zp, zero_n16));
     else
-        VITCU_TRY(launch_kernel(layernorm_kernel<0, NV>, grid, 256, 0, as_stream(s), x, x_row_stride, y, gamma, beta, rows, rev));
+        VITCU_TRY(launch_kernel(layernorm_kernel<0, NV>, grid, 256, 0, as_stream(s), x, x_row_stride, y, gamma, beta, rows, rev, zp, zero_n16));
     VITCU_LAUNCHED_KIND(LK_LAYERNORM);
     return 0;
 }
 } // extern "C++"
 
-int vitcu_layernorm_ex(const float *x, size_t x_row_stride, void *y, int y_bf16, const float *gamma, const float *beta,
-                       int rows, int cols, vitcu_stream s)
+int vitcu_layernorm_zero(const float *x, size_t x_row_stride, void *y, int y_bf16, const float *gamma, const float *beta,
+                         int rows, int cols, void *zero_ptr, size_t zero_bytes, vitcu_stream s)
 {
     VITCU_REQUIRE(x && y && gamma && beta && rows > 0, "bad argument");
     VITCU_REQUIRE(x_row_stride % 4 == 0 && x_row_stride >= (size_t)cols, "row stride must be >= the row width and a multiple of 4");
+    VITCU_REQUIRE(zero_bytes == 0 || (zero_ptr && ((uintptr_t)zero_ptr & 15) == 0 && zero_bytes % 16 == 0),
+                  "the buffer to clear must be 16-byte aligned and a multiple of 16 bytes long");
     switch (cols) {
     case 384:
-        return launch_layernorm<3>(x, x_row_stride, y, y_bf16, gamma, beta, rows, s);
+        return launch_layernorm<3>(x, x_row_stride, y, y_bf16, gamma, beta, rows, s, zero_ptr, zero_bytes);
     case 768:
-        return launch_layernorm<6>(x, x_row_stride, y, y_bf16, gamma, beta, rows, s);
+        return launch_layernorm<6>(x, x_row_stride, y, y_bf16, gamma, beta, rows, s, zero_ptr, zero_bytes);
     case 1024:
-        return launch_layernorm<8>(x, x_row_stride, y, y_bf16, gamma, beta, rows, s);
+        return launch_layernorm<8>(x, x_row_stride, y, y_bf16, gamma, beta, rows, s, zero_ptr, zero_bytes);
     default:
         return set_error(VITCU_E_ARG, __FILE__, __LINE__, "LayerNorm row width must be 384, 768 or 1024");
     }
+}
+int vitcu_layernorm_ex(const float *x, size_t x_row_stride, void *y, int y_bf16, const float *gamma, const float *beta,
+                       int rows, int cols, vitcu_stream s)
+{
+    return vitcu_layernorm_zero(x, x_row_stride, y, y_bf16, gamma, beta, rows, cols, nullptr, 0, s);
 }
 int vitcu_layernorm(const float *x, size_t x_row_stride, void *y, int y_bf16, const float *gamma,
                     const float *beta, int rows, vitcu_stream s)

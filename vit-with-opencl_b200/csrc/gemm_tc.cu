@@ -1118,6 +1118,11 @@ static bool pair_eligible(int M, int N)
 
 extern "C" int vitcu_gemm_bf16_emit_supported(int M, int N) { return M > 0 && N > 0 && pair_eligible(M, N) ? 1 : 0; }
 
+extern "C" int vitcu_gemm_split_k_pays(int M, int N)
+{
+    return M > 0 && N > 0 && N % 128 == 0 && !pair_eligible(M, N) && ((M + BM - 1) / BM) * (N / 128) * 2 <= device_sm_count() ? 1 : 0;
+}
+
 static int gemm_dispatch(const vitcu_bf16 *A, const vitcu_bf16 *W, void *C, const vitcu_gemm_desc *d, bool split3,
                          vitcu_stream s)
 {
@@ -1193,7 +1198,13 @@ static int gemm_dispatch(const vitcu_bf16 *A, const vitcu_bf16 *W, void *C, cons
     // Output through the TMA engine: bf16 / fp32 tiles are stored; the in-place residual update
     // C = C + (acc + bias) becomes a TMA reduce-add, so the fp32 residual stream is never read by the SMs.
     p.tma_out = 0;
-    if (!force_lsu && ((uintptr_t)C & 15) == 0) {
+    if (d->accumulate) {
+        // C was zeroed by the caller: every work item reduce-adds its partial tile (the first K slice carries the bias),
+        // which is what lets a small-M product be cut along K (see the split computation below)
+        VITCU_REQUIRE(!d->out_bf16 && d->epilogue == VITCU_EPI_BIAS && !d->ln_stats && !emit && ((uintptr_t)C & 15) == 0,
+                      "accumulate mode: fp32 output, bias epilogue, 16-byte aligned C");
+        p.tma_out = 2;
+    } else if (!force_lsu && ((uintptr_t)C & 15) == 0) {
         const bool plain = p.epilogue == VITCU_EPI_BIAS || p.epilogue == VITCU_EPI_BIAS_GELU;
         if (p.out_bf16 && plain)
             p.tma_out = 1;

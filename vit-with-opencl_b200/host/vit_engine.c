@@ -229,6 +229,7 @@ int vitb200_create_model(vitb200_engine **out, int device, const vitb200_model *
     /* FP32 precision runs its GEMMs on the tensor cores as split-bf16 (error ~1e-7 relative);
      * VITB200_FP32_SIMT=1 selects the CUDA-core FFMA GEMM instead */
     e->fp32_tc = precision == VITB200_FP32 && getenv("VITB200_FP32_SIMT") == NULL;
+    e->fp32_splitk = !(getenv("VITB200_FP32_SPLITK") && atoi(getenv("VITB200_FP32_SPLITK")) == 0);
     /* VITB200_PE_GATHER=1: separate gather kernel + BF16 GEMM instead of the TMA-gather TF32 GEMM */
     e->pe_gather = getenv("VITB200_PE_GATHER") != NULL || e->patch != 16 || e->D % 256 != 0;
     const int bf = precision != VITB200_FP32; /* FP8 = the BF16 path with fc1 / fc2 on e4m3 operands */
@@ -526,7 +527,10 @@ static int mark(vitb200_engine *e, int kind)
 
 /* fold: 0 = plain; 1 = this GEMM follows a LayerNorm that is folded into it (A = bf16 residual rows, folded weights,
  * statistics from d_lnstats); 2 = residual GEMM that also emits bf16(x) into d_ln and the row partial sums;
- * 3 + layer = the same with an e4m3 copy for that layer's FP8 fc1 */
+ * 3 + layer = the same with an e4m3 copy for that layer's FP8 fc1; -1 = accumulate mode (FP32 chain at small M: C was
+ * zeroed by the preceding LayerNorm launch, the K range is cut into slices that reduce-add into it).
+ * a_split: 0 = A is fp32, split here; 1 = A already holds the three bf16 pieces; 2 = A is the fp32 output of an
+ * accumulate-mode fc1: GELU, then split */
 static int gemm(vitb200_engine *e, const void *A, int a_split, int widx, int bidx, void *C, int M, int N, int K, int epi,
                 int out_bf16, int fold)
 {
@@ -552,6 +556,8 @@ static int gemm(vitb200_engine *e, const void *A, int a_split, int widx, int bid
             d.emit_scale = e->act_scale_x[fold - 3];
         }
     }
+    if (fold == -1)
+        d.accumulate = 1;
     if (epi == VITCU_EPI_BIAS_RESIDUAL)
         d.residual = (const float *)C;
     if (epi == VITCU_EPI_PATCH_EMBED) {
@@ -560,9 +566,10 @@ static int gemm(vitb200_engine *e, const void *A, int a_split, int widx, int bid
         d.tokens = e->T;
     }
     e->launches++;
-    if (e->fp32_tc && !a_split) {
+    if (e->fp32_tc && a_split != 1) {
         VIT_TRY_RC(mark(e, VIT_K_OTHER));
-        int rc = vitcu_split3((const float *)A, (size_t)K, e->d_a3, (size_t)M, K, e->stream);
+        int rc = a_split == 2 ? vitcu_split3_gelu((const float *)A, (size_t)K, e->d_a3, (size_t)M, K, e->stream)
+                              : vitcu_split3((const float *)A, (size_t)K, e->d_a3, (size_t)M, K, e->stream);
         if (rc)
             return rc;
         e->launches++;
@@ -671,6 +678,11 @@ static int enqueue_forward_mode(vitb200_engine *e, int buf, int b, int calibrate
         return vit_fail(__FILE__, __LINE__, VITCU_E_ARG, "FP8 calibration needs a chunk that runs the CTA-pair GEMM");
     if (calibrate)
         VIT_TRY(vitcu_memset(e->d_amax, 0, (size_t)2 * VIT_MAX_DEPTH * sizeof(float), s));
+    /* FP32 chain at small M (batch-1 latency): qkv and fc1 are a few dozen 128 x 128 tiles with the whole K range each
+     * -- 36 and 48 of 148 SMs busy for 72 k-blocks.  In accumulate mode their K range is cut into slices that meet in
+     * the output through TMA reduce-add, like out-proj and fc2 always did; the output is zeroed by the LayerNorm launch
+     * in front of the GEMM and fc1's GELU moves into the split pass in front of fc2 (VITB200_FP32_SPLITK=0: off) */
+    const int acc = e->fp32_tc && e->fp32_splitk && vitcu_gemm_split_k_pays(M, 3 * e->D) && vitcu_gemm_split_k_pays(M, e->HID);
     if (fold && layers > 0) {
         MARK(VIT_K_LAYERNORM);
         VIT_TRY(vitcu_rowstats_cast(e->d_x, (vitcu_bf16 *)e->d_ln, e->d_lnstats, M, e->D, e->D / 128, s));
@@ -681,10 +693,11 @@ static int enqueue_forward_mode(vitb200_engine *e, int buf, int b, int calibrate
         /* x -> LN1 -> QKV -> attention -> out-proj (+x)  (R/ViT_opencl.c:710-730) */
         if (!fold) {
             MARK(VIT_K_LAYERNORM);
-            VIT_TRY(vitcu_layernorm_ex(e->d_x, e->D, e->d_ln, ln_mode, e->w32[w + 0], e->w32[w + 1], M, e->D, s));
+            VIT_TRY(vitcu_layernorm_zero(e->d_x, e->D, e->d_ln, ln_mode, e->w32[w + 0], e->w32[w + 1], M, e->D,
+                                         acc ? e->d_qkv : NULL, acc ? (size_t)M * 3 * e->D * sizeof(float) : 0, s));
             e->launches++;
         }
-        VIT_TRY(gemm(e, e->d_ln, 1, w + 2, w + 3, e->d_qkv, M, 3 * e->D, e->D, VITCU_EPI_BIAS, bf, fold));
+        VIT_TRY(gemm(e, e->d_ln, 1, w + 2, w + 3, e->d_qkv, M, 3 * e->D, e->D, VITCU_EPI_BIAS, bf, acc ? -1 : fold));
         MARK(VIT_K_ATTENTION);
         /* FP32 tensor-core path: the attention kernel writes its output already split into three bf16 pieces */
         VIT_TRY(vitcu_attention_ex(e->d_qkv, e->d_att, b, e->T, e->heads, e->fp32_tc ? 2 : bf, s));
@@ -698,7 +711,8 @@ static int enqueue_forward_mode(vitb200_engine *e, int buf, int b, int calibrate
         /* -> LN2 -> fc1+GELU -> fc2 (+r1)  (R/ViT_opencl.c:732-746) */
         if (!fold) {
             MARK(VIT_K_LAYERNORM);
-            VIT_TRY(vitcu_layernorm_ex(e->d_x, e->D, e->d_ln, ln_mode, e->w32[w + 6], e->w32[w + 7], M, e->D, s));
+            VIT_TRY(vitcu_layernorm_zero(e->d_x, e->D, e->d_ln, ln_mode, e->w32[w + 6], e->w32[w + 7], M, e->D,
+                                         acc ? e->d_hid : NULL, acc ? (size_t)M * e->HID * sizeof(float) : 0, s));
             e->launches++;
         }
         if (fp8) {
@@ -706,13 +720,14 @@ static int enqueue_forward_mode(vitb200_engine *e, int buf, int b, int calibrate
             VIT_TRY_RC(gemm_fp8(e, l, 1, M));
             continue;
         }
-        VIT_TRY(gemm(e, e->d_ln, 1, w + 8, w + 9, e->d_hid, M, e->HID, e->D, VITCU_EPI_BIAS_GELU, bf, fold));
+        VIT_TRY(gemm(e, e->d_ln, 1, w + 8, w + 9, e->d_hid, M, e->HID, e->D, acc ? VITCU_EPI_BIAS : VITCU_EPI_BIAS_GELU, bf,
+                     acc ? -1 : fold));
         if (calibrate) {
             VIT_TRY(vitcu_absmax_bf16((const vitcu_bf16 *)e->d_hid, (size_t)M * e->HID, e->d_amax + 2 * l + 1, s));
             e->launches++;
         }
         /* the last layer's fc2 has no LayerNorm consumer over all rows (the final one visits the class rows only) */
-        VIT_TRY(gemm(e, e->d_hid, 0, w + 10, w + 11, e->d_x, M, e->D, e->HID, VITCU_EPI_BIAS_RESIDUAL, 0,
+        VIT_TRY(gemm(e, e->d_hid, acc ? 2 : 0, w + 10, w + 11, e->d_x, M, e->D, e->HID, VITCU_EPI_BIAS_RESIDUAL, 0,
                      fold && l + 1 < layers ? 2 : 0));
     }
     if (e->stop_after >= 0)
