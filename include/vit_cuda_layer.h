@@ -131,6 +131,12 @@ int vitcu_cls_rows(float *x, const float *cls, const float *pos, int batch, int 
 int vitcu_cls_rows_ex(float *x, const float *cls, const float *pos, int batch, int tokens, int cols,
                       vitcu_stream s);
 
+/* Every token row of every image before an ACCUMULATE-mode patch embedding (vitcu_gemm_desc.accumulate; batch-1
+ * latency): x[b*T + 0, :] = cls + pos[0, :] and x[b*T + t, :] = pos[t, :] for t > 0; the GEMM then adds conv(patch) +
+ * conv_b into rows 1.. of the image.  Same result as the EPI_PATCH_EMBED epilogue + vitcu_cls_rows. */
+int vitcu_token_rows_init(float *x, const float *cls, const float *pos, int batch, int tokens, int cols,
+                          vitcu_stream s);
+
 /* LayerNorm over 768 features (replaces layerNorm, R/layer_norm.cl:3-53; oracle
  * R/ViT_seq.c:120-142).  rows = number of rows normalised; row r is read at
  * x + r*x_row_stride (elements) so the final LN can visit only the class-token

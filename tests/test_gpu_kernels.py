@@ -382,11 +382,20 @@ def test_gemm_bf16_narrow_tiles(pkg, lib, M, N, K):
     _bf16_gemm_case(pkg, lib, M, N, K, pkg.EPI_BIAS, seed=M + K)
 
 
-@pytest.mark.parametrize("M,N,K", [(197, 1024, 4096), (591, 384, 1536), (197, 1024, 1024), (50, 768, 3072), (197, 384, 384)])
-def test_gemm_bf16_split_k_residual(pkg, lib, M, N, K):
+@pytest.mark.parametrize("mode", ["pair", "1cta"])
+@pytest.mark.parametrize("M,N,K", [(197, 1024, 4096), (591, 384, 1536), (197, 1024, 1024), (50, 768, 3072), (197, 384, 384),
+                                   (394, 768, 3072), (197, 768, 768), (300, 2304, 768)])
+def test_gemm_bf16_split_k_residual(pkg, lib, M, N, K, mode, monkeypatch):
     """small-M residual GEMMs are split along K; slice counts that do not divide the k-blocks (64 k-blocks
-    over 9 slices left the ninth empty and its epilogue waiting) and the widths of the S/16 and L/16 models"""
+    over 9 slices left the ninth empty and its epilogue waiting) and the widths of the S/16 and L/16 models.
+    Default: the single-CTA kernel; with VITCU_GEMM_MODE=pair (A/B variant) N % 256 == 0 runs on CTA pairs
+    (256 x 256 tiles, ragged second half of the pair)"""
+    if mode == "pair":
+        monkeypatch.setenv("VITCU_GEMM_MODE", "pair")
+    before = lib.vitcu_launch_count_of(b"gemm_bf16_tc2_kernel")
     _bf16_gemm_case(pkg, lib, M, N, K, pkg.EPI_BIAS_RESIDUAL, seed=M + K)
+    pair_ran = lib.vitcu_launch_count_of(b"gemm_bf16_tc2_kernel") - before
+    assert pair_ran == (1 if mode == "pair" and N % 256 == 0 else 0)
 
 
 @pytest.mark.parametrize("M,N,K,epi", [(6304, 2304, 768, 0), (6304, 3072, 768, 1), (6400, 768, 3072, 2),

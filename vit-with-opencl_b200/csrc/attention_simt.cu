@@ -222,14 +222,18 @@ __global__ void __launch_bounds__(256) attention_simt_kernel(const T *__restrict
 // ---------------------------------------------------------------------------
 // Small-batch variant (batch-1 latency, FP32 storage, tokens <= 256).  The kernel above loads K and V in
 // dependent load -> transposing-store loops, block after block; with a handful of images that chain of L2 round
-// trips IS the kernel (24 us at batch 1 for 1.7 us of arithmetic).  Here one CTA owns QT queries of one
-// (image, head) and requests everything it will ever read in its first instructions: Q + K rows as one cp.async
-// group, V rows as a second that lands under the score phase.  All tiles stay row-major ([row][64 + 4]: eight
-// consecutive rows start four banks apart, so a quarter-warp of float4 reads is conflict-free), scores are kept as
-// Ss[query][key] (row pitch 264 = 8 mod 32: the 4-query x 8-key store pattern of a warp hits 32 distinct banks):
-//   S    thread (tx, ty): queries tx + 4i, keys ty + 64j -> QT/4 x 4 register tile over d
+// trips is most of the kernel (24 us at batch 1 for ~2 us of arithmetic).  Here one CTA owns 18 queries of one
+// (image, head) -- 11 x 12 = 132 CTAs at batch 1: one wave, no SM with two (16-query tiles are 156 CTAs, and the
+// eight SMs that get a second one set the kernel's time) -- and requests its operands with cp.async: Q + K rows in
+// its first instructions, the V rows into the same buffer the moment the scores are done (they land under the
+// softmax).  Everything stays row-major; what the profile showed to matter is shared-memory wavefronts
+// (ncu: 11.5 k per CTA, half of the active cycles, in the first version), so both products are laid out to read every
+// operand element once per CTA, 16 distinct bytes per lane, and to broadcast the other operand:
+//   S    thread (tx, ty) = (tid / 64, tid % 64): queries tx + 4i, keys ty + 64j -- a warp reads 32 different K rows
+//        (pitch 68 floats: conflict-free) and one broadcast Q row per instruction
 //   softmax  a warp per query row (R/ViT_seq.c:216-234: max, expf, sum, divide)
-//   P V  thread (px, py): head dims 4px..4px+3 of queries py + 16i, four keys per step
+//   P V  thread (px, g) = (tid % 16, tid / 16): head dims 4px..4px+3 of ALL 18 queries over the keys g, g + 16, ..;
+//        the 16 key groups are summed by one shuffle + an 8-way pass through shared memory
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ void cp_async16_zfill(void *smem_dst, const void *gmem_src, bool valid)
 {
@@ -238,53 +242,49 @@ __device__ __forceinline__ void cp_async16_zfill(void *smem_dst, const void *gme
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gmem_src), "r"(bytes) : "memory");
 }
 
-constexpr int kSmallLdr = kHeadDim + 4; // Q / K row pitch (floats)
-constexpr int kSmallLds = 256 + 8;      // score row pitch (floats), keys padded to 256
+constexpr int kSmallQT = 18;            // queries per CTA
+constexpr int kSmallLdr = kHeadDim + 4; // Q / K / V row pitch (floats)
 
 template <int QT, bool kSplit>
 __global__ void __launch_bounds__(256) attention_simt_small_kernel(const float *__restrict__ qkv, void *__restrict__ out_, int tokens,
                                                                    int embed)
 {
-    constexpr int NI = QT / 4;  // queries per thread in the score phase
-    constexpr int NQ = QT / 16; // queries per thread in the P V phase
+    constexpr int NI = (QT + 3) / 4; // queries per thread in the score phase
+    constexpr int QPAD = NI * 4;     // staged query rows (the pad rows are zero)
     pdl_trigger();
     pdl_wait();
     extern __shared__ __align__(16) float smem[];
     const int tok4 = (tokens + 3) & ~3;
-    float *Qs = smem;                          // [QT][68]
-    float *Ks = Qs + QT * kSmallLdr;           // [tok4][68]
-    float *Vs = Ks + (size_t)tok4 * kSmallLdr; // [tok4][64]
-    float *Ss = Vs + (size_t)tok4 * kHeadDim;  // [QT][264]
+    float *Qs = smem;                          // [QPAD][68]
+    float *KV = Qs + QPAD * kSmallLdr;         // [tok4][68]: K, then V
+    float *Ss = KV + (size_t)tok4 * kSmallLdr; // [QT][tok4]
+    float *red = Ss + (size_t)QT * tok4;       // [8 warps][QT][64]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int q0 = blockIdx.x * QT, head = blockIdx.y, img = blockIdx.z;
     const size_t ld = 3 * (size_t)embed;
     const float *base = qkv + (size_t)img * tokens * ld + head * kHeadDim;
 
-    // ---- every global read of the kernel, up front ----
-    for (int f = tid; f < QT * 16; f += 256) {
+    for (int f = tid; f < QPAD * 16; f += 256) {
         const int r = f >> 4, c = (f & 15) * 4;
-        const bool ok = q0 + r < tokens;
+        const bool ok = r < QT && q0 + r < tokens;
         cp_async16_zfill(Qs + r * kSmallLdr + c, base + (size_t)(ok ? q0 + r : 0) * ld + c, ok);
     }
-    for (int f = tid; f < tok4 * 16; f += 256) {
-        const int r = f >> 4, c = (f & 15) * 4;
-        const bool ok = r < tokens;
-        cp_async16_zfill(Ks + r * kSmallLdr + c, base + embed + (size_t)(ok ? r : 0) * ld + c, ok);
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    for (int f = tid; f < tok4 * 16; f += 256) {
-        const int r = f >> 4, c = (f & 15) * 4;
-        const bool ok = r < tokens;
-        cp_async16_zfill(Vs + r * kHeadDim + c, base + 2 * embed + (size_t)(ok ? r : 0) * ld + c, ok);
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    auto load_rows = [&](const float *src) { // K or V rows of this head; rows past `tokens` are zero-filled
+        for (int f = tid; f < tok4 * 16; f += 256) {
+            const int r = f >> 4, c = (f & 15) * 4;
+            const bool ok = r < tokens;
+            cp_async16_zfill(KV + r * kSmallLdr + c, src + (size_t)(ok ? r : 0) * ld + c, ok);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    load_rows(base + embed);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
     // ---- S = Q K^T / 8 (scaled after the dot product, R/ViT_seq.c:211) ----
     {
-        const int tx = tid & 3, ty = tid >> 2;
+        const int tx = tid >> 6, ty = tid & 63;
         int kr[4]; // key rows read (clamped into the staged range; results past `tokens` are not stored)
 #pragma unroll
         for (int j = 0; j < 4; j++)
@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(256) attention_simt_small_kernel(const float *
             float4 kv[4];
 #pragma unroll
             for (int j = 0; j < 4; j++)
-                kv[j] = *reinterpret_cast<const float4 *>(Ks + kr[j] * kSmallLdr + d);
+                kv[j] = *reinterpret_cast<const float4 *>(KV + kr[j] * kSmallLdr + d);
 #pragma unroll
             for (int i = 0; i < NI; i++) {
                 const float4 qv = *reinterpret_cast<const float4 *>(Qs + (tx + 4 * i) * kSmallLdr + d);
@@ -315,15 +315,17 @@ __global__ void __launch_bounds__(256) attention_simt_small_kernel(const float *
             if (k < tokens) {
 #pragma unroll
                 for (int i = 0; i < NI; i++)
-                    Ss[(tx + 4 * i) * kSmallLds + k] = acc[i][j] * 0.125f;
+                    if (tx + 4 * i < QT)
+                        Ss[(tx + 4 * i) * tok4 + k] = acc[i][j] * 0.125f;
             }
         }
     }
-    __syncthreads();
+    __syncthreads(); // every read of K is done: its buffer takes V, requested now and landing under the softmax
+    load_rows(base + 2 * embed);
 
     // ---- row softmax, one warp per query ----
     for (int q = warp; q < QT; q += 8) {
-        float *row = Ss + q * kSmallLds;
+        float *row = Ss + q * tok4;
         float m = -INFINITY;
         for (int k = lane; k < tokens; k += 32)
             m = fmaxf(m, row[k]);
@@ -335,50 +337,62 @@ __global__ void __launch_bounds__(256) attention_simt_small_kernel(const float *
             s += e;
         }
         s = warp_sum(s);
-        for (int k = lane; k < tok4; k += 32)
-            row[k] = k < tokens ? row[k] / s : 0.f; // the pad keys of the last step of four contribute nothing
+        for (int k = lane; k < tokens; k += 32)
+            row[k] = row[k] / s;
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
-    // ---- O = P V ----
-    const int px = tid & 15, py = tid >> 4;
-    float o[NQ][4];
+    // ---- O = P V: this thread's key group against all QT queries ----
+    {
+        const int px = tid & 15, g = tid >> 4;
+        float o[QT][4];
 #pragma unroll
-    for (int i = 0; i < NQ; i++)
+        for (int i = 0; i < QT; i++)
 #pragma unroll
-        for (int j = 0; j < 4; j++)
-            o[i][j] = 0.f;
-#pragma unroll 2
-    for (int k = 0; k < tok4; k += 4) {
-        float4 v[4];
+            for (int j = 0; j < 4; j++)
+                o[i][j] = 0.f;
+        for (int k = g; k < tokens; k += 16) {
+            const float4 v = *reinterpret_cast<const float4 *>(KV + k * kSmallLdr + px * 4);
 #pragma unroll
-        for (int j = 0; j < 4; j++)
-            v[j] = *reinterpret_cast<const float4 *>(Vs + (k + j) * kHeadDim + px * 4);
-#pragma unroll
-        for (int i = 0; i < NQ; i++) {
-            const float4 p = *reinterpret_cast<const float4 *>(Ss + (py + 16 * i) * kSmallLds + k);
-            const float pv[4] = {p.x, p.y, p.z, p.w};
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                o[i][0] = fmaf(pv[j], v[j].x, o[i][0]);
-                o[i][1] = fmaf(pv[j], v[j].y, o[i][1]);
-                o[i][2] = fmaf(pv[j], v[j].z, o[i][2]);
-                o[i][3] = fmaf(pv[j], v[j].w, o[i][3]);
+            for (int i = 0; i < QT; i++) {
+                const float p = Ss[i * tok4 + k];
+                o[i][0] = fmaf(p, v.x, o[i][0]);
+                o[i][1] = fmaf(p, v.y, o[i][1]);
+                o[i][2] = fmaf(p, v.z, o[i][2]);
+                o[i][3] = fmaf(p, v.w, o[i][3]);
             }
         }
-    }
+        // the two key groups of a warp meet by shuffle, the eight warps through shared memory
 #pragma unroll
-    for (int i = 0; i < NQ; i++) {
-        const int q = q0 + py + 16 * i;
-        if (q < tokens) {
-            const float4 r = make_float4(o[i][0], o[i][1], o[i][2], o[i][3]);
-            if (kSplit)
-                split3_store4(reinterpret_cast<__nv_bfloat16 *>(out_) + ((size_t)img * tokens + q) * 3 * embed, embed,
-                              head * kHeadDim + px * 4, r);
-            else
-                *reinterpret_cast<float4 *>(reinterpret_cast<float *>(out_) + ((size_t)img * tokens + q) * embed + head * kHeadDim + px * 4) = r;
+        for (int i = 0; i < QT; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                o[i][j] += __shfl_xor_sync(0xffffffffu, o[i][j], 16);
+        if (lane < 16) {
+#pragma unroll
+            for (int i = 0; i < QT; i++)
+                *reinterpret_cast<float4 *>(red + ((size_t)warp * QT + i) * kHeadDim + px * 4) = make_float4(o[i][0], o[i][1], o[i][2], o[i][3]);
         }
+    }
+    __syncthreads();
+    for (int f = tid; f < QT * 16; f += 256) {
+        const int i = f >> 4, c = (f & 15) * 4, q = q0 + i;
+        if (q >= tokens)
+            continue;
+        float4 r = *reinterpret_cast<const float4 *>(red + (size_t)i * kHeadDim + c);
+#pragma unroll
+        for (int w = 1; w < 8; w++) {
+            const float4 t = *reinterpret_cast<const float4 *>(red + ((size_t)w * QT + i) * kHeadDim + c);
+            r.x += t.x;
+            r.y += t.y;
+            r.z += t.z;
+            r.w += t.w;
+        }
+        if (kSplit)
+            split3_store4(reinterpret_cast<__nv_bfloat16 *>(out_) + ((size_t)img * tokens + q) * 3 * embed, embed, head * kHeadDim + c, r);
+        else
+            *reinterpret_cast<float4 *>(reinterpret_cast<float *>(out_) + ((size_t)img * tokens + q) * embed + head * kHeadDim + c) = r;
     }
 }
 
@@ -386,7 +400,7 @@ template <int QT>
 size_t attention_simt_small_smem(int tokens)
 {
     const size_t tok4 = (size_t)(tokens + 3) & ~(size_t)3;
-    return sizeof(float) * ((size_t)QT * kSmallLdr + tok4 * kSmallLdr + tok4 * kHeadDim + (size_t)QT * kSmallLds);
+    return sizeof(float) * ((size_t)((QT + 3) / 4 * 4) * kSmallLdr + tok4 * kSmallLdr + (size_t)QT * tok4 + (size_t)8 * QT * kHeadDim);
 }
 
 template <int QT, bool kSplit>
@@ -459,17 +473,12 @@ extern "C" int vitcu_attention_ex(const void *qkv, void *out, int batch, int tok
     const bool small = ((long)batch * heads * ((tokens + 63) / 64) < 148 || attention_simt_smem<64>(tokens) > 227 * 1024) &&
                        attention_simt_smem<16>(tokens) <= 227 * 1024;
     int rc;
-    // fp32 storage, a few images, all keys in one staged block: the cp.async kernel (16-query tiles while they give
-    // every CTA its own SM, else 32-query tiles); VITCU_ATTN_SMALL=0 keeps the block-by-block kernel (A/B)
+    // fp32 storage, a few images, all keys in one staged block: the cp.async kernel (18-query tiles);
+    // VITCU_ATTN_SMALL=0 keeps the block-by-block kernel (A/B)
     static const bool no_small = getenv("VITCU_ATTN_SMALL") && !strcmp(getenv("VITCU_ATTN_SMALL"), "0");
     if (small && !no_small && is_bf16 != 1 && tokens <= 256) {
-        const bool q16 = (long)batch * heads * ((tokens + 15) / 16) <= device_sm_count();
-        if (is_bf16 == 2)
-            rc = q16 ? launch_attention_simt_small<16, true>(qkv, out, batch, tokens, heads, as_stream(s))
-                     : launch_attention_simt_small<32, true>(qkv, out, batch, tokens, heads, as_stream(s));
-        else
-            rc = q16 ? launch_attention_simt_small<16, false>(qkv, out, batch, tokens, heads, as_stream(s))
-                     : launch_attention_simt_small<32, false>(qkv, out, batch, tokens, heads, as_stream(s));
+        rc = is_bf16 == 2 ? launch_attention_simt_small<kSmallQT, true>(qkv, out, batch, tokens, heads, as_stream(s))
+                          : launch_attention_simt_small<kSmallQT, false>(qkv, out, batch, tokens, heads, as_stream(s));
         if (rc)
             return rc;
         VITCU_LAUNCHED_KIND(LK_ATTN_SIMT);

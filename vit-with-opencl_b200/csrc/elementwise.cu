@@ -100,6 +100,21 @@ __global__ void __launch_bounds__(256) cls_rows_kernel(float *__restrict__ x, co
         make_float4(c.x + p.x, c.y + p.y, c.z + p.z, c.w + p.w);
 }
 
+// every token row before an accumulate-mode patch embedding (vitcu_token_rows_init): row 0 as above, row t > 0 = pos[t]
+__global__ void __launch_bounds__(256) token_rows_init_kernel(float *__restrict__ x, const float *__restrict__ cls,
+                                                              const float *__restrict__ pos, int tokens, int cols)
+{
+    pdl_trigger();
+    pdl_wait();
+    const int t = blockIdx.x, b = blockIdx.y, i = threadIdx.x;
+    float4 p = reinterpret_cast<const float4 *>(pos + (size_t)t * cols)[i];
+    if (t == 0) {
+        const float4 c = reinterpret_cast<const float4 *>(cls)[i];
+        p = make_float4(c.x + p.x, c.y + p.y, c.z + p.z, c.w + p.w);
+    }
+    reinterpret_cast<float4 *>(x + ((size_t)b * tokens + t) * cols)[i] = p;
+}
+
 // ---------------------------------------------------------------------------
 // LayerNorm, one warp per row of NV*128 columns (NV = 6 for the 768-wide model, 3 / 8 for 384 / 1024):
 // NV x float4 per lane held in registers,
@@ -471,6 +486,14 @@ int vitcu_cls_rows_ex(float *x, const float *cls, const float *pos, int batch, i
     VITCU_REQUIRE(x && cls && pos && batch > 0 && tokens > 0, "bad argument");
     VITCU_REQUIRE(cols > 0 && cols % 4 == 0 && cols <= 1024, "row width must be a multiple of 4, at most 1024");
     VITCU_TRY(launch_kernel(cls_rows_kernel, batch, cols / 4, 0, as_stream(s), x, cls, pos, tokens, cols));
+    VITCU_LAUNCHED();
+    return 0;
+}
+int vitcu_token_rows_init(float *x, const float *cls, const float *pos, int batch, int tokens, int cols, vitcu_stream s)
+{
+    VITCU_REQUIRE(x && cls && pos && batch > 0 && tokens > 0, "bad argument");
+    VITCU_REQUIRE(cols > 0 && cols % 4 == 0 && cols <= 1024, "row width must be a multiple of 4, at most 1024");
+    VITCU_TRY(launch_kernel(token_rows_init_kernel, dim3(tokens, batch), cols / 4, 0, as_stream(s), x, cls, pos, tokens, cols));
     VITCU_LAUNCHED();
     return 0;
 }

@@ -25,6 +25,9 @@
 #ifndef VITCU_GELU_FORM
 #define VITCU_GELU_FORM 2 // 0 = (3,3) rational, 1 / 2 = MUFU.TANH form scalar / packed (default), 3 = sigmoid form (EX2 + RCP), packed
 #endif
+#ifndef VITCU_EXIT_WAIT_WRITES
+#define VITCU_EXIT_WAIT_WRITES 0 // 1: the single-CTA GEMM waits for its TMA stores to land in global memory before it retires (A/B)
+#endif
 #ifndef VITCU_GELU_SCALAR
 #define VITCU_GELU_SCALAR 0
 #endif
@@ -761,8 +764,17 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             if (lane == 0)
                 mbar_arrive(&tempty_bar[acc]);
         }
-        if (lane == 0)
-            tma_wait_group<0>(); // this warp's TMA stores have landed before the CTA retires
+        // the staging buffers must outlive the TMA engine's reads of them; the writes themselves are complete and
+        // visible once the grid has completed, which is what the next kernel's griddepcontrol.wait (or the stream)
+        // orders on -- waiting here for the global-memory side as well costs a round trip per launch, which
+        // matters only where launches are a few microseconds long (batch-1 latency)
+        if (lane == 0) {
+#if VITCU_EXIT_WAIT_WRITES
+            tma_wait_group<0>();
+#else
+            tma_wait_group_read<0>();
+#endif
+        }
     }
 
     // ===================== teardown =====================
@@ -860,7 +872,13 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     const Watchdog wd{cta_abort, watchdog_flag};
 
     const int num_m = (p.M + BM2 - 1) / BM2, num_n = p.N / BN;
-    const int num_tiles = num_m * num_n, num_kb = p.nseg * p.seg_kb;
+    const int num_kb = p.nseg * p.seg_kb;
+    // work item = (output tile, K slice).  splits > 1 only with the TMA reduce-add epilogue at small M (batch-1
+    // latency): every slice adds its partial tile into C, slice 0 carries the bias, and a [197 x 768] x [768 x 2304]
+    // product occupies 72 CTA pairs instead of 9.  Against the single-CTA kernel's 128 x 128 items the pair moves
+    // 57 KB instead of 98 KB from L2 per 256 x 256 x 64 block, and those launches are bound by L2 -> SM traffic.
+    const int kb_per = (num_kb + p.splits - 1) / p.splits;
+    const int num_tiles = num_m * num_n * p.splits;
     const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
 
     if (warp == 0) {
@@ -874,12 +892,15 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         // the leader's full barriers as shared::cluster addresses (consecutive 8-byte slots)
         const uint32_t full_leader0 = mapa_u32(smem_u32(&full_bar[0]), 0);
         for (int tile = pair; tile < num_tiles && ok; tile += num_pairs) {
-            const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
+            const int t2 = tile / p.splits, split = tile - t2 * p.splits;
+            const int m_blk = t2 / num_n, n_blk = t2 - m_blk * num_n;
             const int arow = m_blk * BM2 + (int)rank * BM, brow = n_blk * BN + (int)rank * 128;
+            const int kb_begin = split * kb_per, kb_end = min(num_kb, kb_begin + kb_per);
             // running (segment, column) instead of a division per k-block: this warp's instruction
             // stream is what feeds the tensor core (the MMA issuer spends most of its time on the full barrier)
-            int seg = 0, kin = 0, acol = p.a_seg[0], bcol = p.b_seg[0];
-            for (int kb = 0; kb < num_kb; kb++) {
+            int seg = kb_begin / p.seg_kb, kin = kb_begin - seg * p.seg_kb;
+            int acol = p.a_seg[seg] + kin * p.kb_elems, bcol = p.b_seg[seg] + kin * p.kb_elems;
+            for (int kb = kb_begin; kb < kb_end; kb++) {
                 if (!(ok = mbar_wait_warp(&empty_bar[stage], phase ^ 1, wd, 1)))
                     break;
                 if (elect_one()) {
@@ -892,7 +913,7 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                 __syncwarp();
                 acol += p.kb_elems;
                 bcol += p.kb_elems;
-                if (++kin == p.seg_kb && kb + 1 < num_kb) {
+                if (++kin == p.seg_kb && kb + 1 < kb_end) {
                     kin = 0;
                     seg++;
                     acol = p.a_seg[seg];
@@ -915,7 +936,9 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                     break;
                 tcgen05_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int kb = 0; kb < num_kb; kb++) {
+                const int split = tile % p.splits;
+                const int kb_begin = split * kb_per, kb_end = min(num_kb, kb_begin + kb_per);
+                for (int kb = kb_begin; kb < kb_end; kb++) {
                     if (!(ok = mbar_wait_warp(&full_bar[stage], phase, wd, 3)))
                         break;
                     tcgen05_fence_after();
@@ -926,12 +949,12 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
 #pragma unroll
                         for (int k = 0; k < BK / 16; k++) { // four instructions per k-block, 32 bytes of K each
                             if (FP8)
-                                umma_e4m3_ss_2sm(d_tmem, a_desc + 2 * k, b_desc + 2 * k, IDESC, (kb | k) != 0);
+                                umma_e4m3_ss_2sm(d_tmem, a_desc + 2 * k, b_desc + 2 * k, IDESC, ((kb - kb_begin) | k) != 0);
                             else
-                                umma_bf16_ss_2sm(d_tmem, a_desc + 2 * k, b_desc + 2 * k, IDESC, (kb | k) != 0);
+                                umma_bf16_ss_2sm(d_tmem, a_desc + 2 * k, b_desc + 2 * k, IDESC, ((kb - kb_begin) | k) != 0);
                         }
                         umma_commit_2sm(&empty_bar[stage], 0x3); // frees the slot in both CTAs
-                        if (kb == num_kb - 1)
+                        if (kb == kb_end - 1)
                             umma_commit_2sm(&tfull_bar[acc], 0x3); // accumulator complete in both CTAs
                     }
                     __syncwarp();
@@ -958,16 +981,18 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         LnRow ln = {1.0f, 0.0f};
         if (LN && pair < num_tiles) { // first tile: fetched here; later tiles one tile ahead
             float2 part[kMaxLnSlots];
-            ln_row_fetch(p, (pair / num_n) * BM2 + (int)rank * BM + quad * 32 + lane, part);
+            ln_row_fetch(p, (pair / p.splits / num_n) * BM2 + (int)rank * BM + quad * 32 + lane, part);
             ln = ln_row_finish(p, part);
         }
         if (!EMIT && coef_in_smem<LN, SBW, CW / 32>(p) && pair < num_tiles)
             ln_coef_copy<LN, CW / 32>(p, reinterpret_cast<float *>(smem + L::EPI_OFFSET + (warp - 2) * SBW + 4096), lane,
-                                      (pair % num_n) * BN + cgrp * CW);
+                                      ((pair / p.splits) % num_n) * BN + cgrp * CW);
         for (int tile = pair; tile < num_tiles; tile += num_pairs, it++) {
-            const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
-            const int next_row0 = tile + num_pairs < num_tiles ? ((tile + num_pairs) / num_n) * BM2 + (int)rank * BM + quad * 32 : -1;
-            const int next_col = tile + num_pairs < num_tiles ? ((tile + num_pairs) % num_n) * BN + cgrp * CW : -1;
+            const int t2 = tile / p.splits, split = tile - t2 * p.splits;
+            const int m_blk = t2 / num_n, n_blk = t2 - m_blk * num_n;
+            const int t2n = (tile + num_pairs) / p.splits;
+            const int next_row0 = tile + num_pairs < num_tiles ? (t2n / num_n) * BM2 + (int)rank * BM + quad * 32 : -1;
+            const int next_col = tile + num_pairs < num_tiles ? (t2n % num_n) * BN + cgrp * CW : -1;
             const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
             float *stage_tile = reinterpret_cast<float *>(smem + L::EPI_OFFSET + (warp - 2) * SBW);
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + cgrp * CW;
@@ -987,7 +1012,8 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             } else {
                 tile_ok = epilogue_tile<CW / 32, SBW, EW == 8, LN>(p, C, &tmap_c, chunk_ctr, stage_tile, lane,
                                                                m_blk * BM2 + (int)rank * BM + quad * 32, n_blk * BN + cgrp * CW,
-                                                               taddr, &tfull_bar[acc], acc_phase, wd, ln, next_row0, next_col, it);
+                                                               taddr, &tfull_bar[acc], acc_phase, wd, ln, next_row0, next_col, it,
+                                                               split == 0 ? 1.0f : 0.0f);
             }
             if (!tile_ok)
                 break;
@@ -1059,7 +1085,7 @@ int launch_pair(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap 
         VITCU_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::TOTAL));
         configured[dev] = true;
     }
-    const int num_tiles = ((p.M + 255) / 256) * (p.N / 256);
+    const int num_tiles = ((p.M + 255) / 256) * (p.N / 256) * p.splits;
     const int pairs = num_tiles < sms / 2 ? num_tiles : sms / 2;
     VITCU_TRY(launch_kernel(kernel, 2 * pairs, 64 + 32 * EW, L::TOTAL, st, ta, tb, tc, td, C, p, watchdog_flag()));
     VITCU_LAUNCHED_KIND(LK_GEMM_PAIR);
@@ -1257,6 +1283,27 @@ static int gemm_dispatch(const vitcu_bf16 *A, const vitcu_bf16 *W, void *C, cons
         if (p.ln_stats)
             return launch_pair<5, 8, 65536, false, true>(ta, tb, tc, td, C, p, sms, as_stream(s));
         return launch_pair<5, 8>(ta, tb, tc, td, C, p, sms, as_stream(s));
+    }
+    // small M with the reduce-add epilogue (batch-1 latency: out-proj / fc2, and qkv / fc1 / patch embedding of the
+    // FP32 chain in accumulate mode) on CTA pairs with split-K -- VITCU_GEMM_MODE=pair, an A/B variant that is NOT the
+    // default: the 256 x 256 pair tile moves 57 KB instead of 98 KB from L2 per 256 x 256 x 64 block and its k-loop
+    // is 1 - 1.5 us shorter per launch, but a cluster launch with 512 TMEM columns per CTA costs 4.5 us more before
+    // the first load (same box: FP32 batch-1 forward 1.040 vs 0.995 ms, BF16 0.648 vs 0.548 ms)
+    const char *mode = getenv("VITCU_GEMM_MODE"); // read per call: the tests run both kernels in one process
+    const bool force_1cta_small = !(mode && !strcmp(mode, "pair"));
+    if (!force_1cta_small && p.tma_out == 2 && d->N % 256 == 0 && !p.ln_stats) {
+        const int tiles = ((d->M + 255) / 256) * (d->N / 256), total_kb = p.nseg * p.seg_kb;
+        int splits = (sms / 2) / tiles;
+        if (splits > total_kb / 2)
+            splits = total_kb / 2;
+        if (splits < 1)
+            splits = 1;
+        const int kb_per = (total_kb + splits - 1) / splits;
+        p.splits = (total_kb + kb_per - 1) / kb_per; // no empty slice (its accumulator would never be committed)
+        rc = make_tensor_map_2d(&tb, W, 2, (uint64_t)d->N, kphys, kphys * 2, 128, BK);
+        if (rc)
+            return rc;
+        return launch_pair<6, 8, 32768>(ta, tb, tc, td, C, p, sms, as_stream(s));
     }
     // 128x256 tiles when they divide N and still give every SM work; else 128x128
     const bool wide = d->N % 256 == 0 && ((d->M + BM - 1) / BM) * (d->N / 256) >= sms;

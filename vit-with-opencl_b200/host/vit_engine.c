@@ -652,6 +652,12 @@ static int enqueue_forward_mode(vitb200_engine *e, int buf, int b, int calibrate
     vitcu_stream s = e->stream;
     e->launches = 0;
 
+    /* FP32 chain at small M (batch-1 latency): qkv and fc1 are a few dozen 128 x 128 tiles with the whole K range each
+     * -- 36 and 48 of 148 SMs busy for 72 k-blocks.  In accumulate mode their K range is cut into slices that meet in
+     * the output through TMA reduce-add, like out-proj and fc2 always did; the output is zeroed by the LayerNorm launch
+     * in front of the GEMM and fc1's GELU moves into the split pass in front of fc2 (VITB200_FP32_SPLITK=0: off) */
+    const int acc = e->fp32_tc && e->fp32_splitk && vitcu_gemm_split_k_pays(M, 3 * e->D) && vitcu_gemm_split_k_pays(M, e->HID);
+
     /* patch embedding (Conv2d + postConv2d, R/ViT_opencl.c:361-442).  BF16 path: one TF32
      * tensor-core GEMM that gathers the patches by TMA straight from the NCHW image; FP32 path:
      * gather kernel + FP32-accurate GEMM with the class/position epilogue */
@@ -662,11 +668,21 @@ static int enqueue_forward_mode(vitb200_engine *e, int buf, int b, int calibrate
     } else {
         VIT_TRY(vitcu_patch_gather_ex(e->d_images[buf], e->d_patches, b, e->img, e->patch, bf, s));
         e->launches++;
-        VIT_TRY(gemm(e, e->d_patches, 0, 1, 2, e->d_x, b * e->P, e->D, 3 * e->patch * e->patch, VITCU_EPI_PATCH_EMBED, 0, 0));
+        if (acc && b == 1) {
+            /* one image: its patch rows are rows 1..P of x, a plain 2-D tile target -- the token rows start as the
+             * position rows (class row included) and the 12-tile GEMM becomes 144 K slices that add into them */
+            VIT_TRY(vitcu_token_rows_init(e->d_x, e->w32[0], e->w32[3], b, e->T, e->D, s));
+            e->launches++;
+            VIT_TRY(gemm(e, e->d_patches, 0, 1, 2, e->d_x + e->D, e->P, e->D, 3 * e->patch * e->patch, VITCU_EPI_BIAS, 0, -1));
+        } else {
+            VIT_TRY(gemm(e, e->d_patches, 0, 1, 2, e->d_x, b * e->P, e->D, 3 * e->patch * e->patch, VITCU_EPI_PATCH_EMBED, 0, 0));
+        }
     }
-    MARK(VIT_K_OTHER);
-    VIT_TRY(vitcu_cls_rows_ex(e->d_x, e->w32[0], e->w32[3], b, e->T, e->D, s));
-    e->launches++;
+    if (!(acc && b == 1)) { /* (acc implies the FP32 chain, which always takes the gather branch above) */
+        MARK(VIT_K_OTHER);
+        VIT_TRY(vitcu_cls_rows_ex(e->d_x, e->w32[0], e->w32[3], b, e->T, e->D, s));
+        e->launches++;
+    }
 
     const int layers = e->stop_after < 0 ? e->depth : (e->stop_after < e->depth ? e->stop_after : e->depth);
     /* LayerNorm folded into the GEMMs when the chunk is large enough for the CTA-pair kernel, whose residual
@@ -678,11 +694,6 @@ static int enqueue_forward_mode(vitb200_engine *e, int buf, int b, int calibrate
         return vit_fail(__FILE__, __LINE__, VITCU_E_ARG, "FP8 calibration needs a chunk that runs the CTA-pair GEMM");
     if (calibrate)
         VIT_TRY(vitcu_memset(e->d_amax, 0, (size_t)2 * VIT_MAX_DEPTH * sizeof(float), s));
-    /* FP32 chain at small M (batch-1 latency): qkv and fc1 are a few dozen 128 x 128 tiles with the whole K range each
-     * -- 36 and 48 of 148 SMs busy for 72 k-blocks.  In accumulate mode their K range is cut into slices that meet in
-     * the output through TMA reduce-add, like out-proj and fc2 always did; the output is zeroed by the LayerNorm launch
-     * in front of the GEMM and fc1's GELU moves into the split pass in front of fc2 (VITB200_FP32_SPLITK=0: off) */
-    const int acc = e->fp32_tc && e->fp32_splitk && vitcu_gemm_split_k_pays(M, 3 * e->D) && vitcu_gemm_split_k_pays(M, e->HID);
     if (fold && layers > 0) {
         MARK(VIT_K_LAYERNORM);
         VIT_TRY(vitcu_rowstats_cast(e->d_x, (vitcu_bf16 *)e->d_ln, e->d_lnstats, M, e->D, e->D / 128, s));
