@@ -335,6 +335,64 @@ void vitb200_destroy(vitb200_engine *e)
     free(e);
 }
 
+/* The pinned staging ring (VIT_STAGE_SLOTS slots of stage_group images) and the copy threads, created on first
+ * use: by the first pageable image upload or by the first weight upload from pageable blobs. */
+static int ensure_stage(vitb200_engine *e)
+{
+    if (e->stager)
+        return 0;
+    const size_t img_bytes = (size_t)3 * e->img * e->img * sizeof(float);
+    /* small slots: page-locking costs ~0.4 ms per MB and is paid inside the first call */
+    const char *mb = getenv("VITB200_STAGE_SLOT_MB");
+    e->stage_group = (int)(((size_t)(mb && atoi(mb) > 0 ? atoi(mb) : 4) << 20) / img_bytes);
+    if (e->stage_group < 1)
+        e->stage_group = 1;
+    if (e->stage_group > e->B)
+        e->stage_group = e->B;
+    /* a retry after a partial failure reuses what the first attempt got (nothing is allocated twice) */
+    if (!e->h_stage)
+        VIT_TRY(vitcu_host_alloc((void **)&e->h_stage, (size_t)VIT_STAGE_SLOTS * e->stage_group * img_bytes));
+    for (int i = 0; i < VIT_STAGE_SLOTS; i++)
+        if (!e->ev_slot[i])
+            VIT_TRY(vitcu_event_create(&e->ev_slot[i]));
+    e->stager = vit_stager_create(vit_stager_threads_default());
+    if (!e->stager)
+        return vit_fail(__FILE__, __LINE__, VITCU_E_ARG, "out of host memory");
+    return 0;
+}
+
+/* One weight blob to the device.  The reference hands over 152 malloc'd (pageable) blobs (R/Network.c:134-215):
+ * a cudaMemcpy from pageable memory is staged by the driver on the calling thread at a few GB/s and does not
+ * return before it is done, which made the 346 MB upload the longest part of a cold ViT_opencl call.  Here the
+ * copy threads move the blob piece by piece into the pinned ring (streaming stores, host/vit_stage.c) and every
+ * piece leaves by asynchronous DMA, so the host copy of piece i+1 overlaps the transfer of piece i.  Pinned
+ * sources are DMA'd in place.  VITB200_WEIGHT_STAGE=0: plain copies (A/B). */
+static int upload_blob(vitb200_engine *e, void *dst, const void *src, size_t bytes, int staged)
+{
+    int pinned = 0;
+    if (!staged || (vitcu_host_is_pinned(src, &pinned) == 0 && pinned) || bytes < ((size_t)64 << 10))
+        return vitcu_memcpy_h2d(dst, src, bytes, e->stream);
+    const size_t slot_bytes = (size_t)e->stage_group * 3 * e->img * e->img * sizeof(float);
+    for (size_t off = 0; off < bytes; off += slot_bytes) {
+        const size_t len = bytes - off < slot_bytes ? bytes - off : slot_bytes;
+        const int slot = e->stage_next++ % VIT_STAGE_SLOTS;
+        char *h = e->h_stage + (size_t)slot * slot_bytes;
+        if (e->stage_used[slot]) {
+            int rc = vitcu_event_sync(e->ev_slot[slot]);
+            if (rc)
+                return rc;
+        }
+        vit_stager_copy(e->stager, h, NULL, (const char *)src + off, len, 1);
+        int rc = vitcu_memcpy_h2d((char *)dst + off, h, len, e->stream);
+        if (!rc)
+            rc = vitcu_event_record(e->ev_slot[slot], e->stream);
+        if (rc)
+            return rc;
+        e->stage_used[slot] = 1;
+    }
+    return 0;
+}
+
 int vitb200_load_weights(vitb200_engine *e, const vitb200_blob *net)
 {
     if (!e || !net)
@@ -406,6 +464,9 @@ int vitb200_load_weights(vitb200_engine *e, const vitb200_blob *net)
     int rc = (w32 && w16 && wf16 && wf_cs && wf_b && wq8 && wq8_cs && wq8_b && wq8_scale) ? 0 : VITCU_E_ARG;
     if (rc)
         vit_fail(__FILE__, __LINE__, rc, "out of host memory");
+    const int staged = !(getenv("VITB200_WEIGHT_STAGE") && atoi(getenv("VITB200_WEIGHT_STAGE")) == 0);
+    if (!rc && staged)
+        rc = ensure_stage(e);
     if (!rc && (rc = vitcu_malloc(&arena, total)) != 0)
         vit_fail(__FILE__, __LINE__, rc, NULL);
     for (int k = 0; k < 2 && !rc && scratch_elems; k++)
@@ -417,13 +478,13 @@ int vitb200_load_weights(vitb200_engine *e, const vitb200_blob *net)
         w32[i] = off32[i] == (size_t)-1 ? NULL : (float *)((char *)arena + off32[i]);
         w16[i] = off16[i] == (size_t)-1 ? NULL : (vitcu_bf16 *)((char *)arena + off16[i]);
         if (w32[i])
-            rc = vitcu_memcpy_h2d(w32[i], net[i].data, n * sizeof(float), e->stream);
+            rc = upload_blob(e, w32[i], net[i].data, n * sizeof(float), staged);
         if (!rc && w16[i]) {
             /* stream order makes the scratch reuse safe: the conversion that read it two blobs ago
              * precedes this copy on the same stream */
             float *src = w32[i] ? w32[i] : scratch[k++ & 1];
             if (src != w32[i])
-                rc = vitcu_memcpy_h2d(src, net[i].data, n * sizeof(float), e->stream);
+                rc = upload_blob(e, src, net[i].data, n * sizeof(float), staged);
             if (!rc && bf)
                 rc = vitcu_f32_to_bf16(src, w16[i], n, e->stream);
             if (!rc && e->fp32_tc) { /* [N,K] fp32 -> [N,3K] bf16 pieces */
@@ -476,6 +537,8 @@ int vitb200_load_weights(vitb200_engine *e, const vitb200_blob *net)
     }
     if (!rc && (rc = vitcu_stream_sync(e->stream)) != 0)
         vit_fail(__FILE__, __LINE__, rc, NULL);
+    for (int i = 0; i < VIT_STAGE_SLOTS; i++) /* the ring is idle again (the image uploads record on another stream) */
+        e->stage_used[i] = 0;
     vitcu_free(scratch[0]);
     vitcu_free(scratch[1]);
     if (!rc) {
@@ -832,24 +895,7 @@ static int check_ready(vitb200_engine *e)
 static int upload_pageable(vitb200_engine *e, int buf, const float *contig, const vitb200_image *structs, int b)
 {
     const size_t img_elems = (size_t)3 * e->img * e->img, img_bytes = img_elems * sizeof(float);
-    if (!e->stager) {
-        /* small slots: page-locking costs ~0.4 ms per MB and is paid inside the first call */
-        const char *mb = getenv("VITB200_STAGE_SLOT_MB");
-        e->stage_group = (int)(((size_t)(mb && atoi(mb) > 0 ? atoi(mb) : 4) << 20) / img_bytes);
-        if (e->stage_group < 1)
-            e->stage_group = 1;
-        if (e->stage_group > e->B)
-            e->stage_group = e->B;
-        /* a retry after a partial failure reuses what the first attempt got (nothing is allocated twice) */
-        if (!e->h_stage)
-            VIT_TRY(vitcu_host_alloc((void **)&e->h_stage, (size_t)VIT_STAGE_SLOTS * e->stage_group * img_bytes));
-        for (int i = 0; i < VIT_STAGE_SLOTS; i++)
-            if (!e->ev_slot[i])
-                VIT_TRY(vitcu_event_create(&e->ev_slot[i]));
-        e->stager = vit_stager_create(vit_stager_threads_default());
-        if (!e->stager)
-            return vit_fail(__FILE__, __LINE__, VITCU_E_ARG, "out of host memory");
-    }
+    VIT_TRY_RC(ensure_stage(e));
     for (int g0 = 0; g0 < b; g0 += e->stage_group) {
         const int g = b - g0 < e->stage_group ? b - g0 : e->stage_group;
         const int slot = e->stage_next++ % VIT_STAGE_SLOTS;
