@@ -133,8 +133,12 @@ __device__ __forceinline__ LnRow ln_row_finish(const EpiParams &p, const float2 
     return r;
 }
 
-// Per-column epilogue coefficients in shared memory (upper 4 KB of a warp's staging area, two buffers of 256 floats:
-// bias at [0, 128), colsum at [128, 256)): available when the bf16 TMA-store path leaves that half free.
+// Per-column epilogue coefficients in shared memory (last 2 KB of a warp's 8 KB staging area, two buffers of 256 floats:
+// bias at [0, 128), colsum at [128, 256)): available when the bf16 TMA-store path leaves that part free.
+constexpr uint32_t kCoefOffset = 6144;
+#ifndef VITCU_STORE_BUFS
+#define VITCU_STORE_BUFS 2 // bf16 / e4m3 TMA-store tiles in flight per epilogue warp; 3 was measured and is SLOWER (same box: qkv + LN 130.5 -> 135.7 us, fc1 + LN + GELU 204 -> 211 us): the stores are not what the K = 768 epilogue waits for
+#endif
 template <bool LN, int STAGE_BYTES_PER_WARP, int NCHUNK>
 __device__ __forceinline__ bool coef_in_smem(const EpiParams &p)
 {
@@ -195,15 +199,15 @@ __device__ __forceinline__ bool epilogue_tile(const EpiParams &p, void *C, const
     // per chunk on the epilogue's critical path (profiles/r02_layernorm_fold.md).  They are copied asynchronously
     // (cp.async, 16 B per lane) one tile ahead into the upper half of the warp's staging area, which the bf16 TMA-store
     // path does not use.
-    float *coef = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(stage) + 4096) + (tile_it & 1) * 256;
-    static_assert(!LN || (STAGE_BYTES_PER_WARP >= 8192 && NCHUNK <= 4), "coefficient buffers need the upper 4 KB of the staging area");
+    float *coef = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(stage) + kCoefOffset) + (tile_it & 1) * 256;
+    static_assert(!LN || (STAGE_BYTES_PER_WARP >= 8192 && NCHUNK <= 4), "coefficient buffers need the last 2 KB of an 8 KB staging area");
     // the plain bias of the bf16-output GEMMs takes the same route (their FADDs waited on the same loads)
     const bool coef_on = coef_in_smem<LN, STAGE_BYTES_PER_WARP, NCHUNK>(p);
     if (coef_on) {
         asm volatile("cp.async.wait_all;" ::: "memory");
         __syncwarp();
         if (next_col_base >= 0)
-            ln_coef_copy<LN, NCHUNK>(p, reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(stage) + 4096) + ((tile_it + 1) & 1) * 256,
+            ln_coef_copy<LN, NCHUNK>(p, reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(stage) + kCoefOffset) + ((tile_it + 1) & 1) * 256,
                                      lane, next_col_base);
     }
 
@@ -290,10 +294,16 @@ __device__ __forceinline__ bool epilogue_tile(const EpiParams &p, void *C, const
             // memory, clipped at M.  No global-memory latency is left on this warp's critical path.
             // staging tiles: 2 KB (bf16) or 4 KB (fp32) each, double-buffered when the warp's share allows
             const uint32_t tile_bytes = p.tma_out == 5 ? 1024u : (p.tma_out == 1 ? 2048u : 4096u);
-            const bool two = STAGE_BYTES_PER_WARP >= 8192 || (STAGE_BYTES_PER_WARP >= 4096 && (p.tma_out == 1 || p.tma_out == 5));
-            uint8_t *buf = reinterpret_cast<uint8_t *>(stage) + (two ? (chunk_ctr & 1) * tile_bytes : 0u);
+            // staging tiles per warp: VITCU_STORE_BUFS (2) of the 16-bit / 8-bit tiles in an 8 KB share, whose last 2 KB
+            // hold the per-column coefficients; one or two otherwise
+            const bool small_tile = p.tma_out == 1 || p.tma_out == 5;
+            const int nbuf = (STAGE_BYTES_PER_WARP >= 8192 && small_tile) ? VITCU_STORE_BUFS
+                             : ((STAGE_BYTES_PER_WARP >= 8192 || (STAGE_BYTES_PER_WARP >= 4096 && small_tile)) ? 2 : 1);
+            uint8_t *buf = reinterpret_cast<uint8_t *>(stage) + (chunk_ctr % (uint32_t)nbuf) * tile_bytes;
             if (lane == 0) { // the store that used this buffer before has finished reading it
-                if (two)
+                if (nbuf == 3)
+                    tma_wait_group_read<2>();
+                else if (nbuf == 2)
                     tma_wait_group_read<1>();
                 else
                     tma_wait_group_read<0>();
@@ -744,7 +754,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             ln = ln_row_finish(p, part);
         }
         if (coef_in_smem<LN, kStageFloats * 4, BN / 64>(p) && (int)blockIdx.x < num_tiles)
-            ln_coef_copy<LN, BN / 64>(p, reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(smem + L::EPI_OFFSET) + (warp - 2) * kStageFloats * 4 + 4096),
+            ln_coef_copy<LN, BN / 64>(p, reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(smem + L::EPI_OFFSET) + (warp - 2) * kStageFloats * 4 + kCoefOffset),
                                       lane, (((int)blockIdx.x / p.splits) % num_n) * BN + half * (BN / 2));
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
             const int split = tile % p.splits, t2 = tile / p.splits;
@@ -985,7 +995,7 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             ln = ln_row_finish(p, part);
         }
         if (!EMIT && coef_in_smem<LN, SBW, CW / 32>(p) && pair < num_tiles)
-            ln_coef_copy<LN, CW / 32>(p, reinterpret_cast<float *>(smem + L::EPI_OFFSET + (warp - 2) * SBW + 4096), lane,
+            ln_coef_copy<LN, CW / 32>(p, reinterpret_cast<float *>(smem + L::EPI_OFFSET + (warp - 2) * SBW + kCoefOffset), lane,
                                       ((pair / p.splits) % num_n) * BN + cgrp * CW);
         for (int tile = pair; tile < num_tiles; tile += num_pairs, it++) {
             const int t2 = tile / p.splits, split = tile - t2 * p.splits;

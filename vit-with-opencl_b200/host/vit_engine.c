@@ -930,11 +930,18 @@ static int forward_pipeline(vitb200_engine *e, const float *images_host, const v
     VIT_TRY(vitcu_host_is_pinned(images_host ? (const void *)images_host : (const void *)structs[0].data, &pinned));
     if (getenv("VITB200_NO_STAGER"))
         pinned = 1; /* let the driver stage pageable copies itself */
+    const int tail_split = !(getenv("VITB200_TAIL_SPLIT") && atoi(getenv("VITB200_TAIL_SPLIT")) == 0);
     while (done < n || pend_n) {
         const int buf = chunk & 1;
         int b = 0;
         if (done < n) {
             b = n - done < e->B ? n - done : e->B;
+            /* Pageable sources, several chunks: when the host-side staging is the slower side of the pipeline (a call
+             * sharded over many GPUs shares the host's copy bandwidth), everything after the last upload is exposed --
+             * the whole forward of the last chunk.  Cut the last chunk so that what runs after the last byte has
+             * arrived is a quarter chunk (VITB200_TAIL_SPLIT=0: off). */
+            if (!pinned && tail_split && done > 0 && n - done <= e->B && n - done > e->B / 2 && e->B >= 64)
+                b = n - done - e->B / 4;
             /* d_images[buf] is free once the forward that read it (chunk-2) finished */
             VIT_TRY(vitcu_stream_wait_event(e->copy_stream, e->ev_done[buf]));
             if (!pinned) {

@@ -49,7 +49,12 @@ struct vit_stager {
 static void stage_copy(char *dst, const char *src, size_t n)
 {
 #if VIT_STAGE_STREAMING
-    if (((uintptr_t)dst & 15) == 0 && n >= 256) {
+    static int streaming = -1; /* VITB200_STAGE_STREAMING=0: plain memcpy (A/B) */
+    if (streaming < 0) {
+        const char *v = getenv("VITB200_STAGE_STREAMING");
+        streaming = !(v && atoi(v) == 0);
+    }
+    if (streaming && ((uintptr_t)dst & 15) == 0 && n >= 256) {
         size_t i = 0;
         for (; i + 64 <= n; i += 64) {
             const __m128i a = _mm_loadu_si128((const __m128i *)(src + i));
