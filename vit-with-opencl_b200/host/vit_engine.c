@@ -931,6 +931,7 @@ static int forward_pipeline(vitb200_engine *e, const float *images_host, const v
     if (getenv("VITB200_NO_STAGER"))
         pinned = 1; /* let the driver stage pageable copies itself */
     const int tail_split = !(getenv("VITB200_TAIL_SPLIT") && atoi(getenv("VITB200_TAIL_SPLIT")) == 0);
+    const int head_split = !(getenv("VITB200_HEAD_SPLIT") && atoi(getenv("VITB200_HEAD_SPLIT")) == 0);
     while (done < n || pend_n) {
         const int buf = chunk & 1;
         int b = 0;
@@ -942,6 +943,11 @@ static int forward_pipeline(vitb200_engine *e, const float *images_host, const v
              * arrived is a quarter chunk (VITB200_TAIL_SPLIT=0: off). */
             if (!pinned && tail_split && done > 0 && n - done <= e->B && n - done > e->B / 2 && e->B >= 64)
                 b = n - done - e->B / 4;
+            /* ... and at the head of a call nothing can be computed before the first chunk has arrived: a quarter chunk
+             * first (0.8 ms of upload instead of 3 ms at 256 images), the rest of the call in full chunks whose upload
+             * hides under the forward before them (VITB200_HEAD_SPLIT=0: off) */
+            if (head_split && done == 0 && n >= e->B && e->B >= 64)
+                b = e->B / 4;
             /* d_images[buf] is free once the forward that read it (chunk-2) finished */
             VIT_TRY(vitcu_stream_wait_event(e->copy_stream, e->ev_done[buf]));
             if (!pinned) {
