@@ -930,8 +930,13 @@ static int forward_pipeline(vitb200_engine *e, const float *images_host, const v
     VIT_TRY(vitcu_host_is_pinned(images_host ? (const void *)images_host : (const void *)structs[0].data, &pinned));
     if (getenv("VITB200_NO_STAGER"))
         pinned = 1; /* let the driver stage pageable copies itself */
-    const int tail_split = !(getenv("VITB200_TAIL_SPLIT") && atoi(getenv("VITB200_TAIL_SPLIT")) == 0);
-    const int head_split = !(getenv("VITB200_HEAD_SPLIT") && atoi(getenv("VITB200_HEAD_SPLIT")) == 0);
+    /* Chunks are cut (below) only where a quarter chunk still runs the kernels a full chunk runs -- the CTA-pair GEMMs,
+     * whose tiles are anchored at absolute rows, so an image's result does not depend on the chunk it travels in; a
+     * smaller piece would take the single-CTA / split-K kernels and differ in rounding from the same image in a full
+     * chunk (tests/test_gpu_forward.py::test_vit_opencl_multi_gpu_split compares calls bit for bit) */
+    const int split_ok = e->B >= 64 && vitcu_gemm_bf16_emit_supported((e->B / 4) * e->T, e->D);
+    const int tail_split = split_ok && !(getenv("VITB200_TAIL_SPLIT") && atoi(getenv("VITB200_TAIL_SPLIT")) == 0);
+    const int head_split = split_ok && !(getenv("VITB200_HEAD_SPLIT") && atoi(getenv("VITB200_HEAD_SPLIT")) == 0);
     while (done < n || pend_n) {
         const int buf = chunk & 1;
         int b = 0;
@@ -941,12 +946,12 @@ static int forward_pipeline(vitb200_engine *e, const float *images_host, const v
              * sharded over many GPUs shares the host's copy bandwidth), everything after the last upload is exposed --
              * the whole forward of the last chunk.  Cut the last chunk so that what runs after the last byte has
              * arrived is a quarter chunk (VITB200_TAIL_SPLIT=0: off). */
-            if (!pinned && tail_split && done > 0 && n - done <= e->B && n - done > e->B / 2 && e->B >= 64)
+            if (!pinned && tail_split && done > 0 && n - done <= e->B && n - done > e->B / 2)
                 b = n - done - e->B / 4;
             /* ... and at the head of a call nothing can be computed before the first chunk has arrived: a quarter chunk
              * first (0.8 ms of upload instead of 3 ms at 256 images), the rest of the call in full chunks whose upload
              * hides under the forward before them (VITB200_HEAD_SPLIT=0: off) */
-            if (head_split && done == 0 && n >= e->B && e->B >= 64)
+            if (head_split && done == 0 && n >= e->B)
                 b = e->B / 4;
             /* d_images[buf] is free once the forward that read it (chunk-2) finished */
             VIT_TRY(vitcu_stream_wait_event(e->copy_stream, e->ev_done[buf]));
