@@ -42,17 +42,19 @@ struct vit_stager {
 };
 
 /* One piece into the pinned slot.  The destination is written once and next read by a DMA engine, never by this
- * core: ordinary stores would first pull every destination line into the cache (read-for-ownership), so a copy moves
- * three bytes over the memory bus per byte copied.  Streaming (non-temporal) stores write whole lines without reading
- * them -- two bytes per byte -- and a drop-in call over thousands of images on several GPUs is bound by exactly this
- * traffic.  glibc's memcpy switches to streaming stores only for copies of many megabytes. */
+ * core, which is the textbook case for streaming (non-temporal) stores: no read-for-ownership of the destination
+ * lines, two bytes over the memory bus per byte copied instead of three.  MEASURED, it loses: one ViT_opencl call over
+ * 4 096 images on 8 GPUs (8 x 8 copy threads, the saturated case) 87.4 k images/s with streaming stores against 92.5 k
+ * with memcpy, 4 GPUs 74.8 k against 79.9 k, and a single copy thread is 3 % slower too (profiles/r02_batch1_latency.md)
+ * -- glibc's memcpy already picks the fastest path of this host for 128 KB pieces.  VITB200_STAGE_STREAMING=1 selects
+ * the streaming copy for hosts where that is not so. */
 static void stage_copy(char *dst, const char *src, size_t n)
 {
 #if VIT_STAGE_STREAMING
-    static int streaming = -1; /* VITB200_STAGE_STREAMING=0: plain memcpy (A/B) */
+    static int streaming = -1;
     if (streaming < 0) {
         const char *v = getenv("VITB200_STAGE_STREAMING");
-        streaming = !(v && atoi(v) == 0);
+        streaming = v && atoi(v) != 0;
     }
     if (streaming && ((uintptr_t)dst & 15) == 0 && n >= 256) {
         size_t i = 0;
