@@ -50,6 +50,7 @@ struct EpiParams {
     int out_bf16;
     int tma_out; // 0: epilogue writes with LSU stores; 1: bf16 tiles by TMA store; 2: fp32 tiles by TMA reduce-add (C += tile); 3: fp32 tiles by TMA store
     int splits;     // split-K factor (1-CTA kernel, TMA reduce-add epilogue only): work item = (tile, K slice)
+    int prefetch_w; // 1-CTA kernel, one work item per CTA: prefetch the item's W boxes into the L2 before griddepcontrol.wait
     int exact_gelu; // erff instead of the polynomial (fp32 outputs of the split-bf16 FP32 path)
     // K loop as a list of segments (split-bf16 FP32 path: six piece products over one K range)
     int nseg, seg_kb;        // segments, k-blocks per segment
@@ -661,17 +662,31 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    // every CTA holds its TMEM now: the next kernel may start its prologue; our own global-memory
-    // traffic (TMA loads, epilogue stores) waits for the previous kernel to complete
-    pdl_trigger();
-    pdl_wait();
-    const Watchdog wd{cta_abort, watchdog_flag};
-
     const int num_m = (p.M + BM - 1) / BM, num_n = p.N / BN;
     // work item = (output tile, K slice): with splits > 1 every slice reduce-adds its partial tile
     // into C through the TMA engine (only slice 0 carries the bias), so small-M GEMMs fill the SMs
     const int total_kb = p.nseg * p.seg_kb, kb_per = (total_kb + p.splits - 1) / p.splits;
     const int num_tiles = num_m * num_n * p.splits;
+    // every CTA holds its TMEM now: the next kernel may start its prologue; our own global-memory
+    // traffic (TMA loads, epilogue stores) waits for the previous kernel to complete
+    pdl_trigger();
+    // ... except for this: with one work item per CTA (batch-1 latency) the W tiles of the item come straight from
+    // DRAM (the weights of a forward do not fit the L2), and the wait below is idle time -- the CTA is resident while
+    // the kernel in front of it (a LayerNorm, the attention) still runs.  W does not depend on that kernel, so its
+    // boxes are prefetched into the L2 now; A, which does, is only requested after the wait.  An L2 prefetch cannot
+    // return stale data (the L2 is the coherence point), so this is safe even when W was written by the preceding kernel.
+    if (p.prefetch_w && warp == 0 && (int)blockIdx.x < num_tiles && elect_one()) {
+        prefetch_tensormap(&tmap_b);
+        const int tile = blockIdx.x, split = tile % p.splits, n_blk = (tile / p.splits) % num_n;
+        const int kb_end = min(total_kb, (split + 1) * kb_per);
+        for (int kb = split * kb_per; kb < kb_end; kb++) {
+            const int seg = kb / p.seg_kb, kk = (kb - seg * p.seg_kb) * BK;
+            tma_prefetch_l2_2d(&tmap_b, p.b_seg[seg] + kk, n_blk * BN);
+        }
+    }
+    pdl_wait();
+    const Watchdog wd{cta_abort, watchdog_flag};
+
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -1077,7 +1092,12 @@ int launch(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &tc, 
     }
     const int num_tiles = ((p.M + BM - 1) / BM) * (p.N / BN) * p.splits;
     const int grid = num_tiles < sms ? num_tiles : sms;
-    VITCU_TRY(launch_kernel(kernel, grid, kThreads, L::TOTAL, st, ta, tb, tc, C, p, watchdog_flag()));
+    EpiParams q = p;
+    static const bool no_prefetch = getenv("VITCU_W_PREFETCH") && !strcmp(getenv("VITCU_W_PREFETCH"), "0");
+    // one work item per CTA: small M.  Measured (same box, p50 of the batch-1 forward): BF16 0.5438 -> 0.5374 ms; the FP32
+    // chain (six piece products, bound by L2 -> SM bytes) 0.9941 -> 1.0003 ms, so it stays off there (VITCU_W_PREFETCH=0: off)
+    q.prefetch_w = num_tiles <= sms && p.nseg == 1 && !no_prefetch;
+    VITCU_TRY(launch_kernel(kernel, grid, kThreads, L::TOTAL, st, ta, tb, tc, C, q, watchdog_flag()));
     VITCU_LAUNCHED_KIND(LK_GEMM_1CTA);
     return 0;
 }
