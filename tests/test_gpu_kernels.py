@@ -447,10 +447,17 @@ def test_split3_reconstructs_fp32(pkg, lib):
     assert np.abs(recon - x).max() <= 2.0 ** -23 * np.abs(x).max()
 
 
+@pytest.mark.parametrize("fused", ["fused", "one_product_per_slot"])
 @pytest.mark.parametrize("M,N,K,epi", [(197, 2304, 768, 0), (197, 3072, 768, 1), (197, 768, 3072, 2), (6304, 768, 768, 2),
-                                       (12608, 3072, 768, 1)])
-def test_gemm_bf16x3_is_fp32_accurate(pkg, lib, oracle, M, N, K, epi):
-    """six split-bf16 products on tcgen05 == fp32 GEMM to ~1e-6 relative (oracle: R/ViT_seq.c:295-309)"""
+                                       (12608, 3072, 768, 1), (788, 2304, 768, 0), (1000, 768, 768, 2), (6304, 384, 768, 0),
+                                       (130, 768, 64, 2)])
+def test_gemm_bf16x3_is_fp32_accurate(pkg, lib, oracle, M, N, K, epi, fused, monkeypatch):
+    """six split-bf16 products on tcgen05 == fp32 GEMM to ~1e-6 relative (oracle: R/ViT_seq.c:295-309).  On the
+    128 x 128 kernel (small and medium M) the default keeps all three pieces of both operands of a k-block in one ring
+    slot and issues the six products from them; VITCU_FP32_FUSED=0 is the one-product-per-slot form.  (6304, 384): more
+    tiles than SMs, so CTAs walk the two-slot ring across tiles; (130, 768, 64): a single logical k-block."""
+    if fused != "fused":
+        monkeypatch.setenv("VITCU_FP32_FUSED", "0")
     rng = np.random.default_rng(M + N + K)
     x = rng.standard_normal((M, K), dtype=np.float32)
     w = (rng.standard_normal((N, K), dtype=np.float32) * 0.03).astype(np.float32)

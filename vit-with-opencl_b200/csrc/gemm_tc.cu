@@ -79,13 +79,17 @@ constexpr int kEpiWarps = 8;
 constexpr int kStageLd = 36;                // floats per staged epilogue row (32 + 4 pad), LSU path
 constexpr int kStageFloats = 2048;          // per epilogue warp: 2 x 4 KB TMA-store buffers (>= 32 * kStageLd floats)
 
-template <int BN, int STAGES>
+// PIECES = 3: one ring slot holds the three bf16 pieces of BOTH operands for one logical k-block (split-bf16 FP32 path
+// at small M), so that the six piece products are issued from tiles loaded once; the epilogue staging shrinks to 4 KB
+// per warp (one fp32 tile) to make room for two such slots
+template <int BN, int STAGES, int PIECES = 1>
 struct SmemLayout {
-    static constexpr uint32_t A_BYTES = BM * BK * 2;
-    static constexpr uint32_t B_BYTES = BN * BK * 2;
+    static constexpr uint32_t A_BYTES = PIECES * BM * BK * 2;
+    static constexpr uint32_t B_BYTES = PIECES * BN * BK * 2;
     static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr uint32_t EPI_WARP_BYTES = PIECES == 1 ? kStageFloats * 4 : 4096;
     static constexpr uint32_t EPI_OFFSET = STAGES * STAGE_BYTES;              // per-warp transpose tiles
-    static constexpr uint32_t BAR_OFFSET = EPI_OFFSET + kEpiWarps * kStageFloats * 4;
+    static constexpr uint32_t BAR_OFFSET = EPI_OFFSET + kEpiWarps * EPI_WARP_BYTES;
     static constexpr uint32_t NUM_BARS = 2 * STAGES + 4;
     static constexpr uint32_t TOTAL = BAR_OFFSET + NUM_BARS * 8 + 16 + 1024; // + alignment slack
     static_assert(TOTAL <= 227 * 1024, "shared memory budget");
@@ -622,12 +626,13 @@ __device__ __forceinline__ bool epilogue_tile_emit_lsu(const EpiParams &p, uint8
     return true;
 }
 
-template <int BN, int STAGES, bool LN = false>
+template <int BN, int STAGES, bool LN = false, int PIECES = 1>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_c, void *C, const EpiParams p, uint32_t *watchdog_flag)
 {
-    using L = SmemLayout<BN, STAGES>;
+    using L = SmemLayout<BN, STAGES, PIECES>;
+    static_assert(PIECES == 1 || (PIECES == 3 && !LN), "PIECES is 1 or 3 (split-bf16 operands)");
     static_assert(BN % 64 == 0 && BN <= 256, "BN must be 64..256 in steps of 64");
     constexpr uint32_t TMEM_COLS = 2 * BN <= 32 ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
     constexpr uint32_t IDESC = umma_idesc_bf16(BM, BN, false, false);
@@ -665,7 +670,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int num_m = (p.M + BM - 1) / BM, num_n = p.N / BN;
     // work item = (output tile, K slice): with splits > 1 every slice reduce-adds its partial tile
     // into C through the TMA engine (only slice 0 carries the bias), so small-M GEMMs fill the SMs
-    const int total_kb = p.nseg * p.seg_kb, kb_per = (total_kb + p.splits - 1) / p.splits;
+    // (PIECES = 3: a k-block is a LOGICAL one -- all six piece products of 64 columns of K)
+    const int total_kb = PIECES == 3 ? p.seg_kb : p.nseg * p.seg_kb, kb_per = (total_kb + p.splits - 1) / p.splits;
     const int num_tiles = num_m * num_n * p.splits;
     // every CTA holds its TMEM now: the next kernel may start its prologue; our own global-memory
     // traffic (TMA loads, epilogue stores) waits for the previous kernel to complete
@@ -710,9 +716,17 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 if (elect_one()) {
                     uint8_t *sa = smem + stage * L::STAGE_BYTES;
                     mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-                    const int seg = kb / p.seg_kb, kk = (kb - seg * p.seg_kb) * BK;
-                    tma_load_2d(sa, &tmap_a, &full_bar[stage], p.a_seg[seg] + kk, m_blk * BM);
-                    tma_load_2d(sa + L::A_BYTES, &tmap_b, &full_bar[stage], p.b_seg[seg] + kk, n_blk * BN);
+                    if (PIECES == 3) { // piece i of an operand starts at column i * K of its [rows, 3K] matrix
+#pragma unroll
+                        for (int i = 0; i < 3; i++) {
+                            tma_load_2d(sa + i * (L::A_BYTES / 3), &tmap_a, &full_bar[stage], i * p.K + kb * BK, m_blk * BM);
+                            tma_load_2d(sa + L::A_BYTES + i * (L::B_BYTES / 3), &tmap_b, &full_bar[stage], i * p.K + kb * BK, n_blk * BN);
+                        }
+                    } else {
+                        const int seg = kb / p.seg_kb, kk = (kb - seg * p.seg_kb) * BK;
+                        tma_load_2d(sa, &tmap_a, &full_bar[stage], p.a_seg[seg] + kk, m_blk * BM);
+                        tma_load_2d(sa + L::A_BYTES, &tmap_b, &full_bar[stage], p.b_seg[seg] + kk, n_blk * BN);
+                    }
                 }
                 __syncwarp();
                 if (++stage == STAGES) {
@@ -739,11 +753,25 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 tcgen05_fence_after();
                 if (elect_one()) {
                     const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
-                    const uint64_t a_desc = umma_desc_k_sw128(sa);
-                    const uint64_t b_desc = umma_desc_k_sw128(sa + L::A_BYTES);
+                    if (PIECES == 3) {
+                        // the six significant piece products of this logical k-block, small ones first
+                        // (a3 w1, a2 w2, a1 w3, a2 w1, a1 w2, a1 w1), from tiles that were loaded once
+                        constexpr int ai[6] = {2, 1, 0, 1, 0, 0}, bj[6] = {0, 1, 2, 0, 1, 0};
 #pragma unroll
-                    for (int k = 0; k < BK / 16; k++) // +32 bytes per K=16 step inside the 128B swizzle row
-                        umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, IDESC, (kb != kb_begin) | (k != 0));
+                        for (int c = 0; c < 6; c++) {
+                            const uint64_t a_desc = umma_desc_k_sw128(sa + ai[c] * (L::A_BYTES / 3));
+                            const uint64_t b_desc = umma_desc_k_sw128(sa + L::A_BYTES + bj[c] * (L::B_BYTES / 3));
+#pragma unroll
+                            for (int k = 0; k < BK / 16; k++)
+                                umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, IDESC, (kb != kb_begin) | (c != 0) | (k != 0));
+                        }
+                    } else {
+                        const uint64_t a_desc = umma_desc_k_sw128(sa);
+                        const uint64_t b_desc = umma_desc_k_sw128(sa + L::A_BYTES);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; k++) // +32 bytes per K=16 step inside the 128B swizzle row
+                            umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, IDESC, (kb != kb_begin) | (k != 0));
+                    }
                     umma_commit(&empty_bar[stage]); // ring slot reusable once these MMAs retire
                     if (kb == kb_end - 1)
                         umma_commit(&tfull_bar[acc]); // accumulator complete
@@ -768,8 +796,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             ln_row_fetch(p, ((int)blockIdx.x / p.splits / num_n) * BM + quad * 32 + lane, part);
             ln = ln_row_finish(p, part);
         }
-        if (coef_in_smem<LN, kStageFloats * 4, BN / 64>(p) && (int)blockIdx.x < num_tiles)
-            ln_coef_copy<LN, BN / 64>(p, reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(smem + L::EPI_OFFSET) + (warp - 2) * kStageFloats * 4 + kCoefOffset),
+        if (coef_in_smem<LN, L::EPI_WARP_BYTES, BN / 64>(p) && (int)blockIdx.x < num_tiles)
+            ln_coef_copy<LN, BN / 64>(p, reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(smem + L::EPI_OFFSET) + (warp - 2) * L::EPI_WARP_BYTES + kCoefOffset),
                                       lane, (((int)blockIdx.x / p.splits) % num_n) * BN + half * (BN / 2));
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
             const int split = tile % p.splits, t2 = tile / p.splits;
@@ -778,9 +806,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const int next_row0 = tile_n < num_tiles ? (tile_n / p.splits / num_n) * BM + quad * 32 : -1;
             const int next_col = tile_n < num_tiles ? ((tile_n / p.splits) % num_n) * BN + half * (BN / 2) : -1;
             const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-            float *stage_tile = reinterpret_cast<float *>(smem + L::EPI_OFFSET) + (warp - 2) * kStageFloats;
+            float *stage_tile = reinterpret_cast<float *>(smem + L::EPI_OFFSET + (warp - 2) * L::EPI_WARP_BYTES);
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + half * (BN / 2);
-            if (!epilogue_tile<BN / 64, kStageFloats * 4, true, LN>(p, C, &tmap_c, chunk_ctr, stage_tile, lane, m_blk * BM + quad * 32,
+            if (!epilogue_tile<BN / 64, L::EPI_WARP_BYTES, true, LN>(p, C, &tmap_c, chunk_ctr, stage_tile, lane, m_blk * BM + quad * 32,
                                    n_blk * BN + half * (BN / 2), taddr, &tfull_bar[acc], acc_phase, wd, ln, next_row0, next_col, it,
                                    split == 0 ? 1.0f : 0.0f))
                 break;
@@ -1077,12 +1105,12 @@ EncodeTiledFn encode_tiled_fn()
     return fn;
 }
 
-template <int BN, int STAGES, bool LN = false>
+template <int BN, int STAGES, bool LN = false, int PIECES = 1>
 int launch(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &tc, void *C, const EpiParams &p, int sms,
            cudaStream_t st)
 {
-    using L = SmemLayout<BN, STAGES>;
-    auto kernel = gemm_bf16_tc_kernel<BN, STAGES, LN>;
+    using L = SmemLayout<BN, STAGES, PIECES>;
+    auto kernel = gemm_bf16_tc_kernel<BN, STAGES, LN, PIECES>;
     static bool configured[64] = {false};
     int dev = 0;
     VITCU_TRY(cudaGetDevice(&dev));
@@ -1337,13 +1365,21 @@ static int gemm_dispatch(const vitcu_bf16 *A, const vitcu_bf16 *W, void *C, cons
     }
     // 128x256 tiles when they divide N and still give every SM work; else 128x128
     const bool wide = d->N % 256 == 0 && ((d->M + BM - 1) / BM) * (d->N / 256) >= sms;
+    // split-bf16 operands on the 128 x 128 kernel: a ring slot holds all three pieces of both operands for one logical
+    // k-block and the six piece products are issued from tiles loaded ONCE (six tile loads per 64 columns of K instead
+    // of twelve).  These launches are bound by L2 -> SM bytes (profiles/r02_batch1_latency.md).  Needs the TMA output
+    // path (4 KB of epilogue staging per warp).  VITCU_FP32_FUSED=0: one product per ring slot (A/B).
+    const char *fenv = getenv("VITCU_FP32_FUSED"); // read per call: the tests run both forms in one process
+    const bool fused3 = split3 && !wide && p.tma_out != 0 && !p.ln_stats && !(fenv && !strcmp(fenv, "0"));
     if (!wide && p.tma_out == 2) {
         // small M (batch-1 latency): split K so that the work items roughly fill the SMs, at least
-        // two k-blocks per slice; the slices meet in C through TMA reduce-add
-        const int tiles = ((d->M + BM - 1) / BM) * (d->N / 128), total_kb = p.nseg * p.seg_kb;
+        // two k-blocks per slice (one logical k-block = six products in the fused form); the slices meet in C
+        // through TMA reduce-add
+        const int tiles = ((d->M + BM - 1) / BM) * (d->N / 128), total_kb = fused3 ? p.seg_kb : p.nseg * p.seg_kb;
+        const int cap = fused3 ? total_kb : total_kb / 2;
         int splits = sms / tiles;
-        if (splits > total_kb / 2)
-            splits = total_kb / 2;
+        if (splits > cap)
+            splits = cap;
         if (splits < 1)
             splits = 1;
         // no empty slice: a work item without k-blocks would never commit its accumulator and its
@@ -1356,6 +1392,8 @@ static int gemm_dispatch(const vitcu_bf16 *A, const vitcu_bf16 *W, void *C, cons
         return rc;
     if (p.ln_stats)
         return wide ? launch<256, 3, true>(ta, tb, tc, C, p, sms, as_stream(s)) : launch<128, 5, true>(ta, tb, tc, C, p, sms, as_stream(s));
+    if (fused3)
+        return launch<128, 2, false, 3>(ta, tb, tc, C, p, sms, as_stream(s));
     if (wide)
         return launch<256, 3>(ta, tb, tc, C, p, sms, as_stream(s));
     return launch<128, 5>(ta, tb, tc, C, p, sms, as_stream(s));
