@@ -90,7 +90,8 @@ struct SmemLayout {
     static constexpr uint32_t EPI_WARP_BYTES = PIECES == 1 ? kStageFloats * 4 : 4096;
     static constexpr uint32_t EPI_OFFSET = STAGES * STAGE_BYTES;              // per-warp transpose tiles
     static constexpr uint32_t BAR_OFFSET = EPI_OFFSET + kEpiWarps * EPI_WARP_BYTES;
-    static constexpr uint32_t NUM_BARS = 2 * STAGES + 4;
+    static constexpr uint32_t FULLS = STAGES * PIECES; // PIECES = 3: one "landed" barrier per piece pair (a_i, w_i) of a slot
+    static constexpr uint32_t NUM_BARS = FULLS + STAGES + 4;
     static constexpr uint32_t TOTAL = BAR_OFFSET + NUM_BARS * 8 + 16 + 1024; // + alignment slack
     static_assert(TOTAL <= 227 * 1024, "shared memory budget");
 };
@@ -640,7 +641,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + L::BAR_OFFSET);
-    uint64_t *empty_bar = full_bar + STAGES;
+    uint64_t *empty_bar = full_bar + L::FULLS;
     uint64_t *tfull_bar = empty_bar + STAGES;
     uint64_t *tempty_bar = tfull_bar + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty_bar + 2);
@@ -650,10 +651,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < STAGES; i++) {
+        for (int i = 0; i < (int)L::FULLS; i++)
             mbar_init(&full_bar[i], 1);
+        for (int i = 0; i < STAGES; i++)
             mbar_init(&empty_bar[i], 1);
-        }
         for (int i = 0; i < 2; i++) {
             mbar_init(&tfull_bar[i], 1);
             mbar_init(&tempty_bar[i], kEpiWarps);
@@ -715,14 +716,18 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     break;
                 if (elect_one()) {
                     uint8_t *sa = smem + stage * L::STAGE_BYTES;
-                    mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-                    if (PIECES == 3) { // piece i of an operand starts at column i * K of its [rows, 3K] matrix
+                    if (PIECES == 3) {
+                        // piece i of an operand starts at column i * K of its [rows, 3K] matrix; the pair (a_i, w_i)
+                        // has its own barrier, so the issuer starts on a1 w1 when a third of the slot has landed
 #pragma unroll
                         for (int i = 0; i < 3; i++) {
-                            tma_load_2d(sa + i * (L::A_BYTES / 3), &tmap_a, &full_bar[stage], i * p.K + kb * BK, m_blk * BM);
-                            tma_load_2d(sa + L::A_BYTES + i * (L::B_BYTES / 3), &tmap_b, &full_bar[stage], i * p.K + kb * BK, n_blk * BN);
+                            uint64_t *bar = &full_bar[stage * 3 + i];
+                            mbar_arrive_expect_tx(bar, L::STAGE_BYTES / 3);
+                            tma_load_2d(sa + i * (L::A_BYTES / 3), &tmap_a, bar, i * p.K + kb * BK, m_blk * BM);
+                            tma_load_2d(sa + L::A_BYTES + i * (L::B_BYTES / 3), &tmap_b, bar, i * p.K + kb * BK, n_blk * BN);
                         }
                     } else {
+                        mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
                         const int seg = kb / p.seg_kb, kk = (kb - seg * p.seg_kb) * BK;
                         tma_load_2d(sa, &tmap_a, &full_bar[stage], p.a_seg[seg] + kk, m_blk * BM);
                         tma_load_2d(sa + L::A_BYTES, &tmap_b, &full_bar[stage], p.b_seg[seg] + kk, n_blk * BN);
@@ -748,24 +753,37 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const int split = tile % p.splits;
             const int kb_begin = split * kb_per, kb_end = min(total_kb, (split + 1) * kb_per);
             for (int kb = kb_begin; kb < kb_end; kb++) {
-                if (!(ok = mbar_wait_warp(&full_bar[stage], phase, wd, 3)))
-                    break;
-                tcgen05_fence_after();
-                if (elect_one()) {
-                    const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
-                    if (PIECES == 3) {
-                        // the six significant piece products of this logical k-block, small ones first
-                        // (a3 w1, a2 w2, a1 w3, a2 w1, a1 w2, a1 w1), from tiles that were loaded once
-                        constexpr int ai[6] = {2, 1, 0, 1, 0, 0}, bj[6] = {0, 1, 2, 0, 1, 0};
+                const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
+                if (PIECES == 3) {
+                    // the six significant piece products of this logical k-block from tiles that were loaded once,
+                    // in the order their operands land: a1 w1 | a1 w2, a2 w1, a2 w2 | a1 w3, a3 w1
+                    constexpr int ai[6] = {0, 0, 1, 1, 0, 2}, bj[6] = {0, 1, 0, 1, 2, 0}, first_of[3] = {0, 1, 4}, end_of[3] = {1, 4, 6};
 #pragma unroll
-                        for (int c = 0; c < 6; c++) {
-                            const uint64_t a_desc = umma_desc_k_sw128(sa + ai[c] * (L::A_BYTES / 3));
-                            const uint64_t b_desc = umma_desc_k_sw128(sa + L::A_BYTES + bj[c] * (L::B_BYTES / 3));
+                    for (int g = 0; g < 3 && ok; g++) {
+                        if (!(ok = mbar_wait_warp(&full_bar[stage * 3 + g], phase, wd, 3)))
+                            break;
+                        tcgen05_fence_after();
+                        if (elect_one()) {
 #pragma unroll
-                            for (int k = 0; k < BK / 16; k++)
-                                umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, IDESC, (kb != kb_begin) | (c != 0) | (k != 0));
+                            for (int c = first_of[g]; c < end_of[g]; c++) {
+                                const uint64_t a_desc = umma_desc_k_sw128(sa + ai[c] * (L::A_BYTES / 3));
+                                const uint64_t b_desc = umma_desc_k_sw128(sa + L::A_BYTES + bj[c] * (L::B_BYTES / 3));
+#pragma unroll
+                                for (int k = 0; k < BK / 16; k++)
+                                    umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, IDESC, (kb != kb_begin) | (c != 0) | (k != 0));
+                            }
                         }
-                    } else {
+                        __syncwarp();
+                    }
+                    if (!ok)
+                        break;
+                } else {
+                    if (!(ok = mbar_wait_warp(&full_bar[stage], phase, wd, 3)))
+                        break;
+                    tcgen05_fence_after();
+                }
+                if (elect_one()) {
+                    if (PIECES == 1) {
                         const uint64_t a_desc = umma_desc_k_sw128(sa);
                         const uint64_t b_desc = umma_desc_k_sw128(sa + L::A_BYTES);
 #pragma unroll
