@@ -1405,6 +1405,9 @@ static int gemm_dispatch(const vitcu_bf16 *A, const vitcu_bf16 *W, void *C, cons
         const int kb_per = (total_kb + splits - 1) / splits;
         p.splits = (total_kb + kb_per - 1) / kb_per;
     }
+    // (128 x 64 tiles for the outputs that cannot be summed across K slices -- bf16 qkv / fc1 of the BF16 chain at batch 1,
+    // 72 / 96 CTAs instead of 36 / 48 -- were measured and are slower: 0.555 vs 0.538 ms per forward.  Twice the CTAs
+    // re-read the A tile twice as often and these launches are bound by L2 -> SM bytes.)
     rc = make_tensor_map_2d(&tb, W, 2, (uint64_t)d->N, kphys, kphys * 2, wide ? 256 : 128, BK);
     if (rc)
         return rc;
