@@ -74,6 +74,14 @@ void ViT_opencl(vitb200_image *image, vitb200_blob *networks, float **prb);
  * of the n images (arrays of at least `gpus` entries); returns the number of shards (<= gpus). */
 int vitb200_shard_plan(int n, int gpus, int *first, int *count);
 
+/* The chunk schedule of one forward call over n images on an engine whose full chunk is `chunk` images: size of the
+ * next chunk when `done` images have been issued.  Full chunks, except that (a) with head_split the call opens with
+ * a quarter chunk -- nothing can be computed before the first chunk has arrived -- and (b) with tail_split (pageable
+ * sources) a last chunk of more than half a chunk is cut so that only a quarter chunk is left to run after the last
+ * upload.  The engine enables the splits only where a quarter chunk runs the same kernels as a full one, so that an
+ * image's result does not depend on the chunk it travels in. */
+int vitb200_next_chunk(int n, int done, int chunk, int head_split, int tail_split);
+
 /* what the last ViT_opencl call of this process spent where: wall time of the whole call and, per
  * phase, the slowest shard's time (the shards run concurrently, one host thread per GPU) */
 typedef struct {

@@ -164,3 +164,44 @@ def test_shard_plan_covers_every_image_once():
             assert max(count[:used]) == -(-n // min(gpus, n))
     assert L.vitb200_shard_plan(0, 4, (C.c_int * 4)(), (C.c_int * 4)()) == 0
     assert L.vitb200_shard_plan(4096, 8, (C.c_int * 8)(), (C.c_int * 8)()) == 8
+
+
+def test_chunk_schedule_of_a_call():
+    """host logic of the chunk pipeline (vit_engine.c: vitb200_next_chunk): the chunks of a call cover its images once,
+    none is larger than the engine's chunk; a call of at least one chunk opens with a quarter chunk (head split);
+    with pageable sources (tail split) at most a quarter chunk is left after the last upload of a multi-chunk call"""
+    import __graft_entry__ as g
+    L = g.load_package().lib()
+    L.vitb200_next_chunk.argtypes = [C.c_int] * 5
+
+    def schedule(n, chunk, head, tail):
+        done, sizes = 0, []
+        while done < n:
+            b = L.vitb200_next_chunk(n, done, chunk, head, tail)
+            assert 0 < b <= chunk and b <= n - done
+            sizes.append(b)
+            done += b
+        assert L.vitb200_next_chunk(n, done, chunk, head, tail) == 0
+        return sizes
+
+    for chunk in (64, 256):
+        q = chunk // 4
+        for n in (1, q, chunk - 1, chunk, chunk + 1, 2 * chunk, 2 * chunk + q, 4096, 4097, 512):
+            plain = schedule(n, chunk, 0, 0)
+            assert sum(plain) == n and all(b == chunk for b in plain[:-1])
+            for head, tail in ((1, 0), (0, 1), (1, 1)):
+                s = schedule(n, chunk, head, tail)
+                assert sum(s) == n
+                if head and n >= chunk:
+                    assert s[0] == q
+                if not head:
+                    assert s[0] == min(n, chunk)
+                if tail and len(s) > 1:
+                    assert s[-1] <= max(q, chunk // 2)   # never a whole chunk after the last upload
+                if tail and len(plain) > 1 and plain[-1] > chunk // 2:
+                    assert s[-1] == q
+    assert schedule(256, 256, 1, 1) == [64, 128, 64]
+    assert schedule(512, 256, 1, 1) == [64, 256, 128, 64]
+    assert schedule(512, 256, 1, 0) == [64, 256, 192]
+    assert schedule(100, 256, 1, 1) == [100]
+    assert L.vitb200_next_chunk(0, 0, 256, 1, 1) == 0

@@ -912,6 +912,23 @@ static int upload_pageable(vitb200_engine *e, int buf, const float *contig, cons
     return 0;
 }
 
+int vitb200_next_chunk(int n, int done, int chunk, int head_split, int tail_split)
+{
+    if (n <= 0 || done < 0 || done >= n || chunk <= 0)
+        return 0;
+    const int left = n - done;
+    int b = left < chunk ? left : chunk;
+    /* when the host-side staging is the slower side (a call sharded over many GPUs shares the host's copy bandwidth),
+     * everything after the last upload is exposed -- the whole forward of the last chunk: leave a quarter chunk for it */
+    if (tail_split && done > 0 && left <= chunk && left > chunk / 2 && chunk >= 4)
+        b = left - chunk / 4;
+    /* at the head of a call nothing can be computed before the first chunk has arrived: a quarter chunk first (0.8 ms
+     * of upload instead of 3 ms at 256 images), the rest in full chunks whose upload hides under the forward before them */
+    if (head_split && done == 0 && n >= chunk && chunk >= 4)
+        b = chunk / 4;
+    return b;
+}
+
 /* Shared chunk pipeline.  Source of chunk c is either a contiguous host array
  * (images_host) or per-image structs.  While chunk c computes, the host copies
  * chunk c-1's results out of pinned staging and the copy stream uploads chunk
@@ -941,18 +958,9 @@ static int forward_pipeline(vitb200_engine *e, const float *images_host, const v
         const int buf = chunk & 1;
         int b = 0;
         if (done < n) {
-            b = n - done < e->B ? n - done : e->B;
-            /* Pageable sources, several chunks: when the host-side staging is the slower side of the pipeline (a call
-             * sharded over many GPUs shares the host's copy bandwidth), everything after the last upload is exposed --
-             * the whole forward of the last chunk.  Cut the last chunk so that what runs after the last byte has
-             * arrived is a quarter chunk (VITB200_TAIL_SPLIT=0: off). */
-            if (!pinned && tail_split && done > 0 && n - done <= e->B && n - done > e->B / 2)
-                b = n - done - e->B / 4;
-            /* ... and at the head of a call nothing can be computed before the first chunk has arrived: a quarter chunk
-             * first (0.8 ms of upload instead of 3 ms at 256 images), the rest of the call in full chunks whose upload
-             * hides under the forward before them (VITB200_HEAD_SPLIT=0: off) */
-            if (head_split && done == 0 && n >= e->B)
-                b = e->B / 4;
+            /* full chunks, with a quarter chunk cut off the head of the call and (pageable sources, where the host-side
+             * staging can be the slower side of the pipeline) off its tail: vitb200_next_chunk */
+            b = vitb200_next_chunk(n, done, e->B, head_split, !pinned && tail_split);
             /* d_images[buf] is free once the forward that read it (chunk-2) finished */
             VIT_TRY(vitcu_stream_wait_event(e->copy_stream, e->ev_done[buf]));
             if (!pinned) {
