@@ -97,6 +97,61 @@ def test_fp32_batch64_vs_oracle(pkg, lib, blobs224, bench_case):
     assert np.abs(p1[:N_CHECK] - ref["probs"]).max() <= 1e-6
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_batch1_latency_chain_vs_oracle(pkg, lib, blobs224, bench_case, precision, monkeypatch):
+    """BASELINE config 2 at the configuration `latency_batch1` of the bench line times: Engine(max_batch=1), one image
+    resident, eager forward then graph replays.  FP32: the K-sliced chain -- LayerNorm launches that zero the GEMM
+    outputs, qkv / fc1 / patch embedding in accumulate mode with all split-bf16 pieces of a k-block in one ring slot,
+    GELU in the split pass, the cp.async attention kernel -- within 1e-4 of the oracle's logits on each of 8 images, and
+    again with VITB200_FP32_SPLITK=0 / VITCU_FP32_FUSED=0 (the chain it replaced).  BF16: 2e-2 and identical top-1.
+    Replays are deterministic only up to the order in which K slices reduce-add, so replays are compared by tolerance
+    (chunks of 32 images and more do not slice K and are bit-reproducible: test_bf16_batch256_pair_gemm_graph_vs_oracle)."""
+    imgs, ref = bench_case
+    n = 8
+    fp32 = precision == "fp32"
+    results = []
+    for old_chain in ((False, True) if fp32 else (False,)):
+        if old_chain:
+            monkeypatch.setenv("VITB200_FP32_SPLITK", "0")
+            monkeypatch.setenv("VITCU_FP32_FUSED", "0")
+        with pkg.Engine(0, 224, pkg.FP32 if fp32 else pkg.BF16, max_batch=1) as eng:
+            eng.load_weights(blobs224)
+            logits = np.empty((n, 1000), np.float32)
+            counts = None
+            for i in range(n):
+                eng.stage(imgs[i:i + 1])
+                lib.vitcu_launch_count_reset()
+                eng.forward_resident(1)                   # eager on the first image, graph replays afterwards
+                if counts is None:
+                    counts = pkg.launch_counts()          # (a launch captured into a graph counts once, a replay not at all)
+                _, l0 = eng.read_probs(1)
+                eng.forward_resident(1)
+                _, l1 = eng.read_probs(1)
+                # K slices reduce-add in arrival order: fp32 sums differ in the last bits from run to run, and on the BF16
+                # path those bits decide bf16 roundings downstream (observed: up to 5e-3 on a logit)
+                assert np.abs(l1 - l0).max() <= (1e-5 * np.abs(l0).max() if fp32 else 1e-2)
+                logits[i] = l1[0]
+            launches = eng.kernels_per_forward
+            assert lib.vitcu_watchdog_check() == 0
+        if fp32:
+            assert launches == 103 and counts["gemm_bf16_tc_kernel"] == 49 and counts["gemm_bf16_tc2_kernel"] == 0, (launches, counts)
+            assert counts["attention_simt_kernel"] == 12 and counts["layernorm_kernel"] == 25, counts
+        else:
+            assert launches == 89 and counts["gemm_bf16_tc_kernel"] == 48 and counts["attention_duo_tc_kernel"] == 12, (launches, counts)
+        results.append(logits)
+        err = np.abs(logits - ref["logits"][:n]).max(1)
+        scale = np.abs(ref["logits"][:n]).max(1)
+        print(f"\n{precision} batch-1 chain{' (unsliced, unfused)' if old_chain else ''}: max|dlogit| per image {err.max():.3e} "
+              f"(logit scale {scale.min():.2f})")
+        if fp32:
+            assert (err <= FP32_REL * scale).all(), err / scale
+        else:
+            assert err.max() <= BF16_ABS
+        assert np.array_equal(logits.argmax(1), ref["logits"][:n].argmax(1))
+    if fp32:  # both chains are fp32-accurate: they agree far inside the oracle tolerance
+        assert np.abs(results[0] - results[1]).max() <= 2e-5 * np.abs(results[1]).max()
+
+
 def test_bf16_384_flash_batch16_vs_oracle(pkg, lib, oracle):
     """BASELINE config 5 shape: 577 tokens, key-blocked attention, 16 x 12 = 192 items over 148 CTAs"""
     blobs = pkg.synth.model_blobs(None, 384, seed=7)
