@@ -202,13 +202,18 @@ def test_attention_simt_split_output(pkg, lib, oracle, T, batch):
     assert np.array_equal(pieces[:, 0], pkg.bf16_bits_to_f32(pkg.f32_to_bf16_bits(want)))  # first piece = bf16(x)
 
 
-@pytest.mark.parametrize("kernel", ["duo", "solo"])
-@pytest.mark.parametrize("T,batch", [(197, 3), (50, 2), (128, 1), (129, 1), (256, 2), (16, 1), (197, 40), (224, 26), (160, 30)])
+@pytest.mark.parametrize("kernel", ["duo", "duo-nosplit", "solo"])
+@pytest.mark.parametrize("T,batch", [(197, 3), (50, 2), (128, 1), (129, 1), (256, 2), (16, 1), (197, 40), (224, 26), (160, 30),
+                                     (197, 1), (197, 12), (197, 13)])
 def test_attention_tensor_core(pkg, lib, oracle, T, batch, kernel, monkeypatch):
     """tcgen05 attention (bf16 storage, tokens <= 256): one and two query tiles, ragged key counts,
     more work items than CTAs (persistent loop, barrier phases flip), for both single-block kernels:
-    "duo" (two co-resident CTAs per SM, default) and "solo" (one software-pipelined CTA per SM)"""
-    monkeypatch.setenv("VITCU_ATTN_KERNEL", kernel)
+    "duo" (two co-resident CTAs per SM, default; with a handful of images every query tile is an item of its own --
+    (197, 12) is the last batch that does that, (197, 13) the first that does not; "duo-nosplit" switches it off)
+    and "solo" (one software-pipelined CTA per SM)"""
+    monkeypatch.setenv("VITCU_ATTN_KERNEL", kernel.split("-")[0])
+    if kernel == "duo-nosplit":
+        monkeypatch.setenv("VITCU_ATTN_UNIT_SPLIT", "0")
     rng = np.random.default_rng(1000 + T + batch)
     bits = pkg.f32_to_bf16_bits((rng.standard_normal((batch, T, 2304), dtype=np.float32) * 1.5).astype(np.float32))
     qkv = pkg.bf16_bits_to_f32(bits).reshape(batch, T, 2304)

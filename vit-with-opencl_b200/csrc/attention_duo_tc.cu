@@ -78,6 +78,14 @@ struct DuoParams {
     int items;      // batch * heads
     int heads, embed;
     int rev;        // 1: walk the items from the last image down (the freshest QKV rows are still in L2)
+    int unit_split; // 1: an item is ONE query tile of an (image, head) -- items = batch * heads * tiles -- so that a handful
+                    // of images (batch-1 latency: 12 items of two tiles) spreads over twice as many CTAs; K and V are then
+                    // loaded once per tile instead of once per (image, head), which only matters when there are many items
+};
+
+// (image * heads + head, query tile) of the unit with item slot `raw` and tile `t` inside the item
+struct UnitId {
+    int item, tile;
 };
 
 __device__ __forceinline__ float max3(float a, float b, float c)
@@ -88,6 +96,14 @@ __device__ __forceinline__ float max3(float a, float b, float c)
 }
 
 __device__ __forceinline__ int item_of(const DuoParams &p, int raw) { return p.rev ? p.items - 1 - raw : raw; }
+__device__ __forceinline__ UnitId unit_of(const DuoParams &p, int raw, int t, int tiles)
+{
+    const int it = item_of(p, raw);
+    UnitId u;
+    u.item = p.unit_split ? it / tiles : it;
+    u.tile = p.unit_split ? it - u.item * tiles : t;
+    return u;
+}
 
 // TMEM column of the 8 packed-bf16 P columns of key chunk c
 __device__ __forceinline__ constexpr uint32_t p_col(int c) { return c < kHalf ? 8u * c : 128u + 8u * (c - kHalf); }
@@ -177,7 +193,8 @@ attention_duo_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     volatile uint32_t *cta_abort = tmem_slot + 1;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ntiles = (p.tokens + QT - 1) / QT; // 1 or 2
+    const int tiles = (p.tokens + QT - 1) / QT;  // query tiles of an (image, head): 1 or 2
+    const int ntiles = p.unit_split ? 1 : tiles; // ... and of an item
     const int n_items = blockIdx.x < (unsigned)p.items ? (p.items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const int n_units = n_items * ntiles;
 
@@ -215,22 +232,22 @@ attention_duo_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         // S(k-1) has retired (Q and K buffers dead); the V buffer of item il was last read by item il-2.
         auto load_unit = [&](int k) {
             const int il = k / ntiles, t = k - il * ntiles;
-            const int item = item_of(p, blockIdx.x + il * gridDim.x);
-            const int img = item / p.heads, head = item - img * p.heads;
+            const UnitId u = unit_of(p, blockIdx.x + il * gridDim.x, t, tiles);
+            const int img = u.item / p.heads, head = u.item - img * p.heads;
             if (elect_one()) {
                 if (t == 0) { // K first: S needs it together with Q
                     mbar_arrive_expect_tx(&bars[K_FULL], kv_bytes);
                     tma_load_3d(sk, &tmap_kv, &bars[K_FULL], p.embed + head * kHeadDim, 0, img);
                 }
                 mbar_arrive_expect_tx(&bars[Q_FULL], Q_BYTES);
-                tma_load_3d(sq, &tmap_q, &bars[Q_FULL], head * kHeadDim, t * QT, img);
+                tma_load_3d(sq, &tmap_q, &bars[Q_FULL], head * kHeadDim, u.tile * QT, img);
             }
             __syncwarp();
         };
         // V of item il into buffer il & 1, whose last reader was the final P V of item il - 2: requested a whole item
         // ahead (after the first read-out of item il - 1), because under load the 26 KB take several microseconds
         auto load_v = [&](int il) {
-            const int item = item_of(p, blockIdx.x + il * gridDim.x);
+            const int item = unit_of(p, blockIdx.x + il * gridDim.x, 0, tiles).item;
             const int img = item / p.heads, head = item - img * p.heads;
             if (elect_one()) {
                 mbar_arrive_expect_tx(&bars[V_FULL + (il & 1)], kv_bytes);
@@ -304,7 +321,9 @@ attention_duo_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         const float sl2 = 0.125f * 1.4426950408889634f; // log2(e) / sqrt(64)
         uint8_t *tile = ostage + warp * 4096;
         for (int k = 0; k < n_units; k++) {
-            const int il = k / ntiles, t = k - il * ntiles;
+            const int il = k / ntiles;
+            const UnitId u = unit_of(p, blockIdx.x + il * gridDim.x, k - il * ntiles, tiles);
+            const int t = u.tile;
             // a warp whose 32 query rows all lie past T (second tile of a 197-token item: rows 224..255)
             // only keeps the barrier protocol going; its rows of S are exact zeros (Q zero-filled)
             const bool active = t * QT + warp * 32 < p.tokens;
@@ -362,8 +381,7 @@ attention_duo_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
                 break;
             // ---- epilogue: O / sum -> bf16 -> swizzled tile -> TMA store ----
             if (active) {
-                const int item = item_of(p, blockIdx.x + il * gridDim.x);
-                const int img = item / p.heads, head = item - img * p.heads;
+                const int img = u.item / p.heads, head = u.item - img * p.heads;
                 if (lane == 0)
                     tma_wait_group_read<0>(); // the previous unit's store has read this tile
                 __syncwarp();
@@ -463,6 +481,13 @@ int attention_bf16_duo_tc(const void *qkv, void *out, int batch, int tokens, int
     static const bool serp = !(getenv("VITCU_SERPENTINE") && atoi(getenv("VITCU_SERPENTINE")) == 0);
     p.rev = serp;
     const int sms = device_sm_count();
+    // a handful of images: one query tile per item, so that every tile has a CTA of its own
+    // (VITCU_ATTN_UNIT_SPLIT=0: off; read per call, the tests run both forms)
+    const int tiles = (tokens + QT - 1) / QT;
+    const char *us = getenv("VITCU_ATTN_UNIT_SPLIT");
+    p.unit_split = tiles > 1 && p.items * tiles <= 2 * sms && !(us && !strcmp(us, "0"));
+    if (p.unit_split)
+        p.items *= tiles;
     const int grid = p.items < 2 * sms ? p.items : 2 * sms;
     int dev = 0;
     VITCU_TRY(cudaGetDevice(&dev));
