@@ -123,6 +123,12 @@ int vitcu_patch_embed_tc(const float *images, const float *conv_w, const float *
 int vitcu_patch_embed_tc_ex(const float *images, const float *conv_w, const float *conv_b, const float *pos,
                             float *x, int batch, int img, int embed, vitcu_stream s);
 
+/* Accumulate form for a handful of images (batch-1 latency): the token rows of x already hold the position embedding
+ * (vitcu_token_rows_init) and the kernel ADDS conv(patch) + conv_b, with K cut into as many slices as fill the SMs
+ * (one 224 x 224 image: 96 work items instead of 6).  Same TF32 arithmetic; the slices add in arrival order. */
+int vitcu_patch_embed_tc_acc(const float *images, const float *conv_w, const float *conv_b, const float *pos,
+                             float *x, int batch, int img, int embed, vitcu_stream s);
+
 /* Row 0 of every image: x[b*T + 0, :] = cls + pos[0, :]  (R/conv2d.cl:39-80 t==0
  * branch; R/ViT_seq.c:83-118). */
 int vitcu_cls_rows(float *x, const float *cls, const float *pos, int batch, int tokens,

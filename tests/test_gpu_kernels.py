@@ -157,6 +157,17 @@ def test_patch_embed_tma_gather_tf32(pkg, lib, oracle, img, batch):
         ref = oracle.patch_embed(images[i], cls, cw.reshape(768, 3, 16, 16), cb, pos)[1:]
         # TF32 keeps 10 mantissa bits of both operands: 768-term dot products of N(0,1) x N(0,0.03^2) values
         assert np.abs(x[i, 1:] - ref).max() <= 4e-3, np.abs(x[i, 1:] - ref).max()
+    # accumulate form (a handful of images): token rows pre-set to the position rows (class row: cls + pos[0]), K cut
+    # into slices that add -- the same TF32 products, summed in another order
+    dcls = _dev(pkg, cls)
+    dx2 = pkg.DeviceBuffer(batch * T * 768 * 4)
+    pkg.layer_check(lib.vitcu_memset(dx2.ptr, 0xFF, batch * T * 768 * 4, None))
+    pkg.layer_check(lib.vitcu_token_rows_init(dx2.ptr, dcls.ptr, dpos.ptr, batch, T, 768, None))
+    pkg.layer_check(lib.vitcu_patch_embed_tc_acc(di.ptr, dcw.ptr, dcb.ptr, dpos.ptr, dx2.ptr, batch, img, 768, None))
+    assert lib.vitcu_watchdog_check() == 0
+    x2 = dx2.to_numpy(np.float32, (batch, T, 768))
+    assert np.allclose(x2[:, 0], cls + pos[0])
+    assert np.abs(x2[:, 1:] - x[:, 1:]).max() <= 2e-5 * np.abs(x[:, 1:]).max()
 
 
 # ---------------------------------------------------------------- attention

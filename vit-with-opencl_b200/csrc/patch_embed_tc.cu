@@ -40,6 +40,7 @@ struct PEParams {
     const float *bias;         // [768]
     const float *pos;          // [tokens, 768]
     float *x;                  // [batch*tokens, 768]
+    int splits;                // K slices per tile (accumulate form: x already holds the position rows, slices add)
 };
 
 __device__ __forceinline__ void tma_load_5d(void *smem_dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1, int c2,
@@ -122,7 +123,11 @@ patch_embed_tc_kernel(const __grid_constant__ CUtensorMap tmap_img, const __grid
 
     const int NUM_N = p.num_n; // 3 for the 768-wide model
     constexpr int NUM_KB = 3 * kPatch; // (channel, kernel row) slices
-    const int num_tiles = p.batch * p.tiles_per_img * NUM_N;
+    // work item = (tile, K slice).  splits > 1 is the accumulate form (vitcu_patch_embed_tc_acc, a handful of images):
+    // the token rows already hold the position embedding and every slice adds its partial product with red.global
+    // (slice 0 carries the conv bias), so that one image is 96 work items instead of 6
+    const int kb_per = NUM_KB / p.splits; // splits divides 48
+    const int num_tiles = p.batch * p.tiles_per_img * NUM_N * p.splits;
 
     if (warp == 0) {
         // ===================== TMA producer: the gather happens here =====================
@@ -133,9 +138,10 @@ patch_embed_tc_kernel(const __grid_constant__ CUtensorMap tmap_img, const __grid
         uint32_t stage = 0, phase = 0;
         bool ok = true;
         for (int tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x) {
-            const int n_blk = tile % NUM_N, mt = tile / NUM_N;
+            const int split = tile % p.splits, t2 = tile / p.splits;
+            const int n_blk = t2 % NUM_N, mt = t2 / NUM_N;
             const int img = mt / p.tiles_per_img, ph0 = (mt - img * p.tiles_per_img) * p.ph_box;
-            for (int kb = 0; kb < NUM_KB; kb++) {
+            for (int kb = split * kb_per; kb < (split + 1) * kb_per; kb++) {
                 if (!(ok = mbar_wait_warp(&empty_bar[stage], phase ^ 1, wd, 1)))
                     break;
                 if (elect_one()) {
@@ -163,7 +169,7 @@ patch_embed_tc_kernel(const __grid_constant__ CUtensorMap tmap_img, const __grid
                 break;
             tcgen05_fence_after();
             const uint32_t d_tmem = tmem_base + acc * BN;
-            for (int kb = 0; kb < NUM_KB; kb++) {
+            for (int kb = 0; kb < kb_per; kb++) {
                 if (!(ok = mbar_wait_warp(&full_bar[stage], phase, wd, 3)))
                     break;
                 tcgen05_fence_after();
@@ -174,7 +180,7 @@ patch_embed_tc_kernel(const __grid_constant__ CUtensorMap tmap_img, const __grid
                     umma_tf32_ss(d_tmem, a_desc, b_desc, IDESC, kb != 0);
                     umma_tf32_ss(d_tmem, a_desc + 2, b_desc + 2, IDESC, 1);
                     umma_commit(&empty_bar[stage]);
-                    if (kb == NUM_KB - 1)
+                    if (kb == kb_per - 1)
                         umma_commit(&tfull_bar[acc]);
                 }
                 __syncwarp();
@@ -189,7 +195,8 @@ patch_embed_tc_kernel(const __grid_constant__ CUtensorMap tmap_img, const __grid
         const int quad = warp & 3;
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
-            const int n_blk = tile % NUM_N, mt = tile / NUM_N;
+            const int split = tile % p.splits, t2 = tile / p.splits;
+            const int n_blk = t2 % NUM_N, mt = t2 / NUM_N;
             const int img = mt / p.tiles_per_img, ph0 = (mt - img * p.tiles_per_img) * p.ph_box;
             const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
             if (!mbar_wait_warp(&tfull_bar[acc], acc_phase, wd, 4))
@@ -207,7 +214,16 @@ patch_embed_tc_kernel(const __grid_constant__ CUtensorMap tmap_img, const __grid
                 uint32_t v[32];
                 tmem_ld_32x32b_x32(taddr + c * 32, v);
                 tmem_ld_wait();
-                if (valid) {
+                if (valid && p.splits > 1) { // accumulate form: x += partial (+ bias once); the position rows are in x already
+                    const float bias_on = split == 0 ? 1.0f : 0.0f;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + n_blk * BN + c * 32) + j);
+                        atomicAdd(reinterpret_cast<float4 *>(dst + c * 32) + j,
+                                  make_float4(fmaf(b.x, bias_on, __uint_as_float(v[4 * j + 0])), fmaf(b.y, bias_on, __uint_as_float(v[4 * j + 1])),
+                                              fmaf(b.z, bias_on, __uint_as_float(v[4 * j + 2])), fmaf(b.w, bias_on, __uint_as_float(v[4 * j + 3]))));
+                    }
+                } else if (valid) {
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
                         const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + n_blk * BN + c * 32) + j);
@@ -244,8 +260,9 @@ int device_sm_count(); // gemm_tc.cu
 }
 
 // images [B,3,S,S] fp32, conv_w [768, 3*16*16] fp32 -> x[b*T + 1 + p, :] = conv + bias + pos[1 + p, :]
-extern "C" int vitcu_patch_embed_tc_ex(const float *images, const float *conv_w, const float *conv_b, const float *pos,
-                                       float *x, int batch, int img, int embed, vitcu_stream s)
+// accumulate != 0: x[b*T + 1 + p, :] += conv + bias, K cut into slices (the rows hold pos[1 + p, :] already)
+static int patch_embed_tc_launch(const float *images, const float *conv_w, const float *conv_b, const float *pos,
+                                 float *x, int batch, int img, int embed, int accumulate, vitcu_stream s)
 {
     VITCU_REQUIRE(images && conv_w && conv_b && pos && x, "NULL argument");
     VITCU_REQUIRE(embed > 0 && embed % BN == 0, "embedding width must be a multiple of the 256-column tile");
@@ -299,12 +316,33 @@ extern "C" int vitcu_patch_embed_tc_ex(const float *images, const float *conv_w,
         VITCU_TRY(cudaFuncSetAttribute(patch_embed_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TOTAL));
         configured[dev] = true;
     }
-    const int num_tiles = batch * p.tiles_per_img * (embed / BN);
     const int sms = device_sm_count();
+    // accumulate form: as many K slices (a divisor of the 48 k-blocks, at least 3 k-blocks each) as fill the SMs
+    p.splits = 1;
+    if (accumulate) {
+        const int tiles = batch * p.tiles_per_img * (embed / BN);
+        static const int cand[5] = {16, 12, 8, 4, 2};
+        for (int i = 0; i < 5 && p.splits == 1; i++)
+            if (tiles * cand[i] <= sms)
+                p.splits = cand[i];
+    }
+    const int num_tiles = batch * p.tiles_per_img * (embed / BN) * p.splits;
     VITCU_TRY(launch_kernel(patch_embed_tc_kernel, num_tiles < sms ? num_tiles : sms, kThreadsPE, SMEM_TOTAL, as_stream(s),
                             timg, tw, p, watchdog_flag()));
     VITCU_LAUNCHED_KIND(LK_PATCH_EMBED_TC);
     return 0;
+}
+
+extern "C" int vitcu_patch_embed_tc_ex(const float *images, const float *conv_w, const float *conv_b, const float *pos,
+                                       float *x, int batch, int img, int embed, vitcu_stream s)
+{
+    return patch_embed_tc_launch(images, conv_w, conv_b, pos, x, batch, img, embed, 0, s);
+}
+
+extern "C" int vitcu_patch_embed_tc_acc(const float *images, const float *conv_w, const float *conv_b, const float *pos,
+                                        float *x, int batch, int img, int embed, vitcu_stream s)
+{
+    return patch_embed_tc_launch(images, conv_w, conv_b, pos, x, batch, img, embed, 1, s);
 }
 
 extern "C" int vitcu_patch_embed_tc(const float *images, const float *conv_w, const float *conv_b, const float *pos,

@@ -230,6 +230,7 @@ int vitb200_create_model(vitb200_engine **out, int device, const vitb200_model *
      * VITB200_FP32_SIMT=1 selects the CUDA-core FFMA GEMM instead */
     e->fp32_tc = precision == VITB200_FP32 && getenv("VITB200_FP32_SIMT") == NULL;
     e->fp32_splitk = !(getenv("VITB200_FP32_SPLITK") && atoi(getenv("VITB200_FP32_SPLITK")) == 0);
+    e->pe_splitk = !(getenv("VITB200_PE_SPLITK") && atoi(getenv("VITB200_PE_SPLITK")) == 0);
     /* VITB200_PE_GATHER=1: separate gather kernel + BF16 GEMM instead of the TMA-gather TF32 GEMM */
     e->pe_gather = getenv("VITB200_PE_GATHER") != NULL || e->patch != 16 || e->D % 256 != 0;
     const int bf = precision != VITB200_FP32; /* FP8 = the BF16 path with fc1 / fc2 on e4m3 operands */
@@ -725,8 +726,17 @@ static int enqueue_forward_mode(vitb200_engine *e, int buf, int b, int calibrate
      * tensor-core GEMM that gathers the patches by TMA straight from the NCHW image; FP32 path:
      * gather kernel + FP32-accurate GEMM with the class/position epilogue */
     MARK(VIT_K_OTHER);
+    /* BF16 chain, a handful of images: the TF32 patch embedding with K cut into slices that add into token rows which
+     * already hold the position embedding (one image: 6 tiles of 48 k-blocks -> 96 work items of 3; VITB200_PE_SPLITK=0: off) */
+    const int pe_acc = bf && !e->pe_gather && e->pe_splitk && b * ((e->side * e->side + 127) / 128) * (e->D / 256) * 4 <= 148;
     if (bf && !e->pe_gather) {
-        VIT_TRY(vitcu_patch_embed_tc_ex(e->d_images[buf], e->w32[1], e->w32[2], e->w32[3], e->d_x, b, e->img, e->D, s));
+        if (pe_acc) {
+            VIT_TRY(vitcu_token_rows_init(e->d_x, e->w32[0], e->w32[3], b, e->T, e->D, s));
+            e->launches++;
+            VIT_TRY(vitcu_patch_embed_tc_acc(e->d_images[buf], e->w32[1], e->w32[2], e->w32[3], e->d_x, b, e->img, e->D, s));
+        } else {
+            VIT_TRY(vitcu_patch_embed_tc_ex(e->d_images[buf], e->w32[1], e->w32[2], e->w32[3], e->d_x, b, e->img, e->D, s));
+        }
         e->launches++;
     } else {
         VIT_TRY(vitcu_patch_gather_ex(e->d_images[buf], e->d_patches, b, e->img, e->patch, bf, s));
@@ -741,7 +751,7 @@ static int enqueue_forward_mode(vitb200_engine *e, int buf, int b, int calibrate
             VIT_TRY(gemm(e, e->d_patches, 0, 1, 2, e->d_x, b * e->P, e->D, 3 * e->patch * e->patch, VITCU_EPI_PATCH_EMBED, 0, 0));
         }
     }
-    if (!(acc && b == 1)) { /* (acc implies the FP32 chain, which always takes the gather branch above) */
+    if (!(acc && b == 1) && !pe_acc) { /* (acc implies the FP32 chain, which always takes the gather branch above) */
         MARK(VIT_K_OTHER);
         VIT_TRY(vitcu_cls_rows_ex(e->d_x, e->w32[0], e->w32[3], b, e->T, e->D, s));
         e->launches++;

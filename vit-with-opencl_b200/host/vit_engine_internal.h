@@ -17,6 +17,7 @@ struct vitb200_engine {
     int pe_gather;                   /* BF16 path: use the gather kernel + BF16 GEMM for the patch embedding */
     int fp32_tc;                     /* FP32 precision computed as split-bf16 (x3 pieces, 6 products) on the tensor cores */
     int fp32_splitk;                 /* ... with qkv / fc1 in accumulate mode (split-K) when the chunk is a few dozen tiles */
+    int pe_splitk;                   /* BF16 chain: K-sliced (accumulate) TF32 patch embedding for a handful of images */
     int launches, kernels_per_forward;
     vitcu_stream stream, copy_stream;
     vitcu_event ev_h2d[2], ev_done[2], ev_out[2], ev_t0, ev_t1;
