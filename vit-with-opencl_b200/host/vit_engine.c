@@ -365,7 +365,7 @@ static int ensure_stage(vitb200_engine *e)
 /* One weight blob to the device.  The reference hands over 152 malloc'd (pageable) blobs (R/Network.c:134-215):
  * a cudaMemcpy from pageable memory is staged by the driver on the calling thread at a few GB/s and does not
  * return before it is done, which made the 346 MB upload the longest part of a cold ViT_opencl call.  Here the
- * copy threads move the blob piece by piece into the pinned ring (streaming stores, host/vit_stage.c) and every
+ * copy threads move the blob piece by piece into the pinned ring (host/vit_stage.c) and every
  * piece leaves by asynchronous DMA, so the host copy of piece i+1 overlaps the transfer of piece i.  Pinned
  * sources are DMA'd in place.  VITB200_WEIGHT_STAGE=0: plain copies (A/B). */
 static int upload_blob(vitb200_engine *e, void *dst, const void *src, size_t bytes, int staged)
