@@ -28,6 +28,9 @@
 #ifndef VITCU_EXIT_WAIT_WRITES
 #define VITCU_EXIT_WAIT_WRITES 0 // 1: the single-CTA GEMM waits for its TMA stores to land in global memory before it retires (A/B)
 #endif
+#ifndef VITCU_BIAS_AHEAD
+#define VITCU_BIAS_AHEAD 1 // narrow tiles: bias of a chunk requested a chunk ahead (0: at its use, A/B)
+#endif
 #ifndef VITCU_GELU_SCALAR
 #define VITCU_GELU_SCALAR 0
 #endif
@@ -198,6 +201,19 @@ __device__ __forceinline__ bool epilogue_tile(const EpiParams &p, void *C, const
         }
     };
     fetch_add(0); // does not depend on the accumulator: in flight during the wait below
+    // Narrow tiles (the single-CTA kernel at BN = 128: small M, batch-1 latency, one tile per CTA) whose bias is not
+    // staged in shared memory: the bias of a chunk is requested a chunk ahead -- the first one before the wait for the
+    // accumulator -- instead of sitting as an L2 round trip between the accumulator and the store
+    constexpr bool kBiasAhead = VITCU_BIAS_AHEAD && !LN && NCHUNK <= 2;
+    float4 bnext[kBiasAhead ? 8 : 1];
+    auto fetch_bias = [&](int chunk) {
+        if (kBiasAhead) {
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                bnext[kBiasAhead ? j : 0] = __ldg(reinterpret_cast<const float4 *>(p.bias + col_base + chunk * 32) + j);
+        }
+    };
+    fetch_bias(0);
     const float rstd = ln.rstd * p.acc_scale, nrm = ln.nrm; // FP8 operands: the de-quantisation rides on the row factor
     float2 part[kMaxLnSlots];
     // Folded LayerNorm: the per-column coefficients of this warp's columns (bias' and colsum, NCHUNK * 32 floats each)
@@ -257,13 +273,16 @@ __device__ __forceinline__ bool epilogue_tile(const EpiParams &p, void *C, const
         } else {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-                const float4 b = coef_on ? lds128(coef + c * 32 + j)
-                                         : __ldg(reinterpret_cast<const float4 *>(p.bias + col0 + j));
+                const float4 b = kBiasAhead ? bnext[kBiasAhead ? j / 4 : 0]
+                                            : (coef_on ? lds128(coef + c * 32 + j)
+                                                       : __ldg(reinterpret_cast<const float4 *>(p.bias + col0 + j)));
                 v[j + 0] = fmaf(b.x, bias_on, __uint_as_float(acc[c % NACC][j + 0]));
                 v[j + 1] = fmaf(b.y, bias_on, __uint_as_float(acc[c % NACC][j + 1]));
                 v[j + 2] = fmaf(b.z, bias_on, __uint_as_float(acc[c % NACC][j + 2]));
                 v[j + 3] = fmaf(b.w, bias_on, __uint_as_float(acc[c % NACC][j + 3]));
             }
+            if (kBiasAhead && c + 1 < NCHUNK)
+                fetch_bias(c + 1); // in flight during this chunk's GELU / staging / store
         }
         if (p.epilogue == VITCU_EPI_BIAS_GELU) {
             if (p.exact_gelu) {
