@@ -123,7 +123,14 @@ __global__ void __launch_bounds__(256) token_rows_init_kernel(float *__restrict_
 // R/ViT_seq.c:126-135), eps 1e-6, output fp32 or bf16.
 // Algorithmic bytes per row: 768*4 read + 768*(4|2) written.
 // ---------------------------------------------------------------------------
-template <int kOut, int NV> // kOut 0: fp32, 1: bf16, 2: three bf16 pieces [rows, 3*cols]
+// kEarly (a few hundred rows: batch-1 latency): gamma / beta are requested together with the row, ahead of the
+// reductions, instead of as a second memory round trip behind them -- at batch 1 the weights of a forward do not stay
+// in the L2, so that second trip went to DRAM: BF16 batch-1 forward 0.492 -> 0.460 ms, FP32 0.917 -> 0.819 ms (same box).
+// Costs 12 more float4 registers per lane, which the bandwidth-bound many-row launches keep for occupancy.
+// Measured on top of it and NOT kept (+-0.4 % or worse): L2 prefetches of gamma / beta, the head's weight rows, the
+// position rows and the conv filter boxes ahead of griddepcontrol.wait; the head gemv and the softmax with all their
+// loads up front, the zero-fill issued behind the row loads and tensor-map prefetches ahead of the wait (BF16 +1.4 %).
+template <int kOut, int NV, bool kEarly = false> // kOut 0: fp32, 1: bf16, 2: three bf16 pieces [rows, 3*cols]
 __global__ void __launch_bounds__(256) layernorm_kernel(const float *__restrict__ x, size_t x_row_stride,
                                                         void *__restrict__ y, const float *__restrict__ gamma,
                                                         const float *__restrict__ beta, int rows, int rev,
@@ -142,13 +149,23 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float *__restrict_
         row = rows - 1 - row;
     const float4 *xr = reinterpret_cast<const float4 *>(x + (size_t)row * x_row_stride);
     constexpr int kCols = NV * 128;
-    float4 v[NV];
+    const float4 *g4 = reinterpret_cast<const float4 *>(gamma);
+    const float4 *b4 = reinterpret_cast<const float4 *>(beta);
+    float4 v[NV], ge[kEarly ? NV : 1], be[kEarly ? NV : 1];
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < NV; i++) {
+    for (int i = 0; i < NV; i++)
         v[i] = xr[lane + 32 * i];
-        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    if (kEarly) {
+#pragma unroll
+        for (int i = 0; i < NV; i++) {
+            ge[kEarly ? i : 0] = g4[lane + 32 * i];
+            be[kEarly ? i : 0] = b4[lane + 32 * i];
+        }
     }
+#pragma unroll
+    for (int i = 0; i < NV; i++)
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     const float mean = warp_sum(s) * (1.0f / kCols);
     float q = 0.f;
 #pragma unroll
@@ -158,11 +175,9 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float *__restrict_
     }
     const float var = warp_sum(q) * (1.0f / kCols);
     const float inv_std = 1.0f / sqrtf(var + 1e-6f);
-    const float4 *g4 = reinterpret_cast<const float4 *>(gamma);
-    const float4 *b4 = reinterpret_cast<const float4 *>(beta);
 #pragma unroll
     for (int i = 0; i < NV; i++) {
-        const float4 g = g4[lane + 32 * i], bb = b4[lane + 32 * i];
+        const float4 g = kEarly ? ge[kEarly ? i : 0] : g4[lane + 32 * i], bb = kEarly ? be[kEarly ? i : 0] : b4[lane + 32 * i];
         float4 o;
         o.x = (v[i].x - mean) * inv_std * g.x + bb.x;
         o.y = (v[i].y - mean) * inv_std * g.y + bb.y;
@@ -515,12 +530,13 @@ static int launch_layernorm(const float *x, size_t x_row_stride, void *y, int y_
         grid = zgrid < 148 ? zgrid : (grid > 148 ? grid : 148);
     uint4 *zp = reinterpret_cast<uint4 *>(zero_ptr);
     static const int rev = !(getenv("VITCU_SERPENTINE") && atoi(getenv("VITCU_SERPENTINE")) == 0);
+    const bool early = rows <= 148 * 8; // one wave of CTAs: a latency-bound launch
     if (y_bf16 == 1)
-        VITCU_TRY(launch_kernel(layernorm_kernel<1, NV>, grid, 256, 0, as_stream(s), x, x_row_stride, y, gamma, beta, rows, rev, zp, zero_n16));
+        VITCU_TRY(launch_kernel(early ? layernorm_kernel<1, NV, true> : layernorm_kernel<1, NV, false>, grid, 256, 0, as_stream(s), x, x_row_stride, y, gamma, beta, rows, rev, zp, zero_n16));
     else if (y_bf16 == 2)
-        VITCU_TRY(launch_kernel(layernorm_kernel<2, NV>, grid, 256, 0, as_stream(s), x, x_row_stride, y, gamma, beta, rows, rev, zp, zero_n16));
+        VITCU_TRY(launch_kernel(early ? layernorm_kernel<2, NV, true> : layernorm_kernel<2, NV, false>, grid, 256, 0, as_stream(s), x, x_row_stride, y, gamma, beta, rows, rev, zp, zero_n16));
     else
-        VITCU_TRY(launch_kernel(layernorm_kernel<0, NV>, grid, 256, 0, as_stream(s), x, x_row_stride, y, gamma, beta, rows, rev, zp, zero_n16));
+        VITCU_TRY(launch_kernel(early ? layernorm_kernel<0, NV, true> : layernorm_kernel<0, NV, false>, grid, 256, 0, as_stream(s), x, x_row_stride, y, gamma, beta, rows, rev, zp, zero_n16));
     VITCU_LAUNCHED_KIND(LK_LAYERNORM);
     return 0;
 }
