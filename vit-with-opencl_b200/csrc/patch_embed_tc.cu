@@ -199,9 +199,6 @@ patch_embed_tc_kernel(const __grid_constant__ CUtensorMap tmap_img, const __grid
             const int n_blk = t2 % NUM_N, mt = t2 / NUM_N;
             const int img = mt / p.tiles_per_img, ph0 = (mt - img * p.tiles_per_img) * p.ph_box;
             const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-            if (!mbar_wait_warp(&tfull_bar[acc], acc_phase, wd, 4))
-                break;
-            tcgen05_fence_after();
             const int rows_here = min(p.ph_box, p.side - ph0) * p.side; // patches of this tile that exist
             const int r = quad * 32 + lane;
             const int patch = ph0 * p.side + r;
@@ -209,29 +206,44 @@ patch_embed_tc_kernel(const __grid_constant__ CUtensorMap tmap_img, const __grid
             float *dst = p.x + (static_cast<size_t>(img) * p.tokens + 1 + patch) * p.embed + n_blk * BN;
             const float *pos = p.pos + static_cast<size_t>(1 + patch) * p.embed + n_blk * BN;
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
+            // conv bias and position rows of a chunk are requested a chunk ahead, the first before the wait for the
+            // accumulator: read at their use they were an L2 / DRAM round trip per 32 columns on the epilogue's chain
+            const bool acc_form = p.splits > 1;
+            const float bias_on = (!acc_form || split == 0) ? 1.0f : 0.0f;
+            float4 bn[8], en[8];
+            auto fetch_coef = [&](int c) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    bn[j] = __ldg(reinterpret_cast<const float4 *>(p.bias + n_blk * BN + c * 32) + j);
+                    en[j] = (valid && !acc_form) ? __ldg(reinterpret_cast<const float4 *>(pos + c * 32) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            };
+            fetch_coef(0);
+            if (!mbar_wait_warp(&tfull_bar[acc], acc_phase, wd, 4))
+                break;
+            tcgen05_fence_after();
 #pragma unroll 1
             for (int c = 0; c < BN / 32; c++) {
                 uint32_t v[32];
                 tmem_ld_32x32b_x32(taddr + c * 32, v);
                 tmem_ld_wait();
-                if (valid && p.splits > 1) { // accumulate form: x += partial (+ bias once); the position rows are in x already
-                    const float bias_on = split == 0 ? 1.0f : 0.0f;
+                float4 o[8];
 #pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + n_blk * BN + c * 32) + j);
-                        atomicAdd(reinterpret_cast<float4 *>(dst + c * 32) + j,
-                                  make_float4(fmaf(b.x, bias_on, __uint_as_float(v[4 * j + 0])), fmaf(b.y, bias_on, __uint_as_float(v[4 * j + 1])),
-                                              fmaf(b.z, bias_on, __uint_as_float(v[4 * j + 2])), fmaf(b.w, bias_on, __uint_as_float(v[4 * j + 3]))));
-                    }
+                for (int j = 0; j < 8; j++)
+                    o[j] = make_float4(fmaf(bn[j].x, bias_on, __uint_as_float(v[4 * j + 0])) + en[j].x,
+                                       fmaf(bn[j].y, bias_on, __uint_as_float(v[4 * j + 1])) + en[j].y,
+                                       fmaf(bn[j].z, bias_on, __uint_as_float(v[4 * j + 2])) + en[j].z,
+                                       fmaf(bn[j].w, bias_on, __uint_as_float(v[4 * j + 3])) + en[j].w);
+                if (c + 1 < BN / 32)
+                    fetch_coef(c + 1);
+                if (valid && acc_form) { // accumulate form: x += partial (+ bias once); the position rows are in x already
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                        atomicAdd(reinterpret_cast<float4 *>(dst + c * 32) + j, o[j]);
                 } else if (valid) {
 #pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + n_blk * BN + c * 32) + j);
-                        const float4 e = __ldg(reinterpret_cast<const float4 *>(pos + c * 32) + j);
-                        reinterpret_cast<float4 *>(dst + c * 32)[j] =
-                            make_float4(__uint_as_float(v[4 * j + 0]) + b.x + e.x, __uint_as_float(v[4 * j + 1]) + b.y + e.y,
-                                        __uint_as_float(v[4 * j + 2]) + b.z + e.z, __uint_as_float(v[4 * j + 3]) + b.w + e.w);
-                    }
+                    for (int j = 0; j < 8; j++)
+                        reinterpret_cast<float4 *>(dst + c * 32)[j] = o[j];
                 }
             }
             tcgen05_fence_before();
