@@ -481,7 +481,7 @@ def dropin_record(pkg, dist, blobs, n_images=4096):
         dt = time.perf_counter() - t0
         L.vitb200_last_call_stats(C.byref(stats))
         return dt, {"wall_s": round(dt, 4), "bring_up_s": round(stats.create_s, 4), "weights_s": round(stats.weights_s, 4),
-                    "forward_s": round(stats.forward_s, 4), "gpus_used": stats.gpus}
+                    "forward_s": round(stats.forward_s, 4), "teardown_s": round(stats.teardown_s, 4), "gpus_used": stats.gpus}
 
     devnull, saved = os.open(os.devnull, os.O_WRONLY), os.dup(1)
     sys.stdout.flush()

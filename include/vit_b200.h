@@ -87,6 +87,7 @@ int vitb200_next_chunk(int n, int done, int chunk, int head_split, int tail_spli
 typedef struct {
     int images, gpus;
     double wall_s, create_s, weights_s, forward_s;
+    double teardown_s; /* releasing the engine (default semantics: every device and pinned allocation of the call is freed) */
 } vitb200_call_stats;
 void vitb200_last_call_stats(vitb200_call_stats *out);
 

@@ -224,7 +224,7 @@ def vit_opencl(images: np.ndarray, blobs) -> np.ndarray:
 class CallStats(C.Structure):
     """vitb200_call_stats (include/vit_b200.h): where the last ViT_opencl call spent its time"""
     _fields_ = [("images", C.c_int), ("gpus", C.c_int), ("wall_s", C.c_double), ("create_s", C.c_double),
-                ("weights_s", C.c_double), ("forward_s", C.c_double)]
+                ("weights_s", C.c_double), ("forward_s", C.c_double), ("teardown_s", C.c_double)]
 
 
 class Model(C.Structure):

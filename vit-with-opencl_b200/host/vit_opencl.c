@@ -35,7 +35,7 @@ typedef struct {
     int persist;
     unsigned long long wsig;
     int rc;
-    double t_create, t_weights, t_forward; /* seconds spent in each phase by this shard's thread */
+    double t_create, t_weights, t_forward, t_teardown; /* seconds spent in each phase by this shard's thread */
     char msg[640];
 } shard_job;
 
@@ -224,6 +224,7 @@ static void *shard_main(void *arg)
     j->t_forward = now_s() - t2;
     if (j->rc)
         snprintf(j->msg, sizeof(j->msg), "%s", vitb200_last_error());
+    const double t3 = now_s();
     if (c) {
         pthread_mutex_lock(&g_cache_mu);
         c->busy = 0;
@@ -231,6 +232,7 @@ static void *shard_main(void *arg)
     } else {
         vitb200_destroy(e);
     }
+    j->t_teardown = now_s() - t3;
     return NULL;
 }
 
@@ -358,24 +360,27 @@ void ViT_opencl(vitb200_image *image, vitb200_blob *networks, float **prb)
     clock_gettime(CLOCK_MONOTONIC, &t1);
     /* the reference prints its own timings (R/ViT_opencl.c:910,964); keep one line, with the slowest
      * shard's share of each phase (the shards run concurrently, one host thread per GPU) */
-    double mc = 0, mw = 0, mf = 0;
+    double mc = 0, mw = 0, mf = 0, mt = 0;
     for (int g = 0; g < used; g++) {
         mc = jobs[g].t_create > mc ? jobs[g].t_create : mc;
         mw = jobs[g].t_weights > mw ? jobs[g].t_weights : mw;
         mf = jobs[g].t_forward > mf ? jobs[g].t_forward : mf;
+        mt = jobs[g].t_teardown > mt ? jobs[g].t_teardown : mt;
     }
     if (persist)
         printf("ViT_b200: weight signature (every byte of %d blobs hashed) %.4f s\n", 8 + 12 * model.depth, sig_s);
-    printf("ViT_b200: %d images, %d GPU(s), %s%s, %.3f s wall (device bring-up %.3f + weight upload %.3f + forward %.3f, "
-           "slowest shard each)\n", n, used, precision == VITB200_BF16 ? "bf16" : (precision == VITB200_FP8 ? "fp8" : "fp32"),
+    printf("ViT_b200: %d images, %d GPU(s), %s%s, %.3f s wall (device bring-up %.3f + weight upload %.3f + forward %.3f + "
+           "tear-down %.3f, slowest shard each)\n", n, used,
+           precision == VITB200_BF16 ? "bf16" : (precision == VITB200_FP8 ? "fp8" : "fp32"),
            persist ? ", persistent context" : "",
-           (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec), mc, mw, mf);
+           (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec), mc, mw, mf, mt);
     g_last_call.images = n;
     g_last_call.gpus = used;
     g_last_call.wall_s = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
     g_last_call.create_s = mc;
     g_last_call.weights_s = mw;
     g_last_call.forward_s = mf;
+    g_last_call.teardown_s = mt;
     free(jobs);
     free(threads);
 }
