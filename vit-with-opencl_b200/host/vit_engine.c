@@ -16,6 +16,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 static _Thread_local char g_msg[640] = "no error";
 
@@ -258,25 +259,57 @@ int vitb200_create_model(vitb200_engine **out, int device, const vitb200_model *
         ENG_TRY(vitcu_event_create(&e->ev_h2d[i]));
         ENG_TRY(vitcu_event_create(&e->ev_done[i]));
         ENG_TRY(vitcu_event_create(&e->ev_out[i]));
-        ENG_TRY(vitcu_malloc((void **)&e->d_images[i], (size_t)e->B * img_elems * sizeof(float)));
-        ENG_TRY(vitcu_malloc((void **)&e->d_probs[i], (size_t)e->B * VITB200_CLASSES * sizeof(float)));
-        ENG_TRY(vitcu_malloc((void **)&e->d_logits[i], (size_t)e->B * VITB200_CLASSES * sizeof(float)));
     }
     ENG_TRY(vitcu_event_create(&e->ev_t0));
     ENG_TRY(vitcu_event_create(&e->ev_t1));
-    ENG_TRY(vitcu_malloc(&e->d_patches, (size_t)e->B * e->P * 3 * e->patch * e->patch * act));
-    ENG_TRY(vitcu_malloc((void **)&e->d_x, rows * e->D * sizeof(float)));
-    ENG_TRY(vitcu_malloc(&e->d_ln, rows * e->D * (e->fp32_tc ? 6 : act)));
-    if (e->fp32_tc)
-        ENG_TRY(vitcu_malloc((void **)&e->d_a3, rows * (size_t)(e->HID > 3 * e->patch * e->patch ? e->HID : 3 * e->patch * e->patch) * 3 * sizeof(vitcu_bf16)));
-    ENG_TRY(vitcu_malloc(&e->d_qkv, rows * 3 * e->D * act));
-    ENG_TRY(vitcu_malloc(&e->d_att, rows * e->D * (e->fp32_tc ? 6 : act)));
-    ENG_TRY(vitcu_malloc(&e->d_hid, rows * e->HID * act));
-    ENG_TRY(vitcu_malloc((void **)&e->d_cls, (size_t)e->B * e->D * sizeof(float)));
-    if (e->ln_fold)
-        ENG_TRY(vitcu_malloc(&e->d_lnstats, rows * (size_t)(e->D / 128) * 2 * sizeof(float)));
-    if (e->fp8)
-        ENG_TRY(vitcu_malloc((void **)&e->d_amax, (size_t)2 * VIT_MAX_DEPTH * sizeof(float)));
+    /* ONE device allocation for every activation buffer (sixteen cudaMalloc / cudaFree pairs otherwise: the default
+     * ViT_opencl call creates and releases an engine per call, and the driver-side cost of those calls is what makes a
+     * cold call's time jump, profiles/r02_batch1_latency.md); 256-byte aligned pieces (TMA tensor maps need 16) */
+    {
+        size_t sz[16], off[16], total = 0;
+        int k = 0;
+        const size_t a3_elems = (size_t)(e->HID > 3 * e->patch * e->patch ? e->HID : 3 * e->patch * e->patch);
+        sz[k++] = (size_t)e->B * img_elems * sizeof(float);                               /* 0, 1: d_images */
+        sz[k++] = (size_t)e->B * img_elems * sizeof(float);
+        sz[k++] = (size_t)e->B * VITB200_CLASSES * sizeof(float);                         /* 2, 3: d_probs */
+        sz[k++] = (size_t)e->B * VITB200_CLASSES * sizeof(float);
+        sz[k++] = (size_t)e->B * VITB200_CLASSES * sizeof(float);                         /* 4, 5: d_logits */
+        sz[k++] = (size_t)e->B * VITB200_CLASSES * sizeof(float);
+        sz[k++] = (size_t)e->B * e->P * 3 * e->patch * e->patch * act;                    /* 6: d_patches */
+        sz[k++] = rows * e->D * sizeof(float);                                            /* 7: d_x */
+        sz[k++] = rows * e->D * (e->fp32_tc ? 6 : act);                                   /* 8: d_ln */
+        sz[k++] = e->fp32_tc ? rows * a3_elems * 3 * sizeof(vitcu_bf16) : 0;              /* 9: d_a3 */
+        sz[k++] = rows * 3 * e->D * act;                                                  /* 10: d_qkv */
+        sz[k++] = rows * e->D * (e->fp32_tc ? 6 : act);                                   /* 11: d_att */
+        sz[k++] = rows * e->HID * act;                                                    /* 12: d_hid */
+        sz[k++] = (size_t)e->B * e->D * sizeof(float);                                    /* 13: d_cls */
+        sz[k++] = e->ln_fold ? rows * (size_t)(e->D / 128) * 2 * sizeof(float) : 0;       /* 14: d_lnstats */
+        sz[k++] = e->fp8 ? (size_t)2 * VIT_MAX_DEPTH * sizeof(float) : 0;                 /* 15: d_amax */
+        for (int i = 0; i < k; i++) {
+            off[i] = total;
+            total += (sz[i] + 255) & ~(size_t)255;
+        }
+        ENG_TRY(vitcu_malloc(&e->d_arena, total));
+        char *base = (char *)e->d_arena;
+#define PIECE(i) (sz[i] ? (void *)(base + off[i]) : NULL)
+        e->d_images[0] = (float *)PIECE(0);
+        e->d_images[1] = (float *)PIECE(1);
+        e->d_probs[0] = (float *)PIECE(2);
+        e->d_probs[1] = (float *)PIECE(3);
+        e->d_logits[0] = (float *)PIECE(4);
+        e->d_logits[1] = (float *)PIECE(5);
+        e->d_patches = PIECE(6);
+        e->d_x = (float *)PIECE(7);
+        e->d_ln = PIECE(8);
+        e->d_a3 = PIECE(9);
+        e->d_qkv = PIECE(10);
+        e->d_att = PIECE(11);
+        e->d_hid = PIECE(12);
+        e->d_cls = (float *)PIECE(13);
+        e->d_lnstats = PIECE(14);
+        e->d_amax = (float *)PIECE(15);
+#undef PIECE
+    }
     ENG_TRY(vitcu_host_alloc((void **)&e->h_probs, (size_t)e->B * VITB200_CLASSES * sizeof(float) * 2));
     ENG_TRY(vitcu_host_alloc((void **)&e->h_logits, (size_t)e->B * VITB200_CLASSES * sizeof(float) * 2));
 #undef ENG_TRY
@@ -284,17 +317,39 @@ int vitb200_create_model(vitb200_engine **out, int device, const vitb200_model *
     return 0;
 }
 
+static double destroy_now(void)
+{
+    struct timespec t;
+    clock_gettime(CLOCK_MONOTONIC, &t);
+    return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec;
+}
+
 void vitb200_destroy(vitb200_engine *e)
 {
     if (!e)
         return;
+    /* VITB200_DEBUG_TEARDOWN=1: where the tear-down spends its time (device sync / device frees / pinned frees /
+     * copy threads / events, streams, graphs) */
+    const int dbg = getenv("VITB200_DEBUG_TEARDOWN") != NULL;
+    double t[6];
+    t[0] = destroy_now();
     vitcu_set_device(e->device);
     vitcu_device_sync();
+    t[1] = destroy_now();
     vitcu_free(e->w_arena); /* every w32[] / w16[] pointer lives in it */
+    vitcu_free(e->d_arena); /* ... and every activation buffer in this one */
+    vitcu_free(e->d_topi);
+    vitcu_free(e->d_topv);
+    t[2] = destroy_now();
+    vitcu_host_free(e->h_probs);
+    vitcu_host_free(e->h_logits);
+    vitcu_host_free(e->h_topi);
+    vitcu_host_free(e->h_topv);
+    vitcu_host_free(e->h_stage);
+    t[3] = destroy_now();
+    vit_stager_destroy(e->stager);
+    t[4] = destroy_now();
     for (int i = 0; i < 2; i++) {
-        vitcu_free(e->d_images[i]);
-        vitcu_free(e->d_probs[i]);
-        vitcu_free(e->d_logits[i]);
         if (e->ev_h2d[i])
             vitcu_event_destroy(e->ev_h2d[i]);
         if (e->ev_done[i])
@@ -308,24 +363,6 @@ void vitb200_destroy(vitb200_engine *e)
         vitcu_event_destroy(e->ev_t0);
     if (e->ev_t1)
         vitcu_event_destroy(e->ev_t1);
-    vitcu_free(e->d_patches);
-    vitcu_free(e->d_a3);
-    vitcu_free(e->d_x);
-    vitcu_free(e->d_ln);
-    vitcu_free(e->d_qkv);
-    vitcu_free(e->d_att);
-    vitcu_free(e->d_hid);
-    vitcu_free(e->d_cls);
-    vitcu_free(e->d_lnstats);
-    vitcu_free(e->d_amax);
-    vitcu_host_free(e->h_probs);
-    vitcu_host_free(e->h_logits);
-    vitcu_free(e->d_topi);
-    vitcu_free(e->d_topv);
-    vitcu_host_free(e->h_topi);
-    vitcu_host_free(e->h_topv);
-    vit_stager_destroy(e->stager);
-    vitcu_host_free(e->h_stage);
     for (int i = 0; i < VIT_STAGE_SLOTS; i++)
         if (e->ev_slot[i])
             vitcu_event_destroy(e->ev_slot[i]);
@@ -333,6 +370,10 @@ void vitb200_destroy(vitb200_engine *e)
         vitcu_stream_destroy(e->stream);
     if (e->copy_stream)
         vitcu_stream_destroy(e->copy_stream);
+    t[5] = destroy_now();
+    if (dbg)
+        printf("ViT_b200 tear-down: sync %.4f, device frees %.4f, pinned frees %.4f, copy threads %.4f, events / streams / graphs %.4f s\n",
+               t[1] - t[0], t[2] - t[1], t[3] - t[2], t[4] - t[3], t[5] - t[4]);
     free(e);
 }
 

@@ -23,6 +23,7 @@ struct vitb200_engine {
     vitcu_event ev_h2d[2], ev_done[2], ev_out[2], ev_t0, ev_t1;
     vitcu_graph graph[2];
     void *w_arena;                   /* one device allocation holding every weight below */
+    void *d_arena;                   /* one device allocation holding every activation buffer below */
     float *w32[VIT_MAX_BLOBS];         /* fp32 blobs on the device (pointers into w_arena) */
     vitcu_bf16 *w16[VIT_MAX_BLOBS]; /* BF16 path: bf16 GEMM weights [N,K]; FP32 tensor-core path: three bf16 pieces [N,3K] */
     /* LayerNorm folded into the GEMMs (BF16 path, big chunks): folded copies of the weights that follow a LayerNorm
