@@ -205,3 +205,19 @@ def test_chunk_schedule_of_a_call():
     assert schedule(512, 256, 1, 0) == [64, 256, 192]
     assert schedule(100, 256, 1, 1) == [100]
     assert L.vitb200_next_chunk(0, 0, 256, 1, 1) == 0
+
+
+def test_dispatch_predicates_at_the_shapes_of_the_path():
+    """host-side kernel selection (no device needed: the SM count falls back to the B200's 148): which chunks run the
+    CTA-pair GEMMs with the folded LayerNorm (vitcu_gemm_bf16_emit_supported -- also the condition under which the chunk
+    schedule may cut quarter chunks) and which run the K-sliced single-CTA chain (vitcu_gemm_split_k_pays: batch-1 latency)"""
+    import __graft_entry__ as g
+    L = g.load_package().lib()
+    T, D, HID = 197, 768, 3072
+    # 256, 64 and 32 images are CTA-pair chunks, 16 images and fewer are not
+    assert [L.vitcu_gemm_bf16_emit_supported(b * T, D) for b in (256, 64, 32, 16, 4, 1)] == [1, 1, 1, 0, 0, 0]
+    assert L.vitcu_gemm_bf16_emit_supported(256 * T, 384) == 0          # widths that are not a multiple of 256 never pair
+    # K slicing pays while the 128 x 128 tiles of a product occupy at most half of the SMs
+    assert [L.vitcu_gemm_split_k_pays(T, n) for n in (3 * D, HID, D)] == [1, 1, 1]            # one 224 x 224 image
+    assert [L.vitcu_gemm_split_k_pays(2 * T, n) for n in (3 * D, HID)] == [1, 0]              # two images: fc1 is 96 tiles
+    assert L.vitcu_gemm_split_k_pays(577, 3 * D) == 0 and L.vitcu_gemm_split_k_pays(256 * T, D) == 0
