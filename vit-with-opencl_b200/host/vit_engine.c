@@ -509,11 +509,13 @@ int vitb200_load_weights(vitb200_engine *e, const vitb200_blob *net)
     const int staged = !(getenv("VITB200_WEIGHT_STAGE") && atoi(getenv("VITB200_WEIGHT_STAGE")) == 0);
     if (!rc && staged)
         rc = ensure_stage(e);
-    if (!rc && (rc = vitcu_malloc(&arena, total)) != 0)
+    /* the two scratch buffers ride at the end of the arena (19 MB that stay allocated): one cudaMalloc and no cudaFree
+     * per load instead of three and two -- a cold ViT_opencl call pays for every one of them */
+    const size_t scratch_bytes = (scratch_elems * sizeof(float) + 255) & ~(size_t)255;
+    if (!rc && (rc = vitcu_malloc(&arena, total + 2 * scratch_bytes)) != 0)
         vit_fail(__FILE__, __LINE__, rc, NULL);
     for (int k = 0; k < 2 && !rc && scratch_elems; k++)
-        if ((rc = vitcu_malloc((void **)&scratch[k], scratch_elems * sizeof(float))) != 0)
-            vit_fail(__FILE__, __LINE__, rc, NULL);
+        scratch[k] = (float *)((char *)arena + total + (size_t)k * scratch_bytes);
     int k = 0;
     for (int i = 0; i < e->nblobs && !rc; i++) {
         const size_t n = net[i].size;
@@ -581,8 +583,6 @@ int vitb200_load_weights(vitb200_engine *e, const vitb200_blob *net)
         vit_fail(__FILE__, __LINE__, rc, NULL);
     for (int i = 0; i < VIT_STAGE_SLOTS; i++) /* the ring is idle again (the image uploads record on another stream) */
         e->stage_used[i] = 0;
-    vitcu_free(scratch[0]);
-    vitcu_free(scratch[1]);
     if (!rc) {
         for (int i = 0; i < 2; i++) {
             if (e->graph[i])
