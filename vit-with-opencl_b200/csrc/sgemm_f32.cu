@@ -190,10 +190,39 @@ __global__ void __launch_bounds__(256) gemv_rows_kernel(const float *__restrict_
     if (n >= p.N)
         return;
     const float4 *w4 = reinterpret_cast<const float4 *>(W + (size_t)n * p.K);
+    const int k4 = p.K / 4;
+    if (k4 <= 256) {
+        // the weight row (cold: the head's weights come from DRAM on every forward) is requested in one go -- a loop of
+        // dependent load / fma iterations pays that latency once per iteration -- and held in registers for every input row
+        float4 w[8];
+        const float bias = p.bias[n];
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            w[i] = lane + 32 * i < k4 ? __ldg(w4 + lane + 32 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int m = 0; m < p.M; m++) {
+            const float4 *a4 = reinterpret_cast<const float4 *>(A + (size_t)m * p.lda);
+            float4 a[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                a[i] = lane + 32 * i < k4 ? a4[lane + 32 * i] : make_float4(0.f, 0.f, 0.f, 0.f);
+            float acc = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; i++) { // same order of accumulation as the loop below
+                acc = fmaf(a[i].x, w[i].x, acc);
+                acc = fmaf(a[i].y, w[i].y, acc);
+                acc = fmaf(a[i].z, w[i].z, acc);
+                acc = fmaf(a[i].w, w[i].w, acc);
+            }
+            acc = warp_sum(acc);
+            if (lane == 0)
+                C[(size_t)m * p.ldc + n] = acc + bias;
+        }
+        return;
+    }
     for (int m = 0; m < p.M; m++) {
         const float4 *a4 = reinterpret_cast<const float4 *>(A + (size_t)m * p.lda);
         float acc = 0.f;
-        for (int k = lane; k < p.K / 4; k += 32) {
+        for (int k = lane; k < k4; k += 32) {
             const float4 a = a4[k], w = __ldg(w4 + k);
             acc = fmaf(a.x, w.x, acc);
             acc = fmaf(a.y, w.y, acc);
