@@ -221,3 +221,39 @@ def test_dispatch_predicates_at_the_shapes_of_the_path():
     assert [L.vitcu_gemm_split_k_pays(T, n) for n in (3 * D, HID, D)] == [1, 1, 1]            # one 224 x 224 image
     assert [L.vitcu_gemm_split_k_pays(2 * T, n) for n in (3 * D, HID)] == [1, 0]              # two images: fc1 is 96 tiles
     assert L.vitcu_gemm_split_k_pays(577, 3 * D) == 0 and L.vitcu_gemm_split_k_pays(256 * T, D) == 0
+
+
+def test_ctypes_mirrors_match_the_c_headers(tmp_path):
+    """the ctypes structures of the Python mirror against the C headers themselves: a C program compiled from
+    include/*.h prints sizeof / offsetof of every mirrored struct, so that a field added on one side only fails here
+    instead of silently shifting the arguments of the GPU tests"""
+    import subprocess
+    import __graft_entry__ as g
+    pkg = g.load_package()
+    src = tmp_path / "abi.c"
+    src.write_text(r'''
+#include <stddef.h>
+#include <stdio.h>
+#include "vit_b200.h"
+#include "vit_cuda_layer.h"
+int main(void)
+{
+    printf("gemm_desc %zu %zu %zu %zu %zu %zu\n", sizeof(vitcu_gemm_desc), offsetof(vitcu_gemm_desc, lda), offsetof(vitcu_gemm_desc, ldc),
+           offsetof(vitcu_gemm_desc, ln_colsum), offsetof(vitcu_gemm_desc, emit_scale), offsetof(vitcu_gemm_desc, accumulate));
+    printf("call_stats %zu %zu %zu\n", sizeof(vitb200_call_stats), offsetof(vitb200_call_stats, wall_s), offsetof(vitb200_call_stats, teardown_s));
+    printf("model %zu %zu\n", sizeof(vitb200_model), offsetof(vitb200_model, hidden));
+    printf("image %zu %zu\n", sizeof(vitb200_image), offsetof(vitb200_image, data));
+    printf("blob %zu %zu\n", sizeof(vitb200_blob), offsetof(vitb200_blob, size));
+    return 0;
+}
+''')
+    exe = tmp_path / "abi"
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    subprocess.run(["gcc", "-std=c11", "-I", inc, "-o", str(exe), str(src)], check=True)
+    out = dict((l.split()[0], [int(v) for v in l.split()[1:]]) for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    G, S, M = pkg.GemmDesc, pkg.CallStats, pkg.Model
+    assert out["gemm_desc"] == [C.sizeof(G), G.lda.offset, G.ldc.offset, G.ln_colsum.offset, G.emit_scale.offset, G.accumulate.offset]
+    assert out["call_stats"] == [C.sizeof(S), S.wall_s.offset, S.teardown_s.offset]
+    assert out["model"] == [C.sizeof(M), M.hidden.offset]
+    assert out["image"] == [C.sizeof(pkg.ImageData), pkg.ImageData.data.offset]
+    assert out["blob"] == [C.sizeof(pkg.Network), pkg.Network.size.offset]
